@@ -1,0 +1,623 @@
+/* smh_oracle.c — CPU ORACLE (test infrastructure; see smh_oracle.h header comment).
+ *
+ * PARITY STATUS: parity unpinned (no reference golden vectors exist for this path).
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared
+ * All float arithmetic is IEEE binary32, no FMA contraction, evaluated in the order the
+ * Rust source writes it.  `as uN` casts follow Rust semantics (truncate, saturate, NaN->0).
+ */
+#include "smh_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/smh_consts.h"
+
+/* ---------------------------------------------------------------- Rust cast semantics */
+
+static inline uint32_t f32_as_u32(float f) {
+    if (!(f > 0.0f)) return 0; /* NaN, negative, zero */
+    if (f >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)f;
+}
+static inline uint16_t f32_as_u16(float f) {
+    if (!(f > 0.0f)) return 0;
+    if (f >= 65535.0f) return 65535;
+    return (uint16_t)f;
+}
+static inline uint8_t f32_as_u8(float f) {
+    if (!(f > 0.0f)) return 0;
+    if (f >= 255.0f) return 255;
+    return (uint8_t)f;
+}
+static inline uint32_t abs_diff_u(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
+
+static int g_threads = 1;
+void smh_oracle_set_threads(int n) {
+    g_threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+    omp_set_num_threads(g_threads);
+#endif
+}
+int smh_oracle_get_threads(void) { return g_threads; }
+
+/* ---------------------------------------------------------------- ROI geometry */
+
+/* RelativeBound::ScreenH(f).into_absolute — vision-common/src/screen.rs:61-66 */
+static inline uint32_t rel_h(double frac, uint32_t H) { return (uint32_t)round(frac * (double)H); }
+
+int smh_oracle_roi(uint32_t W, uint32_t H, uint32_t out[12]) {
+    /* CLOSE_DEPLOYMENT_BUTTON_BOUNDS: x Right, y Bottom — consts/mod.rs:14-19, screen.rs:8-30,41-46 */
+    uint32_t bw = rel_h(SMH_BTN_W_FRAC, H), bh = rel_h(SMH_BTN_H_FRAC, H);
+    int64_t bx = (int64_t)W - rel_h(SMH_BTN_X_RIGHT_FRAC, H) - bw;
+    int64_t by = (int64_t)H - rel_h(SMH_BTN_Y_BOTTOM_FRAC, H) - bh;
+    /* MAP_BOUNDS: x Left, y Bottom — consts/mod.rs:7-12 */
+    uint32_t w0 = rel_h(SMH_MAP_W_FRAC, H), h = rel_h(SMH_MAP_H_FRAC, H);
+    uint32_t x0 = rel_h(SMH_MAP_X_FRAC, H);
+    int64_t y = (int64_t)H - rel_h(SMH_MAP_Y_BOTTOM_FRAC, H) - h;
+    /* "Map fills remaining space" — vision-cpu/src/lib.rs:139-141 */
+    int64_t w = (int64_t)W - w0;
+    int64_t x = (int64_t)W - x0 - w;
+    if (bx < 0 || by < 0 || y < 0 || w <= 0 || x < 0 || h == 0 || bw == 0 || bh == 0) return -1;
+    /* par_iter_pixels! bounds — util/src/image.rs:9-16 */
+    if (bx + bw > W || by + bh > H) return -1;
+    /* par_crop_into panics when x+w >= W or y+h >= H — util/src/image.rs:67-73 (D12) */
+    if (x + w >= W || y + h >= H) return -1;
+    uint32_t bqw = (uint32_t)w / 2, bqh = h / 2; /* vision-cpu/src/lib.rs:143-145 */
+    if (bqw < SMH_OCR_RADIUS || bqh < SMH_OCR_RADIUS) return -1; /* `w - RADIUS` would underflow */
+    out[0] = (uint32_t)bx; out[1] = (uint32_t)by; out[2] = bw; out[3] = bh;
+    out[4] = (uint32_t)x; out[5] = (uint32_t)y; out[6] = (uint32_t)w; out[7] = h;
+    out[8] = (uint32_t)x + bqw; out[9] = (uint32_t)y + bqh; out[10] = bqw; out[11] = bqh;
+    return 0;
+}
+
+/* ---------------------------------------------------------------- colour helpers */
+
+uint8_t smh_oracle_luma8(uint8_t r, uint8_t g, uint8_t b) {
+    float l = SMH_LUMA_R * (float)r + SMH_LUMA_G * (float)g + SMH_LUMA_B * (float)b;
+    return f32_as_u8(l);
+}
+
+void smh_oracle_hsv(uint8_t r8, uint8_t g8, uint8_t b8, uint16_t *ho, uint8_t *so, uint8_t *vo) {
+    /* util/src/image.rs:159-187 */
+    float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, b = (float)b8 / 255.0f;
+    float max = fmaxf(r, fmaxf(g, b));
+    float min = fminf(r, fminf(g, b));
+    float delta = max - min;
+    float h;
+    if (max == min) h = 0.0f;
+    else if (max == r) h = 60.0f * fmodf((g - b) / delta, 6.0f);
+    else if (max == g) h = 60.0f * (((b - r) / delta) + 2.0f);
+    else h = 60.0f * (((r - g) / delta) + 4.0f);
+    float s = 100.0f * delta / max; /* (100*delta)/max; 0/0 = NaN -> 0 */
+    float v = 100.0f * max;
+    float hm = fmodf(h, 360.0f);
+    if (hm < 0.0f) hm = hm + 360.0f;
+    *ho = f32_as_u16(hm);
+    *so = f32_as_u8(s);
+    *vo = f32_as_u8(v);
+}
+
+/* vision-common/src/markers/mod.rs:17-19 */
+static inline int saturation_ok(uint8_t s, uint8_t ms) {
+    if (abs_diff_u(ms, s) <= SMH_SAT_TOL) return 1;
+    int16_t d = (int16_t)((int16_t)s - ((int16_t)ms - SMH_ARC_SAT));
+    if (d < 0) d = (int16_t)-d;
+    return (uint8_t)d <= SMH_SAT_TOL;
+}
+
+int smh_oracle_is_marker(uint8_t r, uint8_t g, uint8_t b) {
+    /* vision-common/src/markers/mod.rs:40-54 */
+    static const uint16_t MH[3] = {SMH_ALPHA_H, SMH_BRAVO_H, SMH_CHARLIE_H};
+    static const uint8_t MS[3] = {SMH_ALPHA_S, SMH_BRAVO_S, SMH_CHARLIE_S};
+    static const uint8_t MV[3] = {SMH_ALPHA_V, SMH_BRAVO_V, SMH_CHARLIE_V};
+    uint16_t h; uint8_t s, v;
+    smh_oracle_hsv(r, g, b, &h, &s, &v);
+    if (s < SMH_MIN_SAT) return 0;
+    for (int t = 0; t < 3; t++) {
+        if (abs_diff_u(MH[t], h) <= SMH_HUE_TOL && saturation_ok(s, MS[t]) &&
+            abs_diff_u(MV[t], v) <= SMH_VIB_TOL)
+            return 1;
+    }
+    return 0;
+}
+
+void smh_oracle_table_marker(uint8_t *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (1 << 24); c++)
+        out[c] = (uint8_t)smh_oracle_is_marker((uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c);
+}
+void smh_oracle_table_luma(uint8_t *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (1 << 24); c++)
+        out[c] = smh_oracle_luma8((uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c);
+}
+void smh_oracle_table_hsv(uint16_t *h, uint8_t *s, uint8_t *v) {
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < (1 << 24); c++)
+        smh_oracle_hsv((uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c, &h[c], &s[c], &v[c]);
+}
+
+void smh_oracle_ray_table(float *dxdy) {
+    /* vision-cpu/src/lib.rs:437 `((theta as f32) / 10.0).to_radians()`; f32::to_radians is
+     * `self * (PI_f32 / 180.0_f32)`; :398-399 `theta.cos()`, `theta.sin()` -> libm cosf/sinf */
+    const float rads_per_deg = 3.14159265358979323846f / 180.0f;
+    for (uint32_t k = 0; k < SMH_LSD_RAYS; k++) {
+        float theta = ((float)k / 10.0f) * rads_per_deg;
+        dxdy[2 * k] = cosf(theta);
+        dxdy[2 * k + 1] = sinf(theta);
+    }
+}
+
+/* ---------------------------------------------------------------- backend state */
+
+struct smh_oracle {
+    uint8_t *frame; /* BGRA, W*H*4 */
+    uint32_t W, H;
+    uint32_t roi[12];
+    uint8_t *cropped_map;  /* RGB8 w*h */
+    uint8_t *cropped_brq;  /* RGB8 bqw*bqh */
+    uint8_t *ocr_out;      /* L8 bqw*bqh */
+    uint8_t *scales;       /* L8 bqw*bqh */
+    uint8_t *lsd_image;    /* L8 w*h */
+    uint8_t *raw_mask;     /* L8 w*h (oracle-only view of the mask before dilation) */
+    uint8_t *ui_map;       /* RGBA w*h, owned by the oracle, refreshed by crop_to_map */
+    uint16_t *dist;        /* scratch for the distance transform */
+};
+
+smh_oracle *smh_oracle_new(void) { return (smh_oracle *)calloc(1, sizeof(smh_oracle)); }
+
+static void free_buffers(smh_oracle *o) {
+    free(o->cropped_map); free(o->cropped_brq); free(o->ocr_out); free(o->scales);
+    free(o->lsd_image); free(o->raw_mask); free(o->ui_map); free(o->dist);
+    o->cropped_map = o->cropped_brq = o->ocr_out = o->scales = o->lsd_image = o->raw_mask = o->ui_map = NULL;
+    o->dist = NULL;
+}
+
+void smh_oracle_free(smh_oracle *o) {
+    if (!o) return;
+    free_buffers(o);
+    free(o->frame);
+    free(o);
+}
+
+int smh_oracle_load_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uint32_t H) {
+    /* vision-cpu/src/lib.rs:69-93: buffers are re-created (zeroed) only when the frame
+     * dimensions change; otherwise they keep the previous frame's content. */
+    if (!o || !bgra || W == 0 || H == 0) return -2;
+    if (o->W != W || o->H != H || !o->frame) {
+        uint32_t roi[12];
+        if (smh_oracle_roi(W, H, roi) != 0) return -1;
+        free_buffers(o);
+        free(o->frame);
+        o->frame = (uint8_t *)malloc((size_t)W * H * 4);
+        memcpy(o->roi, roi, sizeof roi);
+        size_t n = (size_t)roi[6] * roi[7], nq = (size_t)roi[10] * roi[11];
+        o->cropped_map = (uint8_t *)calloc(n, 3);
+        o->cropped_brq = (uint8_t *)calloc(nq, 3);
+        o->ocr_out = (uint8_t *)calloc(nq, 1);
+        o->scales = (uint8_t *)calloc(nq, 1);
+        o->lsd_image = (uint8_t *)calloc(n, 1);
+        o->raw_mask = (uint8_t *)calloc(n, 1);
+        o->ui_map = (uint8_t *)calloc(n, 4);
+        o->dist = (uint16_t *)calloc(n, sizeof(uint16_t));
+        o->W = W; o->H = H;
+    }
+    memcpy(o->frame, bgra, (size_t)W * H * 4);
+    return 0;
+}
+
+int smh_oracle_crop_to_map(smh_oracle *o, int grayscale, int *map_open, uint32_t xywh[4],
+                           const uint8_t **ui_map_rgba, uint32_t *red_pixels) {
+    if (!o || !o->frame) return -2;
+    const uint32_t W = o->W;
+    const uint8_t *f = o->frame;
+    /* button test — vision-cpu/src/lib.rs:115-135 */
+    const uint32_t bx = o->roi[0], by = o->roi[1], bw = o->roi[2], bh = o->roi[3];
+    static const int16_t C[3] = {SMH_BTN_COLOR_R, SMH_BTN_COLOR_G, SMH_BTN_COLOR_B};
+    uint32_t red = 0;
+#pragma omp parallel for reduction(+ : red) schedule(static)
+    for (uint32_t j = 0; j < bh; j++)
+        for (uint32_t i = 0; i < bw; i++) {
+            const uint8_t *p = f + ((size_t)(by + j) * W + (bx + i)) * 4;
+            const uint8_t rgb[3] = {p[2], p[1], p[0]};
+            int ok = 1;
+            for (int c = 0; c < 3; c++) {
+                int16_t d = (int16_t)(C[c] - (int16_t)rgb[c]);
+                if (d < 0) d = (int16_t)-d;
+                if ((uint16_t)d > SMH_BTN_TOLERANCE) { ok = 0; break; }
+            }
+            red += (uint32_t)ok;
+        }
+    if (red_pixels) *red_pixels = red;
+    float ratio = (float)red / (float)(bw * bh);
+    if (ratio < SMH_BTN_RED_RATIO_THRESHOLD) {
+        if (map_open) *map_open = 0;
+        return 0; /* Ok(None) */
+    }
+    /* crops — vision-cpu/src/lib.rs:137-170 */
+    const uint32_t x = o->roi[4], y = o->roi[5], w = o->roi[6], h = o->roi[7];
+    const uint32_t qx = o->roi[8], qy = o->roi[9], qw = o->roi[10], qh = o->roi[11];
+#pragma omp parallel for schedule(static)
+    for (uint32_t j = 0; j < h; j++)
+        for (uint32_t i = 0; i < w; i++) {
+            const uint8_t *p = f + ((size_t)(y + j) * W + (x + i)) * 4;
+            uint8_t *u = o->ui_map + ((size_t)j * w + i) * 4;
+            uint8_t *c = o->cropped_map + ((size_t)j * w + i) * 3;
+            if (grayscale) {
+                uint8_t l = smh_oracle_luma8(p[2], p[1], p[0]);
+                u[0] = l; u[1] = l; u[2] = l; u[3] = 255;
+            } else {
+                u[0] = p[2]; u[1] = p[1]; u[2] = p[0]; u[3] = 255;
+            }
+            c[0] = p[2]; c[1] = p[1]; c[2] = p[0];
+        }
+#pragma omp parallel for schedule(static)
+    for (uint32_t j = 0; j < qh; j++)
+        for (uint32_t i = 0; i < qw; i++) {
+            const uint8_t *p = f + ((size_t)(qy + j) * W + (qx + i)) * 4;
+            uint8_t *c = o->cropped_brq + ((size_t)j * qw + i) * 3;
+            c[0] = p[2]; c[1] = p[1]; c[2] = p[0];
+        }
+    if (map_open) *map_open = 1;
+    if (xywh) { xywh[0] = x; xywh[1] = y; xywh[2] = w; xywh[3] = h; }
+    if (ui_map_rgba) *ui_map_rgba = o->ui_map;
+    return 0;
+}
+
+/* vision-cpu/src/lib.rs:39-53 */
+static inline uint8_t ocr_brightness(const uint8_t *p) {
+    uint8_t m = p[0] < p[1] ? p[0] : p[1];
+    return m < p[2] ? m : p[2];
+}
+static inline uint16_t ocr_monochromaticy(const uint8_t *p) {
+    uint16_t diff = 0;
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) diff = (uint16_t)(diff + abs_diff_u(p[a], p[b]));
+    return diff;
+}
+
+int smh_oracle_ocr_preprocess(smh_oracle *o, const uint8_t **out, size_t *len) {
+    /* vision-cpu/src/lib.rs:173-231 */
+    if (!o || !o->frame) return -2;
+    const uint32_t w = o->roi[10], h = o->roi[11];
+    const uint8_t *q = o->cropped_brq;
+    const uint32_t R = SMH_OCR_RADIUS;
+#pragma omp parallel for schedule(static)
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            const uint8_t *p = q + ((size_t)y * w + x) * 3;
+            int keep = 0;
+            uint16_t diff = ocr_monochromaticy(p);
+            if (diff <= SMH_OCR_MONO && ocr_brightness(p) >= SMH_OCR_BRIGHT) {
+                keep = 1;
+            } else if (diff <= SMH_OCR_MONO_EDGE && ocr_brightness(p) >= SMH_OCR_BRIGHT_EDGE) {
+                /* window: x.saturating_sub(R) ..= min(x+R, w-R) (lib.rs:201-205, D10) */
+                uint32_t x_lo = x >= R ? x - R : 0, x_hi = (x + R < w - R) ? x + R : w - R;
+                uint32_t y_lo = y >= R ? y - R : 0, y_hi = (y + R < h - R) ? y + R : h - R;
+                for (uint32_t xx = x_lo; xx <= x_hi && !keep; xx++)
+                    for (uint32_t yy = y_lo; yy <= y_hi; yy++) {
+                        const uint8_t *n = q + ((size_t)yy * w + xx) * 3;
+                        if (ocr_brightness(n) < SMH_OCR_BRIGHT) continue;
+                        if (ocr_monochromaticy(n) <= SMH_OCR_MONO) { keep = 1; break; }
+                    }
+            }
+            o->ocr_out[(size_t)y * w + x] =
+                keep ? (uint8_t)(255 - smh_oracle_luma8(p[0], p[1], p[2])) : 255;
+        }
+    if (out) *out = o->ocr_out;
+    if (len) *len = (size_t)w * h;
+    return 0;
+}
+
+int smh_oracle_find_scales_preprocess(smh_oracle *o, uint32_t start_y, const uint8_t **out,
+                                      uint32_t wh[2]) {
+    /* vision-cpu/src/lib.rs:233-251.  Release-build behaviour for start_y >= h: `h - start_y`
+     * wraps, par_iter_pixels' bound check `y + h' > height` wraps back to `h > h` = false and
+     * the row range start_y..h is empty => no-op (D9). */
+    if (!o || !o->frame) return -2;
+    const uint32_t w = o->roi[10], h = o->roi[11];
+    const uint8_t *q = o->cropped_brq;
+    if (start_y < h) {
+#pragma omp parallel for schedule(static)
+        for (uint32_t y = start_y; y < h; y++)
+            for (uint32_t x = 0; x < w; x++) {
+                const uint8_t *p = q + ((size_t)y * w + x) * 3;
+                o->scales[(size_t)y * w + x] = smh_oracle_luma8(p[0], p[1], p[2]) != 0 ? 255 : 0;
+            }
+    }
+    if (out) *out = o->scales;
+    if (wh) { wh[0] = w; wh[1] = h; }
+    return 0;
+}
+
+int smh_oracle_isolate_map_markers(smh_oracle *o) {
+    /* vision-cpu/src/lib.rs:253-280 */
+    if (!o || !o->frame) return -2;
+    const size_t n = (size_t)o->roi[6] * o->roi[7];
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        uint8_t *p = o->cropped_map + i * 3;
+        if (!smh_oracle_is_marker(p[0], p[1], p[2])) { p[0] = 0; p[1] = 0; p[2] = 0; }
+    }
+    return 0;
+}
+
+/* imageproc 0.22.0 morphology::dilate_mut(image, Norm::L1, k):
+ *   distance_transform_mut(image, L1)  — two-pass chamfer over the 4-neighbourhood,
+ *     foreground (non-zero) -> 0, background -> 255, candidate+1 compared in u16;
+ *   then every pixel <= k becomes 255, else 0. */
+static void dilate_l1(uint8_t *img, uint16_t *d, uint32_t w, uint32_t h, uint8_t k) {
+    const size_t n = (size_t)w * h;
+    for (size_t i = 0; i < n; i++) d[i] = img[i] > 0 ? 0 : 255;
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            uint16_t cur = d[(size_t)y * w + x];
+            if (x > 0) { uint16_t c = (uint16_t)(d[(size_t)y * w + x - 1] + 1); if (c < cur) cur = c; }
+            if (y > 0) { uint16_t c = (uint16_t)(d[(size_t)(y - 1) * w + x] + 1); if (c < cur) cur = c; }
+            d[(size_t)y * w + x] = cur;
+        }
+    for (uint32_t y = h; y-- > 0;)
+        for (uint32_t x = w; x-- > 0;) {
+            uint16_t cur = d[(size_t)y * w + x];
+            if (x + 1 < w) { uint16_t c = (uint16_t)(d[(size_t)y * w + x + 1] + 1); if (c < cur) cur = c; }
+            if (y + 1 < h) { uint16_t c = (uint16_t)(d[(size_t)(y + 1) * w + x] + 1); if (c < cur) cur = c; }
+            d[(size_t)y * w + x] = cur;
+        }
+    for (size_t i = 0; i < n; i++) img[i] = d[i] <= k ? 255 : 0;
+}
+
+int smh_oracle_mask_marker_lines(smh_oracle *o) {
+    /* vision-cpu/src/lib.rs:357-375 */
+    if (!o || !o->frame) return -2;
+    const uint32_t w = o->roi[6], h = o->roi[7];
+    const size_t n = (size_t)w * h;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t *p = o->cropped_map + i * 3;
+        o->lsd_image[i] = smh_oracle_is_marker(p[0], p[1], p[2]) ? 255 : 0;
+    }
+    memcpy(o->raw_mask, o->lsd_image, n);
+    dilate_l1(o->lsd_image, o->dist, w, h, 1);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- line search */
+
+static _Thread_local uint64_t t_seeds, t_steps;
+void smh_oracle_lsd_stats(uint64_t *seeds, uint64_t *ray_steps) {
+    if (seeds) *seeds = t_seeds;
+    if (ray_steps) *ray_steps = t_steps;
+}
+
+/* find_line_in_image — vision-cpu/src/lib.rs:388-432 */
+static inline uint32_t march(const uint8_t *img, uint32_t w, uint32_t h, float px, float py,
+                             float max_gap, float dx, float dy, float end[2]) {
+    float x = px, y = py;
+    float gap_n = 0.0f, gap_x = 0.0f, gap_y = 0.0f;
+    float xo = 0.0f, yo = 0.0f;
+    const float wf = (float)w, hf = (float)h;
+    uint32_t steps = 0;
+    while (x >= 0.0f && y >= 0.0f && x < wf && y < hf) {
+        steps++;
+        if (img[(size_t)(uint32_t)y * w + (uint32_t)x] == 255) {
+            gap_n = 0.0f; gap_x = 0.0f; gap_y = 0.0f;
+        } else if (gap_n >= max_gap) {
+            x = gap_x; y = gap_y;
+            break;
+        } else if (gap_n == 0.0f) {
+            gap_n = 1.0f; gap_x = x; gap_y = y;
+        } else {
+            gap_n += 1.0f;
+        }
+        xo += dx; yo += dy;
+        x = xo + px; y = yo + py;
+    }
+    /* image.get_pixel_checked(x as u32, y as u32) == Some(Luma([0])) — lib.rs:426-429,
+     * util/src/image.rs:113-124 (D7) */
+    uint32_t xi = f32_as_u32(x), yi = f32_as_u32(y);
+    if (xi < w && yi < h && img[(size_t)yi * w + xi] == 0) {
+        end[0] = x - dx; end[1] = y - dy;
+    } else {
+        end[0] = px; end[1] = py;
+    }
+    return steps;
+}
+
+static const float *ray_table(void) {
+    static float tab[2 * SMH_LSD_RAYS];
+    static int ready = 0;
+#pragma omp critical(smh_ray_table)
+    {
+        if (!ready) { smh_oracle_ray_table(tab); ready = 1; }
+    }
+    return tab;
+}
+
+int smh_oracle_find_longest_line_in(const uint8_t *img, uint32_t w, uint32_t h, float px, float py,
+                                    float max_gap, float line[4], float *len_sq) {
+    /* vision-cpu/src/lib.rs:434-448: map over theta in 0..3600, reduce(Default, keep a only if
+     * a_len > b_len) => the LAST index among equal maxima wins; the Default identity only ever
+     * sits on the left of the fold, so an all-zero search returns ray 3599's (pt,pt). */
+    const float *tab = ray_table();
+    float best_len = -1.0f; /* any len >= 0 replaces it at k=0, like (identity, item) -> item */
+    float best_end[2] = {px, py};
+    uint64_t steps_total = 0;
+    if (g_threads > 1) {
+        int best_k = -1;
+#pragma omp parallel reduction(+ : steps_total)
+        {
+            float l_len = -1.0f, l_end[2] = {px, py};
+            int l_k = -1;
+#pragma omp for schedule(static) nowait
+            for (int k = 0; k < SMH_LSD_RAYS; k++) {
+                float e[2];
+                steps_total += march(img, w, h, px, py, max_gap, tab[2 * k], tab[2 * k + 1], e);
+                float len = (px - e[0]) * (px - e[0]) + (py - e[1]) * (py - e[1]);
+                if (!(l_len > len)) { l_len = len; l_end[0] = e[0]; l_end[1] = e[1]; l_k = k; }
+            }
+            /* merge thread-local winners by the lexicographic (len, k) maximum: identical to
+             * the sequential right-biased fold whatever the schedule */
+#pragma omp critical(smh_reduce)
+            {
+                if (l_k >= 0 && (l_len > best_len || (l_len == best_len && l_k > best_k))) {
+                    best_len = l_len; best_end[0] = l_end[0]; best_end[1] = l_end[1]; best_k = l_k;
+                }
+            }
+        }
+    } else {
+        for (int k = 0; k < SMH_LSD_RAYS; k++) {
+            float e[2];
+            steps_total += march(img, w, h, px, py, max_gap, tab[2 * k], tab[2 * k + 1], e);
+            /* distance_sqr — util/src/geometry.rs:62-68: (p0-p1)^2 summed, unfused */
+            float len = (px - e[0]) * (px - e[0]) + (py - e[1]) * (py - e[1]);
+            if (!(best_len > len)) { best_len = len; best_end[0] = e[0]; best_end[1] = e[1]; }
+        }
+    }
+    t_steps += steps_total;
+    line[0] = px; line[1] = py; line[2] = best_end[0]; line[3] = best_end[1];
+    *len_sq = best_len;
+    return 0;
+}
+
+int smh_oracle_find_longest_line(smh_oracle *o, float x, float y, float max_gap, float line[4],
+                                 float *len_sq) {
+    if (!o || !o->frame) return -2;
+    return smh_oracle_find_longest_line_in(o->lsd_image, o->roi[6], o->roi[7], x, y, max_gap, line, len_sq);
+}
+
+/* get_centre — vision-common/src/lsd.rs:5-44.  The reference indexes with unchecked
+ * `unsafe_get_pixel`; an index == w or == h can only come from f32 rounding at the right /
+ * bottom border (UB in the reference, D8) — clamp there. */
+static inline uint8_t px_at(const uint8_t *img, uint32_t w, uint32_t h, float fx, float fy) {
+    uint32_t x = f32_as_u32(fx), y = f32_as_u32(fy);
+    if (x >= w) x = w - 1;
+    if (y >= h) y = h - 1;
+    return img[(size_t)y * w + x];
+}
+static void get_centre(const uint8_t *img, uint32_t w, uint32_t h, float ptx, float pty, float out[2]) {
+    const float MAX_DIST = SMH_LSD_CENTRE_MAX_DIST;
+    float left = ptx;
+    while (left > 0.0f && fabsf(left - ptx) < MAX_DIST && px_at(img, w, h, left, pty) == 255) left -= 1.0f;
+    float right = ptx;
+    while (right < (float)(w - 1) && fabsf(right - ptx) < MAX_DIST && px_at(img, w, h, right, pty) == 255) right += 1.0f;
+    float up = pty;
+    while (up > 0.0f && fabsf(up - pty) < MAX_DIST && px_at(img, w, h, ptx, up) == 255) up -= 1.0f;
+    float down = pty;
+    while (down < (float)(h - 1) && fabsf(down - pty) < MAX_DIST && px_at(img, w, h, ptx, down) == 255) down += 1.0f;
+    out[0] = (left + right) / 2.0f;
+    out[1] = (up + down) / 2.0f;
+}
+
+/* nearest_point_on_line — vision-common/src/lsd.rs:46-58 (infinite line, D14) */
+static inline void nearest_point_on_line(float ptx, float pty, const float l[4], float out[2]) {
+    float dx = l[2] - l[0], dy = l[3] - l[1];
+    if (dx == 0.0f && dy == 0.0f) { out[0] = l[0]; out[1] = l[1]; return; }
+    float u = ((ptx - l[0]) * dx + (pty - l[1]) * dy) / (dx * dx + dy * dy);
+    out[0] = l[0] + u * dx;
+    out[1] = l[1] + u * dy;
+}
+
+int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap_u,
+                             float lines[32][4], uint32_t *n_out) {
+    /* vision-common/src/lsd.rs:60-105 with N = 32 (vision-common/src/lib.rs:58) */
+    const float max_gap = (float)max_gap_u;
+    uint32_t n = 0;
+    t_seeds = 0; t_steps = 0;
+    for (uint32_t yi = 0; yi < h && n < SMH_LSD_MAX_LINES; yi++) {
+        for (uint32_t xi = 0; xi < w; xi++) {
+            if (img[(size_t)yi * w + xi] != 255) continue;
+            const float x = (float)xi, y = (float)yi;
+            int suppressed = 0;
+            for (uint32_t l = 0; l < n; l++) {
+                float np[2];
+                nearest_point_on_line(x, y, lines[l], np);
+                float ddx = x - np[0], ddy = y - np[1];
+                if (ddx * ddx + ddy * ddy < SMH_LSD_SUPPRESS_DIST_SQ) { suppressed = 1; break; }
+            }
+            if (suppressed) continue;
+            float c[2];
+            get_centre(img, w, h, x, y, c);
+            float longest[4], len;
+            t_seeds++;
+            smh_oracle_find_longest_line_in(img, w, h, c[0], c[1], max_gap, longest, &len);
+            if (len > SMH_LSD_MIN_LEN_SQ) {
+                float c1[2];
+                get_centre(img, w, h, longest[2], longest[3], c1);
+                lines[n][0] = longest[0]; lines[n][1] = longest[1];
+                lines[n][2] = c1[0]; lines[n][3] = c1[1];
+                n++;
+                if (n == SMH_LSD_MAX_LINES) break; /* break 'row */
+            }
+        }
+    }
+    *n_out = n;
+    return 0;
+}
+
+int smh_oracle_find_marker_lines(smh_oracle *o, uint32_t max_gap, float lines[32][4], uint32_t *n) {
+    if (!o || !o->frame) return -2;
+    return smh_oracle_find_lines_in(o->lsd_image, o->roi[6], o->roi[7], max_gap, lines, n);
+}
+
+/* ---------------------------------------------------------------- debug views / getters */
+
+int smh_oracle_debug_view(smh_oracle *o, uint8_t which, uint8_t *rgba, uint32_t wh[2]) {
+    /* vision-cpu/src/lib.rs:451-460; image's ConvertBuffer: Luma -> (l,l,l,255), Rgb -> (r,g,b,255) */
+    if (!o || !o->frame) return -2;
+    const uint8_t *src; uint32_t w, h; int ch;
+    switch (which) {
+        case 0: return 1;
+        case 1: src = o->ocr_out; w = o->roi[10]; h = o->roi[11]; ch = 1; break;
+        case 2: src = o->scales; w = o->roi[10]; h = o->roi[11]; ch = 1; break;
+        case 3: src = o->cropped_map; w = o->roi[6]; h = o->roi[7]; ch = 3; break;
+        case 4: src = o->lsd_image; w = o->roi[6]; h = o->roi[7]; ch = 1; break;
+        case 5: src = o->cropped_brq; w = o->roi[10]; h = o->roi[11]; ch = 3; break;
+        default: return -3;
+    }
+    if (wh) { wh[0] = w; wh[1] = h; }
+    if (rgba) {
+        const size_t n = (size_t)w * h;
+        for (size_t i = 0; i < n; i++) {
+            if (ch == 1) { rgba[4 * i] = rgba[4 * i + 1] = rgba[4 * i + 2] = src[i]; }
+            else { rgba[4 * i] = src[3 * i]; rgba[4 * i + 1] = src[3 * i + 1]; rgba[4 * i + 2] = src[3 * i + 2]; }
+            rgba[4 * i + 3] = 255;
+        }
+    }
+    return 0;
+}
+
+#define GETTER(name, field, wi, hi)                                     \
+    const uint8_t *smh_oracle_##name(smh_oracle *o, uint32_t wh[2]) {   \
+        if (!o || !o->frame) return NULL;                               \
+        if (wh) { wh[0] = o->roi[wi]; wh[1] = o->roi[hi]; }             \
+        return o->field;                                                \
+    }
+GETTER(cropped_map, cropped_map, 6, 7)
+GETTER(cropped_brq, cropped_brq, 10, 11)
+GETTER(lsd_image, lsd_image, 6, 7)
+GETTER(scales, scales, 10, 11)
+GETTER(raw_mask, raw_mask, 6, 7)
+
+int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uint32_t H,
+                             int grayscale, uint32_t start_y, uint32_t max_gap,
+                             float lines[32][4], uint32_t *n_lines) {
+    /* call order of VisionState::process — src/vision/mod.rs:66-223 */
+    int rc = smh_oracle_load_frame(o, bgra, W, H);
+    if (rc) return rc;
+    int open = 0;
+    rc = smh_oracle_crop_to_map(o, grayscale, &open, NULL, NULL, NULL);
+    if (rc) return rc;
+    *n_lines = 0;
+    if (!open) return 0;
+    smh_oracle_isolate_map_markers(o);
+    smh_oracle_mask_marker_lines(o);
+    smh_oracle_find_marker_lines(o, max_gap, lines, n_lines);
+    smh_oracle_ocr_preprocess(o, NULL, NULL);
+    smh_oracle_find_scales_preprocess(o, start_y, NULL, NULL);
+    return 1;
+}

@@ -1,0 +1,110 @@
+/* smh_oracle.h — CPU ORACLE for the map-analysis vision path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference's `vision-cpu` backend (CPUFallback) and the
+ * shared `lsd::find_lines` driver.  It exists to CHECK the CUDA path; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it.  The product library (libsmh_b200.so) never links or calls it.
+ *
+ * PARITY STATUS: **parity unpinned**.  The reference holds no golden vectors or
+ * known-answer tests for this path and its Rust crates cannot be built
+ * in this image (no cargo/rustc; crates.io deps un-vendored).  The oracle is pinned
+ * only by (i) an independent numpy restatement (oracle/np_oracle.py), (ii) exhaustive
+ * 2^24-colour tables, (iii) self-generated goldens under tests/golden/.
+ *
+ * Third-party arithmetic restated from the published algorithm (sources NOT in
+ * /root/reference): image 0.23.14 (`Pixel::to_luma`, Cargo.lock:1487), imageproc 0.22.0
+ * (`morphology::dilate_mut(Norm::L1, 1)`, Cargo.lock:1503), rayon 1.5.3 (reduce order),
+ * libm cosf/sinf (glibc here).
+ *
+ * Every function cites the reference lines it follows (paths relative to /root/reference).
+ */
+#ifndef SMH_ORACLE_H
+#define SMH_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smh_oracle smh_oracle;
+
+/* ---- pure helpers -------------------------------------------------------------- */
+
+/* vision-common/src/screen.rs:55-66 + consts/mod.rs:7-19 + vision-cpu/src/lib.rs:116,137-145.
+ * out = {btn x,y,w,h, map x,y,w,h, brq x,y,w,h} (brq in FRAME coordinates).
+ * Returns 0, or -1 when the reference would panic (crop out of bounds, D12). */
+int smh_oracle_roi(uint32_t W, uint32_t H, uint32_t out[12]);
+
+/* image 0.23.14 rgb_to_luma: ((0.2126f*r + 0.7152f*g) + 0.0722f*b) as u8, unfused f32 */
+uint8_t smh_oracle_luma8(uint8_t r, uint8_t g, uint8_t b);
+/* util/src/image.rs:159-187 */
+void smh_oracle_hsv(uint8_t r, uint8_t g, uint8_t b, uint16_t *h, uint8_t *s, uint8_t *v);
+/* vision-common/src/markers/mod.rs:17-19,40-54 */
+int smh_oracle_is_marker(uint8_t r, uint8_t g, uint8_t b);
+/* Exhaustive tables over all 2^24 colours, index = r<<16 | g<<8 | b. */
+void smh_oracle_table_marker(uint8_t *out /* 2^24 */);
+void smh_oracle_table_luma(uint8_t *out /* 2^24 */);
+void smh_oracle_table_hsv(uint16_t *h, uint8_t *s, uint8_t *v /* 2^24 each */);
+/* the 3600 (cos, sin) pairs of vision-cpu/src/lib.rs:398-399,437 (f32, libm) */
+void smh_oracle_ray_table(float *dxdy /* 7200: dx0,dy0,dx1,dy1,... */);
+
+/* ---- the backend object (mirrors CPUFallback, vision-cpu/src/lib.rs:11-26) ------ */
+
+smh_oracle *smh_oracle_new(void);
+void smh_oracle_free(smh_oracle *o);
+/* Threads used by the pixel loops and the 3600-ray search (rayon's role). 1 = scalar. */
+void smh_oracle_set_threads(int n);
+int smh_oracle_get_threads(void);
+
+/* vision-cpu/src/lib.rs:69-93.  bgra tightly packed W*H*4 (B,G,R,A).  The oracle copies it. */
+int smh_oracle_load_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uint32_t H);
+/* vision-cpu/src/lib.rs:110-171.  *map_open=0 mirrors Ok(None).  ui_map: borrowed, w*h*4. */
+int smh_oracle_crop_to_map(smh_oracle *o, int grayscale, int *map_open, uint32_t xywh[4],
+                           const uint8_t **ui_map_rgba, uint32_t *red_pixels);
+/* vision-cpu/src/lib.rs:173-231 */
+int smh_oracle_ocr_preprocess(smh_oracle *o, const uint8_t **out, size_t *len);
+/* vision-cpu/src/lib.rs:233-251 (rows < start_y keep their previous content, D9) */
+int smh_oracle_find_scales_preprocess(smh_oracle *o, uint32_t scales_start_y, const uint8_t **out,
+                                      uint32_t wh[2]);
+/* vision-cpu/src/lib.rs:253-280 */
+int smh_oracle_isolate_map_markers(smh_oracle *o);
+/* vision-cpu/src/lib.rs:357-375 (+ imageproc dilate L1,k=1) */
+int smh_oracle_mask_marker_lines(smh_oracle *o);
+/* vision-cpu/src/lib.rs:387-449 on the oracle's own lsd_image */
+int smh_oracle_find_longest_line(smh_oracle *o, float x, float y, float max_gap, float line[4],
+                                 float *len_sq);
+/* same search on a caller-supplied L8 image (the trait passes the image explicitly) */
+int smh_oracle_find_longest_line_in(const uint8_t *img, uint32_t w, uint32_t h, float x, float y,
+                                    float max_gap, float line[4], float *len_sq);
+/* vision-cpu/src/lib.rs:377-385 + vision-common/src/lsd.rs:60-105 */
+int smh_oracle_find_marker_lines(smh_oracle *o, uint32_t max_gap, float lines[32][4], uint32_t *n);
+/* lsd::find_lines on a caller-supplied L8 image */
+int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap,
+                             float lines[32][4], uint32_t *n);
+/* vision-cpu/src/lib.rs:451-460; which = DebugView discriminant (vision-common/src/debug.rs:31-40).
+ * Fills rgba (w*h*4 of that view) if non-NULL; always writes wh. Returns 1 for None. */
+int smh_oracle_debug_view(smh_oracle *o, uint8_t which, uint8_t *rgba, uint32_t wh[2]);
+
+/* borrowed views of the intermediate buffers (valid until the next load_frame/free) */
+const uint8_t *smh_oracle_cropped_map(smh_oracle *o, uint32_t wh[2]);  /* RGB8 */
+const uint8_t *smh_oracle_cropped_brq(smh_oracle *o, uint32_t wh[2]);  /* RGB8 */
+const uint8_t *smh_oracle_lsd_image(smh_oracle *o, uint32_t wh[2]);    /* L8 */
+const uint8_t *smh_oracle_scales(smh_oracle *o, uint32_t wh[2]);       /* L8 */
+/* raw (pre-dilation) marker mask of the last mask_marker_lines call, L8 0/255 */
+const uint8_t *smh_oracle_raw_mask(smh_oracle *o, uint32_t wh[2]);
+
+/* work counters of the last find_marker_lines / find_lines_in call on this thread */
+void smh_oracle_lsd_stats(uint64_t *seeds, uint64_t *ray_steps);
+
+/* Whole per-frame pipeline in the orchestrator's order (src/vision/mod.rs:66-223):
+ * load_frame, crop_to_map, isolate, mask, find_marker_lines(max_gap), ocr_preprocess,
+ * find_scales_preprocess(start_y).  Used by the CPU-baseline timing. Returns map_open. */
+int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uint32_t H,
+                             int grayscale, uint32_t start_y, uint32_t max_gap,
+                             float lines[32][4], uint32_t *n_lines);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
