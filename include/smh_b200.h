@@ -1,0 +1,207 @@
+/* smh_b200.h — C ABI of the B200 (sm_100a) backend for squad-mortar-helper's per-frame
+ * map-analysis vision path.
+ *
+ * This is the drop-in boundary: a Rust struct implementing `vision_common::Vision`
+ * (reference: vision-common/src/lib.rs:30-61) forwards each trait method to the entry
+ * point of the same name below (binding shown in INTEGRATION.md).  Plain pointers and
+ * sizes only; every function returns 0 on success, a positive cudaError_t, or a negative
+ * SMH_E_* code; smh_b200_last_error() gives the text.  "Map closed" is NOT an error
+ * (reference: Ok(None), vision-cpu/src/lib.rs:131-134): it is reported through *map_open.
+ *
+ * Results are bit-identical to the reference's `vision-cpu` backend (the deterministic
+ * one) — see DESIGN.md for the handful of defined deviations (D8, D9).
+ *
+ * Threading (reference: src/vision/mod.rs:219-223): after crop_to_map, the marker branch
+ * {isolate_map_markers, mask_marker_lines, find_marker_lines, find_longest_line} and the
+ * scales branch {ocr_preprocess, find_scales_preprocess} may be called concurrently from
+ * two threads on one handle; they use separate streams and disjoint buffers.
+ * load_frame / crop_to_map / destroy are exclusive (`&mut self` / ordered in the reference).
+ */
+#ifndef SMH_B200_H
+#define SMH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smh_b200 smh_b200;
+
+enum {
+    SMH_OK = 0,
+    SMH_E_ARG = -1,       /* null pointer / bad argument */
+    SMH_E_GEOMETRY = -2,  /* frame size for which the reference panics (crop out of bounds, D12) */
+    SMH_E_STATE = -3,     /* call order violated (e.g. crop_to_map before load_frame) */
+    SMH_E_ALIGN = -4,     /* device-resident input not 16-byte aligned (base, pitch, frame stride) */
+    SMH_E_NOGPU = -5,     /* no CUDA device / driver: the backend has NO CPU fallback */
+    SMH_E_RANGE = -6      /* scales_start_y > height (reference: debug-build panic, D9) */
+};
+
+/* DebugView discriminants — vision-common/src/debug.rs:31-40 */
+enum { SMH_VIEW_NONE = 0, SMH_VIEW_OCR_INPUT, SMH_VIEW_FIND_SCALES_INPUT, SMH_VIEW_LSD_PREPROCESS,
+       SMH_VIEW_LSD_INPUT, SMH_VIEW_CROPPED_BRQ };
+
+/* ---- lifecycle: Vision::init / Drop — vision-gpu/src/cuda.rs:31-93, dylib.rs:79-97 ---------- */
+int32_t smh_b200_create(int32_t device, smh_b200 **out);
+void smh_b200_destroy(smh_b200 *h);
+const char *smh_b200_last_error(smh_b200 *h); /* h may be NULL: error of the last failed create */
+/* Vision::thread_ctx — vision-common/src/lib.rs:37, vision-gpu/src/lib.rs:150-165 */
+int32_t smh_b200_bind_thread(smh_b200 *h);
+
+/* ROI rectangles the reference derives from the frame size (screen.rs:55-66,
+ * consts/mod.rs:7-19, vision-cpu/src/lib.rs:137-145). roi = {button xywh, map xywh, brq xywh},
+ * all in frame coordinates.  Pure host arithmetic, needs no GPU. */
+int32_t smh_b200_roi(uint32_t W, uint32_t H, uint32_t roi[12]);
+
+/* ---- per-frame trait methods ------------------------------------------------------------- */
+
+/* Vision::load_frame — vision-common/src/lib.rs:44; CPU vision-cpu/src/lib.rs:69-93;
+ * GPU vision-gpu/src/lib.rs:167-193.  bgra: HOST pointer, B,G,R,A bytes, pitch_bytes per row.
+ * Uploads only the rows/columns the path reads (map ROI + button ROI). The buffer may be
+ * freed when the call returns. */
+int32_t smh_b200_load_frame(smh_b200 *h, const uint8_t *bgra, uint32_t W, uint32_t H, uint32_t pitch_bytes);
+
+/* Vision::crop_to_map — lib.rs:46; CPU :110-171; GPU :221-297.  Runs the fused pixel pass
+ * (button test, ui_map, marker mask + dilation, OCR/scales preprocessing) once.
+ * *map_open = 0 mirrors Ok(None).  ui_map_rgba: borrowed pinned host image, w*h*4 bytes,
+ * tightly packed, valid until the next load_frame. xywh = map ROI in frame coordinates. */
+int32_t smh_b200_crop_to_map(smh_b200 *h, int32_t grayscale, int32_t *map_open, uint32_t xywh[4],
+                             const uint8_t **ui_map_rgba);
+
+/* Vision::ocr_preprocess — lib.rs:49; CPU :173-231; GPU :300-321.  Borrowed pinned host L8
+ * image of the bottom-right quadrant (len = bqw*bqh), valid until the next load_frame. */
+int32_t smh_b200_ocr_preprocess(smh_b200 *h, const uint8_t **out, size_t *len);
+
+/* Vision::find_scales_preprocess — lib.rs:50; CPU :233-251; GPU :323-346.  Rows >= start_y are
+ * refreshed (luma != 0 ? 255 : 0); rows above keep the previous frame's content (D9; zero on a
+ * fresh handle / after a resolution change).  Borrowed host L8 image bqw*bqh. */
+int32_t smh_b200_find_scales_preprocess(smh_b200 *h, uint32_t scales_start_y, const uint8_t **out,
+                                        uint32_t wh[2]);
+
+/* Vision::isolate_map_markers / mask_marker_lines — lib.rs:52,54; CPU :253-280,357-375;
+ * GPU :348-371,432-475.  The fused pass already produced the dilated mask; these wait for it. */
+int32_t smh_b200_isolate_map_markers(smh_b200 *h);
+int32_t smh_b200_mask_marker_lines(smh_b200 *h);
+
+/* Vision::find_longest_line — lib.rs:55; CPU :387-449; GPU :489-538 (+K10).  Searches the
+ * handle's current dilated mask (the trait's `image` argument is the backend's own LSDImage).
+ * line = {p0.x,p0.y,p1.x,p1.y} — layout of #[repr(C)] Line<f32>, util/src/geometry.rs:168-173. */
+int32_t smh_b200_find_longest_line(smh_b200 *h, float x, float y, float max_gap, float line[4],
+                                   float *len_sq);
+
+/* Vision::find_marker_lines — lib.rs:56; CPU :377-385 + vision-common/src/lsd.rs:60-105.
+ * The whole sequential seed scan runs on the device in one launch. */
+int32_t smh_b200_find_marker_lines(smh_b200 *h, uint32_t max_gap, float lines[32][4], uint32_t *n);
+
+/* Vision::get_debug_view — lib.rs:60; CPU :451-460.  Borrowed host RGBA image; *rgba = NULL for
+ * SMH_VIEW_NONE. Valid until the next debug_view / load_frame. */
+int32_t smh_b200_debug_view(smh_b200 *h, uint8_t which, const uint8_t **rgba, uint32_t wh[2]);
+
+/* Host copy of the dilated marker mask (what the reference GPU backend keeps pinned for the
+ * host-side line search, vision-gpu/src/lib.rs:470-474).  L8 w*h, borrowed. */
+int32_t smh_b200_lsd_image(smh_b200 *h, const uint8_t **l8, uint32_t wh[2]);
+
+/* red-pixel count of the last crop_to_map's button test (vision-gpu/src/lib.rs:236-243) */
+int32_t smh_b200_red_pixels(smh_b200 *h, uint32_t *count);
+
+/* ---- batch extension (not in the trait): N independent frames per launch ------------------ */
+
+/* A device image plane: pixel (i,j) of frame f lives at
+ *   ptr + f*frame_stride + j*pitch + (i + pad)*bytes_per_pixel.
+ * Rows are 16-byte aligned and `pad` (0..3 px) keeps the plane's 16-byte vector grid in phase
+ * with the captured frame's, so the kernels move every plane with aligned 128-bit accesses. */
+typedef struct {
+    uint8_t *ptr;
+    uint64_t frame_stride;
+    uint32_t pitch;
+    uint32_t pad;
+    uint32_t width, height, bytes_per_pixel;
+    uint32_t reserved;
+} smh_b200_plane;
+
+typedef struct {
+    uint32_t n_frames, W, H, reserved;
+    uint32_t roi[12];          /* button, map, brq (frame coordinates) */
+    smh_b200_plane ui_map;     /* RGBA8 w*h */
+    smh_b200_plane lsd_image;  /* L8 w*h, dilated marker mask 0/255 */
+    smh_b200_plane ocr_out;    /* L8 bqw*bqh */
+    smh_b200_plane scales;     /* L8 bqw*bqh (rows < start_y[f] untouched) */
+    float *lines;              /* device, [n][32][4] */
+    uint32_t *n_lines;         /* device, [n] */
+    uint32_t *red_pixels;      /* device, [n] */
+    uint8_t *map_open;         /* device, [n]: 0 = map closed (n_lines = 0, images still written) */
+    uint64_t *lsd_stats;       /* device, [n][2] = {seeds, ray_steps} when stats were requested, else NULL */
+} smh_b200_batch;
+
+#define SMH_BATCH_GRAYSCALE 1u /* ui_map = (L,L,L,255) — settings default, src/settings.rs:135 */
+#define SMH_BATCH_LSD_STATS 2u /* count seeds / ray steps per frame (slower; for reporting) */
+#define SMH_BATCH_SKIP_LSD 4u  /* pixel pass only */
+#define SMH_BATCH_SKIP_PIXELS 8u /* line search only, on the planes of the previous call */
+
+/* Process n device-resident frames (tightly stacked: frame f at d_frames + f*frame_stride,
+ * rows pitch_bytes apart; base, pitch and stride multiples of 16).  start_y: HOST array of n
+ * values or NULL (= 0).  All work is enqueued on `stream` (a cudaStream_t, may be NULL) and NOT
+ * synchronised.  The output planes are owned by the handle and reused by the next call with
+ * the same n/W/H. */
+int32_t smh_b200_process_batch(smh_b200 *h, const uint8_t *d_frames, uint32_t n, uint32_t W, uint32_t H,
+                               uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
+                               uint32_t max_gap, uint32_t flags, void *stream, smh_b200_batch *out);
+
+/* Host-resident results of a batch, tightly packed (what the trait hands back per frame). */
+typedef struct {
+    uint8_t *ui_map;      /* n * w*h*4   (may be NULL to skip) */
+    uint8_t *ocr_out;     /* n * bqw*bqh (may be NULL) */
+    uint8_t *scales;      /* n * bqw*bqh (may be NULL) */
+    uint8_t *lsd_image;   /* n * w*h     (may be NULL) */
+    float *lines;         /* n * 32*4 */
+    uint32_t *n_lines;    /* n */
+    uint32_t *red_pixels; /* n */
+    uint8_t *map_open;    /* n */
+} smh_b200_host_results;
+
+/* End-to-end batch from HOST frames (pinned memory recommended): uploads each frame's ROI band,
+ * runs the path and copies the results back, pipelined over chunks of `chunk` frames on
+ * internal streams; returns after everything has landed in `res`. */
+int32_t smh_b200_process_host_batch(smh_b200 *h, const uint8_t *frames, uint32_t n, uint32_t W, uint32_t H,
+                                    uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
+                                    uint32_t max_gap, uint32_t flags, uint32_t chunk,
+                                    const smh_b200_host_results *res);
+
+/* Copy plane `p` of frames [first, first+count) to tightly packed host memory. */
+int32_t smh_b200_download_plane(smh_b200 *h, const smh_b200_plane *p, uint32_t first, uint32_t count,
+                                uint8_t *host_out, void *stream);
+
+/* cudaStreamSynchronize(stream) on the handle's device (stream may be NULL). */
+int32_t smh_b200_stream_synchronize(smh_b200 *h, void *stream);
+
+/* number of kernel launches this handle has issued (bench.py's gpu_launches claim) */
+uint64_t smh_b200_launch_count(smh_b200 *h);
+
+/* ---- synthetic captures; replaces src/capture.rs in the benchmarks ------- */
+typedef struct {
+    uint64_t seed;        /* frame k uses seed + k */
+    uint32_t W, H;
+    uint32_t n_segments;  /* marker lines (3 px wide, 60..600 px) with an icon disc at the start */
+    uint32_t n_blips;     /* isolated 2..4 px marker-coloured squares */
+    uint32_t n_labels;    /* "NNNm"-like OCR boxes + scale bars in the bottom-right quadrant (<=4) */
+    uint32_t map_open;    /* paint the red close-deployment button */
+    uint32_t blip_band_pct; /* blips confined to the top pct % of the map (100 = anywhere) */
+    uint32_t reserved;
+} smh_b200_synth_params;
+
+/* CPU rasteriser: frames [first, first+n) -> host BGRA, tightly packed. Needs no GPU. */
+int32_t smh_b200_synth_frames_host(const smh_b200_synth_params *p, uint32_t first, uint32_t n, uint8_t *out);
+/* CUDA rasteriser: byte-identical frames written to device memory (frame stride W*H*4). */
+int32_t smh_b200_synth_frames_device(smh_b200 *h, const smh_b200_synth_params *p, uint32_t first, uint32_t n,
+                                     uint8_t *d_out, void *stream);
+
+/* ---- exhaustive colour tables computed ON THE DEVICE (parity tests) ---------------------- */
+/* out[r<<16|g<<8|b] for all 2^24 colours; host output buffers. which: 0 marker predicate,
+ * 1 luma8, 2 button-red, 3 ocr class (bit0 core, bit1 edge). */
+int32_t smh_b200_colour_table(smh_b200 *h, uint32_t which, uint8_t *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMH_B200_H */

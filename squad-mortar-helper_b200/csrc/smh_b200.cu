@@ -1,0 +1,826 @@
+// smh_b200.cu — host side of the C ABI (include/smh_b200.h): device context, buffers,
+// streams and kernel launches.  No CPU fallback: every compute entry point fails with
+// SMH_E_NOGPU / a cudaError_t when there is no usable CUDA device.
+//
+// Reference host code this replaces: vision-gpu/src/lib.rs:33-559 (GpuMemory, launches,
+// copies), vision-gpu/src/cuda.rs:31-93 (context + PTX selection), vision-gpu/src/gpuimage.rs.
+#include "../../include/smh_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Geometry {
+    uint32_t W = 0, H = 0;
+    uint32_t btn[4] = {0, 0, 0, 0}, map[4] = {0, 0, 0, 0}, brq[4] = {0, 0, 0, 0};
+};
+
+// RelativeBound::ScreenH(f).into_absolute — vision-common/src/screen.rs:61-66 (f64 multiply,
+// round half away from zero, `as u32`)
+inline uint32_t rel_h(double frac, uint32_t H) { return (uint32_t)llround(frac * (double)H); }
+
+// vision-common/src/consts/mod.rs:7-19 + screen.rs:8-46 + vision-cpu/src/lib.rs:116,137-145.
+// Fails where the reference panics (util/src/image.rs:9-16,67-73; D12).
+int compute_geometry(uint32_t W, uint32_t H, Geometry* g) {
+    if (W == 0 || H == 0 || W > 16384 || H > 16384) return SMH_E_GEOMETRY;
+    const int64_t bw = rel_h(SMH_BTN_W_FRAC, H), bh = rel_h(SMH_BTN_H_FRAC, H);
+    const int64_t bx = (int64_t)W - rel_h(SMH_BTN_X_RIGHT_FRAC, H) - bw;
+    const int64_t by = (int64_t)H - rel_h(SMH_BTN_Y_BOTTOM_FRAC, H) - bh;
+    const int64_t w0 = rel_h(SMH_MAP_W_FRAC, H), h = rel_h(SMH_MAP_H_FRAC, H), x0 = rel_h(SMH_MAP_X_FRAC, H);
+    const int64_t y = (int64_t)H - rel_h(SMH_MAP_Y_BOTTOM_FRAC, H) - h;
+    const int64_t w = (int64_t)W - w0;   // "Map fills remaining space"
+    const int64_t x = (int64_t)W - x0 - w;
+    if (bx < 0 || by < 0 || bw <= 0 || bh <= 0 || x < 0 || y < 0 || w <= 0 || h <= 0) return SMH_E_GEOMETRY;
+    if (bx + bw > W || by + bh > H) return SMH_E_GEOMETRY;
+    if (x + w >= W || y + h >= H) return SMH_E_GEOMETRY;
+    const int64_t bqw = w / 2, bqh = h / 2;
+    if (bqw < SMH_OCR_RADIUS || bqh < SMH_OCR_RADIUS) return SMH_E_GEOMETRY;
+    g->W = W; g->H = H;
+    g->btn[0] = (uint32_t)bx; g->btn[1] = (uint32_t)by; g->btn[2] = (uint32_t)bw; g->btn[3] = (uint32_t)bh;
+    g->map[0] = (uint32_t)x; g->map[1] = (uint32_t)y; g->map[2] = (uint32_t)w; g->map[3] = (uint32_t)h;
+    g->brq[0] = (uint32_t)(x + bqw); g->brq[1] = (uint32_t)(y + bqh); g->brq[2] = (uint32_t)bqw; g->brq[3] = (uint32_t)bqh;
+    return SMH_OK;
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// Output planes of one batch (or of the single-frame path, n = 1).
+struct Planes {
+    uint32_t n = 0, W = 0, H = 0;
+    Geometry geo;
+    uint32_t pad = 0, qpad = 0, nvec = 0;
+    smh_b200_plane ui{}, lsd{}, ocr{}, scales{};
+    float* lines = nullptr;
+    uint32_t* n_lines = nullptr;
+    uint32_t* red = nullptr;
+    uint8_t* open = nullptr;
+    unsigned long long* stats = nullptr;
+    uint32_t* start_y = nullptr;
+    void release() {
+        cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
+        cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y);
+        *this = Planes();
+    }
+};
+
+}  // namespace
+
+struct smh_b200 {
+    int device = 0;
+    int sm_count = 0;
+    std::mutex err_mu;
+    std::string err;
+    std::atomic<uint64_t> launches{0};
+    float2* d_rays = nullptr;  // 3600 (cos, sin)
+
+    // ---- single-frame (trait) state ----
+    Geometry geo;                 // of the loaded frame
+    bool have_frame = false, cropped = false, map_open = false;
+    uint32_t red_pixels = 0;
+    int grayscale = 0;
+    // device copy of the region the path reads: frame columns [ux0, W), rows [uy0, uy1)
+    uint8_t* d_frame = nullptr;
+    uint32_t ux0 = 0, uy0 = 0, uy1 = 0, upitch = 0;
+    Planes one;                   // n = 1 output planes
+    // pinned host mirrors
+    uint8_t* h_ui = nullptr; uint8_t* h_ocr = nullptr;
+    uint8_t* h_scales = nullptr;  // persistent (stale rows kept, D9)
+    uint8_t* h_lsd = nullptr; uint8_t* h_view = nullptr; uint8_t* d_view = nullptr;
+    size_t view_cap = 0;
+    float* h_small = nullptr;     // pinned scratch: lines[32][4], n, longest[5]
+    float* d_longest = nullptr;
+    bool ocr_fetched = false, lsd_fetched = false;
+    cudaStream_t s_main = nullptr, s_markers = nullptr, s_scales = nullptr;
+    cudaEvent_t ev_pixels = nullptr;
+    std::mutex markers_mu, scales_mu;
+
+    // ---- batch state ----
+    Planes batch;
+    std::vector<cudaStream_t> pipe_streams;
+    uint8_t* d_stage = nullptr; size_t stage_cap = 0;   // host-batch upload staging (device)
+    Planes pipe[2];
+};
+
+namespace {
+
+int fail(smh_b200* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) { std::lock_guard<std::mutex> g(h->err_mu); h->err = buf; }
+    else g_create_error = buf;
+    return code;
+}
+#define CU(h, expr)                                                                         \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(h, (int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint32_t height, uint32_t bpp, uint32_t pad) {
+    p->width = width; p->height = height; p->bytes_per_pixel = bpp; p->pad = pad;
+    p->pitch = round_up((width + pad + 3u) * bpp, 128u);
+    p->frame_stride = (uint64_t)p->pitch * height;
+    CU(h, cudaMalloc(&p->ptr, p->frame_stride * n));
+    CU(h, cudaMemset(p->ptr, 0, p->frame_stride * n));
+    return SMH_OK;
+}
+
+int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool stats) {
+    if (P->n == n && P->W == g.W && P->H == g.H && (!stats || P->stats)) return SMH_OK;
+    P->release();
+    P->geo = g;
+    P->pad = g.map[0] & 3u;
+    P->qpad = (P->pad + g.brq[2]) & 3u;
+    P->nvec = (P->pad + g.map[2] + 3u) / 4u;
+    int rc;
+    if ((rc = alloc_plane(h, &P->ui, n, g.map[2], g.map[3], 4, P->pad))) return rc;
+    if ((rc = alloc_plane(h, &P->lsd, n, g.map[2], g.map[3], 1, P->pad))) return rc;
+    if ((rc = alloc_plane(h, &P->ocr, n, g.brq[2], g.brq[3], 1, P->qpad))) return rc;
+    if ((rc = alloc_plane(h, &P->scales, n, g.brq[2], g.brq[3], 1, P->qpad))) return rc;
+    CU(h, cudaMalloc(&P->lines, (size_t)n * 32 * 4 * sizeof(float)));
+    CU(h, cudaMemset(P->lines, 0, (size_t)n * 32 * 4 * sizeof(float)));
+    CU(h, cudaMalloc(&P->n_lines, (size_t)n * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->n_lines, 0, (size_t)n * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->red, (size_t)n * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->open, (size_t)n));
+    CU(h, cudaMalloc(&P->start_y, (size_t)n * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->start_y, 0, (size_t)n * sizeof(uint32_t)));
+    if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 2 * sizeof(unsigned long long)));
+    P->n = n; P->W = g.W; P->H = g.H;
+    return SMH_OK;
+}
+
+// Launch the fused pixel pass over n frames.  `frames` origin may be a cropped view of the
+// capture: (ox, oy) is the frame coordinate of its first byte.
+int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch,
+                  uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
+                  int grayscale, uint32_t rows_per_band, cudaStream_t st) {
+    const Geometry& g = P.geo;
+    smh::PixelArgs a{};
+    a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
+    a.map_x = g.map[0] - ox; a.map_y = g.map[1] - oy; a.w = g.map[2]; a.h = g.map[3];
+    a.bqw = g.brq[2]; a.bqh = g.brq[3];
+    a.btn_x = g.btn[0] - ox; a.btn_y = g.btn[1] - oy; a.btn_w = g.btn[2]; a.btn_h = g.btn[3];
+    a.pad = P.pad; a.gx0 = a.map_x - a.pad; a.nvec = P.nvec; a.qpad = P.qpad;
+    if ((a.gx0 & 3u) || (pitch & 15u) || (frame_stride & 15u) || ((uintptr_t)frames & 15u))
+        return fail(h, SMH_E_ALIGN, "captured frames must be 16-byte aligned (base %p, pitch %u, stride %llu, x0 %u)",
+                    (const void*)frames, pitch, (unsigned long long)frame_stride, a.gx0);
+    a.ui = P.ui.ptr; a.ui_stride = P.ui.frame_stride; a.ui_pitch = P.ui.pitch;
+    a.lsd = P.lsd.ptr; a.lsd_stride = P.lsd.frame_stride; a.lsd_pitch = P.lsd.pitch;
+    a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch;
+    a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
+    a.red = P.red; a.open = P.open;
+    a.rows_per_band = rows_per_band; a.nbands = (a.h + rows_per_band - 1) / rows_per_band;
+    a.grayscale = grayscale ? 1u : 0u;
+    a.ring_words = a.nvec + 2u;
+    const size_t smem = (size_t)smh::PX_RING * a.ring_words * sizeof(uint32_t);
+    if (smem > 48 * 1024)
+        CU(h, cudaFuncSetAttribute(smh::k_pixels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t blocks = (uint64_t)n * (a.nbands + 1u);
+    smh::k_pixels<<<(unsigned)blocks, smh::PX_THREADS, smem, st>>>(a);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, cudaStream_t st) {
+    smh::LsdArgs a{};
+    a.lsd = P.lsd.ptr; a.stride = P.lsd.frame_stride; a.pitch = P.lsd.pitch; a.pad = P.lsd.pad;
+    a.w = P.geo.map[2]; a.h = P.geo.map[3];
+    a.rays = h->d_rays; a.max_gap = max_gap;
+    a.open = use_open ? P.open : nullptr;
+    a.lines = P.lines; a.n_lines = P.n_lines;
+    a.stats = stats ? P.stats : nullptr;
+    if (stats) {
+        CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
+        smh::k_lsd<true><<<n, smh::LSD_THREADS, 0, st>>>(a);
+    } else {
+        smh::k_lsd<false><<<n, smh::LSD_THREADS, 0, st>>>(a);
+    }
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
+    // batches: 64-row bands (halo re-reads <= 9 %); a lone frame: enough bands to cover the SMs
+    if (n >= 16) return 64;
+    uint32_t want = (uint32_t)h->sm_count * 2u / (n ? n : 1u);
+    uint32_t rows = want ? (map_h + want - 1) / want : map_h;
+    if (rows < 8) rows = 8;
+    if (rows > 64) rows = 64;
+    return rows;
+}
+
+void fill_batch_out(const Planes& P, bool stats, smh_b200_batch* out) {
+    memset(out, 0, sizeof *out);
+    out->n_frames = P.n; out->W = P.W; out->H = P.H;
+    memcpy(out->roi, P.geo.btn, 16); memcpy(out->roi + 4, P.geo.map, 16); memcpy(out->roi + 8, P.geo.brq, 16);
+    out->ui_map = P.ui; out->lsd_image = P.lsd; out->ocr_out = P.ocr; out->scales = P.scales;
+    out->lines = P.lines; out->n_lines = P.n_lines; out->red_pixels = P.red; out->map_open = P.open;
+    out->lsd_stats = stats ? (uint64_t*)P.stats : nullptr;
+}
+
+int download_plane(smh_b200* h, const smh_b200_plane* p, uint32_t first, uint32_t count, uint8_t* host_out, cudaStream_t st) {
+    const size_t row = (size_t)p->width * p->bytes_per_pixel;
+    // one strided copy: rows of all frames are `pitch` apart and frame_stride = pitch*height
+    CU(h, cudaMemcpy2DAsync(host_out, row, p->ptr + (uint64_t)first * p->frame_stride + (size_t)p->pad * p->bytes_per_pixel,
+                            p->pitch, row, (size_t)p->height * count, cudaMemcpyDeviceToHost, st));
+    return SMH_OK;
+}
+
+void free_single(smh_b200* h) {
+    cudaFree(h->d_frame); h->d_frame = nullptr;
+    h->one.release();
+    cudaFreeHost(h->h_ui); cudaFreeHost(h->h_ocr); cudaFreeHost(h->h_scales);
+    cudaFreeHost(h->h_lsd);
+    h->h_ui = h->h_ocr = h->h_scales = h->h_lsd = nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* smh_b200_last_error(smh_b200* h) {
+    if (!h) return g_create_error.c_str();
+    std::lock_guard<std::mutex> g(h->err_mu);
+    return h->err.c_str();
+}
+
+int32_t smh_b200_roi(uint32_t W, uint32_t H, uint32_t roi[12]) {
+    if (!roi) return SMH_E_ARG;
+    Geometry g;
+    int rc = compute_geometry(W, H, &g);
+    if (rc) return rc;
+    memcpy(roi, g.btn, 16); memcpy(roi + 4, g.map, 16); memcpy(roi + 8, g.brq, 16);
+    return SMH_OK;
+}
+
+int32_t smh_b200_create(int32_t device, smh_b200** out) {
+    if (!out) return SMH_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SMH_E_NOGPU, "no CUDA device (%s); this backend has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count) return fail(nullptr, SMH_E_ARG, "device %d out of range (0..%d)", device, count - 1);
+    smh_b200* h = new smh_b200();
+    h->device = device;
+#define CUC(expr)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            fail(nullptr, (int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__));     \
+            delete h;                                                                     \
+            return (int)e__;                                                              \
+        }                                                                                 \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fail(nullptr, SMH_E_NOGPU, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        delete h;
+        return SMH_E_NOGPU;
+    }
+    CUC(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&h->s_markers, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&h->s_scales, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&h->ev_pixels, cudaEventDisableTiming));
+    // ray directions: theta_k = (k as f32 / 10.0).to_radians(); (cos, sin) from the host libm so
+    // that they are the bits vision-cpu computes (vision-cpu/src/lib.rs:398-399,437; D11)
+    std::vector<float2> rays(SMH_LSD_RAYS);
+    const float rads_per_deg = 3.14159265358979323846f / 180.0f;
+    for (int k = 0; k < SMH_LSD_RAYS; k++) {
+        const float theta = ((float)k / 10.0f) * rads_per_deg;
+        rays[k] = make_float2(cosf(theta), sinf(theta));
+    }
+    CUC(cudaMalloc(&h->d_rays, sizeof(float2) * SMH_LSD_RAYS));
+    CUC(cudaMemcpy(h->d_rays, rays.data(), sizeof(float2) * SMH_LSD_RAYS, cudaMemcpyHostToDevice));
+    CUC(cudaMallocHost(&h->h_small, 256 * sizeof(float)));
+    CUC(cudaMalloc(&h->d_longest, 8 * sizeof(float)));
+#undef CUC
+    *out = h;
+    return SMH_OK;
+}
+
+void smh_b200_destroy(smh_b200* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_single(h);
+    h->batch.release(); h->pipe[0].release(); h->pipe[1].release();
+    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_longest); cudaFree(h->d_view);
+    cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
+    for (auto s : h->pipe_streams) cudaStreamDestroy(s);
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    if (h->s_markers) cudaStreamDestroy(h->s_markers);
+    if (h->s_scales) cudaStreamDestroy(h->s_scales);
+    if (h->ev_pixels) cudaEventDestroy(h->ev_pixels);
+    delete h;
+}
+
+int32_t smh_b200_bind_thread(smh_b200* h) {
+    if (!h) return SMH_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    return SMH_OK;
+}
+
+uint64_t smh_b200_launch_count(smh_b200* h) { return h ? h->launches.load() : 0; }
+
+// ------------------------------------------------------------------------------------------
+// per-frame trait methods
+// ------------------------------------------------------------------------------------------
+
+int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t H, uint32_t pitch_bytes) {
+    if (!h || !bgra || pitch_bytes < W * 4u) return fail(h, SMH_E_ARG, "load_frame: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->have_frame || h->geo.W != W || h->geo.H != H) {
+        // resolution change: rebuild every per-resolution buffer (vision-cpu/src/lib.rs:70-88,
+        // vision-gpu/src/lib.rs:118-125); scales_preprocessed starts from zeros again
+        Geometry g;
+        int rc = compute_geometry(W, H, &g);
+        if (rc) return fail(h, rc, "load_frame: %ux%u is a frame size the reference panics on (crop out of bounds)", W, H);
+        CU(h, cudaDeviceSynchronize());
+        free_single(h);
+        h->have_frame = false;
+        h->geo = g;
+        if ((rc = ensure_planes(h, &h->one, 1, g, true))) return rc;
+        // uploaded region: columns [map_x & ~3, W), rows [map_y, max(map bottom, button bottom))
+        h->ux0 = g.map[0] & ~3u;
+        h->uy0 = g.map[1];
+        const uint32_t yb = g.btn[1] + g.btn[3], ym = g.map[1] + g.map[3];
+        h->uy1 = yb > ym ? yb : ym;
+        h->upitch = round_up((W - h->ux0) * 4u, 128u);
+        CU(h, cudaMalloc(&h->d_frame, (size_t)h->upitch * (h->uy1 - h->uy0)));
+        const size_t npx = (size_t)g.map[2] * g.map[3], nq = (size_t)g.brq[2] * g.brq[3];
+        CU(h, cudaMallocHost(&h->h_ui, npx * 4));
+        CU(h, cudaMallocHost(&h->h_lsd, npx));
+        CU(h, cudaMallocHost(&h->h_ocr, nq));
+        CU(h, cudaMallocHost(&h->h_scales, nq));
+        memset(h->h_scales, 0, nq);
+    }
+    const Geometry& g = h->geo;
+    CU(h, cudaMemcpy2DAsync(h->d_frame, h->upitch, bgra + (size_t)h->uy0 * pitch_bytes + (size_t)h->ux0 * 4u, pitch_bytes,
+                            (size_t)(g.W - h->ux0) * 4u, h->uy1 - h->uy0, cudaMemcpyHostToDevice, h->s_main));
+    CU(h, cudaStreamSynchronize(h->s_main));  // the caller may drop the frame now
+    h->have_frame = true; h->cropped = false; h->map_open = false;
+    h->ocr_fetched = h->lsd_fetched = false;
+    return SMH_OK;
+}
+
+int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, uint32_t xywh[4], const uint8_t** ui_map_rgba) {
+    if (!h || !map_open) return fail(h, SMH_E_ARG, "crop_to_map: bad argument");
+    if (!h->have_frame) return fail(h, SMH_E_STATE, "crop_to_map before load_frame");
+    CU(h, cudaSetDevice(h->device));
+    const Geometry& g = h->geo;
+    // the fresh thresholded scales image goes to a scratch plane; find_scales_preprocess merges
+    // rows >= start_y into the persistent host image, so pass start_y = 0 here
+    int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, 0, grayscale,
+                           pick_rows_per_band(h, 1, g.map[3]), h->s_main);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_pixels, h->s_main));
+    uint32_t* h_red = reinterpret_cast<uint32_t*>(h->h_small + 200);
+    CU(h, cudaMemcpyAsync(h_red, h->one.red, 4, cudaMemcpyDeviceToHost, h->s_main));
+    CU(h, cudaMemcpyAsync(h_red + 1, h->one.open, 1, cudaMemcpyDeviceToHost, h->s_main));
+    if ((rc = download_plane(h, &h->one.ui, 0, 1, h->h_ui, h->s_main))) return rc;
+    CU(h, cudaStreamSynchronize(h->s_main));
+    h->red_pixels = h_red[0];
+    h->map_open = (reinterpret_cast<uint8_t*>(h_red + 1))[0] != 0;
+    h->grayscale = grayscale;
+    h->cropped = true; h->ocr_fetched = h->lsd_fetched = false;
+    *map_open = h->map_open ? 1 : 0;
+    if (xywh) memcpy(xywh, g.map, 16);
+    if (ui_map_rgba) *ui_map_rgba = h->map_open ? h->h_ui : nullptr;
+    return SMH_OK;
+}
+
+int32_t smh_b200_red_pixels(smh_b200* h, uint32_t* count) {
+    if (!h || !count) return SMH_E_ARG;
+    if (!h->cropped) return fail(h, SMH_E_STATE, "red_pixels before crop_to_map");
+    *count = h->red_pixels;
+    return SMH_OK;
+}
+
+static int need_open_map(smh_b200* h, const char* who) {
+    if (!h) return SMH_E_ARG;
+    if (!h->cropped) return fail(h, SMH_E_STATE, "%s before crop_to_map", who);
+    if (!h->map_open) return fail(h, SMH_E_STATE, "%s: map is closed (crop_to_map returned None)", who);
+    return SMH_OK;
+}
+
+int32_t smh_b200_ocr_preprocess(smh_b200* h, const uint8_t** out, size_t* len) {
+    int rc = need_open_map(h, "ocr_preprocess");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(h->scales_mu);
+    CU(h, cudaSetDevice(h->device));
+    if (!h->ocr_fetched) {
+        CU(h, cudaStreamWaitEvent(h->s_scales, h->ev_pixels, 0));
+        if ((rc = download_plane(h, &h->one.ocr, 0, 1, h->h_ocr, h->s_scales))) return rc;
+        CU(h, cudaStreamSynchronize(h->s_scales));
+        h->ocr_fetched = true;
+    }
+    if (out) *out = h->h_ocr;
+    if (len) *len = (size_t)h->geo.brq[2] * h->geo.brq[3];
+    return SMH_OK;
+}
+
+int32_t smh_b200_find_scales_preprocess(smh_b200* h, uint32_t start_y, const uint8_t** out, uint32_t wh[2]) {
+    int rc = need_open_map(h, "find_scales_preprocess");
+    if (rc) return rc;
+    const uint32_t qw = h->geo.brq[2], qh = h->geo.brq[3];
+    if (start_y > qh) return fail(h, SMH_E_RANGE, "find_scales_preprocess: scales_start_y %u > height %u", start_y, qh);
+    std::lock_guard<std::mutex> g(h->scales_mu);
+    CU(h, cudaSetDevice(h->device));
+    if (start_y < qh) {
+        // rows >= start_y come from this frame; rows above keep the previous content (D9)
+        const smh_b200_plane& p = h->one.scales;
+        CU(h, cudaStreamWaitEvent(h->s_scales, h->ev_pixels, 0));
+        CU(h, cudaMemcpy2DAsync(h->h_scales + (size_t)start_y * qw, qw, p.ptr + (size_t)start_y * p.pitch + p.pad, p.pitch,
+                                qw, qh - start_y, cudaMemcpyDeviceToHost, h->s_scales));
+        CU(h, cudaStreamSynchronize(h->s_scales));
+    }
+    if (out) *out = h->h_scales;
+    if (wh) { wh[0] = qw; wh[1] = qh; }
+    return SMH_OK;
+}
+
+int32_t smh_b200_isolate_map_markers(smh_b200* h) {
+    int rc = need_open_map(h, "isolate_map_markers");
+    if (rc) return rc;
+    // the marker predicate was evaluated inside the fused pixel pass; nothing left to launch
+    return SMH_OK;
+}
+
+int32_t smh_b200_mask_marker_lines(smh_b200* h) {
+    int rc = need_open_map(h, "mask_marker_lines");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));  // the dilated mask is ready after this
+    return SMH_OK;
+}
+
+int32_t smh_b200_lsd_image(smh_b200* h, const uint8_t** l8, uint32_t wh[2]) {
+    int rc = need_open_map(h, "lsd_image");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    CU(h, cudaSetDevice(h->device));
+    if (!h->lsd_fetched) {
+        CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+        if ((rc = download_plane(h, &h->one.lsd, 0, 1, h->h_lsd, h->s_markers))) return rc;
+        CU(h, cudaStreamSynchronize(h->s_markers));
+        h->lsd_fetched = true;
+    }
+    if (l8) *l8 = h->h_lsd;
+    if (wh) { wh[0] = h->geo.map[2]; wh[1] = h->geo.map[3]; }
+    return SMH_OK;
+}
+
+int32_t smh_b200_find_longest_line(smh_b200* h, float x, float y, float max_gap, float line[4], float* len_sq) {
+    int rc = need_open_map(h, "find_longest_line");
+    if (rc) return rc;
+    if (!line || !len_sq) return fail(h, SMH_E_ARG, "find_longest_line: null output");
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    CU(h, cudaSetDevice(h->device));
+    const smh_b200_plane& p = h->one.lsd;
+    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    smh::k_longest<<<1, smh::LSD_THREADS, 0, h->s_markers>>>(p.ptr, p.pitch, p.pad, p.width, p.height, h->d_rays, x, y,
+                                                            max_gap, h->d_longest);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    float* hs = h->h_small + 160;
+    CU(h, cudaMemcpyAsync(hs, h->d_longest, 5 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaStreamSynchronize(h->s_markers));
+    memcpy(line, hs, 16);
+    *len_sq = hs[4];
+    return SMH_OK;
+}
+
+int32_t smh_b200_find_marker_lines(smh_b200* h, uint32_t max_gap, float lines[32][4], uint32_t* n) {
+    int rc = need_open_map(h, "find_marker_lines");
+    if (rc) return rc;
+    if (!lines || !n) return fail(h, SMH_E_ARG, "find_marker_lines: null output");
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, h->s_markers))) return rc;
+    CU(h, cudaMemcpyAsync(h->h_small, h->one.lines, 128 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaMemcpyAsync(h->h_small + 128, h->one.n_lines, 4, cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaStreamSynchronize(h->s_markers));
+    const uint32_t cnt = *reinterpret_cast<uint32_t*>(h->h_small + 128);
+    *n = cnt;
+    memcpy(lines, h->h_small, (size_t)cnt * 16);
+    return SMH_OK;
+}
+
+int32_t smh_b200_debug_view(smh_b200* h, uint8_t which, const uint8_t** rgba, uint32_t wh[2]) {
+    if (!h || !rgba) return fail(h, SMH_E_ARG, "debug_view: bad argument");
+    *rgba = nullptr;
+    if (which == SMH_VIEW_NONE) return SMH_OK;
+    int rc = need_open_map(h, "debug_view");
+    if (rc) return rc;
+    if (which > SMH_VIEW_CROPPED_BRQ) return fail(h, SMH_E_ARG, "debug_view: unknown view %u", which);
+    const Geometry& g = h->geo;
+    const bool full = which == SMH_VIEW_LSD_PREPROCESS || which == SMH_VIEW_LSD_INPUT;
+    const uint32_t w = full ? g.map[2] : g.brq[2], hh = full ? g.map[3] : g.brq[3];
+    const size_t need = (size_t)w * hh * 4;
+    std::lock_guard<std::mutex> gm(h->markers_mu);
+    std::lock_guard<std::mutex> gs(h->scales_mu);
+    CU(h, cudaSetDevice(h->device));
+    if (h->view_cap < need) {
+        cudaFreeHost(h->h_view); cudaFree(h->d_view); h->h_view = nullptr; h->d_view = nullptr; h->view_cap = 0;
+        CU(h, cudaMallocHost(&h->h_view, need));
+        CU(h, cudaMalloc(&h->d_view, need));
+        h->view_cap = need;
+    }
+    CU(h, cudaStreamSynchronize(h->s_main));
+    if (which == SMH_VIEW_LSD_PREPROCESS || which == SMH_VIEW_CROPPED_BRQ) {
+        // colour views are re-derived from the resident capture (rare path)
+        const uint32_t x0 = (full ? g.map[0] : g.brq[0]) - h->ux0, y0 = (full ? g.map[1] : g.brq[1]) - h->uy0;
+        dim3 grid((w + 255) / 256, hh);
+        smh::k_debug_rgb<<<grid, 256, 0, h->s_main>>>(h->d_frame, h->upitch, x0, y0, w, hh, full ? 1 : 0, h->d_view);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        CU(h, cudaMemcpyAsync(h->h_view, h->d_view, need, cudaMemcpyDeviceToHost, h->s_main));
+        CU(h, cudaStreamSynchronize(h->s_main));
+    } else {
+        // grey views: expand an L8 host image to (l,l,l,255) like image's ConvertBuffer
+        const uint8_t* src;
+        std::vector<uint8_t> tmp;
+        if (which == SMH_VIEW_FIND_SCALES_INPUT) src = h->h_scales;
+        else {
+            const smh_b200_plane& p = which == SMH_VIEW_OCR_INPUT ? h->one.ocr : h->one.lsd;
+            tmp.resize((size_t)w * hh);
+            CU(h, cudaMemcpy2D(tmp.data(), w, p.ptr + p.pad, p.pitch, w, hh, cudaMemcpyDeviceToHost));
+            src = tmp.data();
+        }
+        for (size_t i = 0; i < (size_t)w * hh; i++) {
+            h->h_view[4 * i] = h->h_view[4 * i + 1] = h->h_view[4 * i + 2] = src[i];
+            h->h_view[4 * i + 3] = 255;
+        }
+    }
+    *rgba = h->h_view;
+    if (wh) { wh[0] = w; wh[1] = hh; }
+    return SMH_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch extension
+// ------------------------------------------------------------------------------------------
+
+int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n, uint32_t W, uint32_t H,
+                               uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
+                               uint32_t max_gap, uint32_t flags, void* stream, smh_b200_batch* out) {
+    if (!h || !out || n == 0 || (!d_frames && !(flags & SMH_BATCH_SKIP_PIXELS)))
+        return fail(h, SMH_E_ARG, "process_batch: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    Geometry g;
+    int rc = compute_geometry(W, H, &g);
+    if (rc) return fail(h, rc, "process_batch: %ux%u is a frame size the reference panics on", W, H);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool stats = flags & SMH_BATCH_LSD_STATS;
+    if ((flags & SMH_BATCH_SKIP_PIXELS) && (h->batch.n != n || h->batch.W != W || h->batch.H != H))
+        return fail(h, SMH_E_STATE, "process_batch: SKIP_PIXELS needs a previous batch of the same shape");
+    if ((rc = ensure_planes(h, &h->batch, n, g, stats))) return rc;
+    if (!(flags & SMH_BATCH_SKIP_PIXELS)) {
+        if (start_y) {
+            for (uint32_t i = 0; i < n; i++)
+                if (start_y[i] > g.brq[3]) return fail(h, SMH_E_RANGE, "process_batch: start_y[%u]=%u > %u", i, start_y[i], g.brq[3]);
+            CU(h, cudaMemcpyAsync(h->batch.start_y, start_y, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, start_y != nullptr, 0,
+                                flags & SMH_BATCH_GRAYSCALE, pick_rows_per_band(h, n, g.map[3]), st)))
+            return rc;
+    }
+    if (!(flags & SMH_BATCH_SKIP_LSD))
+        if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, st))) return rc;
+    fill_batch_out(h->batch, stats, out);
+    return SMH_OK;
+}
+
+int32_t smh_b200_download_plane(smh_b200* h, const smh_b200_plane* p, uint32_t first, uint32_t count, uint8_t* host_out, void* stream) {
+    if (!h || !p || !host_out) return fail(h, SMH_E_ARG, "download_plane: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    return download_plane(h, p, first, count, host_out, (cudaStream_t)stream);
+}
+
+int32_t smh_b200_stream_synchronize(smh_b200* h, void* stream) {
+    if (!h) return SMH_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return SMH_OK;
+}
+
+int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H,
+                                    uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
+                                    uint32_t max_gap, uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
+    if (!h || !frames || !res || n == 0 || !res->lines || !res->n_lines || !res->red_pixels || !res->map_open)
+        return fail(h, SMH_E_ARG, "process_host_batch: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    Geometry g;
+    int rc = compute_geometry(W, H, &g);
+    if (rc) return fail(h, rc, "process_host_batch: %ux%u is a frame size the reference panics on", W, H);
+    if (chunk == 0) chunk = 32;
+    if (chunk > n) chunk = n;
+    if (h->pipe_streams.size() < 2) {
+        h->pipe_streams.resize(2);
+        for (auto& s : h->pipe_streams) CU(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
+    // device staging: per frame only the region the path reads (columns [x0&~3, W), rows [map_y, y1))
+    const uint32_t ux0 = g.map[0] & ~3u, uy0 = g.map[1];
+    const uint32_t yb = g.btn[1] + g.btn[3], ym = g.map[1] + g.map[3];
+    const uint32_t uy1 = yb > ym ? yb : ym, rows = uy1 - uy0;
+    const uint32_t upitch = round_up((W - ux0) * 4u, 128u);
+    const uint64_t ustride = (uint64_t)upitch * rows;
+    const size_t need = (size_t)ustride * chunk * 2;
+    if (h->stage_cap < need) {
+        CU(h, cudaDeviceSynchronize());
+        cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_cap = 0;
+        CU(h, cudaMalloc(&h->d_stage, need));
+        h->stage_cap = need;
+    }
+    const size_t npx = (size_t)g.map[2] * g.map[3], nq = (size_t)g.brq[2] * g.brq[3];
+    for (int b = 0; b < 2; b++)
+        if ((rc = ensure_planes(h, &h->pipe[b], chunk, g, false))) return rc;
+    uint32_t done = 0;
+    int b = 0;
+    while (done < n) {
+        const uint32_t c = n - done < chunk ? n - done : chunk;
+        cudaStream_t st = h->pipe_streams[b];
+        Planes& P = h->pipe[b];
+        uint8_t* stage = h->d_stage + (size_t)b * ustride * chunk;
+        // (stream order makes reuse of pipe[b]/stage safe: the previous work on this stream is done first)
+        for (uint32_t i = 0; i < c; i++) {
+            const uint8_t* src = frames + (uint64_t)(done + i) * frame_stride + (size_t)uy0 * pitch_bytes + (size_t)ux0 * 4u;
+            CU(h, cudaMemcpy2DAsync(stage + (uint64_t)i * ustride, upitch, src, pitch_bytes, (size_t)(W - ux0) * 4u, rows,
+                                    cudaMemcpyHostToDevice, st));
+        }
+        if (start_y) CU(h, cudaMemcpyAsync(P.start_y, start_y + done, (size_t)c * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = launch_pixels(h, P, stage, ustride, upitch, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
+                                pick_rows_per_band(h, c, g.map[3]), st)))
+            return rc;
+        if (!(flags & SMH_BATCH_SKIP_LSD))
+            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, st))) return rc;
+        if (res->ui_map && (rc = download_plane(h, &P.ui, 0, c, res->ui_map + (size_t)done * npx * 4, st))) return rc;
+        if (res->ocr_out && (rc = download_plane(h, &P.ocr, 0, c, res->ocr_out + (size_t)done * nq, st))) return rc;
+        if (res->scales && (rc = download_plane(h, &P.scales, 0, c, res->scales + (size_t)done * nq, st))) return rc;
+        if (res->lsd_image && (rc = download_plane(h, &P.lsd, 0, c, res->lsd_image + (size_t)done * npx, st))) return rc;
+        CU(h, cudaMemcpyAsync(res->lines + (size_t)done * 128, P.lines, (size_t)c * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->n_lines + done, P.n_lines, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->red_pixels + done, P.red, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->map_open + done, P.open, (size_t)c, cudaMemcpyDeviceToHost, st));
+        done += c;
+        b ^= 1;
+    }
+    for (auto s : h->pipe_streams) CU(h, cudaStreamSynchronize(s));
+    return SMH_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic captures + colour tables
+// ------------------------------------------------------------------------------------------
+
+namespace {
+struct Scene {
+    std::vector<smh_synth_frame_desc> desc;
+    std::vector<smh_synth_segment> segs;
+    std::vector<smh_synth_blip> blips;
+};
+struct Rng {
+    uint64_t s;
+    uint64_t next() { s = smh_splitmix64(s); return s; }
+    uint32_t below(uint32_t n) { return n ? (uint32_t)(next() % n) : 0u; }
+};
+int build_scene(const smh_b200_synth_params* p, uint32_t first, uint32_t n, Scene* sc) {
+    Geometry g;
+    int rc = compute_geometry(p->W, p->H, &g);
+    if (rc) return rc;
+    if (p->n_labels > SMH_SYNTH_MAX_LABELS) return SMH_E_ARG;
+    sc->desc.resize(n); sc->segs.resize((size_t)n * p->n_segments); sc->blips.resize((size_t)n * p->n_blips);
+    const int32_t mx = (int32_t)g.map[0], my = (int32_t)g.map[1], mw = (int32_t)g.map[2], mh = (int32_t)g.map[3];
+    for (uint32_t f = 0; f < n; f++) {
+        smh_synth_frame_desc& d = sc->desc[f];
+        memset(&d, 0, sizeof d);
+        d.seed = p->seed + first + f;
+        d.W = p->W; d.H = p->H;
+        memcpy(d.btn, g.btn, 16); memcpy(d.map, g.map, 16);
+        d.map_open = p->map_open; d.n_segments = p->n_segments; d.n_blips = p->n_blips; d.n_labels = p->n_labels;
+        Rng rng{smh_splitmix64(d.seed ^ 0x534D4800ull)};
+        for (uint32_t k = 0; k < p->n_segments; k++) {
+            smh_synth_segment& s = sc->segs[(size_t)f * p->n_segments + k];
+            for (;;) {  // random end points inside the map, 60..600 px apart
+                s.x0 = mx + 10 + (int32_t)rng.below((uint32_t)mw - 20); s.y0 = my + 10 + (int32_t)rng.below((uint32_t)mh - 20);
+                s.x1 = mx + 10 + (int32_t)rng.below((uint32_t)mw - 20); s.y1 = my + 10 + (int32_t)rng.below((uint32_t)mh - 20);
+                const int64_t dx = s.x1 - s.x0, dy = s.y1 - s.y0, l2 = dx * dx + dy * dy;
+                if (l2 >= 60 * 60 && l2 <= 600 * 600) break;
+            }
+            s.team = rng.below(3);
+        }
+        const uint32_t band = p->blip_band_pct == 0 || p->blip_band_pct > 100 ? 100 : p->blip_band_pct;
+        const uint32_t bh = (uint32_t)((uint64_t)mh * band / 100u);
+        for (uint32_t k = 0; k < p->n_blips; k++) {
+            smh_synth_blip& q = sc->blips[(size_t)f * p->n_blips + k];
+            q.size = 2 + rng.below(3);
+            q.x = mx + 6 + (int32_t)rng.below((uint32_t)mw - 12);
+            q.y = my + 6 + (int32_t)rng.below((bh > 12 ? bh : 13) - 12);
+            q.team = rng.below(3);
+        }
+        // labels inside the bottom-right quadrant; the last one hugs the right/bottom edge (D10 clip)
+        const int32_t qx = (int32_t)g.brq[0], qy = (int32_t)g.brq[1], qw = (int32_t)g.brq[2], qh = (int32_t)g.brq[3];
+        for (uint32_t k = 0; k < p->n_labels; k++) {
+            const int32_t spanx = qw - SMH_SYNTH_BAR_W, spany = qh - (SMH_SYNTH_LABEL_H + 8);
+            if (k + 1 == p->n_labels && k > 0) {
+                d.labels[k].x = qx + qw - SMH_SYNTH_LABEL_W + 2;           // crosses the right edge of the map
+                d.labels[k].y = qy + qh - SMH_SYNTH_LABEL_H + 3;           // crosses the bottom edge
+            } else {
+                d.labels[k].x = qx + (spanx > 1 ? (int32_t)rng.below((uint32_t)spanx) : 0);
+                d.labels[k].y = qy + (spany > 1 ? (int32_t)rng.below((uint32_t)spany) : 0);
+            }
+        }
+    }
+    return SMH_OK;
+}
+}  // namespace
+
+int32_t smh_b200_synth_frames_host(const smh_b200_synth_params* p, uint32_t first, uint32_t n, uint8_t* out) {
+    if (!p || !out) return SMH_E_ARG;
+    Scene sc;
+    int rc = build_scene(p, first, n, &sc);
+    if (rc) return rc;
+    for (uint32_t f = 0; f < n; f++) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)f * p->W * p->H * 4);
+        const smh_synth_segment* segs = sc.segs.data() + (size_t)f * p->n_segments;
+        const smh_synth_blip* blips = sc.blips.data() + (size_t)f * p->n_blips;
+        for (uint32_t y = 0; y < p->H; y++)
+            for (uint32_t x = 0; x < p->W; x++)
+                dst[(size_t)y * p->W + x] = smh_synth_pixel(&sc.desc[f], segs, blips, (int32_t)x, (int32_t)y);
+    }
+    return SMH_OK;
+}
+
+int32_t smh_b200_synth_frames_device(smh_b200* h, const smh_b200_synth_params* p, uint32_t first, uint32_t n,
+                                     uint8_t* d_out, void* stream) {
+    if (!h || !p || !d_out || n == 0) return fail(h, SMH_E_ARG, "synth_frames_device: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    Scene sc;
+    int rc = build_scene(p, first, n, &sc);
+    if (rc) return fail(h, rc, "synth_frames_device: bad parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    smh_synth_frame_desc* d_desc; smh_synth_segment* d_segs = nullptr; smh_synth_blip* d_blips = nullptr;
+    CU(h, cudaMalloc(&d_desc, sizeof(smh_synth_frame_desc) * n));
+    CU(h, cudaMemcpyAsync(d_desc, sc.desc.data(), sizeof(smh_synth_frame_desc) * n, cudaMemcpyHostToDevice, st));
+    if (!sc.segs.empty()) {
+        CU(h, cudaMalloc(&d_segs, sizeof(smh_synth_segment) * sc.segs.size()));
+        CU(h, cudaMemcpyAsync(d_segs, sc.segs.data(), sizeof(smh_synth_segment) * sc.segs.size(), cudaMemcpyHostToDevice, st));
+    }
+    if (!sc.blips.empty()) {
+        CU(h, cudaMalloc(&d_blips, sizeof(smh_synth_blip) * sc.blips.size()));
+        CU(h, cudaMemcpyAsync(d_blips, sc.blips.data(), sizeof(smh_synth_blip) * sc.blips.size(), cudaMemcpyHostToDevice, st));
+    }
+    smh::SynthArgs a{d_desc, d_segs, d_blips, p->n_segments, p->n_blips, p->W, p->H, d_out};
+    for (uint32_t f0 = 0; f0 < n; f0 += 32768) {  // gridDim.z limit
+        const uint32_t c = n - f0 < 32768 ? n - f0 : 32768;
+        smh::SynthArgs b = a;
+        b.desc += f0; b.segs += (size_t)f0 * p->n_segments; b.blips += (size_t)f0 * p->n_blips;
+        b.out += (size_t)f0 * p->W * p->H * 4;
+        smh::k_synth<<<dim3((p->W + 255) / 256, p->H, c), 256, 0, st>>>(b);
+        h->launches++;
+    }
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(st));
+    cudaFree(d_desc); cudaFree(d_segs); cudaFree(d_blips);
+    return SMH_OK;
+}
+
+int32_t smh_b200_colour_table(smh_b200* h, uint32_t which, uint8_t* host_out) {
+    if (!h || !host_out || which > 3) return fail(h, SMH_E_ARG, "colour_table: bad argument");
+    CU(h, cudaSetDevice(h->device));
+    uint8_t* d;
+    CU(h, cudaMalloc(&d, 1u << 24));
+    smh::k_colour_table<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which, d);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(host_out, d, 1u << 24, cudaMemcpyDeviceToHost, h->s_main));
+    CU(h, cudaStreamSynchronize(h->s_main));
+    cudaFree(d);
+    return SMH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Shared test helpers: run a frame through the oracle / through the CUDA backend and compare."""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def oracle_run(frame, grayscale=True, start_y=0, max_gap=15, oracle=None):
+    """Whole per-frame pipeline on the CPU oracle -> dict of every trait-visible output."""
+    from oracle import oracle_py as O
+    o = oracle or O.Oracle()
+    o.load_frame(frame)
+    got = o.crop_to_map(grayscale)
+    out = {"red_pixels": o.red_pixels, "map_open": got is not None, "roi": o.roi}
+    if got is None:
+        return out
+    out["ui_map"], out["xywh"] = got
+    o.isolate_map_markers()
+    out["cropped_map_isolated"] = o.cropped_map()
+    o.mask_marker_lines()
+    out["lsd_image"] = o.lsd_image()
+    out["lines"] = o.find_marker_lines(max_gap)
+    out["lsd_stats"] = o.lsd_stats()
+    out["ocr_out"] = o.ocr_preprocess()
+    out["scales"] = o.find_scales_preprocess(start_y)
+    out["cropped_brq"] = o.cropped_brq()
+    return out
+
+
+def gpu_run(v, frame, grayscale=True, start_y=0, max_gap=15):
+    """Same call order as VisionState::process (src/vision/mod.rs:66-223) on the CUDA backend."""
+    v.load_frame(frame)
+    got = v.crop_to_map(grayscale)
+    out = {"red_pixels": v.red_pixels(), "map_open": got is not None}
+    if got is None:
+        return out
+    out["ui_map"], out["xywh"] = got
+    v.thread_ctx()
+    v.isolate_map_markers()
+    v.mask_marker_lines()
+    out["lines"] = v.find_marker_lines(max_gap)
+    out["lsd_image"] = v.lsd_image().copy()
+    v.thread_ctx()
+    out["ocr_out"] = v.ocr_preprocess().copy()
+    out["scales"] = v.find_scales_preprocess(start_y).copy()
+    return out
+
+
+def assert_same(got: dict, want: dict, what=""):
+    assert got["map_open"] == want["map_open"], f"{what}: map_open"
+    assert got["red_pixels"] == want["red_pixels"], f"{what}: red_pixels {got['red_pixels']} != {want['red_pixels']}"
+    if not want["map_open"]:
+        return
+    assert list(got["xywh"]) == list(want["xywh"]), f"{what}: xywh"
+    for k in ("ui_map", "lsd_image", "ocr_out", "scales"):
+        g, w = got[k], want[k]
+        assert g.shape == w.shape, f"{what}: {k} shape {g.shape} != {w.shape}"
+        if not np.array_equal(g, w):
+            bad = np.argwhere(g != w)
+            raise AssertionError(f"{what}: {k} differs at {len(bad)} positions, first {bad[0].tolist()} "
+                                 f"got {g[tuple(bad[0])]} want {w[tuple(bad[0])]}")
+    gl, wl = got["lines"], want["lines"]
+    assert gl.shape == wl.shape, f"{what}: {gl.shape[0]} lines, oracle has {wl.shape[0]}\n{gl}\n{wl}"
+    # bit-exact: compare the raw f32 bit patterns
+    assert np.array_equal(gl.view(np.uint32), wl.view(np.uint32)), f"{what}: line endpoints differ\n{gl}\n{wl}"
