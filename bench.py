@@ -143,6 +143,53 @@ def run_reference(args, rank: int, world: int) -> None:
     }))
 
 
+def run_e2e(args, vision, frames, roi, n, world, barrier):
+    """Same metric through smh_b200_process_host_batch: pinned HOST frames in, host results out."""
+    import torch
+    import torch.distributed as dist
+    ne = min(args.e2e_frames, n)
+    host_frames = torch.empty((ne, H, W, 4), dtype=torch.uint8).pin_memory()
+    host_frames.copy_(frames[:ne])
+    _, _, mw, mh = roi["map"]; _, _, qw, qh = roi["brq"]
+    outs = {"ui_map": torch.empty((ne, mh, mw, 4), dtype=torch.uint8).pin_memory(),
+            "ocr_out": torch.empty((ne, qh, qw), dtype=torch.uint8).pin_memory(),
+            "scales": torch.empty((ne, qh, qw), dtype=torch.uint8).pin_memory(),
+            "lines": torch.empty((ne, 32, 4), dtype=torch.float32).pin_memory(),
+            "n_lines": torch.empty((ne,), dtype=torch.int32).pin_memory(),
+            "red_pixels": torch.empty((ne,), dtype=torch.int32).pin_memory(),
+            "map_open": torch.empty((ne,), dtype=torch.uint8).pin_memory()}
+    out_ptrs = {k: v.data_ptr() for k, v in outs.items()}
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        vision.process_host_batch(None, frames_ptr=host_frames.data_ptr(), shape=(ne, H, W), max_gap=MAX_GAP,
+                                  grayscale=True, chunk=32, want=("ui_map", "ocr_out", "scales"), out=dict(out_ptrs))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.cpu()[0])
+    e2e_fps = world * ne * e_steps / e_dt
+    ux0 = min(roi["map"][0], roi["button"][0]) & ~3
+    rows = max(roi["button"][1] + roi["button"][3], roi["map"][1] + roi["map"][3]) - min(roi["map"][1], roi["button"][1])
+    h2d = ne * rows * (W - ux0) * 4
+    d2h = ne * (mw * mh * 4 + 2 * qw * qh + 512 + 9)
+    e2e_check = int(outs["n_lines"].sum())
+
+    return {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "frames_per_step": ne, "steps": e_steps, "lines_checksum": e2e_check,
+            "note": "smh_b200_process_host_batch: pinned host frames -> ROI upload -> kernels -> ui_map/ocr/scales/lines back"}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -152,6 +199,7 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -240,43 +288,9 @@ def main() -> None:
     seeds_pf, steps_pf = float(stats[:, 0].mean()), float(stats[:, 1].mean())
 
     # ---- e2e: host frames through the C ABI, H2D + D2H inside the timed region ------------
-    ne = min(args.e2e_frames, n)
-    host_frames = torch.empty((ne, H, W, 4), dtype=torch.uint8).pin_memory()
-    host_frames.copy_(frames[:ne])
-    _, _, mw, mh = roi["map"]; _, _, qw, qh = roi["brq"]
-    outs = {"ui_map": torch.empty((ne, mh, mw, 4), dtype=torch.uint8).pin_memory(),
-            "ocr_out": torch.empty((ne, qh, qw), dtype=torch.uint8).pin_memory(),
-            "scales": torch.empty((ne, qh, qw), dtype=torch.uint8).pin_memory(),
-            "lines": torch.empty((ne, 32, 4), dtype=torch.float32).pin_memory(),
-            "n_lines": torch.empty((ne,), dtype=torch.int32).pin_memory(),
-            "red_pixels": torch.empty((ne,), dtype=torch.int32).pin_memory(),
-            "map_open": torch.empty((ne,), dtype=torch.uint8).pin_memory()}
-    out_ptrs = {k: v.data_ptr() for k, v in outs.items()}
-    torch.cuda.synchronize()
-
-    def e2e_step():
-        vision.process_host_batch(None, frames_ptr=host_frames.data_ptr(), shape=(ne, H, W), max_gap=MAX_GAP,
-                                  grayscale=True, chunk=32, want=("ui_map", "ocr_out", "scales"), out=dict(out_ptrs))
-
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_dt = float(t.cpu()[0])
-    e2e_fps = world * ne * e_steps / e_dt
-    ux0 = roi["map"][0] & ~3
-    rows = max(roi["button"][1] + roi["button"][3], roi["map"][1] + roi["map"][3]) - roi["map"][1]
-    h2d = ne * rows * (W - ux0) * 4
-    d2h = ne * (mw * mh * 4 + 2 * qw * qh + 512 + 9)
-    e2e_check = int(outs["n_lines"].sum())
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, vision, frames, roi, n, world, barrier)
 
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -312,9 +326,7 @@ def main() -> None:
                                   "ray_steps_per_s": steps_pf * n / (lsd_ms * 1e-3)}},
             "frames_per_s_pixels_only": n / (px_ms * 1e-3),
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_step": ne, "steps": e_steps, "lines_checksum": e2e_check,
-                    "note": "smh_b200_process_host_batch: pinned host frames -> ROI upload -> kernels -> ui_map/ocr/scales/lines back"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "cpu_baseline": cpu,
         }

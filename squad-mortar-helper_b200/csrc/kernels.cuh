@@ -58,6 +58,7 @@ struct PixelArgs {
     uint32_t rows_per_band, nbands;
     uint32_t grayscale;
     uint32_t ring_words;  // words per ring row = nvec + 2 (one zero guard word each side)
+    const uint32_t* lut;  // marker predicate, 1 bit per colour (r<<16|g<<8|b)
 };
 
 constexpr int PX_THREADS = 256;
@@ -71,27 +72,71 @@ constexpr uint32_t FL_M = 1u;      // marker colour
 constexpr uint32_t FL_CORE = 2u;   // bright monochrome pixel that an OCR neighbour search may find
 constexpr uint32_t FL_EDGE = 4u;   // OCR edge candidate (keep only with a core pixel in its window)
 
-__device__ __forceinline__ uint32_t px_flags(uint32_t word, bool valid, bool inq_row, int i, const PixelArgs& a,
-                                             int jq, uint32_t& luma, bool need_luma, uint32_t& ocr_byte) {
-    const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
-    uint32_t fl = 0;
-    if (valid && smh_marker_prefilter(r, g, b)) fl |= smh_is_marker_exact(r, g, b) ? FL_M : 0u;
-    ocr_byte = 255u;
-    const bool inq = inq_row && valid && i >= (int)a.bqw && i < (int)(2u * a.bqw);
-    if (need_luma || inq) luma = smh_luma8(r, g, b);
-    if (inq) {
-        const int iq = i - (int)a.bqw;
-        if (smh_ocr_core(r, g, b)) {
-            // reachable from a neighbour's window only below the upper clip min(x+3, w-3) (D10)
-            if (iq <= (int)a.bqw - SMH_OCR_RADIUS && jq <= (int)a.bqh - SMH_OCR_RADIUS) fl |= FL_CORE;
-            ocr_byte = 255u - luma;
-        } else if (smh_ocr_edge(r, g, b)) {
-            fl |= FL_EDGE;
-        }
-    }
-    return fl;
+// byte `k` of a little-endian word as an exact float: PRMT builds 0x4B0000xx (= 2^23 + xx), one
+// FADD removes the bias.  Full-rate replacement for I2F.
+template <int K>
+__device__ __forceinline__ float byte_as_f32(uint32_t word) {
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + K)), 8388608.0f);
+}
+// luma8 of a BGRA word (image 0.23.14 rgb_to_luma, unfused, truncating): identical bits to
+// smh_luma8 (proved over all 2^24 colours on the device, tests/test_gpu_parity.py); the
+// truncation is a round-down add of 2^23 whose low mantissa byte is floor(l) (l < 256).
+__device__ __forceinline__ uint32_t luma8_bgra(uint32_t word) {
+    const float l = __fadd_rn(__fadd_rn(__fmul_rn(SMH_LUMA_R, byte_as_f32<2>(word)), __fmul_rn(SMH_LUMA_G, byte_as_f32<1>(word))),
+                              __fmul_rn(SMH_LUMA_B, byte_as_f32<0>(word)));
+    return __float_as_uint(__fadd_rd(l, 8388608.0f)) & 0xFFu;
 }
 
+// Marker predicate of a BGRA word: integer fast-reject, then one bit of the 2^24-entry table
+// that k_build_marker_lut fills with smh_is_marker_exact (2 MB, L2 resident).
+__device__ __forceinline__ uint32_t marker_bit(uint32_t word, uint32_t mx, uint32_t mn, const uint32_t* __restrict__ lut) {
+    if (mx >= 178u && 100u * (mx - mn) >= 34u * mx) {
+        const uint32_t c = word & 0x00FFFFFFu;  // r<<16 | g<<8 | b
+        return (__ldg(lut + (c >> 5)) >> (c & 31u)) & 1u;
+    }
+    return 0u;
+}
+
+// One pixel of phase 1.  MODE 0: interior vector outside the OCR quadrant; MODE 1: interior vector
+// wholly inside the quadrant and below the neighbour-search clip (D10); MODE 2: generic (row ends,
+// quadrant borders) with every test per pixel.
+template <bool GRAY, int MODE>
+__device__ __forceinline__ void classify_px(uint32_t word, int e, int i, int jq, bool owned, bool inq_row,
+                                            const PixelArgs& a, uint32_t& fl, uint32_t& uo, uint32_t& ocrw, uint32_t& scw) {
+    const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
+    const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
+    const bool valid = MODE != 2 || (i >= 0 && i < (int)a.w);
+    uint32_t fe = valid ? marker_bit(word, mx, mn, a.lut) : 0u;
+    const bool inq = MODE == 1 || (MODE == 2 && inq_row && valid && i >= (int)a.bqw && i < (int)(2u * a.bqw));
+    uint32_t luma = 0;
+    if ((GRAY && owned) || inq) luma = luma8_bgra(word);
+    if (inq) {
+        // OCR classes — vision-cpu/src/lib.rs:39-53,188-193 (mono = 4*(max-min))
+        if (mx == mn && mn >= SMH_OCR_BRIGHT) {
+            // visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
+            if (MODE == 1 || (i - (int)a.bqw <= (int)a.bqw - SMH_OCR_RADIUS && jq <= (int)a.bqh - SMH_OCR_RADIUS)) fe |= FL_CORE;
+            ocrw ^= luma << (8 * e);  // 255 - luma
+        } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) {
+            fe |= FL_EDGE;
+        }
+        scw |= (luma != 0u ? 255u : 0u) << (8 * e);
+    }
+    fl |= fe << (8 * e);
+    // ui_map: (L,L,L,255) or (r,g,b,255) — vision-cpu/src/lib.rs:150-163
+    uo = GRAY ? (luma * 0x00010101u) | 0xFF000000u : __byte_perm(word, 0xFF000000u, 0x7012);
+}
+
+template <bool GRAY, int MODE>
+__device__ __forceinline__ void classify_vec(const uint4& v, int q, int jq, bool owned, bool inq_row, const PixelArgs& a,
+                                             uint32_t& fl, uint4& uo, uint32_t& ocrw, uint32_t& scw) {
+    const int i0 = 4 * q - (int)a.pad;
+    classify_px<GRAY, MODE>(v.x, 0, i0 + 0, jq, owned, inq_row, a, fl, uo.x, ocrw, scw);
+    classify_px<GRAY, MODE>(v.y, 1, i0 + 1, jq, owned, inq_row, a, fl, uo.y, ocrw, scw);
+    classify_px<GRAY, MODE>(v.z, 2, i0 + 2, jq, owned, inq_row, a, fl, uo.z, ocrw, scw);
+    classify_px<GRAY, MODE>(v.w, 3, i0 + 3, jq, owned, inq_row, a, fl, uo.w, ocrw, scw);
+}
+
+template <bool GRAY>
 __global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
     extern __shared__ __align__(16) uint32_t ring[];  // [PX_RING][ring_words]
     const uint32_t per_frame = a.nbands + 1u;
@@ -174,26 +219,19 @@ __global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
                         for (int u = 0; u < PX_UNR; u++) {
                             const int q = q0 + u * PX_TX;
                             if (q >= (int)a.nvec) continue;
-                            const uint32_t wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                            uint32_t fl = 0, ocrw = 0, scw = 0;
-                            uint32_t uo[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int i = 4 * q + e - (int)a.pad;
-                                const bool valid = i >= 0 && i < (int)a.w;
-                                uint32_t luma = 0, ob;
-                                const uint32_t fe = px_flags(wd[e], valid, inq_row, i, a, jq, luma,
-                                                             owned && a.grayscale, ob);
-                                fl |= fe << (8 * e);
-                                ocrw |= ob << (8 * e);
-                                scw |= (luma != 0u ? 255u : 0u) << (8 * e);
-                                // ui_map: (L,L,L,255) or (r,g,b,255) — vision-cpu/src/lib.rs:150-163
-                                uo[e] = a.grayscale ? (luma * 0x00010101u) | 0xFF000000u
-                                                    : __byte_perm(wd[e], 0xFF000000u, 0x7012);
-                            }
+                            uint32_t fl = 0, ocrw = 0xFFFFFFFFu, scw = 0;
+                            uint4 uo;
+                            const int i_lo = 4 * q - (int)a.pad, i_hi = i_lo + 3;
+                            const bool row_end = q == 0 || q == (int)a.nvec - 1;
+                            const bool q_out = !inq_row || i_hi < (int)a.bqw || i_lo >= (int)(2u * a.bqw);
+                            const bool q_in = inq_row && i_lo >= (int)a.bqw && i_hi <= (int)(2u * a.bqw) - SMH_OCR_RADIUS &&
+                                              jq <= bqh - SMH_OCR_RADIUS;
+                            if (!row_end && q_out) classify_vec<GRAY, 0>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
+                            else if (!row_end && q_in) classify_vec<GRAY, 1>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
+                            else classify_vec<GRAY, 2>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
                             rrow[q] = fl;
                             if (owned) {
-                                stg_v4(ui_row + (uint64_t)q * 16u, make_uint4(uo[0], uo[1], uo[2], uo[3]));
+                                stg_v4(ui_row + (uint64_t)q * 16u, uo);
                                 if (inq_row && q >= qv_lo && q <= qv_hi) {
                                     const int pos = qword0 + 4 * q;  // multiple of 4, >= 0
                                     stg_u32(ocr_row + pos, ocrw);
@@ -256,7 +294,7 @@ __global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
                                 const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
                                     frame + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch +
                                     (uint64_t)(a.map_x + (uint32_t)i) * 4u));
-                                const uint32_t L = smh_luma8((word >> 16) & 0xFFu, (word >> 8) & 0xFFu, word & 0xFFu);
+                                const uint32_t L = luma8_bgra(word);
                                 ocr_f[(uint64_t)jq * a.q_pitch + (uint32_t)(i - (int)a.bqw) + a.qpad] = (uint8_t)(255u - L);
                             }
                         }
@@ -547,6 +585,26 @@ __global__ void k_debug_rgb(const uint8_t* frame, uint32_t pitch, uint32_t x0, u
 // ------------------------------------------------------------------------------------------
 // exhaustive colour tables + synthetic captures
 // ------------------------------------------------------------------------------------------
+// 2^24-bit table of the exact marker predicate: thread t fills word t (colours 32t .. 32t+31)
+__global__ void k_build_marker_lut(uint32_t* lut) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t word = 0;
+    for (uint32_t k = 0; k < 32; k++) {
+        const uint32_t c = t * 32u + k;
+        word |= (smh_is_marker(c >> 16, (c >> 8) & 0xFFu, c & 0xFFu) ? 1u : 0u) << k;
+    }
+    lut[t] = word;
+}
+
+__global__ void k_colour_table_fast(uint32_t which, const uint32_t* lut, uint8_t* out) {
+    // the exact code paths k_pixels uses: which 0 = fast-reject + table bit, 1 = luma8_bgra
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = c >> 16, g = (c >> 8) & 0xFFu, b = c & 0xFFu;
+    const uint32_t word = c | 0xFF000000u;
+    const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
+    out[c] = which == 0 ? (uint8_t)marker_bit(word, mx, mn, lut) : (uint8_t)luma8_bgra(word);
+}
+
 __global__ void k_colour_table(uint32_t which, uint8_t* out) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t r = c >> 16, g = (c >> 8) & 0xFFu, b = c & 0xFFu;

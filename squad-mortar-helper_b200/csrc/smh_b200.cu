@@ -85,6 +85,7 @@ struct smh_b200 {
     std::string err;
     std::atomic<uint64_t> launches{0};
     float2* d_rays = nullptr;  // 3600 (cos, sin)
+    uint32_t* d_lut = nullptr; // marker predicate bit table, 2^24 bits
 
     // ---- single-frame (trait) state ----
     Geometry geo;                 // of the loaded frame
@@ -140,7 +141,10 @@ int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint
 }
 
 int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool stats) {
-    if (P->n == n && P->W == g.W && P->H == g.H && (!stats || P->stats)) return SMH_OK;
+    if (P->n == n && P->W == g.W && P->H == g.H) {
+        if (stats && !P->stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 2 * sizeof(unsigned long long)));
+        return SMH_OK;
+    }
     P->release();
     P->geo = g;
     P->pad = g.map[0] & 3u;
@@ -187,11 +191,13 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.rows_per_band = rows_per_band; a.nbands = (a.h + rows_per_band - 1) / rows_per_band;
     a.grayscale = grayscale ? 1u : 0u;
     a.ring_words = a.nvec + 2u;
+    a.lut = h->d_lut;
     const size_t smem = (size_t)smh::PX_RING * a.ring_words * sizeof(uint32_t);
+    auto kern = grayscale ? smh::k_pixels<true> : smh::k_pixels<false>;
     if (smem > 48 * 1024)
-        CU(h, cudaFuncSetAttribute(smh::k_pixels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t blocks = (uint64_t)n * (a.nbands + 1u);
-    smh::k_pixels<<<(unsigned)blocks, smh::PX_THREADS, smem, st>>>(a);
+    kern<<<(unsigned)blocks, smh::PX_THREADS, smem, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
@@ -313,6 +319,12 @@ int32_t smh_b200_create(int32_t device, smh_b200** out) {
     }
     CUC(cudaMalloc(&h->d_rays, sizeof(float2) * SMH_LSD_RAYS));
     CUC(cudaMemcpy(h->d_rays, rays.data(), sizeof(float2) * SMH_LSD_RAYS, cudaMemcpyHostToDevice));
+    // exact marker predicate memoised over all 2^24 colours (2 MB, stays in L2)
+    CUC(cudaMalloc(&h->d_lut, (1u << 24) / 8));
+    smh::k_build_marker_lut<<<(1u << 19) / 256, 256, 0, h->s_main>>>(h->d_lut);
+    h->launches++;
+    CUC(cudaGetLastError());
+    CUC(cudaStreamSynchronize(h->s_main));
     CUC(cudaMallocHost(&h->h_small, 256 * sizeof(float)));
     CUC(cudaMalloc(&h->d_longest, 8 * sizeof(float)));
 #undef CUC
@@ -326,7 +338,7 @@ void smh_b200_destroy(smh_b200* h) {
     cudaDeviceSynchronize();
     free_single(h);
     h->batch.release(); h->pipe[0].release(); h->pipe[1].release();
-    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_longest); cudaFree(h->d_view);
+    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
     if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -362,9 +374,9 @@ int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32
         h->have_frame = false;
         h->geo = g;
         if ((rc = ensure_planes(h, &h->one, 1, g, true))) return rc;
-        // uploaded region: columns [map_x & ~3, W), rows [map_y, max(map bottom, button bottom))
-        h->ux0 = g.map[0] & ~3u;
-        h->uy0 = g.map[1];
+        // uploaded region: columns [min(map_x, btn_x) & ~3, W), rows [min y, max(map bottom, button bottom))
+        h->ux0 = (g.map[0] < g.btn[0] ? g.map[0] : g.btn[0]) & ~3u;
+        h->uy0 = g.map[1] < g.btn[1] ? g.map[1] : g.btn[1];
         const uint32_t yb = g.btn[1] + g.btn[3], ym = g.map[1] + g.map[3];
         h->uy1 = yb > ym ? yb : ym;
         h->upitch = round_up((W - h->ux0) * 4u, 128u);
@@ -644,7 +656,8 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         for (auto& s : h->pipe_streams) CU(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     }
     // device staging: per frame only the region the path reads (columns [x0&~3, W), rows [map_y, y1))
-    const uint32_t ux0 = g.map[0] & ~3u, uy0 = g.map[1];
+    const uint32_t ux0 = (g.map[0] < g.btn[0] ? g.map[0] : g.btn[0]) & ~3u;
+    const uint32_t uy0 = g.map[1] < g.btn[1] ? g.map[1] : g.btn[1];
     const uint32_t yb = g.btn[1] + g.btn[3], ym = g.map[1] + g.map[3];
     const uint32_t uy1 = yb > ym ? yb : ym, rows = uy1 - uy0;
     const uint32_t upitch = round_up((W - ux0) * 4u, 128u);
@@ -810,11 +823,12 @@ int32_t smh_b200_synth_frames_device(smh_b200* h, const smh_b200_synth_params* p
 }
 
 int32_t smh_b200_colour_table(smh_b200* h, uint32_t which, uint8_t* host_out) {
-    if (!h || !host_out || which > 3) return fail(h, SMH_E_ARG, "colour_table: bad argument");
+    if (!h || !host_out || which > 5) return fail(h, SMH_E_ARG, "colour_table: bad argument");
     CU(h, cudaSetDevice(h->device));
     uint8_t* d;
     CU(h, cudaMalloc(&d, 1u << 24));
-    smh::k_colour_table<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which, d);
+    if (which <= 1) smh::k_colour_table_fast<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which, h->d_lut, d);
+    else smh::k_colour_table<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which >= 4 ? which - 4 : which, d);
     h->launches++;
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(host_out, d, 1u << 24, cudaMemcpyDeviceToHost, h->s_main));

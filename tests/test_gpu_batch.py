@@ -73,7 +73,7 @@ def test_device_batch_matches_oracle_per_frame(vision, W, H, n):
         want = oracle_run(host[i], True, int(start_y[i]), 15)
         got = _frame_result(res, i)
         got["xywh"] = want["xywh"]
-        assert_same(got, want, f"batch frame {i}")
+        assert_same(got, want, f"batch frame {i}", scales_from=int(start_y[i]))
         assert tuple(int(x) for x in res["stats"][i]) == tuple(want["lsd_stats"]), "seed / ray-step counters"
 
 

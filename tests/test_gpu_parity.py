@@ -35,8 +35,10 @@ def _golden_frame(name):
 
 # ---- exhaustive colour tables evaluated on the device ---------------------------------------
 def test_device_colour_tables_exhaustive(vision):
-    assert np.array_equal(vision.colour_table(0), O.table_marker()), "marker predicate (device) != oracle"
-    assert np.array_equal(vision.colour_table(1), O.table_luma()), "luma8 (device) != oracle"
+    assert np.array_equal(vision.colour_table(0), O.table_marker()), "marker predicate (kernel path: fast-reject + table) != oracle"
+    assert np.array_equal(vision.colour_table(4), O.table_marker()), "marker predicate (float formula on device) != oracle"
+    assert np.array_equal(vision.colour_table(1), O.table_luma()), "luma8 (kernel path) != oracle"
+    assert np.array_equal(vision.colour_table(5), O.table_luma()), "luma8 (float formula on device) != oracle"
     c = np.arange(1 << 24, dtype=np.int64)
     r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
     red = (np.abs(217 - r) <= 25) & (np.abs(67 - g) <= 25) & (np.abs(49 - b) <= 25)
@@ -49,7 +51,7 @@ def test_golden_synthetic_cases(vision, name):
     frame, p, rec = _golden_frame(name)
     got = gpu_run(vision, frame, p["grayscale"], p["start_y"], p["max_gap"])
     want = oracle_run(frame, p["grayscale"], p["start_y"], p["max_gap"])
-    assert_same(got, want, name)
+    assert_same(got, want, name, scales_from=p["start_y"])
     # and against the committed hashes (catches an oracle that drifted together with the kernels)
     assert got["red_pixels"] == rec["red_pixels"] and got["map_open"] == rec["map_open"]
     if rec["map_open"]:
@@ -88,8 +90,7 @@ def test_real_screenshots(vision, name):
                                  (1281, 721), (1279, 717), (1000, 1000), (5120, 1440)])
 def test_odd_resolutions(vision, W, H):
     frame = synth.frames_host(synth.SynthParams(W, H, n_segments=5, n_blips=4, n_labels=3), 1, 1)[0]
-    o = O.Oracle()
-    assert_same(gpu_run(vision, frame, True, 3, 15), oracle_run(frame, True, 3, 15, oracle=None), f"{W}x{H}")
+    assert_same(gpu_run(vision, frame, True, 3, 15), oracle_run(frame, True, 3, 15), f"{W}x{H}", scales_from=3)
 
 
 def test_random_noise_frames(vision):
@@ -109,7 +110,7 @@ def test_random_noise_frames(vision):
         f[qy:qy + qh, qx:qx + qw, :3] = np.clip(g.astype(np.int32) + jitter, 0, 255).astype(np.uint8)
         f[qy + 5:qy + 9, qx:qx + qw, :3] = 0   # luma == 0 rows for the scales threshold
         assert_same(gpu_run(vision, f, True, 0, 15), oracle_run(f, True, 0, 15), f"noise {W}x{H}")
-        assert_same(gpu_run(vision, f, False, 2, 4), oracle_run(f, False, 2, 4), f"noise rgb {W}x{H}")
+        assert_same(gpu_run(vision, f, False, 2, 4), oracle_run(f, False, 2, 4), f"noise rgb {W}x{H}", scales_from=2)
 
 
 def test_map_closed_and_threshold_boundary(vision):
