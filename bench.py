@@ -283,9 +283,9 @@ def main() -> None:
     class _H:
         pass
     hld = _H()
-    hld.__cuda_array_interface__ = {"shape": (n * 16,), "typestr": "|u1", "data": (int(b.lsd_stats), False), "version": 2}
-    stats = torch.as_tensor(hld, device="cuda").cpu().numpy().view(np.uint64).reshape(n, 2)
-    seeds_pf, steps_pf = float(stats[:, 0].mean()), float(stats[:, 1].mean())
+    hld.__cuda_array_interface__ = {"shape": (n * 24,), "typestr": "|u1", "data": (int(b.lsd_stats), False), "version": 2}
+    stats = torch.as_tensor(hld, device="cuda").cpu().numpy().view(np.uint64).reshape(n, 3)
+    seeds_pf, steps_pf, pruned_pf = float(stats[:, 0].mean()), float(stats[:, 1].mean()), float(stats[:, 2].mean())
 
     # ---- e2e: host frames through the C ABI, H2D + D2H inside the timed region ------------
     e2e = None
@@ -322,7 +322,7 @@ def main() -> None:
             "kernels": {"dominant_by_time": dominant,
                         "k_pixels": {"ms": px_ms, "share": px_ms / (px_ms + lsd_ms)},
                         "k_lsd": {"ms": lsd_ms, "share": lsd_ms / (px_ms + lsd_ms), "bound": "instruction issue / L1 latency",
-                                  "seeds_per_frame": seeds_pf, "ray_steps_per_frame": steps_pf,
+                                  "seeds_per_frame": seeds_pf, "seeds_pruned_per_frame": pruned_pf, "ray_steps_per_frame": steps_pf,
                                   "ray_steps_per_s": steps_pf * n / (lsd_ms * 1e-3)}},
             "frames_per_s_pixels_only": n / (px_ms * 1e-3),
             "clocks": clocks,

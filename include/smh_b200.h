@@ -131,13 +131,15 @@ typedef struct {
     uint32_t *n_lines;         /* device, [n] */
     uint32_t *red_pixels;      /* device, [n] */
     uint8_t *map_open;         /* device, [n]: 0 = map closed (n_lines = 0, images still written) */
-    uint64_t *lsd_stats;       /* device, [n][2] = {seeds, ray_steps} when stats were requested, else NULL */
+    uint64_t *lsd_stats;       /* device, [n][3] = {seeds, ray_steps, pruned seeds} when stats were requested, else NULL */
 } smh_b200_batch;
 
 #define SMH_BATCH_GRAYSCALE 1u /* ui_map = (L,L,L,255) — settings default, src/settings.rs:135 */
 #define SMH_BATCH_LSD_STATS 2u /* count seeds / ray steps per frame (slower; for reporting) */
 #define SMH_BATCH_SKIP_LSD 4u  /* pixel pass only */
 #define SMH_BATCH_SKIP_PIXELS 8u /* line search only, on the planes of the previous call */
+#define SMH_BATCH_LSD_EXHAUSTIVE 16u /* march all 3600 rays of every seed (no isolated-blob pruning): makes
+                                        the ray-step counter comparable with the CPU oracle's */
 
 /* Process n device-resident frames (tightly stacked: frame f at d_frames + f*frame_stride,
  * rows pitch_bytes apart; base, pitch and stride multiples of 16).  start_y: HOST array of n

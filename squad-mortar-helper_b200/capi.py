@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libsmh_b200.so"
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
-BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS = 1, 2, 4, 8
+BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE = 1, 2, 4, 8, 16
 
 # every symbol include/smh_b200.h declares (tests assert the library exports all of them)
 SYMBOLS = [

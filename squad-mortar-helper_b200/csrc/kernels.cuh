@@ -61,34 +61,38 @@ struct PixelArgs {
     const uint32_t* lut;  // marker predicate, 1 bit per colour (r<<16|g<<8|b)
 };
 
-constexpr int PX_THREADS = 256;
-constexpr int PX_TX = 64;              // threads along a row
-constexpr int PX_G = PX_THREADS / PX_TX;  // rows per group (4)
+constexpr int PX_MAX_THREADS = 1024;   // one thread per 16-byte vector column of the map row
+constexpr int PX_G = 4;                // rows per group = 16-byte loads in flight per thread
 constexpr int PX_RING = 16;            // ring rows (power of two >= G + 6 + G)
-constexpr int PX_UNR = 4;              // 16-byte loads in flight per thread
 
 // flag bits per pixel byte in the ring
 constexpr uint32_t FL_M = 1u;      // marker colour
 constexpr uint32_t FL_CORE = 2u;   // bright monochrome pixel that an OCR neighbour search may find
 constexpr uint32_t FL_EDGE = 4u;   // OCR edge candidate (keep only with a core pixel in its window)
 
-// byte `k` of a little-endian word as an exact float: PRMT builds 0x4B0000xx (= 2^23 + xx), one
-// FADD removes the bias.  Full-rate replacement for I2F.
+// Channel k of a BGRA word as the bit pattern of the float 2^23 + value (0x4B0000vv).  The same
+// word serves three purposes: FADD -2^23 turns it into the exact float (full-rate replacement for
+// I2F), unsigned min/max of these words order like the channel values, and the low byte is the value.
+constexpr uint32_t BIAS = 0x4B000000u;
 template <int K>
-__device__ __forceinline__ float byte_as_f32(uint32_t word) {
-    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + K)), 8388608.0f);
+__device__ __forceinline__ uint32_t chan(uint32_t word) { return __byte_perm(word, BIAS, 0x7540 + K); }
+__device__ __forceinline__ float unbias(uint32_t c) { return __fsub_rn(__uint_as_float(c), 8388608.0f); }
+
+// luma8 (image 0.23.14 rgb_to_luma: unfused f32, truncating) as a biased word 0x4B0000LL: the
+// truncation is a round-down add of 2^23 (l < 256).  Same bits as smh_luma8 for all 2^24 colours
+// (device-side exhaustive test in tests/test_gpu_parity.py).
+__device__ __forceinline__ uint32_t luma_biased(uint32_t cr, uint32_t cg, uint32_t cb) {
+    const float l = __fadd_rn(__fadd_rn(__fmul_rn(SMH_LUMA_R, unbias(cr)), __fmul_rn(SMH_LUMA_G, unbias(cg))),
+                              __fmul_rn(SMH_LUMA_B, unbias(cb)));
+    return __float_as_uint(__fadd_rd(l, 8388608.0f));
 }
-// luma8 of a BGRA word (image 0.23.14 rgb_to_luma, unfused, truncating): identical bits to
-// smh_luma8 (proved over all 2^24 colours on the device, tests/test_gpu_parity.py); the
-// truncation is a round-down add of 2^23 whose low mantissa byte is floor(l) (l < 256).
 __device__ __forceinline__ uint32_t luma8_bgra(uint32_t word) {
-    const float l = __fadd_rn(__fadd_rn(__fmul_rn(SMH_LUMA_R, byte_as_f32<2>(word)), __fmul_rn(SMH_LUMA_G, byte_as_f32<1>(word))),
-                              __fmul_rn(SMH_LUMA_B, byte_as_f32<0>(word)));
-    return __float_as_uint(__fadd_rd(l, 8388608.0f)) & 0xFFu;
+    return luma_biased(chan<2>(word), chan<1>(word), chan<0>(word)) & 0xFFu;
 }
 
-// Marker predicate of a BGRA word: integer fast-reject, then one bit of the 2^24-entry table
-// that k_build_marker_lut fills with smh_is_marker_exact (2 MB, L2 resident).
+// Marker predicate of a BGRA word given max/min channel values: integer fast-reject (a necessary
+// condition, smh_marker_prefilter), then one bit of the 2^24-entry table that k_build_marker_lut
+// fills with the exact float predicate (2 MB, L2 resident).
 __device__ __forceinline__ uint32_t marker_bit(uint32_t word, uint32_t mx, uint32_t mn, const uint32_t* __restrict__ lut) {
     if (mx >= 178u && 100u * (mx - mn) >= 34u * mx) {
         const uint32_t c = word & 0x00FFFFFFu;  // r<<16 | g<<8 | b
@@ -97,71 +101,145 @@ __device__ __forceinline__ uint32_t marker_bit(uint32_t word, uint32_t mx, uint3
     return 0u;
 }
 
-// One pixel of phase 1.  MODE 0: interior vector outside the OCR quadrant; MODE 1: interior vector
-// wholly inside the quadrant and below the neighbour-search clip (D10); MODE 2: generic (row ends,
-// quadrant borders) with every test per pixel.
-template <bool GRAY, int MODE>
-__device__ __forceinline__ void classify_px(uint32_t word, int e, int i, int jq, bool owned, bool inq_row,
-                                            const PixelArgs& a, uint32_t& fl, uint32_t& uo, uint32_t& ocrw, uint32_t& scw) {
-    const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
-    const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
-    const bool valid = MODE != 2 || (i >= 0 && i < (int)a.w);
-    uint32_t fe = valid ? marker_bit(word, mx, mn, a.lut) : 0u;
-    const bool inq = MODE == 1 || (MODE == 2 && inq_row && valid && i >= (int)a.bqw && i < (int)(2u * a.bqw));
-    uint32_t luma = 0;
-    if ((GRAY && owned) || inq) luma = luma8_bgra(word);
-    if (inq) {
-        // OCR classes — vision-cpu/src/lib.rs:39-53,188-193 (mono = 4*(max-min))
-        if (mx == mn && mn >= SMH_OCR_BRIGHT) {
-            // visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
-            if (MODE == 1 || (i - (int)a.bqw <= (int)a.bqw - SMH_OCR_RADIUS && jq <= (int)a.bqh - SMH_OCR_RADIUS)) fe |= FL_CORE;
-            ocrw ^= luma << (8 * e);  // 255 - luma
-        } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) {
-            fe |= FL_EDGE;
-        }
-        scw |= (luma != 0u ? 255u : 0u) << (8 * e);
-    }
-    fl |= fe << (8 * e);
-    // ui_map: (L,L,L,255) or (r,g,b,255) — vision-cpu/src/lib.rs:150-163
-    uo = GRAY ? (luma * 0x00010101u) | 0xFF000000u : __byte_perm(word, 0xFF000000u, 0x7012);
-}
+struct PxOut {
+    uint32_t fl;    // ring flags of the 4 pixels
+    uint4 ui;       // ui_map words
+    uint32_t ocrw;  // provisional ocr_out bytes (255 or 255-luma)
+    uint32_t scw;   // scales bytes (luma != 0 ? 255 : 0)
+};
 
-template <bool GRAY, int MODE>
-__device__ __forceinline__ void classify_vec(const uint4& v, int q, int jq, bool owned, bool inq_row, const PixelArgs& a,
-                                             uint32_t& fl, uint4& uo, uint32_t& ocrw, uint32_t& scw) {
-    const int i0 = 4 * q - (int)a.pad;
-    classify_px<GRAY, MODE>(v.x, 0, i0 + 0, jq, owned, inq_row, a, fl, uo.x, ocrw, scw);
-    classify_px<GRAY, MODE>(v.y, 1, i0 + 1, jq, owned, inq_row, a, fl, uo.y, ocrw, scw);
-    classify_px<GRAY, MODE>(v.z, 2, i0 + 2, jq, owned, inq_row, a, fl, uo.z, ocrw, scw);
-    classify_px<GRAY, MODE>(v.w, 3, i0 + 3, jq, owned, inq_row, a, fl, uo.w, ocrw, scw);
-}
-
+// ---- interior vector, no pixel inside the OCR quadrant -------------------------------------
 template <bool GRAY>
-__global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
+__device__ __forceinline__ void vec_plain(const uint4& v, bool owned, const uint32_t* __restrict__ lut, PxOut& o) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mxw[4], uo[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t cb = chan<0>(wd[e]), cg = chan<1>(wd[e]), cr = chan<2>(wd[e]);
+        mxw[e] = max(cr, max(cg, cb));
+        if (GRAY) uo[e] = owned ? __byte_perm(luma_biased(cr, cg, cb), 0xFF000000u, 0x7000) : 0u;  // (L,L,L,255)
+        else uo[e] = __byte_perm(wd[e], 0xFF000000u, 0x7012);                                         // (r,g,b,255)
+    }
+    o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+    o.fl = 0;
+    if (max(max(mxw[0], mxw[1]), max(mxw[2], mxw[3])) >= BIAS + 178u) {  // rare: some pixel may be a marker
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (mxw[e] >= BIAS + 178u) {
+                const uint32_t mn = min(chan<2>(wd[e]), min(chan<1>(wd[e]), chan<0>(wd[e]))) & 0xFFu;
+                o.fl |= marker_bit(wd[e], mxw[e] & 0xFFu, mn, lut) << (8 * e);
+            }
+        }
+    }
+}
+
+// ---- interior vector wholly inside the OCR quadrant and below the neighbour-search clip -----
+template <bool GRAY>
+__device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const uint32_t* __restrict__ lut, PxOut& o) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mxw[4], mnw[4], lb[4], uo[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t cb = chan<0>(wd[e]), cg = chan<1>(wd[e]), cr = chan<2>(wd[e]);
+        mxw[e] = max(cr, max(cg, cb));
+        mnw[e] = min(cr, min(cg, cb));
+        lb[e] = owned ? luma_biased(cr, cg, cb) : BIAS + 1u;
+        if (GRAY) uo[e] = __byte_perm(lb[e], 0xFF000000u, 0x7000);
+        else uo[e] = __byte_perm(wd[e], 0xFF000000u, 0x7012);
+    }
+    o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+    o.fl = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
+    if (max(max(mxw[0], mxw[1]), max(mxw[2], mxw[3])) >= BIAS + 178u) {
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (mxw[e] >= BIAS + 178u) o.fl |= marker_bit(wd[e], mxw[e] & 0xFFu, mnw[e] & 0xFFu, lut) << (8 * e);
+    }
+    // OCR classes — vision-cpu/src/lib.rs:39-53,188-193; mono = sum |ci-cj| = 4*(max-min)
+    const uint32_t d0 = mxw[0] - mnw[0], d1 = mxw[1] - mnw[1], d2 = mxw[2] - mnw[2], d3 = mxw[3] - mnw[3];
+    if (min(min(d0, d1), min(d2, d3)) <= SMH_OCR_MONO_EDGE / 4u) {  // rare: a near-grey pixel
+        const uint32_t dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (dd[e] == 0u && mnw[e] >= BIAS + SMH_OCR_BRIGHT) {
+                o.fl |= FL_CORE << (8 * e);
+                o.ocrw ^= (lb[e] & 0xFFu) << (8 * e);  // 255 - luma
+            } else if (4u * dd[e] <= SMH_OCR_MONO_EDGE && mnw[e] >= BIAS + SMH_OCR_BRIGHT_EDGE) {
+                o.fl |= FL_EDGE << (8 * e);
+            }
+        }
+    }
+    if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) == BIAS) {  // rare: a pixel with luma 0
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (lb[e] == BIAS) o.scw &= ~(0xFFu << (8 * e));
+    }
+}
+
+// ---- generic vector: row ends, quadrant borders, clip zone — every test per pixel -----------
+template <bool GRAY>
+__device__ __forceinline__ void vec_generic(const uint4& v, int i0, int jq, bool owned, bool inq_row, const PixelArgs& a,
+                                            PxOut& o) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    uint32_t uo[4];
+    o.fl = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = i0 + e;
+        const uint32_t b = wd[e] & 0xFFu, g = (wd[e] >> 8) & 0xFFu, r = (wd[e] >> 16) & 0xFFu;
+        const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
+        const bool valid = i >= 0 && i < (int)a.w;
+        uint32_t fe = valid ? marker_bit(wd[e], mx, mn, a.lut) : 0u;
+        const bool inq = inq_row && valid && i >= (int)a.bqw && i < (int)(2u * a.bqw);
+        uint32_t luma = 0;
+        if (owned && (GRAY || inq)) luma = luma8_bgra(wd[e]);
+        if (inq) {
+            if (mx == mn && mn >= SMH_OCR_BRIGHT) {
+                // visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
+                if (i - (int)a.bqw <= (int)a.bqw - SMH_OCR_RADIUS && jq <= (int)a.bqh - SMH_OCR_RADIUS) fe |= FL_CORE;
+                o.ocrw ^= luma << (8 * e);
+            } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) {
+                fe |= FL_EDGE;
+            }
+            if (luma == 0u) o.scw &= ~(0xFFu << (8 * e));
+        }
+        o.fl |= fe << (8 * e);
+        uo[e] = GRAY ? (luma * 0x00010101u) | 0xFF000000u : __byte_perm(wd[e], 0xFF000000u, 0x7012);
+    }
+    o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+}
+
+// Fused pixel pass.  CTA = one band of rows of one frame (or the frame's button test); thread q
+// owns the 16-byte vector column q of the map ROI and walks down the band G rows at a time:
+//   phase 1  G independent 128-bit loads, classify, store ui_map / provisional ocr_out / scales,
+//            publish per-pixel flag bytes (marker, OCR core, OCR edge) into a 16-row smem ring;
+//   phase 2  (3 rows behind) 3x3-cross dilation of the marker bits -> lsd_image, and the 7x7
+//            neighbour search for the rare OCR edge pixels.
+template <bool GRAY>
+__global__ void __launch_bounds__(PX_MAX_THREADS) k_pixels(const PixelArgs a) {
     extern __shared__ __align__(16) uint32_t ring[];  // [PX_RING][ring_words]
     const uint32_t per_frame = a.nbands + 1u;
     const uint32_t f = blockIdx.x / per_frame;
     const uint32_t band = blockIdx.x % per_frame;
     const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
 
     if (band == a.nbands) {
         // ---- close-deployment button test (vision-cpu/src/lib.rs:115-135) -----------------
         uint32_t cnt = 0;
         const uint32_t npx = a.btn_w * a.btn_h;
-        for (uint32_t idx = tid; idx < npx; idx += PX_THREADS) {
+        for (uint32_t idx = tid; idx < npx; idx += nthreads) {
             const uint32_t y = idx / a.btn_w, x = idx - y * a.btn_w;
             const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
                 frame + (uint64_t)(a.btn_y + y) * a.pitch + (uint64_t)(a.btn_x + x) * 4u));
             cnt += smh_button_red((word >> 16) & 0xFFu, (word >> 8) & 0xFFu, word & 0xFFu) ? 1u : 0u;
         }
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        __shared__ uint32_t s_cnt[PX_THREADS / 32];
+        __shared__ uint32_t s_cnt[PX_MAX_THREADS / 32];
         if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
         __syncthreads();
         if (tid == 0) {
             uint32_t total = 0;
-            for (int k = 0; k < PX_THREADS / 32; k++) total += s_cnt[k];
+            for (int k = 0; k < (nthreads + 31) / 32; k++) total += s_cnt[k];
             a.red[f] = total;
             // `red_pixels as f32 / (w*h) as f32 < 0.65` -> map closed
             a.open[f] = __fdiv_rn((float)total, (float)npx) < SMH_BTN_RED_RATIO_THRESHOLD ? 0 : 1;
@@ -169,134 +247,111 @@ __global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
         return;
     }
 
-    const int tx = tid % PX_TX, ty = tid / PX_TX;
     const int r0 = (int)(band * a.rows_per_band);
     const int r1 = min(r0 + (int)a.rows_per_band, (int)a.h);
-    const int bqh = (int)a.bqh;
+    const int bqh = (int)a.bqh, bqw = (int)a.bqw, h = (int)a.h;
     const bool band_has_brq = r1 > bqh && r0 < 2 * bqh;
     const int halo = band_has_brq ? SMH_OCR_RADIUS : 1;
     const uint32_t start_y = a.start_y ? a.start_y[f] : a.start_y_uniform;
     const uint32_t rw = a.ring_words;
+    const uint32_t* __restrict__ lut = a.lut;
 
     // zero the guard words of every ring row (never written afterwards)
-    for (int k = tid; k < PX_RING; k += PX_THREADS) { ring[k * rw] = 0u; ring[k * rw + rw - 1] = 0u; }
+    for (int k = tid; k < PX_RING; k += nthreads) { ring[k * rw] = 0u; ring[k * rw + rw - 1] = 0u; }
 
-    uint8_t* ui_f = a.ui + (uint64_t)f * a.ui_stride;
-    uint8_t* lsd_f = a.lsd + (uint64_t)f * a.lsd_stride;
+    // ---- per-thread column constants --------------------------------------------------------
+    const int q = tid;
+    const bool active = q < (int)a.nvec;
+    const int i_lo = 4 * q - (int)a.pad, i_hi = i_lo + 3;
+    uint32_t vm = 0;  // bit 0 of every byte whose pixel lies inside [0, w)
+#pragma unroll
+    for (int e = 0; e < 4; e++) vm |= (i_lo + e >= 0 && i_lo + e < (int)a.w) ? (1u << (8 * e)) : 0u;
+    const bool row_end = i_lo < 0 || i_hi >= (int)a.w;
+    const bool col_out = i_hi < bqw || i_lo >= 2 * bqw;                              // no pixel in the quadrant
+    const bool col_in = i_lo >= bqw && i_hi <= 2 * bqw - SMH_OCR_RADIUS;             // all four, below the clip
+    const int qpos = (int)a.qpad - (int)a.pad - bqw + 4 * q;                         // byte position in a brq row
+    const uint8_t* src_col = frame + (uint64_t)a.map_y * a.pitch + ((uint64_t)a.gx0 + 4u * (uint32_t)q) * 4u;
+    uint8_t* ui_col = a.ui + (uint64_t)f * a.ui_stride + (uint64_t)q * 16u;
+    uint8_t* lsd_col = a.lsd + (uint64_t)f * a.lsd_stride + (uint64_t)q * 4u;
     uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
     uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
-    // vector range that intersects the brq columns [bqw, 2*bqw)
-    const int qv_lo = ((int)a.bqw + (int)a.pad) / 4;                  // first vector with i >= bqw
-    const int qv_hi = ((int)(2u * a.bqw) - 1 + (int)a.pad) / 4;       // last vector with i < 2*bqw
-    const int qword0 = ((int)a.qpad - (int)a.pad - (int)a.bqw);       // + 4q = byte position in the brq row
 
     for (int a0 = r0 - halo; a0 - SMH_OCR_RADIUS < r1; a0 += PX_G) {
         // ---------------- phase 1: load, classify, emit the stencil-free outputs -----------
-        {
-            const int j = a0 + ty;
-            const bool needed = j < r1 + halo;
-            if (needed) {
+        if (active) {
+            uint4 v[PX_G];
+#pragma unroll
+            for (int r = 0; r < PX_G; r++) {
+                const int j = a0 + r;
+                if (j >= 0 && j < h && j < r1 + halo) v[r] = ldg_nc_v4(src_col + (uint64_t)j * a.pitch);
+            }
+#pragma unroll
+            for (int r = 0; r < PX_G; r++) {
+                const int j = a0 + r;
+                if (j >= r1 + halo) continue;
                 uint32_t* rrow = ring + (uint32_t)(j & (PX_RING - 1)) * rw + 1;
-                if (j < 0 || j >= (int)a.h) {
-                    for (int q = tx; q < (int)a.nvec; q += PX_TX) rrow[q] = 0u;
-                } else {
-                    const bool owned = j >= r0 && j < r1;
-                    const int jq = j - bqh;
-                    const bool inq_row = jq >= 0 && jq < bqh;
-                    const uint8_t* src = frame + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch + (uint64_t)a.gx0 * 4u;
-                    uint8_t* ui_row = ui_f + (uint64_t)j * a.ui_pitch;
-                    uint8_t* ocr_row = ocr_f + (uint64_t)(inq_row ? jq : 0) * a.q_pitch;
-                    uint8_t* sc_row = sc_f + (uint64_t)(inq_row ? jq : 0) * a.q_pitch;
-                    const bool write_scales = inq_row && (uint32_t)jq >= start_y;
-                    for (int q0 = tx; q0 < (int)a.nvec; q0 += PX_TX * PX_UNR) {
-                        uint4 v[PX_UNR];
-#pragma unroll
-                        for (int u = 0; u < PX_UNR; u++) {
-                            const int q = q0 + u * PX_TX;
-                            if (q < (int)a.nvec) v[u] = ldg_nc_v4(src + (uint64_t)q * 16u);
-                        }
-#pragma unroll
-                        for (int u = 0; u < PX_UNR; u++) {
-                            const int q = q0 + u * PX_TX;
-                            if (q >= (int)a.nvec) continue;
-                            uint32_t fl = 0, ocrw = 0xFFFFFFFFu, scw = 0;
-                            uint4 uo;
-                            const int i_lo = 4 * q - (int)a.pad, i_hi = i_lo + 3;
-                            const bool row_end = q == 0 || q == (int)a.nvec - 1;
-                            const bool q_out = !inq_row || i_hi < (int)a.bqw || i_lo >= (int)(2u * a.bqw);
-                            const bool q_in = inq_row && i_lo >= (int)a.bqw && i_hi <= (int)(2u * a.bqw) - SMH_OCR_RADIUS &&
-                                              jq <= bqh - SMH_OCR_RADIUS;
-                            if (!row_end && q_out) classify_vec<GRAY, 0>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
-                            else if (!row_end && q_in) classify_vec<GRAY, 1>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
-                            else classify_vec<GRAY, 2>(v[u], q, jq, owned, inq_row, a, fl, uo, ocrw, scw);
-                            rrow[q] = fl;
-                            if (owned) {
-                                stg_v4(ui_row + (uint64_t)q * 16u, uo);
-                                if (inq_row && q >= qv_lo && q <= qv_hi) {
-                                    const int pos = qword0 + 4 * q;  // multiple of 4, >= 0
-                                    stg_u32(ocr_row + pos, ocrw);
-                                    if (write_scales) stg_u32(sc_row + pos, scw);
-                                }
-                            }
-                        }
+                if (j < 0 || j >= h) { rrow[q] = 0u; continue; }
+                const bool owned = j >= r0 && j < r1;
+                const int jq = j - bqh;
+                const bool inq_row = jq >= 0 && jq < bqh;
+                PxOut o;
+                if (row_end || (inq_row && !col_out && !(col_in && jq <= bqh - SMH_OCR_RADIUS)))
+                    vec_generic<GRAY>(v[r], i_lo, jq, owned, inq_row, a, o);
+                else if (inq_row && !col_out)
+                    vec_quadrant<GRAY>(v[r], owned, lut, o);
+                else
+                    vec_plain<GRAY>(v[r], owned, lut, o);
+                rrow[q] = o.fl;
+                if (owned) {
+                    stg_v4(ui_col + (uint64_t)j * a.ui_pitch, o.ui);
+                    if (inq_row && !col_out) {
+                        stg_u32(ocr_f + (uint64_t)jq * a.q_pitch + qpos, o.ocrw);
+                        if ((uint32_t)jq >= start_y) stg_u32(sc_f + (uint64_t)jq * a.q_pitch + qpos, o.scw);
                     }
                 }
             }
         }
         __syncthreads();
         // ---------------- phase 2: stencils (3x3 cross dilation, OCR neighbour search) -----
-        {
-            const int j = a0 - SMH_OCR_RADIUS + ty;
-            if (j >= r0 && j < r1) {
-                const uint32_t* rc = ring + (uint32_t)(j & (PX_RING - 1)) * rw + 1;
-                const uint32_t* ru = ring + (uint32_t)((j - 1) & (PX_RING - 1)) * rw + 1;
-                const uint32_t* rd = ring + (uint32_t)((j + 1) & (PX_RING - 1)) * rw + 1;
-                const bool has_u = j > 0, has_d = j + 1 < (int)a.h;
-                uint8_t* lsd_row = lsd_f + (uint64_t)j * a.lsd_pitch;
-                const int jq = j - bqh;
-                const bool inq_row = jq >= 0 && jq < bqh;
-                for (int q = tx; q < (int)a.nvec; q += PX_TX) {
-                    const uint32_t c = rc[q], l = rc[q - 1], r = rc[q + 1];
-                    const uint32_t mc = c & 0x01010101u;
-                    uint32_t d = mc | (mc << 8) | ((l & 0x01000000u) >> 24) | (mc >> 8) | ((r & 1u) << 24);
-                    if (has_u) d |= ru[q] & 0x01010101u;
-                    if (has_d) d |= rd[q] & 0x01010101u;
-                    // bytes of pixels outside [0, w) stay 0
-                    uint32_t vm = 0;
+        if (active) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int i = 4 * q + e - (int)a.pad;
-                        vm |= (i >= 0 && i < (int)a.w) ? (1u << (8 * e)) : 0u;
-                    }
-                    stg_u32(lsd_row + (uint64_t)q * 4u, (d & vm) * 255u);
+            for (int r = 0; r < PX_G; r++) {
+                const int j = a0 - SMH_OCR_RADIUS + r;
+                if (j < r0 || j >= r1) continue;
+                const uint32_t* rc = ring + (uint32_t)(j & (PX_RING - 1)) * rw + 1;
+                const uint32_t c = rc[q], l = rc[q - 1], rr = rc[q + 1];
+                const uint32_t mc = c & 0x01010101u;
+                uint32_t d = mc | (mc << 8) | (mc >> 8) | ((l >> 24) & 1u) | ((rr & 1u) << 24);
+                if (j > 0) d |= ring[(uint32_t)((j - 1) & (PX_RING - 1)) * rw + 1 + q] & 0x01010101u;
+                if (j + 1 < h) d |= ring[(uint32_t)((j + 1) & (PX_RING - 1)) * rw + 1 + q] & 0x01010101u;
+                stg_u32(lsd_col + (uint64_t)j * a.lsd_pitch, (d & vm) * 255u);  // pixels outside [0, w) stay 0
 
-                    uint32_t eb = (c >> 2) & 0x01010101u;
-                    if (inq_row && eb) {
+                const uint32_t eb = (c >> 2) & 0x01010101u;
+                const int jq = j - bqh;
+                if (eb && jq >= 0 && jq < bqh) {  // rare: OCR edge pixels look for a core pixel in their 7x7 window
 #pragma unroll 1
-                        for (int e = 0; e < 4; e++) {
-                            if (!((eb >> (8 * e)) & 1u)) continue;
-                            const int col = 4 * q + e;  // byte column in the ring row (pad included)
-                            bool found = false;
+                    for (int e = 0; e < 4; e++) {
+                        if (!((eb >> (8 * e)) & 1u)) continue;
+                        const int col = 4 * q + e;  // byte column in the ring row (pad included)
+                        bool found = false;
 #pragma unroll 1
-                            for (int dy = -SMH_OCR_RADIUS; dy <= SMH_OCR_RADIUS && !found; dy++) {
-                                const int jj = j + dy;
-                                if (jj < bqh || jj >= 2 * bqh) continue;
-                                const uint8_t* rb = reinterpret_cast<const uint8_t*>(
-                                    ring + (uint32_t)(jj & (PX_RING - 1)) * rw + 1);
-                                for (int dx = -SMH_OCR_RADIUS; dx <= SMH_OCR_RADIUS; dx++) {
-                                    const int cc = col + dx;
-                                    if (cc < 0 || cc >= 4 * (int)a.nvec) continue;
-                                    if (rb[cc] & FL_CORE) { found = true; break; }
-                                }
+                        for (int dy = -SMH_OCR_RADIUS; dy <= SMH_OCR_RADIUS && !found; dy++) {
+                            const int jj = j + dy;
+                            if (jj < bqh || jj >= 2 * bqh) continue;
+                            const uint8_t* rb = reinterpret_cast<const uint8_t*>(
+                                ring + (uint32_t)(jj & (PX_RING - 1)) * rw + 1);
+                            for (int dx = -SMH_OCR_RADIUS; dx <= SMH_OCR_RADIUS; dx++) {
+                                const int cc = col + dx;
+                                if (cc < 0 || cc >= 4 * (int)a.nvec) continue;
+                                if (rb[cc] & FL_CORE) { found = true; break; }
                             }
-                            if (found) {
-                                const int i = col - (int)a.pad;
-                                const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
-                                    frame + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch +
-                                    (uint64_t)(a.map_x + (uint32_t)i) * 4u));
-                                const uint32_t L = luma8_bgra(word);
-                                ocr_f[(uint64_t)jq * a.q_pitch + (uint32_t)(i - (int)a.bqw) + a.qpad] = (uint8_t)(255u - L);
-                            }
+                        }
+                        if (found) {
+                            const int i = col - (int)a.pad;
+                            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                                frame + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch +
+                                (uint64_t)(a.map_x + (uint32_t)i) * 4u));
+                            ocr_f[(uint64_t)jq * a.q_pitch + (uint32_t)(i - bqw) + a.qpad] = (uint8_t)(255u - luma8_bgra(word));
                         }
                     }
                 }
@@ -315,6 +370,10 @@ struct LsdArgs {
     const uint8_t* lsd; uint64_t stride; uint32_t pitch, pad, w, h;
     const float2* rays;  // 3600 (cos, sin) pairs built on the host with libm (D11)
     float max_gap;
+    int gap_limit;        // ceil(max_gap): `gap.0 >= max_gap` on the integer-valued counter
+    int prune;            // 1: skip seeds proven unable to yield a line (isolated blobs)
+    uint32_t n_frames;
+    uint32_t* counter;    // persistent-CTA frame dispenser (zeroed before the launch)
     const uint8_t* open;  // nullptr: every frame open
     float* lines;         // [n][32][4]
     uint32_t* n_lines;    // [n]
@@ -395,12 +454,102 @@ __device__ __forceinline__ bool suppressed_by(const float4& l, float x, float y)
     return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < SMH_LSD_SUPPRESS_DIST_SQ;
 }
 
+// Same automaton for seeds that lie inside the image (all coordinates within (-2^22, 2^22)):
+// floor() by a round-down add of 1.5*2^23 (full-rate FADD instead of F2I), both bounds in one
+// unsigned compare, integer gap counter against gap_limit = ceil(max_gap).  Bit-identical
+// end points to march() — floor(x) in [0,w) <=> 0 <= x < w, and floor == trunc for x >= 0.
+template <bool STATS>
+__device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uint32_t pitch, uint32_t w, uint32_t h,
+                                            float px, float py, int gap_limit, float dx, float dy,
+                                            float& ex, float& ey, uint32_t& steps) {
+    float x = px, y = py, xo = 0.0f, yo = 0.0f, gap_x = 0.0f, gap_y = 0.0f;
+    int gap = 0;
+    while (true) {
+        const int ix = __float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000;
+        const int iy = __float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000;
+        if ((uint32_t)ix >= w || (uint32_t)iy >= h) break;
+        if (STATS) steps++;
+        const uint32_t v = __ldg(img + ((uint32_t)iy * pitch + (uint32_t)ix));
+        if (v == 255u) {
+            gap = 0; gap_x = 0.0f; gap_y = 0.0f;
+        } else if (gap >= gap_limit) {
+            x = gap_x; y = gap_y;
+            break;
+        } else if (gap == 0) {
+            gap = 1; gap_x = x; gap_y = y;
+        } else {
+            gap++;
+        }
+        xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
+        x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
+    }
+    const uint32_t xi = __float2uint_rz(x), yi = __float2uint_rz(y);  // `as u32`: saturating (D7)
+    if (xi < w && yi < h && __ldg(img + (yi * pitch + xi)) == 0u) {
+        ex = __fsub_rn(x, dx); ey = __fsub_rn(y, dy);
+    } else {
+        ex = px; ey = py;
+    }
+    const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
+    return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+}
+
+// Exact pruning of hopeless seeds.  A ray stops at its K-th consecutive non-white sample,
+// K = gap_limit + 1.  Samples move by at most one pixel per step in Chebyshev distance d from
+// the seed pixel (monotonically; a float rounding can make one step span two pixels, hence the
+// +1 below).  If no white pixel has d in [a+1, a+K+1], every ray stops inside that ring, its
+// restored gap start lies within d <= a+2 and its squared length is < 2(a+3)^2; a ray can only
+// leave through the left/top border first (the D7 quirk that still yields a long line) when the
+// seed is closer than a+K+2 to that border, and then its length is < 2(a+K+2)^2.  When the bound
+// is <= 2500 = SMH_LSD_MIN_LEN_SQ the seed cannot produce a line (lsd.rs:95) and the 3600-ray
+// search is skipped — find_lines' output is unchanged.  Uniform result for the whole CTA.
+template <int T>
+__device__ __forceinline__ bool seed_is_isolated(const uint8_t* __restrict__ base, uint32_t pitch, uint32_t pad, uint32_t w,
+                                                 uint32_t h, float px, float py, int gap_limit,
+                                                 unsigned long long* s_mask) {
+    if (gap_limit < 0 || gap_limit > 22) return false;  // keep the inspected window <= 113 px wide
+    const int K = gap_limit + 1;
+    const int R = 32 + K + 1;
+    const int cx = (int)floorf(px), cy = (int)floorf(py);
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, (int)w - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, (int)h - 1);
+    const int wlo = (x0 + (int)pad) >> 2, whi = (x1 + (int)pad) >> 2;
+    const int nw = whi - wlo + 1, total = nw * (y1 - y0 + 1);
+    if (threadIdx.x == 0) *s_mask = 0ull;
+    __syncthreads();
+    unsigned long long m = 0ull;
+    for (int t = threadIdx.x; t < total; t += T) {
+        const int r = t / nw, c = t - r * nw;
+        const int y = y0 + r;
+        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(base + (uint32_t)y * pitch) + (wlo + c));
+        if (word) {
+            const int dy = abs(y - cy);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int x = (wlo + c) * 4 + b - (int)pad;
+                if (((word >> (8 * b)) & 0xFFu) == 255u && x >= x0 && x <= x1) m |= 1ull << max(abs(x - cx), dy);
+            }
+        }
+    }
+    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m), hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m >> 32));
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(s_mask, ((unsigned long long)hi << 32) | lo);
+    __syncthreads();
+    const unsigned long long mask = *s_mask;
+    const unsigned long long ring = (1ull << (K + 1)) - 1ull;
+    for (int a = 0; a <= 32; a++) {
+        if ((mask & (ring << (a + 1))) == 0ull) {
+            const bool border_exit = cx < a + K + 2 || cy < a + K + 2;
+            return !border_exit || a + K <= 33;
+        }
+    }
+    return false;
+}
+
 // All 3600 rays from (px,py), spread over the CTA; the winner is the LAST index among the
 // longest rays (rayon's right-biased reduce, vision-cpu/src/lib.rs:440-446, D6).
 // Result broadcast through shared memory: s_best = {len, ex, ey}.
-template <int T>
+template <int T, bool FAST, bool STATS>
 __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __restrict__ rays, float px, float py,
-                                                float max_gap, float* s_best, unsigned long long* s_keys,
+                                                float max_gap, int gap_limit, float* s_best, unsigned long long* s_keys,
                                                 float2* s_ends, uint32_t& steps) {
     const int tid = threadIdx.x;
     unsigned long long best_key = 0ull;  // (len_bits << 32) | k ; len >= 0 so the bit pattern is monotone
@@ -409,7 +558,8 @@ __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __r
     for (int k = tid; k < SMH_LSD_RAYS; k += T) {
         const float2 d = __ldg(&rays[k]);
         float ex, ey;
-        const float len = march(im, px, py, max_gap, d.x, d.y, ex, ey, steps);
+        const float len = FAST ? march_fast<STATS>(im.p, im.pitch, im.w, im.h, px, py, gap_limit, d.x, d.y, ex, ey, steps)
+                               : march(im, px, py, max_gap, d.x, d.y, ex, ey, steps);
         const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k;
         if (!any || key >= best_key) { best_key = key; bex = ex; bey = ey; any = true; }
     }
@@ -445,114 +595,125 @@ __global__ void __launch_bounds__(LSD_THREADS) k_lsd(const LsdArgs a) {
     __shared__ float2 s_ends[T / 32];
     __shared__ float s_best[3];
     __shared__ float s_pt[2];
-    __shared__ int s_n;
+    __shared__ unsigned long long s_mask;
+    __shared__ uint32_t s_frame;
 
-    const uint32_t f = blockIdx.x;
     const int tid = threadIdx.x;
-    float* out_lines = a.lines + (uint64_t)f * SMH_LSD_MAX_LINES * 4;
-    if (a.open && a.open[f] == 0) {  // map closed: the reference returns before any line search
-        if (tid == 0) { a.n_lines[f] = 0; if (STATS) { a.stats[2 * f] = 0; a.stats[2 * f + 1] = 0; } }
-        return;
-    }
-    const uint8_t* base = a.lsd + (uint64_t)f * a.stride;  // 16-byte aligned rows; pixel i at byte i+pad
-    Img im{base + a.pad, a.pitch, a.w, a.h};
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-
-    uint32_t steps = 0, seeds = 0;
-    int n = 0;
-    const uint32_t vpr = (a.pad + a.w + 15u) / 16u;      // vectors per row
+    const uint32_t vpr = (a.pad + a.w + 15u) / 16u;  // 16-byte vectors per mask row
     const uint32_t rows_per_chunk = max(1u, (uint32_t)(T * LSD_VPT) / vpr);
     const uint32_t items = rows_per_chunk * vpr;
 
-    for (uint32_t row0 = 0; row0 < a.h && n < SMH_LSD_MAX_LINES; row0 += rows_per_chunk) {
-        // ---- load this thread's slice of the chunk and find its white, in-image pixels ----
-        uint32_t alive[LSD_VPT];  // 16 bits per vector: candidate pixels still to be tried
-        uint32_t vrow[LSD_VPT], vcol[LSD_VPT];
-        bool any_white = false;
+    // persistent CTAs: frames are handed out one at a time, so a frame with many seeds does not
+    // hold back a whole wave
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_frame = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const uint32_t f = s_frame;
+        if (f >= a.n_frames) break;
+        float* out_lines = a.lines + (uint64_t)f * SMH_LSD_MAX_LINES * 4;
+        if (a.open && a.open[f] == 0) {  // map closed: the reference returns before any line search
+            if (tid == 0) { a.n_lines[f] = 0; if (STATS) { a.stats[3 * f] = 0; a.stats[3 * f + 1] = 0; a.stats[3 * f + 2] = 0; } }
+            continue;
+        }
+        const uint8_t* base = a.lsd + (uint64_t)f * a.stride;  // 16-byte aligned rows; pixel i at byte i+pad
+        const Img im{base + a.pad, a.pitch, a.w, a.h};
+
+        uint32_t steps = 0, seeds = 0, pruned = 0;
+        int n = 0;
+        for (uint32_t row0 = 0; row0 < a.h && n < SMH_LSD_MAX_LINES; row0 += rows_per_chunk) {
+            // ---- load this thread's slice of the chunk and find its white, in-image pixels ----
+            uint32_t alive[LSD_VPT];  // 16 bits per vector: candidate pixels still to be tried
+            uint32_t vrow[LSD_VPT], vcol[LSD_VPT];
+            bool any_white = false;
 #pragma unroll
-        for (int k = 0; k < LSD_VPT; k++) {
-            const uint32_t item = (uint32_t)tid * LSD_VPT + k;  // consecutive items => increasing raster order
-            alive[k] = 0; vrow[k] = 0; vcol[k] = 0;
-            if (item < items) {
-                const uint32_t r = row0 + item / vpr, c = item % vpr;
-                vrow[k] = r; vcol[k] = c;
-                if (r < a.h) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(base + (uint64_t)r * a.pitch + (uint64_t)c * 16u);
-                    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-                    if (v.x | v.y | v.z | v.w) {
+            for (int k = 0; k < LSD_VPT; k++) {
+                const uint32_t item = (uint32_t)tid * LSD_VPT + k;  // consecutive items => increasing raster order
+                alive[k] = 0; vrow[k] = 0; vcol[k] = 0;
+                if (item < items) {
+                    const uint32_t r = row0 + item / vpr, c = item % vpr;
+                    vrow[k] = r; vcol[k] = c;
+                    if (r < a.h) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(base + (uint64_t)r * a.pitch + (uint64_t)c * 16u);
+                        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+                        if (v.x | v.y | v.z | v.w) {
 #pragma unroll
-                        for (int b = 0; b < 16; b++) {
-                            const int i = (int)(c * 16u) + b - (int)a.pad;
-                            const bool white = ((wd[b >> 2] >> (8 * (b & 3))) & 0xFFu) == 255u;
-                            if (white && i >= 0 && i < (int)a.w) alive[k] |= 1u << b;
+                            for (int b = 0; b < 16; b++) {
+                                const int i = (int)(c * 16u) + b - (int)a.pad;
+                                const bool white = ((wd[b >> 2] >> (8 * (b & 3))) & 0xFFu) == 255u;
+                                if (white && i >= 0 && i < (int)a.w) alive[k] |= 1u << b;
+                            }
                         }
                     }
                 }
+                any_white |= alive[k] != 0;
             }
-            any_white |= alive[k] != 0;
-        }
-        if (!__syncthreads_or(any_white)) continue;
+            if (!__syncthreads_or(any_white)) continue;
 
-        // ---- seeds of this chunk, in raster order ------------------------------------------
-        while (true) {
-            // first untried, unsuppressed candidate of this thread (its items are in raster order)
-            uint32_t cand = 0xFFFFFFFFu;
-#pragma unroll
-            for (int k = 0; k < LSD_VPT; k++) {
-                while (cand == 0xFFFFFFFFu && alive[k]) {
-                    const int b = __ffs(alive[k]) - 1;
-                    const uint32_t xi = vcol[k] * 16u + (uint32_t)b - a.pad, yi = vrow[k];
-                    bool sup = false;
-                    for (int l = 0; l < n && !sup; l++) sup = suppressed_by(s_lines[l], (float)xi, (float)yi);
-                    if (sup) alive[k] &= ~(1u << b);  // lines only accumulate: suppressed for good
-                    else cand = yi * a.w + xi;
-                }
-            }
-            const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, cand);
-            if ((tid & 31) == 0) s_min[tid >> 5] = wmin;
-            __syncthreads();
-            uint32_t seed = 0xFFFFFFFFu;
-#pragma unroll
-            for (int k = 0; k < T / 32; k++) seed = min(seed, s_min[k]);
-            if (seed == 0xFFFFFFFFu) break;  // uniform
-            if (cand == seed) {
-                // this thread owns the seed: retire it and publish its centre
+            // ---- seeds of this chunk, in raster order ------------------------------------------
+            while (true) {
+                // first untried, unsuppressed candidate of this thread (its items are in raster order)
+                uint32_t cand = 0xFFFFFFFFu;
 #pragma unroll
                 for (int k = 0; k < LSD_VPT; k++) {
-                    if (alive[k]) {
+                    while (cand == 0xFFFFFFFFu && alive[k]) {
                         const int b = __ffs(alive[k]) - 1;
-                        if (vrow[k] * a.w + vcol[k] * 16u + (uint32_t)b - a.pad == seed) alive[k] &= ~(1u << b);
+                        const uint32_t xi = vcol[k] * 16u + (uint32_t)b - a.pad, yi = vrow[k];
+                        bool sup = false;
+                        for (int l = 0; l < n && !sup; l++) sup = suppressed_by(s_lines[l], (float)xi, (float)yi);
+                        if (sup) alive[k] &= ~(1u << b);  // lines only accumulate: suppressed for good
+                        else cand = yi * a.w + xi;
                     }
                 }
-                float cx, cy;
-                get_centre(im, (float)(seed % a.w), (float)(seed / a.w), cx, cy);
-                s_pt[0] = cx; s_pt[1] = cy;
-            }
-            __syncthreads();
-            const float px = s_pt[0], py = s_pt[1];
-            seeds++;
-            longest_ray_cta<T>(im, a.rays, px, py, a.max_gap, s_best, s_keys, s_ends, steps);
-            if (s_best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
-                if (tid == 0) {
-                    float c1x, c1y;
-                    get_centre(im, s_best[1], s_best[2], c1x, c1y);
-                    s_lines[n] = make_float4(px, py, c1x, c1y);
-                    out_lines[4 * n + 0] = px; out_lines[4 * n + 1] = py;
-                    out_lines[4 * n + 2] = c1x; out_lines[4 * n + 3] = c1y;
+                const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, cand);
+                if ((tid & 31) == 0) s_min[tid >> 5] = wmin;
+                __syncthreads();
+                uint32_t seed = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < T / 32; k++) seed = min(seed, s_min[k]);
+                if (seed == 0xFFFFFFFFu) break;  // uniform
+                if (cand == seed) {
+                    // this thread owns the seed: retire it and publish its centre
+#pragma unroll
+                    for (int k = 0; k < LSD_VPT; k++) {
+                        if (alive[k]) {
+                            const int b = __ffs(alive[k]) - 1;
+                            if (vrow[k] * a.w + vcol[k] * 16u + (uint32_t)b - a.pad == seed) alive[k] &= ~(1u << b);
+                        }
+                    }
+                    float cx, cy;
+                    get_centre(im, (float)(seed % a.w), (float)(seed / a.w), cx, cy);
+                    s_pt[0] = cx; s_pt[1] = cy;
                 }
-                n++;
-                if (n == SMH_LSD_MAX_LINES) break;  // `break 'row`
+                __syncthreads();
+                const float px = s_pt[0], py = s_pt[1];
+                seeds++;
+                if (a.prune && seed_is_isolated<T>(base, a.pitch, a.pad, a.w, a.h, px, py, a.gap_limit, &s_mask)) {
+                    pruned++;
+                    continue;  // uniform; s_min is rewritten only after the barriers inside the test
+                }
+                longest_ray_cta<T, true, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, s_best, s_keys, s_ends, steps);
+                if (s_best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
+                    if (tid == 0) {
+                        float c1x, c1y;
+                        get_centre(im, s_best[1], s_best[2], c1x, c1y);
+                        s_lines[n] = make_float4(px, py, c1x, c1y);
+                        out_lines[4 * n + 0] = px; out_lines[4 * n + 1] = py;
+                        out_lines[4 * n + 2] = c1x; out_lines[4 * n + 3] = c1y;
+                    }
+                    n++;
+                    if (n == SMH_LSD_MAX_LINES) break;  // `break 'row`
+                }
+                __syncthreads();
             }
             __syncthreads();
         }
-        __syncthreads();
-    }
-    if (tid == 0) a.n_lines[f] = (uint32_t)n;
-    if (STATS) {
-        steps = __reduce_add_sync(0xFFFFFFFFu, steps);
-        if ((tid & 31) == 0) atomicAdd(&a.stats[2 * f + 1], (unsigned long long)steps);
-        if (tid == 0) a.stats[2 * f] = seeds;
+        if (tid == 0) a.n_lines[f] = (uint32_t)n;
+        if (STATS) {
+            steps = __reduce_add_sync(0xFFFFFFFFu, steps);
+            if ((tid & 31) == 0) atomicAdd(&a.stats[3 * f + 1], (unsigned long long)steps);
+            if (tid == 0) { a.stats[3 * f] = seeds; a.stats[3 * f + 2] = pruned; }
+        }
     }
 }
 
@@ -565,7 +726,7 @@ __global__ void __launch_bounds__(LSD_THREADS) k_longest(const uint8_t* lsd, uin
     __shared__ float s_best[3];
     Img im{lsd + pad, pitch, w, h};
     uint32_t steps = 0;
-    longest_ray_cta<LSD_THREADS>(im, rays, px, py, max_gap, s_best, s_keys, s_ends, steps);
+    longest_ray_cta<LSD_THREADS, false, false>(im, rays, px, py, max_gap, 0, s_best, s_keys, s_ends, steps);
     if (threadIdx.x == 0) { out[0] = px; out[1] = py; out[2] = s_best[1]; out[3] = s_best[2]; out[4] = s_best[0]; }
 }
 

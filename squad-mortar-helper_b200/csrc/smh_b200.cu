@@ -69,9 +69,10 @@ struct Planes {
     uint8_t* open = nullptr;
     unsigned long long* stats = nullptr;
     uint32_t* start_y = nullptr;
+    uint32_t* counter = nullptr;  // frame dispenser of the persistent line-search CTAs
     void release() {
         cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
-        cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y);
+        cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y); cudaFree(counter);
         *this = Planes();
     }
 };
@@ -81,6 +82,7 @@ struct Planes {
 struct smh_b200 {
     int device = 0;
     int sm_count = 0;
+    int lsd_ctas_per_sm = 0;
     std::mutex err_mu;
     std::string err;
     std::atomic<uint64_t> launches{0};
@@ -142,7 +144,7 @@ int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint
 
 int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool stats) {
     if (P->n == n && P->W == g.W && P->H == g.H) {
-        if (stats && !P->stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 2 * sizeof(unsigned long long)));
+        if (stats && !P->stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
         return SMH_OK;
     }
     P->release();
@@ -163,7 +165,8 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     CU(h, cudaMalloc(&P->open, (size_t)n));
     CU(h, cudaMalloc(&P->start_y, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMemset(P->start_y, 0, (size_t)n * sizeof(uint32_t)));
-    if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 2 * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&P->counter, sizeof(uint32_t)));
+    if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
     P->n = n; P->W = g.W; P->H = g.H;
     return SMH_OK;
 }
@@ -197,25 +200,41 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     if (smem > 48 * 1024)
         CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t blocks = (uint64_t)n * (a.nbands + 1u);
-    kern<<<(unsigned)blocks, smh::PX_THREADS, smem, st>>>(a);
+    const uint32_t threads = round_up(a.nvec, 32u);
+    if (threads > (uint32_t)smh::PX_MAX_THREADS)
+        return fail(h, SMH_E_GEOMETRY, "map ROI wider than %d px is not supported (w = %u)", smh::PX_MAX_THREADS * 4 - 3, a.w);
+    kern<<<(unsigned)blocks, threads, smem, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
 }
 
-int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, cudaStream_t st) {
+int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st) {
     smh::LsdArgs a{};
     a.lsd = P.lsd.ptr; a.stride = P.lsd.frame_stride; a.pitch = P.lsd.pitch; a.pad = P.lsd.pad;
     a.w = P.geo.map[2]; a.h = P.geo.map[3];
     a.rays = h->d_rays; a.max_gap = max_gap;
+    // `gap.0 >= max_gap` on an integer-valued counter <=> counter >= ceil(max_gap)
+    a.gap_limit = (max_gap != max_gap || max_gap >= 2147483648.0f) ? 2147483647 : (max_gap <= -2147483648.0f ? -2147483647 : (int)ceilf(max_gap));
+    a.prune = prune ? 1 : 0;
+    a.n_frames = n; a.counter = P.counter;
     a.open = use_open ? P.open : nullptr;
     a.lines = P.lines; a.n_lines = P.n_lines;
     a.stats = stats ? P.stats : nullptr;
+    CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
+    // persistent grid: as many CTAs as stay resident (or one per frame when there are fewer)
+    if (h->lsd_ctas_per_sm == 0) {
+        int nb = 0;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, 0));
+        h->lsd_ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    const uint32_t resident = (uint32_t)(h->sm_count * h->lsd_ctas_per_sm);
+    const uint32_t grid = n < resident ? n : resident;
     if (stats) {
-        CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 2 * sizeof(unsigned long long), st));
-        smh::k_lsd<true><<<n, smh::LSD_THREADS, 0, st>>>(a);
+        CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
+        smh::k_lsd<true><<<grid, smh::LSD_THREADS, 0, st>>>(a);
     } else {
-        smh::k_lsd<false><<<n, smh::LSD_THREADS, 0, st>>>(a);
+        smh::k_lsd<false><<<grid, smh::LSD_THREADS, 0, st>>>(a);
     }
     h->launches++;
     CU(h, cudaGetLastError());
@@ -532,7 +551,7 @@ int32_t smh_b200_find_marker_lines(smh_b200* h, uint32_t max_gap, float lines[32
     std::lock_guard<std::mutex> g(h->markers_mu);
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
-    if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, h->s_markers))) return rc;
+    if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, true, h->s_markers))) return rc;
     CU(h, cudaMemcpyAsync(h->h_small, h->one.lines, 128 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
     CU(h, cudaMemcpyAsync(h->h_small + 128, h->one.n_lines, 4, cudaMemcpyDeviceToHost, h->s_markers));
     CU(h, cudaStreamSynchronize(h->s_markers));
@@ -622,7 +641,7 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
             return rc;
     }
     if (!(flags & SMH_BATCH_SKIP_LSD))
-        if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, st))) return rc;
+        if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
     fill_batch_out(h->batch, stats, out);
     return SMH_OK;
 }
@@ -690,7 +709,7 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
                                 pick_rows_per_band(h, c, g.map[3]), st)))
             return rc;
         if (!(flags & SMH_BATCH_SKIP_LSD))
-            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, st))) return rc;
+            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st))) return rc;
         if (res->ui_map && (rc = download_plane(h, &P.ui, 0, c, res->ui_map + (size_t)done * npx * 4, st))) return rc;
         if (res->ocr_out && (rc = download_plane(h, &P.ocr, 0, c, res->ocr_out + (size_t)done * nq, st))) return rc;
         if (res->scales && (rc = download_plane(h, &P.scales, 0, c, res->scales + (size_t)done * nq, st))) return rc;

@@ -46,7 +46,7 @@ def _results(v, b, n):
     out["red_pixels"] = _device_array(b.red_pixels, n * 4).cpu().numpy().view(np.uint32)
     out["map_open"] = _device_array(b.map_open, n).cpu().numpy()
     if b.lsd_stats:
-        out["stats"] = _device_array(b.lsd_stats, n * 16).cpu().numpy().view(np.uint64).reshape(n, 2)
+        out["stats"] = _device_array(b.lsd_stats, n * 24).cpu().numpy().view(np.uint64).reshape(n, 3)
     return out
 
 
@@ -67,14 +67,21 @@ def test_device_batch_matches_oracle_per_frame(vision, W, H, n):
     assert np.array_equal(dev.cpu().numpy(), host), "CUDA rasteriser != CPU rasteriser"
     start_y = np.arange(n, dtype=np.uint32) * 7 % 50
     b = vision.process_batch(dev.data_ptr(), n, W, H, start_y=start_y, max_gap=15, grayscale=True, lsd_stats=True,
-                             stream=torch.cuda.current_stream().cuda_stream)
+                             lsd_exhaustive=True, stream=torch.cuda.current_stream().cuda_stream)
     res = _results(vision, b, n)
+    # default mode (isolated-blob pruning on) must give the same lines with fewer marched rays
+    b2 = vision.process_batch(dev.data_ptr(), n, W, H, start_y=start_y, max_gap=15, grayscale=True, lsd_stats=True,
+                              stream=torch.cuda.current_stream().cuda_stream)
+    res2 = _results(vision, b2, n)
+    assert np.array_equal(res["n_lines"], res2["n_lines"]) and np.array_equal(res["lines"].view(np.uint32), res2["lines"].view(np.uint32))
+    assert np.array_equal(res["stats"][:, 0], res2["stats"][:, 0]) and (res2["stats"][:, 1] <= res["stats"][:, 1]).all()
+    assert (res["stats"][:, 2] == 0).all()
     for i in range(n):
         want = oracle_run(host[i], True, int(start_y[i]), 15)
         got = _frame_result(res, i)
         got["xywh"] = want["xywh"]
         assert_same(got, want, f"batch frame {i}", scales_from=int(start_y[i]))
-        assert tuple(int(x) for x in res["stats"][i]) == tuple(want["lsd_stats"]), "seed / ray-step counters"
+        assert tuple(int(x) for x in res["stats"][i][:2]) == tuple(want["lsd_stats"]), "seed / ray-step counters"
 
 
 def test_batch_with_closed_maps_and_rgb(vision):
@@ -156,7 +163,7 @@ def test_4k_frame_and_lsd_stress(vision):
         p = synth.SynthParams(W, H, **kw)
         dev = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")
         synth.frames_device(vision, p, 0, n, dev.data_ptr())
-        b = vision.process_batch(dev.data_ptr(), n, W, H, max_gap=15, lsd_stats=True,
+        b = vision.process_batch(dev.data_ptr(), n, W, H, max_gap=15, lsd_stats=True, lsd_exhaustive=True,
                                  stream=torch.cuda.current_stream().cuda_stream)
         res = _results(vision, b, n)
         host = dev.cpu().numpy()
@@ -164,4 +171,4 @@ def test_4k_frame_and_lsd_stress(vision):
             want = oracle_run(host[i], True, 0, 15)
             got = _frame_result(res, i); got["xywh"] = want["xywh"]
             assert_same(got, want, f"{W}x{H} {kw} frame {i}")
-            assert tuple(int(x) for x in res["stats"][i]) == tuple(want["lsd_stats"])
+            assert tuple(int(x) for x in res["stats"][i][:2]) == tuple(want["lsd_stats"])
