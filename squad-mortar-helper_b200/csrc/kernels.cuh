@@ -454,35 +454,32 @@ __device__ __forceinline__ bool suppressed_by(const float4& l, float x, float y)
     return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < SMH_LSD_SUPPRESS_DIST_SQ;
 }
 
-// Same automaton for seeds that lie inside the image (all coordinates within (-2^22, 2^22)):
-// floor() by a round-down add of 1.5*2^23 (full-rate FADD instead of F2I), both bounds in one
-// unsigned compare, integer gap counter against gap_limit = ceil(max_gap).  Bit-identical
-// end points to march() — floor(x) in [0,w) <=> 0 <= x < w, and floor == trunc for x >= 0.
+// Same automaton for seeds that lie inside the image (all coordinates within (-2^22, 2^22)) and
+// gap_limit = ceil(max_gap) >= 1: floor() by a round-down add of 1.5*2^23 (full-rate FADD instead
+// of F2I), both bounds in one unsigned compare each, integer gap counter.  With gap_limit >= 1 a
+// ray can only stop on a gap that has a recorded start, so the reference's reset of the saved
+// position to (0,0) on white pixels is unobservable and dropped.  Bit-identical end points to
+// march() — floor(x) in [0,w) <=> 0 <= x < w, and floor == trunc for x >= 0.
 template <bool STATS>
 __device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uint32_t pitch, uint32_t w, uint32_t h,
                                             float px, float py, int gap_limit, float dx, float dy,
                                             float& ex, float& ey, uint32_t& steps) {
-    float x = px, y = py, xo = 0.0f, yo = 0.0f, gap_x = 0.0f, gap_y = 0.0f;
+    float x = px, y = py, xo = 0.0f, yo = 0.0f, gap_x = px, gap_y = py;
     int gap = 0;
+    bool broke = false;
     while (true) {
-        const int ix = __float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000;
-        const int iy = __float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000;
-        if ((uint32_t)ix >= w || (uint32_t)iy >= h) break;
+        const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000);
+        const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000);
+        if (ix >= w || iy >= h) break;
         if (STATS) steps++;
-        const uint32_t v = __ldg(img + ((uint32_t)iy * pitch + (uint32_t)ix));
-        if (v == 255u) {
-            gap = 0; gap_x = 0.0f; gap_y = 0.0f;
-        } else if (gap >= gap_limit) {
-            x = gap_x; y = gap_y;
-            break;
-        } else if (gap == 0) {
-            gap = 1; gap_x = x; gap_y = y;
-        } else {
-            gap++;
-        }
+        const bool black = __ldg(img + (iy * pitch + ix)) != 255u;
+        if (black && gap >= gap_limit) { broke = true; break; }
+        if (black && gap == 0) { gap_x = x; gap_y = y; }
+        gap = black ? gap + 1 : 0;
         xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
         x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
     }
+    if (broke) { x = gap_x; y = gap_y; }
     const uint32_t xi = __float2uint_rz(x), yi = __float2uint_rz(y);  // `as u32`: saturating (D7)
     if (xi < w && yi < h && __ldg(img + (yi * pitch + xi)) == 0u) {
         ex = __fsub_rn(x, dx); ey = __fsub_rn(y, dy);
@@ -491,6 +488,25 @@ __device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uin
     }
     const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+}
+
+// get_centre evaluated by one warp in parallel (every lane returns the result): lane = 8*dir + t
+// tests the loop condition of step t of direction dir (left, right, up, down); the walk stops at
+// the first failing t, so the stop index is the number of trailing ones of the ballot byte.
+// `v -= 1.0` t times is exact for these magnitudes, so v = pt -/+ t are the reference's values.
+__device__ __forceinline__ void get_centre_warp(const Img& im, float ptx, float pty, float& cx, float& cy) {
+    const int lane = threadIdx.x & 31, dir = lane >> 3, t = lane & 7;
+    const float ft = (float)t;
+    bool ok = t < 5;  // |v - pt| = t < MAX_DIST
+    if (dir == 0) { const float v = __fsub_rn(ptx, ft); ok = ok && v > 0.0f && px_clamped(im, v, pty) == 255u; }
+    else if (dir == 1) { const float v = __fadd_rn(ptx, ft); ok = ok && v < (float)(im.w - 1u) && px_clamped(im, v, pty) == 255u; }
+    else if (dir == 2) { const float v = __fsub_rn(pty, ft); ok = ok && v > 0.0f && px_clamped(im, ptx, v) == 255u; }
+    else { const float v = __fadd_rn(pty, ft); ok = ok && v < (float)(im.h - 1u) && px_clamped(im, ptx, v) == 255u; }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+    const float kl = (float)(__ffs(~(bal & 0xFFu)) - 1), kr = (float)(__ffs(~((bal >> 8) & 0xFFu)) - 1);
+    const float ku = (float)(__ffs(~((bal >> 16) & 0xFFu)) - 1), kd = (float)(__ffs(~((bal >> 24) & 0xFFu)) - 1);
+    cx = __fdiv_rn(__fadd_rn(__fsub_rn(ptx, kl), __fadd_rn(ptx, kr)), 2.0f);
+    cy = __fdiv_rn(__fadd_rn(__fsub_rn(pty, ku), __fadd_rn(pty, kd)), 2.0f);
 }
 
 // Exact pruning of hopeless seeds.  A ray stops at its K-th consecutive non-white sample,
@@ -514,8 +530,7 @@ __device__ __forceinline__ bool seed_is_isolated(const uint8_t* __restrict__ bas
     const int y0 = max(cy - R, 0), y1 = min(cy + R, (int)h - 1);
     const int wlo = (x0 + (int)pad) >> 2, whi = (x1 + (int)pad) >> 2;
     const int nw = whi - wlo + 1, total = nw * (y1 - y0 + 1);
-    if (threadIdx.x == 0) *s_mask = 0ull;
-    __syncthreads();
+    // *s_mask was zeroed one seed ago (double-buffered by the caller)
     unsigned long long m = 0ull;
     for (int t = threadIdx.x; t < total; t += T) {
         const int r = t / nw, c = t - r * nw;
@@ -546,10 +561,10 @@ __device__ __forceinline__ bool seed_is_isolated(const uint8_t* __restrict__ bas
 
 // All 3600 rays from (px,py), spread over the CTA; the winner is the LAST index among the
 // longest rays (rayon's right-biased reduce, vision-cpu/src/lib.rs:440-446, D6).
-// Result broadcast through shared memory: s_best = {len, ex, ey}.
+// Every thread returns best = {len, ex, ey} (one barrier; s_keys/s_ends may be reused after the next one).
 template <int T, bool FAST, bool STATS>
 __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __restrict__ rays, float px, float py,
-                                                float max_gap, int gap_limit, float* s_best, unsigned long long* s_keys,
+                                                float max_gap, int gap_limit, float (&best)[3], unsigned long long* s_keys,
                                                 float2* s_ends, uint32_t& steps) {
     const int tid = threadIdx.x;
     unsigned long long best_key = 0ull;  // (len_bits << 32) | k ; len >= 0 so the bit pattern is monotone
@@ -573,41 +588,43 @@ __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __r
     const int warp = tid >> 5;
     if (any && best_key == wkey) { s_keys[warp] = wkey; s_ends[warp] = make_float2(bex, bey); }
     __syncthreads();
-    if (tid == 0) {
-        int bw = 0;
-        for (int k = 1; k < T / 32; k++) if (s_keys[k] > s_keys[bw]) bw = k;
-        s_best[0] = __uint_as_float((uint32_t)(s_keys[bw] >> 32));
-        s_best[1] = s_ends[bw].x;
-        s_best[2] = s_ends[bw].y;
-    }
-    __syncthreads();
+    int bw = 0;
+    unsigned long long bk = s_keys[0];
+#pragma unroll
+    for (int k = 1; k < T / 32; k++) { const unsigned long long o = s_keys[k]; if (o > bk) { bk = o; bw = k; } }
+    best[0] = __uint_as_float((uint32_t)(bk >> 32));
+    best[1] = s_ends[bw].x;
+    best[2] = s_ends[bw].y;
 }
 
 constexpr int LSD_THREADS = 256;
 constexpr int LSD_VPT = 4;  // 16-byte mask vectors per thread per scan chunk
 
+// lsd::find_lines for whole frames (vision-common/src/lsd.rs:60-105).  One CTA works on one frame
+// at a time (persistent CTAs pull frames from a counter).  Per frame: the mask is scanned in
+// raster order in chunks held in registers as per-thread bitmaps of white pixels; pixels are
+// struck off as soon as a line suppresses them, so the next seed is just the lowest remaining
+// bit (block-wide min).  Per seed: get_centre (per warp, redundantly), the exact isolated-seed
+// test, then the 3600-ray search spread over the CTA with a last-index argmax.
 template <bool STATS>
-__global__ void __launch_bounds__(LSD_THREADS) k_lsd(const LsdArgs a) {
+__global__ void __launch_bounds__(LSD_THREADS, 4) k_lsd(const LsdArgs a) {
     constexpr int T = LSD_THREADS;
     __shared__ float4 s_lines[SMH_LSD_MAX_LINES];
     __shared__ uint32_t s_min[T / 32];
     __shared__ unsigned long long s_keys[T / 32];
     __shared__ float2 s_ends[T / 32];
-    __shared__ float s_best[3];
-    __shared__ float s_pt[2];
-    __shared__ unsigned long long s_mask;
+    __shared__ unsigned long long s_mask[2];
     __shared__ uint32_t s_frame;
 
     const int tid = threadIdx.x;
     const uint32_t vpr = (a.pad + a.w + 15u) / 16u;  // 16-byte vectors per mask row
     const uint32_t rows_per_chunk = max(1u, (uint32_t)(T * LSD_VPT) / vpr);
     const uint32_t items = rows_per_chunk * vpr;
+    const bool fast = a.gap_limit >= 1;  // march_fast's precondition
 
-    // persistent CTAs: frames are handed out one at a time, so a frame with many seeds does not
-    // hold back a whole wave
     while (true) {
         __syncthreads();
-        if (tid == 0) s_frame = atomicAdd(a.counter, 1u);
+        if (tid == 0) { s_frame = atomicAdd(a.counter, 1u); s_mask[0] = 0ull; s_mask[1] = 0ull; }
         __syncthreads();
         const uint32_t f = s_frame;
         if (f >= a.n_frames) break;
@@ -620,19 +637,19 @@ __global__ void __launch_bounds__(LSD_THREADS) k_lsd(const LsdArgs a) {
         const Img im{base + a.pad, a.pitch, a.w, a.h};
 
         uint32_t steps = 0, seeds = 0, pruned = 0;
-        int n = 0;
+        int n = 0, par = 0;
         for (uint32_t row0 = 0; row0 < a.h && n < SMH_LSD_MAX_LINES; row0 += rows_per_chunk) {
-            // ---- load this thread's slice of the chunk and find its white, in-image pixels ----
-            uint32_t alive[LSD_VPT];  // 16 bits per vector: candidate pixels still to be tried
-            uint32_t vrow[LSD_VPT], vcol[LSD_VPT];
+            // ---- this thread's slice of the chunk: bitmaps of its white, in-image pixels -------
+            uint32_t alive[LSD_VPT];  // 16 bits per vector
+            uint32_t vrow[LSD_VPT], vx0[LSD_VPT];
             bool any_white = false;
 #pragma unroll
             for (int k = 0; k < LSD_VPT; k++) {
                 const uint32_t item = (uint32_t)tid * LSD_VPT + k;  // consecutive items => increasing raster order
-                alive[k] = 0; vrow[k] = 0; vcol[k] = 0;
+                alive[k] = 0; vrow[k] = 0; vx0[k] = 0;
                 if (item < items) {
                     const uint32_t r = row0 + item / vpr, c = item % vpr;
-                    vrow[k] = r; vcol[k] = c;
+                    vrow[k] = r; vx0[k] = c * 16u - a.pad;  // x of byte 0 (may wrap below 0 for c = 0)
                     if (r < a.h) {
                         const uint4 v = *reinterpret_cast<const uint4*>(base + (uint64_t)r * a.pitch + (uint64_t)c * 16u);
                         const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
@@ -646,25 +663,23 @@ __global__ void __launch_bounds__(LSD_THREADS) k_lsd(const LsdArgs a) {
                         }
                     }
                 }
+                // strike off what the lines found so far already suppress (lsd.rs:84-89)
+                for (uint32_t bits = alive[k]; bits && n > 0; bits &= bits - 1u) {
+                    const int b = __ffs(bits) - 1;
+                    const float fx = (float)(vx0[k] + (uint32_t)b), fy = (float)vrow[k];
+                    for (int l = 0; l < n; l++)
+                        if (suppressed_by(s_lines[l], fx, fy)) { alive[k] &= ~(1u << b); break; }
+                }
                 any_white |= alive[k] != 0;
             }
             if (!__syncthreads_or(any_white)) continue;
 
             // ---- seeds of this chunk, in raster order ------------------------------------------
             while (true) {
-                // first untried, unsuppressed candidate of this thread (its items are in raster order)
-                uint32_t cand = 0xFFFFFFFFu;
+                uint32_t cand = 0xFFFFFFFFu;  // lowest remaining pixel of this thread (items are in raster order)
 #pragma unroll
-                for (int k = 0; k < LSD_VPT; k++) {
-                    while (cand == 0xFFFFFFFFu && alive[k]) {
-                        const int b = __ffs(alive[k]) - 1;
-                        const uint32_t xi = vcol[k] * 16u + (uint32_t)b - a.pad, yi = vrow[k];
-                        bool sup = false;
-                        for (int l = 0; l < n && !sup; l++) sup = suppressed_by(s_lines[l], (float)xi, (float)yi);
-                        if (sup) alive[k] &= ~(1u << b);  // lines only accumulate: suppressed for good
-                        else cand = yi * a.w + xi;
-                    }
-                }
+                for (int k = LSD_VPT - 1; k >= 0; k--)
+                    if (alive[k]) cand = vrow[k] * a.w + vx0[k] + (uint32_t)(__ffs(alive[k]) - 1);
                 const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, cand);
                 if ((tid & 31) == 0) s_min[tid >> 5] = wmin;
                 __syncthreads();
@@ -673,38 +688,41 @@ __global__ void __launch_bounds__(LSD_THREADS) k_lsd(const LsdArgs a) {
                 for (int k = 0; k < T / 32; k++) seed = min(seed, s_min[k]);
                 if (seed == 0xFFFFFFFFu) break;  // uniform
                 if (cand == seed) {
-                    // this thread owns the seed: retire it and publish its centre
 #pragma unroll
-                    for (int k = 0; k < LSD_VPT; k++) {
-                        if (alive[k]) {
-                            const int b = __ffs(alive[k]) - 1;
-                            if (vrow[k] * a.w + vcol[k] * 16u + (uint32_t)b - a.pad == seed) alive[k] &= ~(1u << b);
-                        }
-                    }
-                    float cx, cy;
-                    get_centre(im, (float)(seed % a.w), (float)(seed / a.w), cx, cy);
-                    s_pt[0] = cx; s_pt[1] = cy;
+                    for (int k = 0; k < LSD_VPT; k++)
+                        if (alive[k] && vrow[k] * a.w + vx0[k] + (uint32_t)(__ffs(alive[k]) - 1) == seed) alive[k] &= alive[k] - 1u;
                 }
-                __syncthreads();
-                const float px = s_pt[0], py = s_pt[1];
+                float px, py;
+                get_centre_warp(im, (float)(seed % a.w), (float)(seed / a.w), px, py);  // same value in every warp
                 seeds++;
-                if (a.prune && seed_is_isolated<T>(base, a.pitch, a.pad, a.w, a.h, px, py, a.gap_limit, &s_mask)) {
-                    pruned++;
-                    continue;  // uniform; s_min is rewritten only after the barriers inside the test
+                if (a.prune) {
+                    const bool isolated = seed_is_isolated<T>(base, a.pitch, a.pad, a.w, a.h, px, py, a.gap_limit, &s_mask[par]);
+                    if (tid == 0) s_mask[par ^ 1] = 0ull;  // last read one seed ago, behind two barriers
+                    par ^= 1;
+                    if (isolated) { pruned++; continue; }  // uniform
                 }
-                longest_ray_cta<T, true, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, s_best, s_keys, s_ends, steps);
-                if (s_best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
+                float best[3];
+                if (fast) longest_ray_cta<T, true, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, best, s_keys, s_ends, steps);
+                else longest_ray_cta<T, false, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, best, s_keys, s_ends, steps);
+                if (best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
+                    float c1x, c1y;
+                    get_centre_warp(im, best[1], best[2], c1x, c1y);
+                    const float4 line = make_float4(px, py, c1x, c1y);
                     if (tid == 0) {
-                        float c1x, c1y;
-                        get_centre(im, s_best[1], s_best[2], c1x, c1y);
-                        s_lines[n] = make_float4(px, py, c1x, c1y);
+                        s_lines[n] = line;  // read by later chunks only, behind the barriers in between
                         out_lines[4 * n + 0] = px; out_lines[4 * n + 1] = py;
                         out_lines[4 * n + 2] = c1x; out_lines[4 * n + 3] = c1y;
                     }
                     n++;
                     if (n == SMH_LSD_MAX_LINES) break;  // `break 'row`
+                    // the new line suppresses pixels for good: strike them off now
+#pragma unroll
+                    for (int k = 0; k < LSD_VPT; k++)
+                        for (uint32_t bits = alive[k]; bits; bits &= bits - 1u) {
+                            const int b = __ffs(bits) - 1;
+                            if (suppressed_by(line, (float)(vx0[k] + (uint32_t)b), (float)vrow[k])) alive[k] &= ~(1u << b);
+                        }
                 }
-                __syncthreads();
             }
             __syncthreads();
         }
@@ -723,11 +741,11 @@ __global__ void __launch_bounds__(LSD_THREADS) k_longest(const uint8_t* lsd, uin
                                                          float max_gap, float* out) {
     __shared__ unsigned long long s_keys[LSD_THREADS / 32];
     __shared__ float2 s_ends[LSD_THREADS / 32];
-    __shared__ float s_best[3];
     Img im{lsd + pad, pitch, w, h};
     uint32_t steps = 0;
-    longest_ray_cta<LSD_THREADS, false, false>(im, rays, px, py, max_gap, 0, s_best, s_keys, s_ends, steps);
-    if (threadIdx.x == 0) { out[0] = px; out[1] = py; out[2] = s_best[1]; out[3] = s_best[2]; out[4] = s_best[0]; }
+    float best[3];
+    longest_ray_cta<LSD_THREADS, false, false>(im, rays, px, py, max_gap, 0, best, s_keys, s_ends, steps);
+    if (threadIdx.x == 0) { out[0] = px; out[1] = py; out[2] = best[1]; out[3] = best[2]; out[4] = best[0]; }
 }
 
 // ------------------------------------------------------------------------------------------
