@@ -493,20 +493,28 @@ __device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uin
 // get_centre evaluated by one warp in parallel (every lane returns the result): lane = 8*dir + t
 // tests the loop condition of step t of direction dir (left, right, up, down); the walk stops at
 // the first failing t, so the stop index is the number of trailing ones of the ballot byte.
-// `v -= 1.0` t times is exact for these magnitudes, so v = pt -/+ t are the reference's values.
+// Each lane rebuilds its v by t successive +-1.0 adds, because the reference's `(v - pt).abs() < 5`
+// sees the accumulated rounding: across a binade boundary (e.g. 511.6 -> 512.6) five increments can
+// leave |v - pt| just below 5 and the walk takes a sixth step.
 __device__ __forceinline__ void get_centre_warp(const Img& im, float ptx, float pty, float& cx, float& cy) {
     const int lane = threadIdx.x & 31, dir = lane >> 3, t = lane & 7;
-    const float ft = (float)t;
-    bool ok = t < 5;  // |v - pt| = t < MAX_DIST
-    if (dir == 0) { const float v = __fsub_rn(ptx, ft); ok = ok && v > 0.0f && px_clamped(im, v, pty) == 255u; }
-    else if (dir == 1) { const float v = __fadd_rn(ptx, ft); ok = ok && v < (float)(im.w - 1u) && px_clamped(im, v, pty) == 255u; }
-    else if (dir == 2) { const float v = __fsub_rn(pty, ft); ok = ok && v > 0.0f && px_clamped(im, ptx, v) == 255u; }
-    else { const float v = __fadd_rn(pty, ft); ok = ok && v < (float)(im.h - 1u) && px_clamped(im, ptx, v) == 255u; }
+    const float pt = dir < 2 ? ptx : pty;
+    const float step = (dir & 1) ? 1.0f : -1.0f;
+    float v = pt;
+    for (int i = 0; i < t; i++) v = __fadd_rn(v, step);
+    bool ok = fabsf(__fsub_rn(v, pt)) < SMH_LSD_CENTRE_MAX_DIST;
+    if (dir == 0) ok = ok && v > 0.0f && px_clamped(im, v, pty) == 255u;
+    else if (dir == 1) ok = ok && v < (float)(im.w - 1u) && px_clamped(im, v, pty) == 255u;
+    else if (dir == 2) ok = ok && v > 0.0f && px_clamped(im, ptx, v) == 255u;
+    else ok = ok && v < (float)(im.h - 1u) && px_clamped(im, ptx, v) == 255u;
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
-    const float kl = (float)(__ffs(~(bal & 0xFFu)) - 1), kr = (float)(__ffs(~((bal >> 8) & 0xFFu)) - 1);
-    const float ku = (float)(__ffs(~((bal >> 16) & 0xFFu)) - 1), kd = (float)(__ffs(~((bal >> 24) & 0xFFu)) - 1);
-    cx = __fdiv_rn(__fadd_rn(__fsub_rn(ptx, kl), __fadd_rn(ptx, kr)), 2.0f);
-    cy = __fdiv_rn(__fadd_rn(__fsub_rn(pty, ku), __fadd_rn(pty, kd)), 2.0f);
+    // value after k steps = the v of lane 8*dir + k (k <= 7: lane t = 7 always fails the distance test)
+    const int kl = __ffs(~(bal & 0xFFu)) - 1, kr = __ffs(~((bal >> 8) & 0xFFu)) - 1;
+    const int ku = __ffs(~((bal >> 16) & 0xFFu)) - 1, kd = __ffs(~((bal >> 24) & 0xFFu)) - 1;
+    const float left = __shfl_sync(0xFFFFFFFFu, v, kl), right = __shfl_sync(0xFFFFFFFFu, v, 8 + kr);
+    const float up = __shfl_sync(0xFFFFFFFFu, v, 16 + ku), down = __shfl_sync(0xFFFFFFFFu, v, 24 + kd);
+    cx = __fdiv_rn(__fadd_rn(left, right), 2.0f);
+    cy = __fdiv_rn(__fadd_rn(up, down), 2.0f);
 }
 
 // Exact pruning of hopeless seeds.  A ray stops at its K-th consecutive non-white sample,
@@ -663,12 +671,22 @@ __global__ void __launch_bounds__(LSD_THREADS, 4) k_lsd(const LsdArgs a) {
                         }
                     }
                 }
-                // strike off what the lines found so far already suppress (lsd.rs:84-89)
-                for (uint32_t bits = alive[k]; bits && n > 0; bits &= bits - 1u) {
-                    const int b = __ffs(bits) - 1;
-                    const float fx = (float)(vx0[k] + (uint32_t)b), fy = (float)vrow[k];
-                    for (int l = 0; l < n; l++)
-                        if (suppressed_by(s_lines[l], fx, fy)) { alive[k] &= ~(1u << b); break; }
+                // strike off what the lines found so far already suppress (lsd.rs:84-89): one pixel
+                // per warp step, lane l tests line l (n <= 32), the vote decides
+                if (n > 0) {
+                    const int lane = tid & 31;
+                    uint32_t pend = alive[k];
+                    uint32_t bal;
+                    while ((bal = __ballot_sync(0xFFFFFFFFu, pend != 0u)) != 0u) {
+                        const int src = __ffs(bal) - 1;
+                        const uint32_t bits = __shfl_sync(0xFFFFFFFFu, pend, src);
+                        const int b = __ffs(bits) - 1;
+                        const float fx = (float)(__shfl_sync(0xFFFFFFFFu, vx0[k], src) + (uint32_t)b);
+                        const float fy = (float)__shfl_sync(0xFFFFFFFFu, vrow[k], src);
+                        const bool sup = lane < n && suppressed_by(s_lines[lane], fx, fy);
+                        const bool hit = __any_sync(0xFFFFFFFFu, sup);
+                        if (lane == src) { pend &= pend - 1u; if (hit) alive[k] &= ~(1u << b); }
+                    }
                 }
                 any_white |= alive[k] != 0;
             }
