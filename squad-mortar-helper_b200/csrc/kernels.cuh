@@ -57,15 +57,13 @@ struct PixelArgs {
     uint32_t* red; uint8_t* open;
     uint32_t rows_per_band, nbands;
     uint32_t grayscale;
-    uint32_t ring_words;  // words per ring row = nvec + 2 (one zero guard word each side)
+    uint32_t n_frames, nstrips;  // strips of PX_STRIP vector columns per row
     const uint32_t* lut;  // marker predicate, 1 bit per colour (r<<16|g<<8|b)
 };
 
-constexpr int PX_MAX_THREADS = 1024;   // one thread per 16-byte vector column of the map row
-constexpr int PX_G = 4;                // rows per group = 16-byte loads in flight per thread
-constexpr int PX_RING = 16;            // ring rows (power of two >= G + 6 + G)
+constexpr int PX_G = 4;                // rows per group = 16-byte loads in flight per lane
 
-// flag bits per pixel byte in the ring
+// flag bits per pixel byte
 constexpr uint32_t FL_M = 1u;      // marker colour
 constexpr uint32_t FL_CORE = 2u;   // bright monochrome pixel that an OCR neighbour search may find
 constexpr uint32_t FL_EDGE = 4u;   // OCR edge candidate (keep only with a core pixel in its window)
@@ -102,7 +100,7 @@ __device__ __forceinline__ uint32_t marker_bit(uint32_t word, uint32_t mx, uint3
 }
 
 struct PxOut {
-    uint32_t fl;    // ring flags of the 4 pixels
+    uint32_t fl;    // flag bytes of the 4 pixels
     uint4 ui;       // ui_map words
     uint32_t ocrw;  // provisional ocr_out bytes (255 or 255-luma)
     uint32_t scw;   // scales bytes (luma != 0 ? 255 : 0)
@@ -175,191 +173,156 @@ __device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const u
     }
 }
 
-// ---- generic vector: row ends, quadrant borders, clip zone — every test per pixel -----------
-template <bool GRAY>
-__device__ __forceinline__ void vec_generic(const uint4& v, int i0, int jq, bool owned, bool inq_row, const PixelArgs& a,
-                                            PxOut& o) {
-    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-    uint32_t uo[4];
-    o.fl = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const int i = i0 + e;
-        const uint32_t b = wd[e] & 0xFFu, g = (wd[e] >> 8) & 0xFFu, r = (wd[e] >> 16) & 0xFFu;
-        const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
-        const bool valid = i >= 0 && i < (int)a.w;
-        uint32_t fe = valid ? marker_bit(wd[e], mx, mn, a.lut) : 0u;
-        const bool inq = inq_row && valid && i >= (int)a.bqw && i < (int)(2u * a.bqw);
-        uint32_t luma = 0;
-        if (owned && (GRAY || inq)) luma = luma8_bgra(wd[e]);
-        if (inq) {
-            if (mx == mn && mn >= SMH_OCR_BRIGHT) {
-                // visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
-                if (i - (int)a.bqw <= (int)a.bqw - SMH_OCR_RADIUS && jq <= (int)a.bqh - SMH_OCR_RADIUS) fe |= FL_CORE;
-                o.ocrw ^= luma << (8 * e);
-            } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) {
-                fe |= FL_EDGE;
-            }
-            if (luma == 0u) o.scw &= ~(0xFFu << (8 * e));
-        }
-        o.fl |= fe << (8 * e);
-        uo[e] = GRAY ? (luma * 0x00010101u) | 0xFF000000u : __byte_perm(wd[e], 0xFF000000u, 0x7012);
-    }
-    o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+// Fused pixel pass, warp-autonomous.  A work item is (frame, band of rows, strip of 30 vector
+// columns) or a frame's button test; every warp takes one item and needs no shared memory or
+// block barrier.  Lane L owns the 16-byte vector column q = 30*strip - 1 + L: lanes 0 and 31 are a
+// one-vector halo (enough for the 3x3 dilation and the 7x7 OCR window) that classify but never
+// store.  Walking down the band G rows at a time, a lane
+//   phase 1  issues G independent 128-bit loads, classifies its 4 pixels per row, stores ui_map /
+//            provisional ocr_out / scales, and pushes the per-pixel flag bytes (marker, OCR core,
+//            OCR edge) into a 7-row register window of its own column;
+//   phase 2  (3 rows behind) dilates the marker bits with a 3x3 cross — up/down from its own
+//            window, left/right by warp shuffle — into lsd_image, and runs the 7x7 neighbour
+//            search for the rare OCR edge pixels, again by shuffle.
+constexpr int PX_THREADS = 128;
+constexpr int PX_WARPS = PX_THREADS / 32;
+constexpr int PX_STRIP = 30;  // inner vector columns per warp
+
+__device__ __forceinline__ uint32_t pack_bits(uint32_t t) {  // bit 0 of each byte -> bits 0..3
+    t &= 0x01010101u;
+    return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xFu;
 }
 
-// Fused pixel pass.  CTA = one band of rows of one frame (or the frame's button test); thread q
-// owns the 16-byte vector column q of the map ROI and walks down the band G rows at a time:
-//   phase 1  G independent 128-bit loads, classify, store ui_map / provisional ocr_out / scales,
-//            publish per-pixel flag bytes (marker, OCR core, OCR edge) into a 16-row smem ring;
-//   phase 2  (3 rows behind) 3x3-cross dilation of the marker bits -> lsd_image, and the 7x7
-//            neighbour search for the rare OCR edge pixels.
 template <bool GRAY>
-__global__ void __launch_bounds__(PX_MAX_THREADS) k_pixels(const PixelArgs a) {
-    extern __shared__ __align__(16) uint32_t ring[];  // [PX_RING][ring_words]
-    const uint32_t per_frame = a.nbands + 1u;
-    const uint32_t f = blockIdx.x / per_frame;
-    const uint32_t band = blockIdx.x % per_frame;
+__global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t item = blockIdx.x * PX_WARPS + (threadIdx.x >> 5);
+    const uint32_t per_frame = a.nbands * a.nstrips + 1u;
+    const uint32_t f = item / per_frame;
+    if (f >= a.n_frames) return;
+    const uint32_t sub = item - f * per_frame;
     const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
 
-    if (band == a.nbands) {
+    if (sub == per_frame - 1u) {
         // ---- close-deployment button test (vision-cpu/src/lib.rs:115-135) -----------------
         uint32_t cnt = 0;
         const uint32_t npx = a.btn_w * a.btn_h;
-        for (uint32_t idx = tid; idx < npx; idx += nthreads) {
+        for (uint32_t idx = lane; idx < npx; idx += 32) {
             const uint32_t y = idx / a.btn_w, x = idx - y * a.btn_w;
             const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
                 frame + (uint64_t)(a.btn_y + y) * a.pitch + (uint64_t)(a.btn_x + x) * 4u));
             cnt += smh_button_red((word >> 16) & 0xFFu, (word >> 8) & 0xFFu, word & 0xFFu) ? 1u : 0u;
         }
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        __shared__ uint32_t s_cnt[PX_MAX_THREADS / 32];
-        if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t total = 0;
-            for (int k = 0; k < (nthreads + 31) / 32; k++) total += s_cnt[k];
-            a.red[f] = total;
+        if (lane == 0) {
+            a.red[f] = cnt;
             // `red_pixels as f32 / (w*h) as f32 < 0.65` -> map closed
-            a.open[f] = __fdiv_rn((float)total, (float)npx) < SMH_BTN_RED_RATIO_THRESHOLD ? 0 : 1;
+            a.open[f] = __fdiv_rn((float)cnt, (float)npx) < SMH_BTN_RED_RATIO_THRESHOLD ? 0 : 1;
         }
         return;
     }
 
+    const uint32_t band = sub / a.nstrips, strip = sub - band * a.nstrips;
     const int r0 = (int)(band * a.rows_per_band);
     const int r1 = min(r0 + (int)a.rows_per_band, (int)a.h);
     const int bqh = (int)a.bqh, bqw = (int)a.bqw, h = (int)a.h;
-    const bool band_has_brq = r1 > bqh && r0 < 2 * bqh;
-    const int halo = band_has_brq ? SMH_OCR_RADIUS : 1;
+    const int halo = (r1 > bqh && r0 < 2 * bqh) ? SMH_OCR_RADIUS : 1;
     const uint32_t start_y = a.start_y ? a.start_y[f] : a.start_y_uniform;
-    const uint32_t rw = a.ring_words;
     const uint32_t* __restrict__ lut = a.lut;
 
-    // zero the guard words of every ring row (never written afterwards)
-    for (int k = tid; k < PX_RING; k += nthreads) { ring[k * rw] = 0u; ring[k * rw + rw - 1] = 0u; }
-
-    // ---- per-thread column constants --------------------------------------------------------
-    const int q = tid;
-    const bool active = q < (int)a.nvec;
-    const int i_lo = 4 * q - (int)a.pad, i_hi = i_lo + 3;
-    uint32_t vm = 0;  // bit 0 of every byte whose pixel lies inside [0, w)
+    // ---- per-lane column constants ----------------------------------------------------------
+    const int q = (int)strip * PX_STRIP - 1 + lane;
+    const bool active = q >= 0 && q < (int)a.nvec;
+    const bool inner = active && lane >= 1 && lane <= PX_STRIP;  // lanes that store
+    const int i_lo = 4 * q - (int)a.pad;
+    uint32_t vm = 0, fmask = 0;  // bit 0 of every in-image byte; flag bits each pixel may carry
 #pragma unroll
-    for (int e = 0; e < 4; e++) vm |= (i_lo + e >= 0 && i_lo + e < (int)a.w) ? (1u << (8 * e)) : 0u;
-    const bool row_end = i_lo < 0 || i_hi >= (int)a.w;
-    const bool col_out = i_hi < bqw || i_lo >= 2 * bqw;                              // no pixel in the quadrant
-    const bool col_in = i_lo >= bqw && i_hi <= 2 * bqw - SMH_OCR_RADIUS;             // all four, below the clip
-    const int qpos = (int)a.qpad - (int)a.pad - bqw + 4 * q;                         // byte position in a brq row
-    const uint8_t* src_col = frame + (uint64_t)a.map_y * a.pitch + ((uint64_t)a.gx0 + 4u * (uint32_t)q) * 4u;
-    uint8_t* ui_col = a.ui + (uint64_t)f * a.ui_stride + (uint64_t)q * 16u;
-    uint8_t* lsd_col = a.lsd + (uint64_t)f * a.lsd_stride + (uint64_t)q * 4u;
-    uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
-    uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
+    for (int e = 0; e < 4; e++) {
+        const int i = i_lo + e;
+        const bool valid = active && i >= 0 && i < (int)a.w;
+        const bool inq = valid && i >= bqw && i < 2 * bqw;
+        vm |= valid ? (1u << (8 * e)) : 0u;
+        // an OCR core pixel is visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
+        fmask |= ((valid ? FL_M : 0u) | (inq ? FL_EDGE : 0u) | (inq && i - bqw <= bqw - SMH_OCR_RADIUS ? FL_CORE : 0u)) << (8 * e);
+    }
+    const bool col_brq = active && i_lo + 3 >= bqw && i_lo < 2 * bqw;  // some pixel inside the quadrant columns
+    const int qpos = (int)a.qpad - (int)a.pad - bqw + 4 * q;           // byte position in a brq row
+    const uint8_t* src_col = frame + (uint64_t)a.map_y * a.pitch + ((int64_t)a.gx0 + 4 * (int64_t)q) * 4;
+    uint8_t* ui_col = a.ui + (uint64_t)f * a.ui_stride + (int64_t)q * 16;
+    uint8_t* lsd_col = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)q * 4;
+    uint8_t* ocr_col = a.ocr + (uint64_t)f * a.q_stride + qpos;
+    uint8_t* sc_col = a.scales + (uint64_t)f * a.q_stride + qpos;
+
+    uint32_t fw[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};  // flag words of rows jn-6 .. jn of this column
 
     for (int a0 = r0 - halo; a0 - SMH_OCR_RADIUS < r1; a0 += PX_G) {
-        // ---------------- phase 1: load, classify, emit the stencil-free outputs -----------
-        if (active) {
-            uint4 v[PX_G];
+        uint4 v[PX_G];
 #pragma unroll
-            for (int r = 0; r < PX_G; r++) {
-                const int j = a0 + r;
-                if (j >= 0 && j < h && j < r1 + halo) v[r] = ldg_nc_v4(src_col + (uint64_t)j * a.pitch);
-            }
+        for (int r = 0; r < PX_G; r++) {
+            const int j = a0 + r;
+            if (active && j >= 0 && j < h && j < r1 + halo) v[r] = ldg_nc_v4(src_col + (int64_t)j * a.pitch);
+        }
 #pragma unroll
-            for (int r = 0; r < PX_G; r++) {
-                const int j = a0 + r;
-                if (j >= r1 + halo) continue;
-                uint32_t* rrow = ring + (uint32_t)(j & (PX_RING - 1)) * rw + 1;
-                if (j < 0 || j >= h) { rrow[q] = 0u; continue; }
-                const bool owned = j >= r0 && j < r1;
-                const int jq = j - bqh;
+        for (int r = 0; r < PX_G; r++) {
+            // ---------------- phase 1: row jn ---------------------------------------------------
+            const int jn = a0 + r;
+            uint32_t fl = 0;
+            if (active && jn >= 0 && jn < h && jn < r1 + halo) {
+                const bool owned = jn >= r0 && jn < r1;
+                const int jq = jn - bqh;
                 const bool inq_row = jq >= 0 && jq < bqh;
                 PxOut o;
-                if (row_end || (inq_row && !col_out && !(col_in && jq <= bqh - SMH_OCR_RADIUS)))
-                    vec_generic<GRAY>(v[r], i_lo, jq, owned, inq_row, a, o);
-                else if (inq_row && !col_out)
-                    vec_quadrant<GRAY>(v[r], owned, lut, o);
-                else
-                    vec_plain<GRAY>(v[r], owned, lut, o);
-                rrow[q] = o.fl;
-                if (owned) {
-                    stg_v4(ui_col + (uint64_t)j * a.ui_pitch, o.ui);
-                    if (inq_row && !col_out) {
-                        stg_u32(ocr_f + (uint64_t)jq * a.q_pitch + qpos, o.ocrw);
-                        if ((uint32_t)jq >= start_y) stg_u32(sc_f + (uint64_t)jq * a.q_pitch + qpos, o.scw);
+                if (inq_row && col_brq) vec_quadrant<GRAY>(v[r], owned, lut, o);
+                else vec_plain<GRAY>(v[r], owned, lut, o);
+                fl = o.fl & (inq_row ? (jq <= bqh - SMH_OCR_RADIUS ? fmask : fmask & ~(FL_CORE * 0x01010101u))
+                                     : fmask & (FL_M * 0x01010101u));
+                if (owned && inner) {
+                    stg_v4(ui_col + (int64_t)jn * a.ui_pitch, o.ui);
+                    if (inq_row && col_brq) {
+                        stg_u32(ocr_col + (int64_t)jq * a.q_pitch, o.ocrw);
+                        if ((uint32_t)jq >= start_y) stg_u32(sc_col + (int64_t)jq * a.q_pitch, o.scw);
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ---------------- phase 2: stencils (3x3 cross dilation, OCR neighbour search) -----
-        if (active) {
 #pragma unroll
-            for (int r = 0; r < PX_G; r++) {
-                const int j = a0 - SMH_OCR_RADIUS + r;
-                if (j < r0 || j >= r1) continue;
-                const uint32_t* rc = ring + (uint32_t)(j & (PX_RING - 1)) * rw + 1;
-                const uint32_t c = rc[q], l = rc[q - 1], rr = rc[q + 1];
-                const uint32_t mc = c & 0x01010101u;
-                uint32_t d = mc | (mc << 8) | (mc >> 8) | ((l >> 24) & 1u) | ((rr & 1u) << 24);
-                if (j > 0) d |= ring[(uint32_t)((j - 1) & (PX_RING - 1)) * rw + 1 + q] & 0x01010101u;
-                if (j + 1 < h) d |= ring[(uint32_t)((j + 1) & (PX_RING - 1)) * rw + 1 + q] & 0x01010101u;
-                stg_u32(lsd_col + (uint64_t)j * a.lsd_pitch, (d & vm) * 255u);  // pixels outside [0, w) stay 0
+            for (int k = 0; k < 6; k++) fw[k] = fw[k + 1];
+            fw[6] = fl;
 
-                const uint32_t eb = (c >> 2) & 0x01010101u;
-                const int jq = j - bqh;
-                if (eb && jq >= 0 && jq < bqh) {  // rare: OCR edge pixels look for a core pixel in their 7x7 window
+            // ---------------- phase 2: row jc = jn - 3 ------------------------------------------
+            const int jc = jn - SMH_OCR_RADIUS;
+            if (jc < r0 || jc >= r1) continue;  // warp-uniform
+            const uint32_t c = fw[3];
+            const uint32_t l = __shfl_up_sync(0xFFFFFFFFu, c, 1), rr = __shfl_down_sync(0xFFFFFFFFu, c, 1);
+            const uint32_t mc = c & 0x01010101u;
+            const uint32_t d = mc | (mc << 8) | (mc >> 8) | ((l >> 24) & 1u) | ((rr & 1u) << 24) |
+                               ((fw[2] | fw[4]) & 0x01010101u);  // rows outside the image hold 0
+            if (inner) stg_u32(lsd_col + (int64_t)jc * a.lsd_pitch, (d & vm) * 255u);  // pixels outside [0, w) stay 0
+
+            const int jqc = jc - bqh;
+            const uint32_t eb = (inner && jqc >= 0 && jqc < bqh) ? (c >> 2) & 0x01010101u : 0u;
+            if (__any_sync(0xFFFFFFFFu, eb != 0u)) {
+                // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
+                // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit
+                uint32_t found = 0;  // bit e: pixel e has a core neighbour
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const uint32_t cw = fw[k] >> 1;
+                    const uint32_t lw = __shfl_up_sync(0xFFFFFFFFu, cw, 1), rw = __shfl_down_sync(0xFFFFFFFFu, cw, 1);
+                    const uint32_t cm = pack_bits(lw) | (pack_bits(cw) << 4) | (pack_bits(rw) << 8);  // columns -4 .. +7
+#pragma unroll
+                    for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
+                }
 #pragma unroll 1
-                    for (int e = 0; e < 4; e++) {
-                        if (!((eb >> (8 * e)) & 1u)) continue;
-                        const int col = 4 * q + e;  // byte column in the ring row (pad included)
-                        bool found = false;
-#pragma unroll 1
-                        for (int dy = -SMH_OCR_RADIUS; dy <= SMH_OCR_RADIUS && !found; dy++) {
-                            const int jj = j + dy;
-                            if (jj < bqh || jj >= 2 * bqh) continue;
-                            const uint8_t* rb = reinterpret_cast<const uint8_t*>(
-                                ring + (uint32_t)(jj & (PX_RING - 1)) * rw + 1);
-                            for (int dx = -SMH_OCR_RADIUS; dx <= SMH_OCR_RADIUS; dx++) {
-                                const int cc = col + dx;
-                                if (cc < 0 || cc >= 4 * (int)a.nvec) continue;
-                                if (rb[cc] & FL_CORE) { found = true; break; }
-                            }
-                        }
-                        if (found) {
-                            const int i = col - (int)a.pad;
-                            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
-                                frame + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch +
-                                (uint64_t)(a.map_x + (uint32_t)i) * 4u));
-                            ocr_f[(uint64_t)jq * a.q_pitch + (uint32_t)(i - bqw) + a.qpad] = (uint8_t)(255u - luma8_bgra(word));
-                        }
+                for (int e = 0; e < 4; e++) {
+                    if (((eb >> (8 * e)) & 1u) && ((found >> e) & 1u)) {
+                        const int i = i_lo + e;
+                        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                            frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)i) * 4u));
+                        ocr_col[(int64_t)jqc * a.q_pitch + e] = (uint8_t)(255u - luma8_bgra(word));
                     }
                 }
             }
         }
-        // no second barrier: the next group's phase 1 writes ring rows a0+G..a0+2G-1, disjoint
-        // (mod PX_RING) from the rows a0-6..a0+G-1 this phase 2 reads; the barrier of the next
-        // group orders everything after that.
     }
 }
 

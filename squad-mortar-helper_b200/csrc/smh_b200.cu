@@ -193,17 +193,15 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.red = P.red; a.open = P.open;
     a.rows_per_band = rows_per_band; a.nbands = (a.h + rows_per_band - 1) / rows_per_band;
     a.grayscale = grayscale ? 1u : 0u;
-    a.ring_words = a.nvec + 2u;
     a.lut = h->d_lut;
-    const size_t smem = (size_t)smh::PX_RING * a.ring_words * sizeof(uint32_t);
+    a.n_frames = n;
+    a.nstrips = (a.nvec + smh::PX_STRIP - 1) / smh::PX_STRIP;
     auto kern = grayscale ? smh::k_pixels<true> : smh::k_pixels<false>;
-    if (smem > 48 * 1024)
-        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t blocks = (uint64_t)n * (a.nbands + 1u);
-    const uint32_t threads = round_up(a.nvec, 32u);
-    if (threads > (uint32_t)smh::PX_MAX_THREADS)
-        return fail(h, SMH_E_GEOMETRY, "map ROI wider than %d px is not supported (w = %u)", smh::PX_MAX_THREADS * 4 - 3, a.w);
-    kern<<<(unsigned)blocks, threads, smem, st>>>(a);
+    // one warp per (frame, band, strip) item plus one per frame for the button test
+    const uint64_t items = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips + 1u);
+    const uint64_t blocks = (items + smh::PX_WARPS - 1) / smh::PX_WARPS;
+    if (blocks > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
+    kern<<<(unsigned)blocks, smh::PX_THREADS, 0, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
