@@ -201,8 +201,9 @@ int32_t smh_b200_synth_frames_device(smh_b200 *h, const smh_b200_synth_params *p
 /* ---- exhaustive colour tables computed ON THE DEVICE (parity tests) ---------------------- */
 /* out[r<<16|g<<8|b] for all 2^24 colours; host output buffer. which: 0 marker predicate and
  * 1 luma8 through the exact code paths the pixel kernel uses (integer fast-reject + bit table;
- * magic-number conversions); 2 button-red; 3 ocr class (bit0 core, bit1 edge); 4 marker
- * predicate and 5 luma8 through the plain float formulas. */
+ * I2F byte-select conversions); 2 button-red; 3 ocr class (bit0 core, bit1 edge); 4 marker
+ * predicate and 5 luma8 through the plain float formulas; 6 luma8 through the biased-word
+ * (PRMT) conversions the quadrant vectors use. */
 int32_t smh_b200_colour_table(smh_b200 *h, uint32_t which, uint8_t *host_out);
 
 #ifdef __cplusplus

@@ -7,7 +7,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libsmh_b200.so"
+import os
+
+# SMH_B200_LIB lets tuning runs load an alternative build of the same library
+LIB_PATH = Path(os.environ.get("SMH_B200_LIB", PKG / "libsmh_b200.so"))
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
 BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE = 1, 2, 4, 8, 16

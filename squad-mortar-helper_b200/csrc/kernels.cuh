@@ -32,6 +32,18 @@ __device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16-byte asynchronous global->shared copy (LDGSTS) bypassing L1, plus group bookkeeping
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t smem_addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr));
+    return r;
+}
 __device__ __forceinline__ void stg_u32(void* p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -61,12 +73,7 @@ struct PixelArgs {
     const uint32_t* lut;  // marker predicate, 1 bit per colour (r<<16|g<<8|b)
 };
 
-constexpr int PX_G = 4;                // rows per group = 16-byte loads in flight per lane
 
-// flag bits per pixel byte
-constexpr uint32_t FL_M = 1u;      // marker colour
-constexpr uint32_t FL_CORE = 2u;   // bright monochrome pixel that an OCR neighbour search may find
-constexpr uint32_t FL_EDGE = 4u;   // OCR edge candidate (keep only with a core pixel in its window)
 
 // Channel k of a BGRA word as the bit pattern of the float 2^23 + value (0x4B0000vv).  The same
 // word serves three purposes: FADD -2^23 turns it into the exact float (full-rate replacement for
@@ -100,76 +107,105 @@ __device__ __forceinline__ uint32_t marker_bit(uint32_t word, uint32_t mx, uint3
 }
 
 struct PxOut {
-    uint32_t fl;    // flag bytes of the 4 pixels
-    uint4 ui;       // ui_map words
-    uint32_t ocrw;  // provisional ocr_out bytes (255 or 255-luma)
-    uint32_t scw;   // scales bytes (luma != 0 ? 255 : 0)
+    uint32_t m4, c4, e4;  // per-pixel flag nibbles: marker colour, OCR core, OCR edge candidate
+    uint4 ui;             // ui_map words
+    uint32_t ocrw;        // provisional ocr_out bytes (255 or 255-luma)
+    uint32_t scw;         // scales bytes (luma != 0 ? 255 : 0)
 };
 
-// ---- interior vector, no pixel inside the OCR quadrant -------------------------------------
-template <bool GRAY>
-__device__ __forceinline__ void vec_plain(const uint4& v, bool owned, const uint32_t* __restrict__ lut, PxOut& o) {
-    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-    uint32_t mxw[4], uo[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const uint32_t cb = chan<0>(wd[e]), cg = chan<1>(wd[e]), cr = chan<2>(wd[e]);
-        mxw[e] = max(cr, max(cg, cb));
-        if (GRAY) uo[e] = owned ? __byte_perm(luma_biased(cr, cg, cb), 0xFF000000u, 0x7000) : 0u;  // (L,L,L,255)
-        else uo[e] = __byte_perm(wd[e], 0xFF000000u, 0x7012);                                         // (r,g,b,255)
-    }
-    o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
-    o.fl = 0;
-    if (max(max(mxw[0], mxw[1]), max(mxw[2], mxw[3])) >= BIAS + 178u) {  // rare: some pixel may be a marker
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (mxw[e] >= BIAS + 178u) {
-                const uint32_t mn = min(chan<2>(wd[e]), min(chan<1>(wd[e]), chan<0>(wd[e]))) & 0xFFu;
-                o.fl |= marker_bit(wd[e], mxw[e] & 0xFFu, mn, lut) << (8 * e);
-            }
-        }
-    }
+// An opaque 0xFF000000 so that PRMT takes it as a register operand and keeps its selector immediate.
+__device__ __forceinline__ uint32_t opaque_alpha() {
+    uint32_t c;
+    asm("mov.u32 %0, 0xFF000000;" : "=r"(c));
+    return c;
 }
 
-// ---- interior vector wholly inside the OCR quadrant and below the neighbour-search clip -----
-template <bool GRAY>
-__device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const uint32_t* __restrict__ lut, PxOut& o) {
+// luma8 of a BGRA word through I2F.U8 byte-select conversions (one XU op per channel instead of
+// PRMT + FADD), result biased (0x4B0000LL); bit-identical to smh_luma8 (device-side exhaustive test).
+__device__ __forceinline__ uint32_t luma_biased_i2f(uint32_t w) {
+    const float r = (float)((w >> 16) & 0xFFu), g = (float)((w >> 8) & 0xFFu), b = (float)(w & 0xFFu);
+    const float l = __fadd_rn(__fadd_rn(__fmul_rn(SMH_LUMA_R, r), __fmul_rn(SMH_LUMA_G, g)), __fmul_rn(SMH_LUMA_B, b));
+    return __float_as_uint(__fadd_rd(l, 8388608.0f));
+}
+
+// rare path shared by both vector kinds: exact marker bits of the 4 pixels
+__device__ __noinline__ uint32_t marker_nibble(uint4 v, const uint32_t* __restrict__ lut) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-    uint32_t mxw[4], mnw[4], lb[4], uo[4];
+    uint32_t m4 = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
+        m4 |= marker_bit(wd[e], max(cr, max(cg, cb)), min(cr, min(cg, cb)), lut) << e;
+    }
+    return m4;
+}
+
+// ---- vector with no pixel inside the OCR quadrant (flags: marker only), owned row -------------
+// Marker fast-reject for the whole vector: a marker colour has max(r,g,b) >= 178, i.e. some colour
+// byte with bit 7 set and low 7 bits >= 50; SIMD-in-register test over the three colour bytes.
+__device__ __forceinline__ uint32_t bright_bytes(uint32_t w) {  // nonzero iff some of b,g,r is >= 178
+    return ((w & 0x007F7F7Fu) + 0x004E4E4Eu) & w & 0x00808080u;
+}
+
+template <bool GRAY>
+__device__ __forceinline__ void vec_plain(const uint4& v, const uint32_t* __restrict__ lut, uint32_t alpha, PxOut& o) {
+    if (GRAY) {  // (L,L,L,255) — vision-cpu/src/lib.rs:150-157
+        o.ui.x = __byte_perm(luma_biased_i2f(v.x), alpha, 0x7000);
+        o.ui.y = __byte_perm(luma_biased_i2f(v.y), alpha, 0x7000);
+        o.ui.z = __byte_perm(luma_biased_i2f(v.z), alpha, 0x7000);
+        o.ui.w = __byte_perm(luma_biased_i2f(v.w), alpha, 0x7000);
+    } else {     // (r,g,b,255) — vision-cpu/src/lib.rs:158-163
+        o.ui.x = __byte_perm(v.x, alpha, 0x7012);
+        o.ui.y = __byte_perm(v.y, alpha, 0x7012);
+        o.ui.z = __byte_perm(v.z, alpha, 0x7012);
+        o.ui.w = __byte_perm(v.w, alpha, 0x7012);
+    }
+    o.m4 = 0;
+    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) o.m4 = marker_nibble(v, lut);  // rare
+}
+
+// marker flags only (halo rows: nothing is stored)
+__device__ __forceinline__ uint32_t vec_marker_only(const uint4& v, const uint32_t* __restrict__ lut) {
+    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) return marker_nibble(v, lut);
+    return 0u;
+}
+
+// ---- vector with pixels inside the OCR quadrant (flags: marker, core, edge; the caller masks
+//      out what a pixel may not carry: outside the quadrant, above the search clip) ------------
+template <bool GRAY>
+__device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const uint32_t* __restrict__ lut, uint32_t alpha, PxOut& o) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    uint32_t uo[4], dmin = 0xFFFFFFFFu, lmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         const uint32_t cb = chan<0>(wd[e]), cg = chan<1>(wd[e]), cr = chan<2>(wd[e]);
-        mxw[e] = max(cr, max(cg, cb));
-        mnw[e] = min(cr, min(cg, cb));
-        lb[e] = owned ? luma_biased(cr, cg, cb) : BIAS + 1u;
-        if (GRAY) uo[e] = __byte_perm(lb[e], 0xFF000000u, 0x7000);
-        else uo[e] = __byte_perm(wd[e], 0xFF000000u, 0x7012);
+        dmin = min(dmin, max(cr, max(cg, cb)) - min(cr, min(cg, cb)));
+        const uint32_t lb = owned ? luma_biased(cr, cg, cb) : BIAS + 1u;
+        lmin = min(lmin, lb);
+        if (GRAY) uo[e] = __byte_perm(lb, alpha, 0x7000);
+        else uo[e] = __byte_perm(wd[e], alpha, 0x7012);
     }
     o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
-    o.fl = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
-    if (max(max(mxw[0], mxw[1]), max(mxw[2], mxw[3])) >= BIAS + 178u) {
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-            if (mxw[e] >= BIAS + 178u) o.fl |= marker_bit(wd[e], mxw[e] & 0xFFu, mnw[e] & 0xFFu, lut) << (8 * e);
-    }
+    o.m4 = 0; o.c4 = 0; o.e4 = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
+    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) o.m4 = marker_nibble(v, lut);  // rare
     // OCR classes — vision-cpu/src/lib.rs:39-53,188-193; mono = sum |ci-cj| = 4*(max-min)
-    const uint32_t d0 = mxw[0] - mnw[0], d1 = mxw[1] - mnw[1], d2 = mxw[2] - mnw[2], d3 = mxw[3] - mnw[3];
-    if (min(min(d0, d1), min(d2, d3)) <= SMH_OCR_MONO_EDGE / 4u) {  // rare: a near-grey pixel
-        const uint32_t dd[4] = {d0, d1, d2, d3};
+    if (dmin <= SMH_OCR_MONO_EDGE / 4u) {  // rare: a near-grey pixel
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            if (dd[e] == 0u && mnw[e] >= BIAS + SMH_OCR_BRIGHT) {
-                o.fl |= FL_CORE << (8 * e);
-                o.ocrw ^= (lb[e] & 0xFFu) << (8 * e);  // 255 - luma
-            } else if (4u * dd[e] <= SMH_OCR_MONO_EDGE && mnw[e] >= BIAS + SMH_OCR_BRIGHT_EDGE) {
-                o.fl |= FL_EDGE << (8 * e);
+            const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
+            const uint32_t mx = max(cr, max(cg, cb)), mn = min(cr, min(cg, cb));
+            if (mx == mn && mn >= SMH_OCR_BRIGHT) {
+                o.c4 |= 1u << e;
+                if (owned) o.ocrw ^= luma8_bgra(wd[e]) << (8 * e);  // 255 - luma
+            } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) {
+                o.e4 |= 1u << e;
             }
         }
     }
-    if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) == BIAS) {  // rare: a pixel with luma 0
+    if (lmin == BIAS) {  // rare: a pixel with luma 0
 #pragma unroll
         for (int e = 0; e < 4; e++)
-            if (lb[e] == BIAS) o.scw &= ~(0xFFu << (8 * e));
+            if (luma8_bgra(wd[e]) == 0u) o.scw &= ~(0xFFu << (8 * e));
     }
 }
 
@@ -177,24 +213,28 @@ __device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const u
 // columns) or a frame's button test; every warp takes one item and needs no shared memory or
 // block barrier.  Lane L owns the 16-byte vector column q = 30*strip - 1 + L: lanes 0 and 31 are a
 // one-vector halo (enough for the 3x3 dilation and the 7x7 OCR window) that classify but never
-// store.  Walking down the band G rows at a time, a lane
-//   phase 1  issues G independent 128-bit loads, classifies its 4 pixels per row, stores ui_map /
-//            provisional ocr_out / scales, and pushes the per-pixel flag bytes (marker, OCR core,
-//            OCR edge) into a 7-row register window of its own column;
-//   phase 2  (3 rows behind) dilates the marker bits with a 3x3 cross — up/down from its own
-//            window, left/right by warp shuffle — into lsd_image, and runs the 7x7 neighbour
-//            search for the rare OCR edge pixels, again by shuffle.
+// store.  A lane walks down the band with PX_DEPTH rows of 16-byte cp.async copies in flight into
+// a per-warp shared-memory ring (each lane only ever reads back its own 16 bytes, so no barrier):
+//   phase 1  classify the 4 pixels of row jn, store ui_map / provisional ocr_out / scales, and
+//            shift the row's flag nibbles (marker, OCR core, OCR edge) into three window
+//            registers that hold the last 5 / 7 / 4 rows of the lane's own column;
+//   phase 2  (3 rows behind) dilate the marker bits with a 3x3 cross — up/down from the window,
+//            left/right by warp shuffle — into lsd_image, and run the 7x7 neighbour search for
+//            the rare OCR edge pixels, again by shuffle.
 constexpr int PX_THREADS = 128;
 constexpr int PX_WARPS = PX_THREADS / 32;
 constexpr int PX_STRIP = 30;  // inner vector columns per warp
-
-__device__ __forceinline__ uint32_t pack_bits(uint32_t t) {  // bit 0 of each byte -> bits 0..3
-    t &= 0x01010101u;
-    return (t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xFu;
-}
+#ifndef PX_MIN_BLOCKS
+#define PX_MIN_BLOCKS 8  // register cap 64/thread -> 32 warps per SM
+#endif
+#ifndef PX_DEPTH
+#define PX_DEPTH 3       // rows of 128-bit copies in flight per lane (3 measured best on B200; 5-7 are ~4% slower)
+#endif
+constexpr int PX_SLOTS = 8;  // ring slots per warp (power of two > PX_DEPTH), 512 B each
+constexpr int PX_SMEM_BYTES = PX_WARPS * PX_SLOTS * 512;
 
 template <bool GRAY>
-__global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
+__global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const PixelArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * PX_WARPS + (threadIdx.x >> 5);
     const uint32_t per_frame = a.nbands * a.nstrips + 1u;
@@ -225,104 +265,138 @@ __global__ void __launch_bounds__(PX_THREADS) k_pixels(const PixelArgs a) {
     const uint32_t band = sub / a.nstrips, strip = sub - band * a.nstrips;
     const int r0 = (int)(band * a.rows_per_band);
     const int r1 = min(r0 + (int)a.rows_per_band, (int)a.h);
-    const int bqh = (int)a.bqh, bqw = (int)a.bqw, h = (int)a.h;
+    const int bqh = (int)a.bqh, bqw = (int)a.bqw;
     const int halo = (r1 > bqh && r0 < 2 * bqh) ? SMH_OCR_RADIUS : 1;
     const uint32_t start_y = a.start_y ? a.start_y[f] : a.start_y_uniform;
     const uint32_t* __restrict__ lut = a.lut;
+    const uint32_t alpha = opaque_alpha();
 
     // ---- per-lane column constants ----------------------------------------------------------
     const int q = (int)strip * PX_STRIP - 1 + lane;
     const bool active = q >= 0 && q < (int)a.nvec;
     const bool inner = active && lane >= 1 && lane <= PX_STRIP;  // lanes that store
     const int i_lo = 4 * q - (int)a.pad;
-    uint32_t vm = 0, fmask = 0;  // bit 0 of every in-image byte; flag bits each pixel may carry
+    uint32_t vm4 = 0, cm4 = 0, em4 = 0;  // nibble masks: pixel in the image / may carry a core bit / an edge bit
 #pragma unroll
     for (int e = 0; e < 4; e++) {
         const int i = i_lo + e;
         const bool valid = active && i >= 0 && i < (int)a.w;
         const bool inq = valid && i >= bqw && i < 2 * bqw;
-        vm |= valid ? (1u << (8 * e)) : 0u;
+        vm4 |= valid ? (1u << e) : 0u;
+        em4 |= inq ? (1u << e) : 0u;
         // an OCR core pixel is visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
-        fmask |= ((valid ? FL_M : 0u) | (inq ? FL_EDGE : 0u) | (inq && i - bqw <= bqw - SMH_OCR_RADIUS ? FL_CORE : 0u)) << (8 * e);
+        cm4 |= (inq && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
     }
-    const bool col_brq = active && i_lo + 3 >= bqw && i_lo < 2 * bqw;  // some pixel inside the quadrant columns
-    const int qpos = (int)a.qpad - (int)a.pad - bqw + 4 * q;           // byte position in a brq row
-    const uint8_t* src_col = frame + (uint64_t)a.map_y * a.pitch + ((int64_t)a.gx0 + 4 * (int64_t)q) * 4;
-    uint8_t* ui_col = a.ui + (uint64_t)f * a.ui_stride + (int64_t)q * 16;
-    uint8_t* lsd_col = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)q * 4;
-    uint8_t* ocr_col = a.ocr + (uint64_t)f * a.q_stride + qpos;
-    uint8_t* sc_col = a.scales + (uint64_t)f * a.q_stride + qpos;
+    const bool col_brq = em4 != 0u;  // some pixel inside the quadrant columns
+    const bool brq_strip = __any_sync(0xFFFFFFFFu, col_brq && inner);
+    const uint32_t qo = active ? (uint32_t)q : 0u;
+    const uint32_t qpos = (uint32_t)((int)a.qpad - (int)a.pad - bqw + 4 * (int)qo);  // byte position in a quadrant row (used when col_brq)
+    uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
+    uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
 
-    uint32_t fw[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};  // flag words of rows jn-6 .. jn of this column
+    // rows this item reads: [j_lo, j_hi); rows it owns (stores): [r0, r1)
+    const int j_lo = max(r0 - halo, 0), j_hi = min(r1 + halo, (int)a.h);
+    const int j_first = r0 - halo;  // the windows also slide over rows outside the image (flags 0)
 
-    for (int a0 = r0 - halo; a0 - SMH_OCR_RADIUS < r1; a0 += PX_G) {
-        uint4 v[PX_G];
-#pragma unroll
-        for (int r = 0; r < PX_G; r++) {
-            const int j = a0 + r;
-            if (active && j >= 0 && j < h && j < r1 + halo) v[r] = ldg_nc_v4(src_col + (int64_t)j * a.pitch);
-        }
-#pragma unroll
-        for (int r = 0; r < PX_G; r++) {
-            // ---------------- phase 1: row jn ---------------------------------------------------
-            const int jn = a0 + r;
-            uint32_t fl = 0;
-            if (active && jn >= 0 && jn < h && jn < r1 + halo) {
-                const bool owned = jn >= r0 && jn < r1;
-                const int jq = jn - bqh;
-                const bool inq_row = jq >= 0 && jq < bqh;
+    // running per-lane pointers: row jn of the capture and of ui_map, row jn-3 of lsd_image
+    const uint8_t* src_p = frame + ((int64_t)a.map_y + j_first) * (int64_t)a.pitch + ((uint64_t)a.gx0 + 4u * qo) * 4u;
+    uint8_t* ui_p = a.ui + (uint64_t)f * a.ui_stride + (int64_t)j_first * (int64_t)a.ui_pitch + qo * 16u;
+    uint8_t* lsd_p = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)(j_first - SMH_OCR_RADIUS) * (int64_t)a.lsd_pitch + qo * 4u;
+
+    uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
+
+    auto row = [&](const uint4& cur, int jn) {
+        // ---------------- phase 1: row jn -------------------------------------------------------
+        uint32_t m4 = 0, c4 = 0, e4 = 0;
+        if (active && jn >= j_lo && jn < j_hi) {
+            const bool owned = jn >= r0 && jn < r1;
+            const int jq = jn - bqh;
+            if ((uint32_t)jq < (uint32_t)bqh && col_brq) {
                 PxOut o;
-                if (inq_row && col_brq) vec_quadrant<GRAY>(v[r], owned, lut, o);
-                else vec_plain<GRAY>(v[r], owned, lut, o);
-                fl = o.fl & (inq_row ? (jq <= bqh - SMH_OCR_RADIUS ? fmask : fmask & ~(FL_CORE * 0x01010101u))
-                                     : fmask & (FL_M * 0x01010101u));
+                vec_quadrant<GRAY>(cur, owned, lut, alpha, o);
+                c4 = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
+                e4 = o.e4 & em4;
+                m4 = o.m4;
                 if (owned && inner) {
-                    stg_v4(ui_col + (int64_t)jn * a.ui_pitch, o.ui);
-                    if (inq_row && col_brq) {
-                        stg_u32(ocr_col + (int64_t)jq * a.q_pitch, o.ocrw);
-                        if ((uint32_t)jq >= start_y) stg_u32(sc_col + (int64_t)jq * a.q_pitch, o.scw);
-                    }
+                    stg_v4(ui_p, o.ui);
+                    stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), o.ocrw);
+                    if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), o.scw);
                 }
+            } else if (owned) {
+                PxOut o;
+                vec_plain<GRAY>(cur, lut, alpha, o);
+                m4 = o.m4;
+                if (inner) stg_v4(ui_p, o.ui);
+            } else {
+                m4 = vec_marker_only(cur, lut);  // halo row: flags only
             }
-#pragma unroll
-            for (int k = 0; k < 6; k++) fw[k] = fw[k + 1];
-            fw[6] = fl;
+            m4 &= vm4;
+        }
+        mwin = (mwin << 4) | m4;
+        if (brq_strip) { cwin = (cwin << 4) | c4; ewin = (ewin << 4) | e4; }
+        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
 
-            // ---------------- phase 2: row jc = jn - 3 ------------------------------------------
-            const int jc = jn - SMH_OCR_RADIUS;
-            if (jc < r0 || jc >= r1) continue;  // warp-uniform
-            const uint32_t c = fw[3];
-            const uint32_t l = __shfl_up_sync(0xFFFFFFFFu, c, 1), rr = __shfl_down_sync(0xFFFFFFFFu, c, 1);
-            const uint32_t mc = c & 0x01010101u;
-            const uint32_t d = mc | (mc << 8) | (mc >> 8) | ((l >> 24) & 1u) | ((rr & 1u) << 24) |
-                               ((fw[2] | fw[4]) & 0x01010101u);  // rows outside the image hold 0
-            if (inner) stg_u32(lsd_col + (int64_t)jc * a.lsd_pitch, (d & vm) * 255u);  // pixels outside [0, w) stay 0
+        // ---------------- phase 2: row jc = jn - 3 ----------------------------------------------
+        const int jc = jn - SMH_OCR_RADIUS;
+        if (jc < r0 || jc >= r1) return;  // warp-uniform
+        const uint32_t mc = (mwin >> 12) & 0xFu;  // centre row; up = bits 16-19, down = bits 8-11 (0 outside the image)
+        const uint32_t l = __shfl_up_sync(0xFFFFFFFFu, mc, 1), rr = __shfl_down_sync(0xFFFFFFFFu, mc, 1);
+        const uint32_t d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> 16) | (mwin >> 8)) & vm4;
+        // nibble -> 4 bytes of 0/255 (pixels outside [0, w) stay 0); lsd_p already points one row ahead
+        if (inner) stg_u32(lsd_p - a.lsd_pitch, ((d4 * 0x00204081u) & 0x01010101u) * 255u);
 
-            const int jqc = jc - bqh;
-            const uint32_t eb = (inner && jqc >= 0 && jqc < bqh) ? (c >> 2) & 0x01010101u : 0u;
-            if (__any_sync(0xFFFFFFFFu, eb != 0u)) {
-                // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
-                // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit
-                uint32_t found = 0;  // bit e: pixel e has a core neighbour
+        const int jqc = jc - bqh;
+        if (!brq_strip || (uint32_t)jqc >= (uint32_t)bqh) return;  // warp-uniform
+        const uint32_t eb = inner ? (ewin >> 12) & 0xFu : 0u;
+        if (__any_sync(0xFFFFFFFFu, eb != 0u)) {
+            // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
+            // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit
+            const uint32_t lwin = __shfl_up_sync(0xFFFFFFFFu, cwin, 1), rwin = __shfl_down_sync(0xFFFFFFFFu, cwin, 1);
+            uint32_t found = 0;  // bit e: pixel e has a core neighbour
 #pragma unroll
-                for (int k = 0; k < 7; k++) {
-                    const uint32_t cw = fw[k] >> 1;
-                    const uint32_t lw = __shfl_up_sync(0xFFFFFFFFu, cw, 1), rw = __shfl_down_sync(0xFFFFFFFFu, cw, 1);
-                    const uint32_t cm = pack_bits(lw) | (pack_bits(cw) << 4) | (pack_bits(rw) << 8);  // columns -4 .. +7
+            for (int k = 0; k < 7; k++) {
+                // core bits of columns -4 .. +7 around the lane's first pixel, row jn - k
+                const uint32_t cm = ((lwin >> (4 * k)) & 0xFu) | (((cwin >> (4 * k)) & 0xFu) << 4) | (((rwin >> (4 * k)) & 0xFu) << 8);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
-                }
+                for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
+            }
+            const uint32_t todo = eb & found;
 #pragma unroll 1
-                for (int e = 0; e < 4; e++) {
-                    if (((eb >> (8 * e)) & 1u) && ((found >> e) & 1u)) {
-                        const int i = i_lo + e;
-                        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
-                            frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)i) * 4u));
-                        ocr_col[(int64_t)jqc * a.q_pitch + e] = (uint8_t)(255u - luma8_bgra(word));
-                    }
+            for (int e = 0; e < 4; e++) {
+                if ((todo >> e) & 1u) {
+                    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                        frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)(i_lo + e)) * 4u));
+                    ocr_f[(uint32_t)jqc * a.q_pitch + qpos + e] = (uint8_t)(255u - luma8_bgra(word));
                 }
             }
         }
+    };
+
+    // software pipeline through the warp's shared-memory ring: row jn + PX_DEPTH is requested while
+    // row jn is consumed; one commit group per row (empty when the row is not read)
+    extern __shared__ __align__(16) uint8_t px_ring[];
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(px_ring) + (uint32_t)(threadIdx.x >> 5) * (PX_SLOTS * 512u) + (uint32_t)lane * 16u;
+    const uint8_t* fetch_p = src_p;  // row j_first + k of the lane's column
+#pragma unroll
+    for (int k = 0; k < PX_DEPTH; k++) {
+        const int j = j_first + k;
+        if (active && j >= j_lo && j < j_hi) cp_async16(ring0 + (uint32_t)(k & (PX_SLOTS - 1)) * 512u, fetch_p);
+        cp_async_commit();
+        fetch_p += a.pitch;
+    }
+    uint32_t slot = 0;
+#pragma unroll 1
+    for (int jn = j_first; jn - SMH_OCR_RADIUS < r1; jn++) {
+        {
+            const int j = jn + PX_DEPTH;
+            if (active && j >= j_lo && j < j_hi) cp_async16(ring0 + ((slot + PX_DEPTH) & (PX_SLOTS - 1)) * 512u, fetch_p);
+            cp_async_commit();
+            fetch_p += a.pitch;
+        }
+        cp_async_wait<PX_DEPTH>();  // the group of row jn has landed
+        const uint4 cur = lds_v4(ring0 + slot * 512u);
+        slot = (slot + 1) & (PX_SLOTS - 1);
+        row(cur, jn);
     }
 }
 
@@ -757,12 +831,13 @@ __global__ void k_build_marker_lut(uint32_t* lut) {
 }
 
 __global__ void k_colour_table_fast(uint32_t which, const uint32_t* lut, uint8_t* out) {
-    // the exact code paths k_pixels uses: which 0 = fast-reject + table bit, 1 = luma8_bgra
+    // the exact code paths k_pixels uses: which 0 = vector fast-reject + table bit,
+    // 1 = luma through I2F.U8 (plain vectors), 6 = luma through PRMT-biased words (quadrant vectors)
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t r = c >> 16, g = (c >> 8) & 0xFFu, b = c & 0xFFu;
     const uint32_t word = c | 0xFF000000u;
-    const uint32_t mx = max(r, max(g, b)), mn = min(r, min(g, b));
-    out[c] = which == 0 ? (uint8_t)marker_bit(word, mx, mn, lut) : (uint8_t)luma8_bgra(word);
+    if (which == 0) out[c] = (uint8_t)(bright_bytes(word) ? marker_nibble(make_uint4(word, 0u, 0u, 0u), lut) & 1u : 0u);
+    else if (which == 1) out[c] = (uint8_t)(luma_biased_i2f(word) & 0xFFu);
+    else out[c] = (uint8_t)luma8_bgra(word);
 }
 
 __global__ void k_colour_table(uint32_t which, uint8_t* out) {

@@ -201,7 +201,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     const uint64_t items = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips + 1u);
     const uint64_t blocks = (items + smh::PX_WARPS - 1) / smh::PX_WARPS;
     if (blocks > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
-    kern<<<(unsigned)blocks, smh::PX_THREADS, 0, st>>>(a);
+    kern<<<(unsigned)blocks, smh::PX_THREADS, smh::PX_SMEM_BYTES, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
@@ -240,12 +240,13 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
 }
 
 uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
-    // batches: 64-row bands (halo re-reads <= 9 %); a lone frame: enough bands to cover the SMs
-    if (n >= 16) return 64;
+    // batches: 128-row bands (halo re-reads <= 5 %, few generic groups); a lone frame: enough
+    // bands to cover the SMs
+    if (n >= 16) return 128;
     uint32_t want = (uint32_t)h->sm_count * 2u / (n ? n : 1u);
     uint32_t rows = want ? (map_h + want - 1) / want : map_h;
     if (rows < 8) rows = 8;
-    if (rows > 64) rows = 64;
+    if (rows > 128) rows = 128;
     return rows;
 }
 
@@ -840,11 +841,11 @@ int32_t smh_b200_synth_frames_device(smh_b200* h, const smh_b200_synth_params* p
 }
 
 int32_t smh_b200_colour_table(smh_b200* h, uint32_t which, uint8_t* host_out) {
-    if (!h || !host_out || which > 5) return fail(h, SMH_E_ARG, "colour_table: bad argument");
+    if (!h || !host_out || which > 6) return fail(h, SMH_E_ARG, "colour_table: bad argument");
     CU(h, cudaSetDevice(h->device));
     uint8_t* d;
     CU(h, cudaMalloc(&d, 1u << 24));
-    if (which <= 1) smh::k_colour_table_fast<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which, h->d_lut, d);
+    if (which <= 1 || which == 6) smh::k_colour_table_fast<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which, h->d_lut, d);
     else smh::k_colour_table<<<(1u << 24) / 256, 256, 0, h->s_main>>>(which >= 4 ? which - 4 : which, d);
     h->launches++;
     CU(h, cudaGetLastError());

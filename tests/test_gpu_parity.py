@@ -39,6 +39,7 @@ def test_device_colour_tables_exhaustive(vision):
     assert np.array_equal(vision.colour_table(4), O.table_marker()), "marker predicate (float formula on device) != oracle"
     assert np.array_equal(vision.colour_table(1), O.table_luma()), "luma8 (kernel path) != oracle"
     assert np.array_equal(vision.colour_table(5), O.table_luma()), "luma8 (float formula on device) != oracle"
+    assert np.array_equal(vision.colour_table(6), O.table_luma()), "luma8 (biased-word path) != oracle"
     c = np.arange(1 << 24, dtype=np.int64)
     r, g, b = (c >> 16) & 255, (c >> 8) & 255, c & 255
     red = (np.abs(217 - r) <= 25) & (np.abs(67 - g) <= 25) & (np.abs(49 - b) <= 25)
