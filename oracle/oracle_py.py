@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
                                                   C.c_float, f32p, f32p]
     L.smh_oracle_find_marker_lines.argtypes = [vp, C.c_uint32, vp, u32p]
     L.smh_oracle_find_lines_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, u32p]
+    L.smh_oracle_ray_lengths_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp]
+    L.smh_oracle_get_centre_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, f32p]
     L.smh_oracle_debug_view.argtypes = [vp, C.c_uint8, vp, u32p]
     for g in ("cropped_map", "cropped_brq", "lsd_image", "scales", "raw_mask"):
         f = getattr(L, "smh_oracle_" + g)
@@ -244,3 +246,20 @@ def find_longest_line_in(img: np.ndarray, x: float, y: float, max_gap: float):
     ln = C.c_float()
     lib().smh_oracle_find_longest_line_in(img.ctypes.data, w, h, x, y, max_gap, line, C.byref(ln))
     return np.array(list(line), np.float32), np.float32(ln.value)
+
+
+def ray_lengths_in(img: np.ndarray, x: float, y: float, max_gap: float) -> np.ndarray:
+    """Squared length of each of the 3600 rays from (x, y) (test helper)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty(3600, np.float32)
+    lib().smh_oracle_ray_lengths_in(img.ctypes.data, w, h, x, y, max_gap, out.ctypes.data)
+    return out
+
+
+def get_centre_in(img: np.ndarray, x: float, y: float):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = (C.c_float * 2)()
+    lib().smh_oracle_get_centre_in(img.ctypes.data, w, h, x, y, out)
+    return float(out[0]), float(out[1])

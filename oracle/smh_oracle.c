@@ -484,6 +484,19 @@ int smh_oracle_find_longest_line_in(const uint8_t *img, uint32_t w, uint32_t h, 
     return 0;
 }
 
+/* Test helper: squared length of every one of the 3600 rays of one seed (same march as above). */
+int smh_oracle_ray_lengths_in(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                              float *len_sq) {
+    const float *tab = ray_table();
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < SMH_LSD_RAYS; k++) {
+        float e[2];
+        march(img, w, h, px, py, max_gap, tab[2 * k], tab[2 * k + 1], e);
+        len_sq[k] = (px - e[0]) * (px - e[0]) + (py - e[1]) * (py - e[1]);
+    }
+    return 0;
+}
+
 int smh_oracle_find_longest_line(smh_oracle *o, float x, float y, float max_gap, float line[4],
                                  float *len_sq) {
     if (!o || !o->frame) return -2;
@@ -514,6 +527,11 @@ static void get_centre(const uint8_t *img, uint32_t w, uint32_t h, float ptx, fl
 }
 
 /* nearest_point_on_line — vision-common/src/lsd.rs:46-58 (infinite line, D14) */
+/* Test helper: get_centre on a caller-supplied image (the seed positions find_lines searches from). */
+void smh_oracle_get_centre_in(const uint8_t *img, uint32_t w, uint32_t h, float x, float y, float out[2]) {
+    get_centre(img, w, h, x, y, out);
+}
+
 static inline void nearest_point_on_line(float ptx, float pty, const float l[4], float out[2]) {
     float dx = l[2] - l[0], dy = l[3] - l[1];
     if (dx == 0.0f && dy == 0.0f) { out[0] = l[0]; out[1] = l[1]; return; }

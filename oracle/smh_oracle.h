@@ -77,6 +77,10 @@ int smh_oracle_find_longest_line(smh_oracle *o, float x, float y, float max_gap,
 /* same search on a caller-supplied L8 image (the trait passes the image explicitly) */
 int smh_oracle_find_longest_line_in(const uint8_t *img, uint32_t w, uint32_t h, float x, float y,
                                     float max_gap, float line[4], float *len_sq);
+/* test helpers: squared length of each of the 3600 rays of one seed; get_centre on an image */
+int smh_oracle_ray_lengths_in(const uint8_t *img, uint32_t w, uint32_t h, float x, float y, float max_gap,
+                              float *len_sq);
+void smh_oracle_get_centre_in(const uint8_t *img, uint32_t w, uint32_t h, float x, float y, float out[2]);
 /* vision-cpu/src/lib.rs:377-385 + vision-common/src/lsd.rs:60-105 */
 int smh_oracle_find_marker_lines(smh_oracle *o, uint32_t max_gap, float lines[32][4], uint32_t *n);
 /* lsd::find_lines on a caller-supplied L8 image */

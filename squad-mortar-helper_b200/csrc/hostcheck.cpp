@@ -3,6 +3,9 @@
 // run without a GPU.  Test helper only; never loaded by the product path.
 // Build: g++ -O2 -ffp-contract=off -fPIC -shared hostcheck.cpp -o ../libsmh_hostcheck.so
 #include "smh_pixel.h"
+#include "smh_lsd_filter.h"
+
+#include <string.h>
 
 extern "C" {
 // which: 0 marker (prefilter && exact), 1 luma8, 2 button-red, 3 ocr class, 4 exact only, 5 prefilter only
@@ -20,5 +23,39 @@ void smh_hostcheck_table(uint32_t which, uint8_t* out) {
         }
         out[c] = v;
     }
+}
+
+// The ray filter of k_lsd (smh_lsd_filter.h) evaluated on the CPU for one seed of an L8 mask:
+// marked[k] = 1 for the rays k_lsd would march.  Returns the number of windows used (0: filter
+// off, everything marked).  Same window scan, ring test, span and AND as the kernel, minus the
+// parallel plumbing.
+static inline void or_bits(uint32_t* p, uint32_t m) { *p |= m; }
+int smh_hostcheck_lsd_filter(const uint8_t* img, uint32_t w, uint32_t h, float px, float py, int gap_limit, uint8_t* marked) {
+    smh_lsd_filter F;
+    smh_lsd_filter_init(&F, gap_limit);
+    if (F.nw == 0) { memset(marked, 1, SMH_LSD_RAYS); return 0; }
+    static uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
+    memset(bits, 0, sizeof bits);
+    const int fx = (int)px, fy = (int)py, R = F.radius;
+    const int x0 = fx - R < 0 ? 0 : fx - R, x1 = fx + R > (int)w - 1 ? (int)w - 1 : fx + R;
+    const int y0 = fy - R < 0 ? 0 : fy - R, y1 = fy + R > (int)h - 1 ? (int)h - 1 : fy + R;
+    for (int y = y0; y <= y1; y++)
+        for (int x = x0; x <= x1; x++) {
+            if (img[(size_t)y * w + x] != 255) continue;
+            const float cx = ((float)x + 0.5f) - px, cy = ((float)y + 0.5f) - py;
+            const float d2 = cx * cx + cy * cy;
+            if (d2 < F.r2_lo[0] || d2 > F.r2_hi[F.nw - 1]) continue;
+            int lo, hi;
+            smh_lsd_filter_span(cx, cy, d2, &lo, &hi);
+            for (int j = 0; j < F.nw; j++)
+                if (d2 >= F.r2_lo[j] && d2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(bits[j], lo, hi, or_bits);
+        }
+    for (int k = 0; k < SMH_LSD_RAYS; k++) {
+        int on = 1;
+        for (int j = 0; j < F.nw; j++)
+            if (smh_lsd_filter_window_on(&F, j, px, py) && !((bits[j][k >> 5] >> (k & 31)) & 1u)) on = 0;
+        marked[k] = (uint8_t)on;
+    }
+    return F.nw;
 }
 }

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "smh_pixel.h"
+#include "smh_lsd_filter.h"
 #include "smh_synth.h"
 
 namespace smh {
@@ -403,18 +404,58 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
 // ------------------------------------------------------------------------------------------
 // line search
 // ------------------------------------------------------------------------------------------
+// The line search reads the dilated marker mask as a 1-bit-per-pixel, TILE-MAJOR bitmap: tiles of
+// 32 x 32 pixels, 128 bytes each (word r of a tile = row r, bit b = pixel column 32*tx + b), tiles
+// of a tile-row contiguous.  Columns are in padded coordinates X = x + pad (the byte mask's
+// 16-byte vector grid).  A ray then touches a new 128-byte line every ~32 steps whatever its
+// direction, the whole frame is 8x smaller than the L8 mask, and a tile-row is one contiguous
+// block for the raster seed scan.
+struct BitsGeom {
+    uint32_t tx, ty;      // tiles per tile-row, tile-rows
+    uint32_t pad, w, h;   // mask geometry (pixels); bit X = x + pad
+};
+struct Bits {
+    const uint32_t* __restrict__ p;
+    uint32_t tx, pad, w, h;
+    __device__ __forceinline__ uint32_t word(uint32_t X32, uint32_t y) const { return __ldg(p + ((((y >> 5) * tx + X32) << 5) + (y & 31u))); }
+    __device__ __forceinline__ bool white(uint32_t x, uint32_t y) const {
+        const uint32_t X = x + pad;
+        return (word(X >> 5, y) >> (X & 31u)) & 1u;
+    }
+};
+
+// L8 mask -> tile-major bitmap.  Warp = one tile, lane = row of the tile: 32 bytes in, one word out
+// (coalesced 128-byte stores).  grid = (ceil(tx / 8), ty, n_frames), block = 256.
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ lsd, uint64_t stride, uint32_t pitch, BitsGeom g,
+                                                   uint32_t* __restrict__ bits, uint64_t bits_stride) {
+    const uint32_t tile = blockIdx.x * 8u + (threadIdx.x >> 5), r = threadIdx.x & 31u, tyi = blockIdx.y, f = blockIdx.z;
+    if (tile >= g.tx) return;
+    const uint32_t y = tyi * 32u + r;
+    uint32_t out = 0;
+    if (y < g.h) {
+        const uint4* src = reinterpret_cast<const uint4*>(lsd + (uint64_t)f * stride + (uint64_t)y * pitch + tile * 32u);
+        const uint4 v0 = ldg_nc_v4(src), v1 = ldg_nc_v4(src + 1);
+        const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int q = 0; q < 8; q++)  // bytes equal to 255 -> 4 bits (the multiply gathers bits 0,8,16,24 into 24..27)
+            out |= (((__vcmpeq4(wd[q], 0xFFFFFFFFu) & 0x01010101u) * 0x01020408u) >> 24) << (4 * q);
+    }
+    bits[(uint64_t)f * bits_stride + (((uint64_t)tyi * g.tx + tile) << 5) + r] = out;
+}
+
 struct LsdArgs {
-    const uint8_t* lsd; uint64_t stride; uint32_t pitch, pad, w, h;
+    const uint32_t* bits; uint64_t bits_stride;  // tile-major bitmaps, words per frame
+    BitsGeom g;
     const float2* rays;  // 3600 (cos, sin) pairs built on the host with libm (D11)
     float max_gap;
     int gap_limit;        // ceil(max_gap): `gap.0 >= max_gap` on the integer-valued counter
-    int prune;            // 1: skip seeds proven unable to yield a line (isolated blobs)
+    int prune;            // 1: exact ray filter + dead clusters; 0: march all 3600 rays of every seed
     uint32_t n_frames;
     uint32_t* counter;    // persistent-CTA frame dispenser (zeroed before the launch)
     const uint8_t* open;  // nullptr: every frame open
     float* lines;         // [n][32][4]
     uint32_t* n_lines;    // [n]
-    unsigned long long* stats;  // [n][2] or nullptr
+    unsigned long long* stats;  // [n][3] or nullptr
 };
 
 struct Img {
@@ -422,16 +463,17 @@ struct Img {
     __device__ __forceinline__ uint32_t at(uint32_t x, uint32_t y) const { return __ldg(p + (uint64_t)y * pitch + x); }
 };
 
-// find_line_in_image — vision-cpu/src/lib.rs:388-432.  Returns the squared length, writes the end point.
-__device__ __forceinline__ float march(const Img& im, float px, float py, float max_gap, float dx, float dy,
+// find_line_in_image — vision-cpu/src/lib.rs:388-432, literally (any max_gap, any seed).  Used by the
+// single-call trait method and when ceil(max_gap) < 1.  Returns the squared length, writes the end point.
+template <typename IMG>
+__device__ __forceinline__ float march(const IMG& im, float px, float py, float max_gap, float dx, float dy,
                                        float& ex, float& ey, uint32_t& steps) {
     float x = px, y = py, xo = 0.0f, yo = 0.0f;
     float gap_n = 0.0f, gap_x = 0.0f, gap_y = 0.0f;
     const float wf = (float)im.w, hf = (float)im.h;
     while (x >= 0.0f && y >= 0.0f && x < wf && y < hf) {
         steps++;
-        const uint32_t v = im.at(__float2uint_rz(x), __float2uint_rz(y));
-        if (v == 255u) {
+        if (im.white(__float2uint_rz(x), __float2uint_rz(y))) {
             gap_n = 0.0f; gap_x = 0.0f; gap_y = 0.0f;
         } else if (gap_n >= max_gap) {
             x = gap_x; y = gap_y;
@@ -446,7 +488,7 @@ __device__ __forceinline__ float march(const Img& im, float px, float py, float 
     }
     // get_pixel_checked(x as u32, y as u32) == Some(0) — lib.rs:426-429 (D7)
     const uint32_t xi = __float2uint_rz(x), yi = __float2uint_rz(y);  // saturating, NaN -> 0
-    if (xi < im.w && yi < im.h && im.at(xi, yi) == 0u) {
+    if (xi < im.w && yi < im.h && !im.white(xi, yi)) {
         ex = __fsub_rn(x, dx); ey = __fsub_rn(y, dy);
     } else {
         ex = px; ey = py;
@@ -454,26 +496,10 @@ __device__ __forceinline__ float march(const Img& im, float px, float py, float 
     const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));  // distance_sqr, util/src/geometry.rs:62-68
 }
-
-// get_centre — vision-common/src/lsd.rs:5-44 (indices clamped where the reference is UB, D8)
-__device__ __forceinline__ uint32_t px_clamped(const Img& im, float fx, float fy) {
-    uint32_t x = __float2uint_rz(fx), y = __float2uint_rz(fy);
-    x = min(x, im.w - 1u); y = min(y, im.h - 1u);
-    return im.at(x, y);
-}
-__device__ void get_centre(const Img& im, float ptx, float pty, float& cx, float& cy) {
-    const float MAXD = SMH_LSD_CENTRE_MAX_DIST;
-    float left = ptx;
-    while (left > 0.0f && fabsf(__fsub_rn(left, ptx)) < MAXD && px_clamped(im, left, pty) == 255u) left = __fsub_rn(left, 1.0f);
-    float right = ptx;
-    while (right < (float)(im.w - 1u) && fabsf(__fsub_rn(right, ptx)) < MAXD && px_clamped(im, right, pty) == 255u) right = __fadd_rn(right, 1.0f);
-    float up = pty;
-    while (up > 0.0f && fabsf(__fsub_rn(up, pty)) < MAXD && px_clamped(im, ptx, up) == 255u) up = __fsub_rn(up, 1.0f);
-    float down = pty;
-    while (down < (float)(im.h - 1u) && fabsf(__fsub_rn(down, pty)) < MAXD && px_clamped(im, ptx, down) == 255u) down = __fadd_rn(down, 1.0f);
-    cx = __fdiv_rn(__fadd_rn(left, right), 2.0f);
-    cy = __fdiv_rn(__fadd_rn(up, down), 2.0f);
-}
+struct ImgL8 {  // byte-mask view with the accessor the generic march wants
+    Img im; uint32_t w, h;
+    __device__ __forceinline__ bool white(uint32_t x, uint32_t y) const { return im.at(x, y) == 255u; }
+};
 
 // seed suppression — lsd.rs:46-58,84-89: squared distance to the INFINITE line through l (D14)
 __device__ __forceinline__ bool suppressed_by(const float4& l, float x, float y) {
@@ -491,34 +517,81 @@ __device__ __forceinline__ bool suppressed_by(const float4& l, float x, float y)
     return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < SMH_LSD_SUPPRESS_DIST_SQ;
 }
 
+// Columns of row y that line l suppresses FOR SURE: exact distance to the infinite line < 6.99, i.e.
+// squared distance < 48.9, while the float formula above errs by < 0.02 around its threshold of 50.
+// Pixels of the thin fringe in between (and degenerate lines) are left to the exact test.
+// Returns false when the interval is empty.  Integer pixel columns, clamped to [0, w-1].
+__device__ __forceinline__ bool sure_interval(const float4& l, float y, int w, int& xlo, int& xhi) {
+    const float dx = l.z - l.x, dy = l.w - l.y;
+    const float len = sqrtf(dx * dx + dy * dy);
+    if (!(len > 1.0f)) return false;
+    const float c = 6.99f * len, a = (y - l.y) * dx;
+    if (fabsf(dy) < 1.0e-4f * len) {  // (x - p0x) * dy stays below 0.25 * len for |x - p0x| < 2500
+        if (w > 2500 || !(fabsf(a) < c - 0.25f * len)) return false;
+        xlo = 0; xhi = w - 1;
+        return true;
+    }
+    const float t1 = (a - c) / dy, t2 = (a + c) / dy;
+    const float lo = fmaxf(l.x + fminf(t1, t2) + 0.01f, 0.0f), hi = fminf(l.x + fmaxf(t1, t2) - 0.01f, (float)(w - 1));
+    if (!(lo <= hi)) return false;
+    xlo = (int)ceilf(lo); xhi = (int)floorf(hi);
+    return xlo <= xhi;
+}
+
 // Same automaton for seeds that lie inside the image (all coordinates within (-2^22, 2^22)) and
 // gap_limit = ceil(max_gap) >= 1: floor() by a round-down add of 1.5*2^23 (full-rate FADD instead
 // of F2I), both bounds in one unsigned compare each, integer gap counter.  With gap_limit >= 1 a
 // ray can only stop on a gap that has a recorded start, so the reference's reset of the saved
 // position to (0,0) on white pixels is unobservable and dropped.  Bit-identical end points to
 // march() — floor(x) in [0,w) <=> 0 <= x < w, and floor == trunc for x >= 0.
+// The samples are generated and fetched LSD_BATCH at a time: the positions of a ray do not depend
+// on the pixels it reads, so the loads of a batch are independent and their latency overlaps; the
+// gap automaton then consumes the batch in order and ignores what lies beyond the stopping sample.
+#ifndef LSD_BATCH
+#define LSD_BATCH 8
+#endif
 template <bool STATS>
-__device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uint32_t pitch, uint32_t w, uint32_t h,
-                                            float px, float py, int gap_limit, float dx, float dy,
+__device__ __forceinline__ float march_fast(const Bits& im, float px, float py, int gap_limit, float dx, float dy,
                                             float& ex, float& ey, uint32_t& steps) {
     float x = px, y = py, xo = 0.0f, yo = 0.0f, gap_x = px, gap_y = py;
     int gap = 0;
-    bool broke = false;
-    while (true) {
-        const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000);
-        const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000);
-        if (ix >= w || iy >= h) break;
-        if (STATS) steps++;
-        const bool black = __ldg(img + (iy * pitch + ix)) != 255u;
-        if (black && gap >= gap_limit) { broke = true; break; }
-        if (black && gap == 0) { gap_x = x; gap_y = y; }
-        gap = black ? gap + 1 : 0;
-        xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
-        x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
+    int state = 0;  // 0 marching, 1 stopped on a gap, 2 left the image
+    while (state == 0) {
+        float xs[LSD_BATCH], ys[LSD_BATCH];
+        uint32_t wh = 0, inb = 0;  // bit u: sample u is white / inside the image
+#pragma unroll
+        for (int u = 0; u < LSD_BATCH; u++) {
+            xs[u] = x; ys[u] = y;
+            const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000);
+            const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000);
+            if (ix < im.w && iy < im.h) {
+                inb |= 1u << u;
+                const uint32_t X = ix + im.pad;
+                wh |= ((im.word(X >> 5, iy) >> (X & 31u)) & 1u) << u;
+            }
+            xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
+            x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
+        }
+#pragma unroll
+        for (int u = 0; u < LSD_BATCH; u++) {
+            if (state == 0) {
+                if (!((inb >> u) & 1u)) { state = 2; gap_x = xs[u]; gap_y = ys[u]; }
+                else {
+                    if (STATS) steps++;
+                    const bool black = !((wh >> u) & 1u);
+                    if (black && gap >= gap_limit) state = 1;
+                    else {
+                        if (black && gap == 0) { gap_x = xs[u]; gap_y = ys[u]; }
+                        gap = black ? gap + 1 : 0;
+                    }
+                }
+            }
+        }
     }
-    if (broke) { x = gap_x; y = gap_y; }
+    // stopped on a gap: back to where the gap began; left the image: the first outside sample
+    x = gap_x; y = gap_y;
     const uint32_t xi = __float2uint_rz(x), yi = __float2uint_rz(y);  // `as u32`: saturating (D7)
-    if (xi < w && yi < h && __ldg(img + (yi * pitch + xi)) == 0u) {
+    if (xi < im.w && yi < im.h && !im.white(xi, yi)) {
         ex = __fsub_rn(x, dx); ey = __fsub_rn(y, dy);
     } else {
         ex = px; ey = py;
@@ -527,23 +600,29 @@ __device__ __forceinline__ float march_fast(const uint8_t* __restrict__ img, uin
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
 }
 
-// get_centre evaluated by one warp in parallel (every lane returns the result): lane = 8*dir + t
-// tests the loop condition of step t of direction dir (left, right, up, down); the walk stops at
-// the first failing t, so the stop index is the number of trailing ones of the ballot byte.
-// Each lane rebuilds its v by t successive +-1.0 adds, because the reference's `(v - pt).abs() < 5`
-// sees the accumulated rounding: across a binade boundary (e.g. 511.6 -> 512.6) five increments can
-// leave |v - pt| just below 5 and the walk takes a sixth step.
-__device__ __forceinline__ void get_centre_warp(const Img& im, float ptx, float pty, float& cx, float& cy) {
+// get_centre — vision-common/src/lsd.rs:5-44 (indices clamped where the reference is UB, D8) —
+// evaluated by one warp in parallel (every lane returns the result): lane = 8*dir + t tests the
+// loop condition of step t of direction dir (left, right, up, down); the walk stops at the first
+// failing t, so the stop index is the number of trailing ones of the ballot byte.  Each lane
+// rebuilds its v by t successive +-1.0 adds, because the reference's `(v - pt).abs() < 5` sees the
+// accumulated rounding: across a binade boundary (e.g. 511.6 -> 512.6) five increments can leave
+// |v - pt| just below 5 and the walk takes a sixth step.
+__device__ __forceinline__ bool white_clamped(const Bits& im, float fx, float fy) {
+    uint32_t x = __float2uint_rz(fx), y = __float2uint_rz(fy);
+    x = min(x, im.w - 1u); y = min(y, im.h - 1u);
+    return im.white(x, y);
+}
+__device__ __forceinline__ void get_centre_warp(const Bits& im, float ptx, float pty, float& cx, float& cy) {
     const int lane = threadIdx.x & 31, dir = lane >> 3, t = lane & 7;
     const float pt = dir < 2 ? ptx : pty;
     const float step = (dir & 1) ? 1.0f : -1.0f;
     float v = pt;
     for (int i = 0; i < t; i++) v = __fadd_rn(v, step);
     bool ok = fabsf(__fsub_rn(v, pt)) < SMH_LSD_CENTRE_MAX_DIST;
-    if (dir == 0) ok = ok && v > 0.0f && px_clamped(im, v, pty) == 255u;
-    else if (dir == 1) ok = ok && v < (float)(im.w - 1u) && px_clamped(im, v, pty) == 255u;
-    else if (dir == 2) ok = ok && v > 0.0f && px_clamped(im, ptx, v) == 255u;
-    else ok = ok && v < (float)(im.h - 1u) && px_clamped(im, ptx, v) == 255u;
+    if (dir == 0) ok = ok && v > 0.0f && white_clamped(im, v, pty);
+    else if (dir == 1) ok = ok && v < (float)(im.w - 1u) && white_clamped(im, v, pty);
+    else if (dir == 2) ok = ok && v > 0.0f && white_clamped(im, ptx, v);
+    else ok = ok && v < (float)(im.h - 1u) && white_clamped(im, ptx, v);
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
     // value after k steps = the v of lane 8*dir + k (k <= 7: lane t = 7 always fails the distance test)
     const int kl = __ffs(~(bal & 0xFFu)) - 1, kr = __ffs(~((bal >> 8) & 0xFFu)) - 1;
@@ -554,76 +633,160 @@ __device__ __forceinline__ void get_centre_warp(const Img& im, float ptx, float 
     cy = __fdiv_rn(__fadd_rn(up, down), 2.0f);
 }
 
-// Exact pruning of hopeless seeds.  A ray stops at its K-th consecutive non-white sample,
-// K = gap_limit + 1.  Samples move by at most one pixel per step in Chebyshev distance d from
-// the seed pixel (monotonically; a float rounding can make one step span two pixels, hence the
-// +1 below).  If no white pixel has d in [a+1, a+K+1], every ray stops inside that ring, its
-// restored gap start lies within d <= a+2 and its squared length is < 2(a+3)^2; a ray can only
-// leave through the left/top border first (the D7 quirk that still yields a long line) when the
-// seed is closer than a+K+2 to that border, and then its length is < 2(a+K+2)^2.  When the bound
-// is <= 2500 = SMH_LSD_MIN_LEN_SQ the seed cannot produce a line (lsd.rs:95) and the 3600-ray
-// search is skipped — find_lines' output is unchanged.  Uniform result for the whole CTA.
+// ---- exact ray filter (smh_lsd_filter.h): per seed, scan the pixel window around it, list the
+//      white pixels that lie in one of the step-window rings, mark the rays each can serve, and
+//      march only the rays marked in every window ---------------------------------------------
+#ifndef LSD_THREADS_N
+#define LSD_THREADS_N 256
+#endif
+#ifndef LSD_MIN_CTAS
+#define LSD_MIN_CTAS 4
+#endif
+constexpr int LSD_THREADS = LSD_THREADS_N;
+constexpr int LSD_PX_CAP = 2048;  // ring pixels listed per seed (beyond that every ray is marched)
+constexpr int LSD_DEAD = 16;      // remembered dead clusters per frame
+
+struct LsdShared {
+    float4 lines[SMH_LSD_MAX_LINES];
+    float4 dead[LSD_DEAD];  // (x, y, rho^2, raw^2): centred seeds closer than rho to (x, y) cannot yield a line
+    unsigned long long keys[LSD_THREADS / 32];
+    float2 ends[LSD_THREADS / 32];
+    uint32_t smin[2][LSD_THREADS / 32];  // double-buffered: a seed may be dismissed without another barrier
+    uint32_t wsum[LSD_THREADS / 32];
+    uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
+    uint32_t list_n, near2, far2, n_dead, frame;
+    union {
+        uint32_t px[LSD_PX_CAP];       // packed (ox + 128) | (oy + 128) << 8 of listed ring pixels
+        uint16_t rays[SMH_LSD_RAYS];   // compacted indices of the rays to march
+    };
+};
+
+// Stage 1: lane group = one bitmap word of a window row; white pixels in a ring are appended to
+// sh.px, and the nearest/farthest white distances around the inner disc are reduced into
+// sh.near2 / sh.far2 (float bits; positive floats order like their bit patterns).
 template <int T>
-__device__ __forceinline__ bool seed_is_isolated(const uint8_t* __restrict__ base, uint32_t pitch, uint32_t pad, uint32_t w,
-                                                 uint32_t h, float px, float py, int gap_limit,
-                                                 unsigned long long* s_mask) {
-    if (gap_limit < 0 || gap_limit > 22) return false;  // keep the inspected window <= 113 px wide
-    const int K = gap_limit + 1;
-    const int R = 32 + K + 1;
-    const int cx = (int)floorf(px), cy = (int)floorf(py);
-    const int x0 = max(cx - R, 0), x1 = min(cx + R, (int)w - 1);
-    const int y0 = max(cy - R, 0), y1 = min(cy + R, (int)h - 1);
-    const int wlo = (x0 + (int)pad) >> 2, whi = (x1 + (int)pad) >> 2;
-    const int nw = whi - wlo + 1, total = nw * (y1 - y0 + 1);
-    // *s_mask was zeroed one seed ago (double-buffered by the caller)
-    unsigned long long m = 0ull;
-    for (int t = threadIdx.x; t < total; t += T) {
-        const int r = t / nw, c = t - r * nw;
-        const int y = y0 + r;
-        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(base + (uint32_t)y * pitch) + (wlo + c));
-        if (word) {
-            const int dy = abs(y - cy);
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int x = (wlo + c) * 4 + b - (int)pad;
-                if (((word >> (8 * b)) & 0xFFu) == 255u && x >= x0 && x <= x1) m |= 1ull << max(abs(x - cx), dy);
+__device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
+    const int fx = (int)px, fy = (int)py, R = F.radius;  // px, py >= 0
+    const int x0 = max(fx - R, 0), x1 = min(fx + R, (int)im.w - 1);
+    const int y0 = max(fy - R, 0), y1 = min(fy + R, (int)im.h - 1);
+    const int X0 = x0 + (int)im.pad, X1 = x1 + (int)im.pad;
+    const int wlo = X0 >> 5, nwords = (X1 >> 5) - wlo + 1;  // <= 8 for R <= 99
+    const float a2 = F.r2_lo[0], z2 = F.r2_hi[F.nw - 1];
+    float near2 = 0.0f, far2 = 3.0e38f;
+    const int sub = threadIdx.x & 7;
+    if (sub < nwords) {
+        const int Xw = (wlo + sub) << 5;
+        uint32_t keep = 0xFFFFFFFFu;  // bits of this word inside [X0, X1]
+        if (Xw < X0) keep &= 0xFFFFFFFFu << (X0 - Xw);
+        if (Xw + 31 > X1) keep &= 0xFFFFFFFFu >> (Xw + 31 - X1);
+        for (int y = y0 + (int)(threadIdx.x >> 3); y <= y1; y += T / 8) {
+            uint32_t m = im.word((uint32_t)(wlo + sub), (uint32_t)y) & keep;
+            if (!m) continue;
+            const float cy = __fsub_rn((float)y + 0.5f, py);
+            const float cy2 = __fmul_rn(cy, cy);
+            while (m) {
+                const int x = Xw + __ffs(m) - 1 - (int)im.pad;
+                m &= m - 1u;
+                const float cx = __fsub_rn((float)x + 0.5f, px);
+                const float d2 = __fadd_rn(__fmul_rn(cx, cx), cy2);
+                if (d2 < a2) near2 = fmaxf(near2, d2);
+                else {
+                    far2 = fminf(far2, d2);
+                    if (d2 <= z2) {
+                        const uint32_t i = atomicAdd(&sh.list_n, 1u);
+                        if (i < (uint32_t)LSD_PX_CAP) sh.px[i] = (uint32_t)(x - fx + 128) | ((uint32_t)(y - fy + 128) << 8);
+                    }
+                }
             }
         }
     }
-    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m), hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m >> 32));
-    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(s_mask, ((unsigned long long)hi << 32) | lo);
-    __syncthreads();
-    const unsigned long long mask = *s_mask;
-    const unsigned long long ring = (1ull << (K + 1)) - 1ull;
-    for (int a = 0; a <= 32; a++) {
-        if ((mask & (ring << (a + 1))) == 0ull) {
-            const bool border_exit = cx < a + K + 2 || cy < a + K + 2;
-            return !border_exit || a + K <= 33;
-        }
+    const uint32_t n2 = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(near2));
+    const uint32_t f2 = __reduce_min_sync(0xFFFFFFFFu, __float_as_uint(far2));
+    if ((threadIdx.x & 31) == 0) {
+        if (n2) atomicMax(&sh.near2, n2);
+        if (f2 != __float_as_uint(3.0e38f)) atomicMin(&sh.far2, f2);
     }
-    return false;
 }
 
-// All 3600 rays from (px,py), spread over the CTA; the winner is the LAST index among the
-// longest rays (rayon's right-biased reduce, vision-cpu/src/lib.rs:440-446, D6).
-// Every thread returns best = {len, ex, ey} (one barrier; s_keys/s_ends may be reused after the next one).
-template <int T, bool FAST, bool STATS>
-__device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __restrict__ rays, float px, float py,
-                                                float max_gap, int gap_limit, float (&best)[3], unsigned long long* s_keys,
-                                                float2* s_ends, uint32_t& steps) {
+// Stage 2: one listed pixel per thread -> OR its ray interval into the bitmap of each ring it lies in.
+template <int T>
+__device__ __forceinline__ void lsd_mark_rays(float px, float py, const smh_lsd_filter& F, uint32_t n_listed, LsdShared& sh) {
+    const int fx = (int)px, fy = (int)py;
+    if (n_listed > (uint32_t)LSD_PX_CAP) {  // too many ring pixels: mark everything (uniform)
+        for (int i = threadIdx.x; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0xFFFFFFFFu;
+        return;
+    }
+    for (uint32_t i = threadIdx.x; i < n_listed; i += T) {
+        const uint32_t e = sh.px[i];
+        const float cx = __fsub_rn((float)(fx + (int)(e & 0xFFu) - 128) + 0.5f, px);
+        const float cy = __fsub_rn((float)(fy + (int)((e >> 8) & 0xFFu) - 128) + 0.5f, py);
+        const float d2 = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));
+        int lo, hi;
+        smh_lsd_filter_span(cx, cy, d2, &lo, &hi);
+#pragma unroll
+        for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+            if (j < F.nw && d2 >= F.r2_lo[j] && d2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(sh.bits[j], lo, hi, atomicOr);
+    }
+}
+
+// Stage 3: AND the usable windows, compact the surviving ray indices into sh.rays (ascending).
+// Returns the number of rays (uniform).  Two barriers inside; clears the per-seed scratch.
+template <int T>
+__device__ __forceinline__ uint32_t lsd_build_ray_list(float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
+    static_assert(T >= 128, "one thread per bitmap word");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t wv = 0;
+    if (tid < SMH_LSD_BITMAP_WORDS) {
+        wv = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+            if (j < F.nw && smh_lsd_filter_window_on(&F, j, px, py)) wv &= sh.bits[j][tid];
+        if (tid == SMH_LSD_BITMAP_WORDS - 1) wv &= (1u << (SMH_LSD_RAYS & 31)) - 1u;  // 3600 = 112*32 + 16
+    }
+    const uint32_t c = __popc(wv);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) sh.wsum[warp] = incl;
+    __syncthreads();  // bitmaps and the pixel list are dead from here on
+    uint32_t off = incl - c, total = 0;
+#pragma unroll
+    for (int k = 0; k < T / 32; k++) { const uint32_t s = sh.wsum[k]; if (k < warp) off += s; total += s; }
+    while (wv) {
+        sh.rays[off++] = (uint16_t)(tid * 32 + __ffs(wv) - 1);
+        wv &= wv - 1u;
+    }
+    for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
+    if (tid == 0) { sh.list_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    __syncthreads();
+    return total;
+}
+
+// The rays of one seed, spread over the CTA; the winner is the LAST index among the longest rays
+// (rayon's right-biased reduce, vision-cpu/src/lib.rs:440-446, D6).  n_rays < 0: all 3600 rays,
+// else the first n_rays entries of `list`.  Every thread returns best = {len, ex, ey} (one
+// barrier; keys/ends may be reused after the next one).
+template <int T, typename MARCH>
+__device__ __forceinline__ void longest_ray_cta(const float2* __restrict__ rays, const uint16_t* list, int n_rays,
+                                                float px, float py, float (&best)[3],
+                                                unsigned long long* s_keys, float2* s_ends, MARCH march_one) {
     const int tid = threadIdx.x;
     unsigned long long best_key = 0ull;  // (len_bits << 32) | k ; len >= 0 so the bit pattern is monotone
     float bex = px, bey = py;
     bool any = false;
-    for (int k = tid; k < SMH_LSD_RAYS; k += T) {
+    const int n = n_rays < 0 ? SMH_LSD_RAYS : n_rays;
+    for (int i = tid; i < n; i += T) {
+        const int k = n_rays < 0 ? i : (int)list[i];
         const float2 d = __ldg(&rays[k]);
         float ex, ey;
-        const float len = FAST ? march_fast<STATS>(im.p, im.pitch, im.w, im.h, px, py, gap_limit, d.x, d.y, ex, ey, steps)
-                               : march(im, px, py, max_gap, d.x, d.y, ex, ey, steps);
+        const float len = march_one(d.x, d.y, ex, ey);
         const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k;
         if (!any || key >= best_key) { best_key = key; bex = ex; bey = ey; any = true; }
     }
-    // warp argmax on the 64-bit key
+    // warp argmax on the 64-bit key (threads without a ray carry key 0 and never claim the slot)
     unsigned long long wkey = best_key;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -631,6 +794,8 @@ __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __r
         wkey = other > wkey ? other : wkey;
     }
     const int warp = tid >> 5;
+    const bool warp_any = __any_sync(0xFFFFFFFFu, any);
+    if ((tid & 31) == 0 && !warp_any) { s_keys[warp] = 0ull; s_ends[warp] = make_float2(px, py); }
     if (any && best_key == wkey) { s_keys[warp] = wkey; s_ends[warp] = make_float2(bex, bey); }
     __syncthreads();
     int bw = 0;
@@ -642,141 +807,223 @@ __device__ __forceinline__ void longest_ray_cta(const Img& im, const float2* __r
     best[2] = s_ends[bw].y;
 }
 
-constexpr int LSD_THREADS = 256;
-constexpr int LSD_VPT = 4;  // 16-byte mask vectors per thread per scan chunk
+// Clear columns [xlo, xhi] (pixel coordinates) of row r of the tile-row held row-major in shared memory.
+__device__ __forceinline__ void chunk_clear(uint32_t* chunk, uint32_t tx, uint32_t pad, int r, int xlo, int xhi) {
+    const int Xlo = xlo + (int)pad, Xhi = xhi + (int)pad;
+    for (int wd = Xlo >> 5; wd <= (Xhi >> 5); wd++) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (wd == (Xlo >> 5)) m &= 0xFFFFFFFFu << (Xlo & 31);
+        if (wd == (Xhi >> 5)) m &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
+        atomicAnd(&chunk[(uint32_t)r * tx + (uint32_t)wd], ~m);
+    }
+}
 
 // lsd::find_lines for whole frames (vision-common/src/lsd.rs:60-105).  One CTA works on one frame
-// at a time (persistent CTAs pull frames from a counter).  Per frame: the mask is scanned in
-// raster order in chunks held in registers as per-thread bitmaps of white pixels; pixels are
-// struck off as soon as a line suppresses them, so the next seed is just the lowest remaining
-// bit (block-wide min).  Per seed: get_centre (per warp, redundantly), the exact isolated-seed
-// test, then the 3600-ray search spread over the CTA with a last-index argmax.
+// at a time (persistent CTAs pull frames from a counter).  Per frame the bitmap is walked one
+// tile-row (32 pixel rows) at a time, held row-major in shared memory as the set of pixels that
+// can still become seeds:
+//   * lines found so far strike off what they suppress (lsd.rs:84-89) — per (row, line) the
+//     interval that is suppressed for sure is cleared with word masks, the few remaining pixels
+//     take the reference's float test — so the next seed is simply the first set bit;
+//   * per seed: dead-cluster test, get_centre, the exact ray filter, the search over the surviving
+//     rays with a last-index argmax, get_centre of the far end;
+//   * a seed whose first ring is empty proves a whole disc of seeds hopeless (dead cluster): they
+//     are struck off in bulk (or, when counting seeds for the statistics, dismissed one by one).
 template <bool STATS>
-__global__ void __launch_bounds__(LSD_THREADS, 4) k_lsd(const LsdArgs a) {
+__global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs a) {
     constexpr int T = LSD_THREADS;
-    __shared__ float4 s_lines[SMH_LSD_MAX_LINES];
-    __shared__ uint32_t s_min[T / 32];
-    __shared__ unsigned long long s_keys[T / 32];
-    __shared__ float2 s_ends[T / 32];
-    __shared__ unsigned long long s_mask[2];
-    __shared__ uint32_t s_frame;
+    __shared__ LsdShared sh;
+    extern __shared__ uint32_t chunk[];  // [32][tx] current tile-row, row-major
 
-    const int tid = threadIdx.x;
-    const uint32_t vpr = (a.pad + a.w + 15u) / 16u;  // 16-byte vectors per mask row
-    const uint32_t rows_per_chunk = max(1u, (uint32_t)(T * LSD_VPT) / vpr);
-    const uint32_t items = rows_per_chunk * vpr;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t TX = a.g.tx, W = a.g.w, H = a.g.h, PAD = a.g.pad;
+    const uint32_t NW = 32u * TX;             // words per tile-row
+    const uint32_t E = (NW + T - 1) / T;      // consecutive raster words owned by a thread
+    const uint32_t own0 = min((uint32_t)tid * E, NW), own1 = min(own0 + E, NW);
     const bool fast = a.gap_limit >= 1;  // march_fast's precondition
+    smh_lsd_filter F;
+    smh_lsd_filter_init(&F, a.prune ? a.gap_limit : 0);
+    const bool dead_ok = F.nw >= 1 && F.border[0] == 0;  // "ring 1 empty => no line" holds for every seed
+
+    for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
+    if (tid == 0) { sh.list_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
 
     while (true) {
         __syncthreads();
-        if (tid == 0) { s_frame = atomicAdd(a.counter, 1u); s_mask[0] = 0ull; s_mask[1] = 0ull; }
+        if (tid == 0) { sh.frame = atomicAdd(a.counter, 1u); sh.n_dead = 0u; }
         __syncthreads();
-        const uint32_t f = s_frame;
+        const uint32_t f = sh.frame;
         if (f >= a.n_frames) break;
         float* out_lines = a.lines + (uint64_t)f * SMH_LSD_MAX_LINES * 4;
         if (a.open && a.open[f] == 0) {  // map closed: the reference returns before any line search
             if (tid == 0) { a.n_lines[f] = 0; if (STATS) { a.stats[3 * f] = 0; a.stats[3 * f + 1] = 0; a.stats[3 * f + 2] = 0; } }
             continue;
         }
-        const uint8_t* base = a.lsd + (uint64_t)f * a.stride;  // 16-byte aligned rows; pixel i at byte i+pad
-        const Img im{base + a.pad, a.pitch, a.w, a.h};
+        const Bits im{a.bits + (uint64_t)f * a.bits_stride, TX, PAD, W, H};
 
         uint32_t steps = 0, seeds = 0, pruned = 0;
         int n = 0, par = 0;
-        for (uint32_t row0 = 0; row0 < a.h && n < SMH_LSD_MAX_LINES; row0 += rows_per_chunk) {
-            // ---- this thread's slice of the chunk: bitmaps of its white, in-image pixels -------
-            uint32_t alive[LSD_VPT];  // 16 bits per vector
-            uint32_t vrow[LSD_VPT], vx0[LSD_VPT];
+        for (uint32_t tyi = 0; tyi < a.g.ty && n < SMH_LSD_MAX_LINES; tyi++) {
+            // ---- load the tile-row (contiguous in memory), transposed to row-major ------------
+            {
+                const uint32_t* src = im.p + (uint64_t)tyi * NW;
+                for (uint32_t i = tid; i < NW; i += T) chunk[(i & 31u) * TX + (i >> 5)] = __ldg(src + i);
+                if (tyi + 1 < a.g.ty)  // pull the next tile-row into L2 while this one is searched
+                    for (uint32_t i = tid * 32u; i < NW; i += T * 32u) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + NW + i));
+            }
+            __syncthreads();
+            const int row0 = (int)(tyi * 32u);
+            const int nd = STATS ? 0 : (int)min(sh.n_dead, (uint32_t)LSD_DEAD);
+            // ---- strike off what the lines (and dead clusters) found so far cover for sure -----
+            for (int i = tid; i < 32 * (n + nd); i += T) {
+                const int r = i & 31, l = i >> 5, y = row0 + r;
+                int xlo, xhi;
+                if (l < n) {
+                    if (sure_interval(sh.lines[l], (float)y, (int)W, xlo, xhi)) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
+                } else {
+                    const float4 d = sh.dead[l - n];
+                    const float dy = (float)y - d.y, r2 = d.w - dy * dy;
+                    if (r2 > 0.0f) {
+                        const float hw = sqrtf(r2) - 0.01f;
+                        xlo = max((int)ceilf(d.x - hw), 0); xhi = min((int)floorf(d.x + hw), (int)W - 1);
+                        if (xlo <= xhi) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- the reference's float test for what is left (own words only) ------------------
             bool any_white = false;
-#pragma unroll
-            for (int k = 0; k < LSD_VPT; k++) {
-                const uint32_t item = (uint32_t)tid * LSD_VPT + k;  // consecutive items => increasing raster order
-                alive[k] = 0; vrow[k] = 0; vx0[k] = 0;
-                if (item < items) {
-                    const uint32_t r = row0 + item / vpr, c = item % vpr;
-                    vrow[k] = r; vx0[k] = c * 16u - a.pad;  // x of byte 0 (may wrap below 0 for c = 0)
-                    if (r < a.h) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(base + (uint64_t)r * a.pitch + (uint64_t)c * 16u);
-                        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-                        if (v.x | v.y | v.z | v.w) {
-#pragma unroll
-                            for (int b = 0; b < 16; b++) {
-                                const int i = (int)(c * 16u) + b - (int)a.pad;
-                                const bool white = ((wd[b >> 2] >> (8 * (b & 3))) & 0xFFu) == 255u;
-                                if (white && i >= 0 && i < (int)a.w) alive[k] |= 1u << b;
-                            }
-                        }
-                    }
-                }
-                // strike off what the lines found so far already suppress (lsd.rs:84-89): one pixel
-                // per warp step, lane l tests line l (n <= 32), the vote decides
-                if (n > 0) {
-                    const int lane = tid & 31;
-                    uint32_t pend = alive[k];
-                    uint32_t bal;
-                    while ((bal = __ballot_sync(0xFFFFFFFFu, pend != 0u)) != 0u) {
-                        const int src = __ffs(bal) - 1;
-                        const uint32_t bits = __shfl_sync(0xFFFFFFFFu, pend, src);
+            for (uint32_t i = own0; i < own1; i++) {
+                uint32_t m = chunk[i];
+                if (m && n > 0) {
+                    const uint32_t r = i / TX, wd = i - r * TX;
+                    for (uint32_t bits = m; bits; bits &= bits - 1u) {
                         const int b = __ffs(bits) - 1;
-                        const float fx = (float)(__shfl_sync(0xFFFFFFFFu, vx0[k], src) + (uint32_t)b);
-                        const float fy = (float)__shfl_sync(0xFFFFFFFFu, vrow[k], src);
-                        const bool sup = lane < n && suppressed_by(s_lines[lane], fx, fy);
-                        const bool hit = __any_sync(0xFFFFFFFFu, sup);
-                        if (lane == src) { pend &= pend - 1u; if (hit) alive[k] &= ~(1u << b); }
+                        const float fx = (float)((int)(wd * 32u) + b - (int)PAD), fy = (float)(row0 + (int)r);
+                        for (int l = 0; l < n; l++)
+                            if (suppressed_by(sh.lines[l], fx, fy)) { m &= ~(1u << b); break; }
                     }
+                    chunk[i] = m;
                 }
-                any_white |= alive[k] != 0;
+                any_white |= m != 0u;
             }
             if (!__syncthreads_or(any_white)) continue;
 
-            // ---- seeds of this chunk, in raster order ------------------------------------------
+            // ---- seeds of this tile-row, in raster order ---------------------------------------
             while (true) {
-                uint32_t cand = 0xFFFFFFFFu;  // lowest remaining pixel of this thread (items are in raster order)
-#pragma unroll
-                for (int k = LSD_VPT - 1; k >= 0; k--)
-                    if (alive[k]) cand = vrow[k] * a.w + vx0[k] + (uint32_t)(__ffs(alive[k]) - 1);
+                uint32_t cand = 0xFFFFFFFFu;  // first remaining pixel among this thread's words: raster word index * 32 + bit
+                for (uint32_t i = own0; i < own1; i++) {
+                    const uint32_t m = chunk[i];
+                    if (m) { cand = i * 32u + (uint32_t)(__ffs(m) - 1); break; }
+                }
                 const uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, cand);
-                if ((tid & 31) == 0) s_min[tid >> 5] = wmin;
+                if (lane == 0) sh.smin[par][tid >> 5] = wmin;
                 __syncthreads();
                 uint32_t seed = 0xFFFFFFFFu;
 #pragma unroll
-                for (int k = 0; k < T / 32; k++) seed = min(seed, s_min[k]);
+                for (int k = 0; k < T / 32; k++) seed = min(seed, sh.smin[par][k]);
+                par ^= 1;
                 if (seed == 0xFFFFFFFFu) break;  // uniform
-                if (cand == seed) {
-#pragma unroll
-                    for (int k = 0; k < LSD_VPT; k++)
-                        if (alive[k] && vrow[k] * a.w + vx0[k] + (uint32_t)(__ffs(alive[k]) - 1) == seed) alive[k] &= alive[k] - 1u;
+                if (cand == seed) chunk[seed >> 5] &= ~(1u << (seed & 31u));  // the owner takes it off
+                const uint32_t sr = (seed >> 5) / TX, swd = (seed >> 5) - sr * TX;
+                const float sx = (float)((int)(swd * 32u + (seed & 31u)) - (int)PAD), sy = (float)(row0 + (int)sr);
+                seeds++;
+                const bool have_dead = dead_ok && lane < (int)min(sh.n_dead, (uint32_t)LSD_DEAD);
+                if (dead_ok) {
+                    // deep inside a remembered dead cluster?  get_centre moves a seed by at most 2.5 px per
+                    // axis, so the raw pixel decides when it is sqrt(12.5) closer.  Lane l tests entry l.
+                    bool in = false;
+                    if (have_dead) {
+                        const float4 d = sh.dead[lane];
+                        const float ex = sx - d.x, ey = sy - d.y;
+                        in = ex * ex + ey * ey < d.w;
+                    }
+                    if (__any_sync(0xFFFFFFFFu, in)) { pruned++; continue; }  // uniform: same data in every warp
                 }
                 float px, py;
-                get_centre_warp(im, (float)(seed % a.w), (float)(seed / a.w), px, py);  // same value in every warp
-                seeds++;
-                if (a.prune) {
-                    const bool isolated = seed_is_isolated<T>(base, a.pitch, a.pad, a.w, a.h, px, py, a.gap_limit, &s_mask[par]);
-                    if (tid == 0) s_mask[par ^ 1] = 0ull;  // last read one seed ago, behind two barriers
-                    par ^= 1;
-                    if (isolated) { pruned++; continue; }  // uniform
+                get_centre_warp(im, sx, sy, px, py);  // same value in every warp
+                int n_rays = -1;  // all
+                if (F.nw > 0) {
+                    if (dead_ok) {
+                        bool in = false;
+                        if (have_dead) {
+                            const float4 d = sh.dead[lane];
+                            const float ex = px - d.x, ey = py - d.y;
+                            in = ex * ex + ey * ey < d.z;
+                        }
+                        if (__any_sync(0xFFFFFFFFu, in)) { pruned++; continue; }
+                    }
+                    lsd_scan_window<T>(im, px, py, F, sh);
+                    __syncthreads();
+                    const uint32_t n_listed = sh.list_n;
+                    const float near2 = __uint_as_float(sh.near2), far2 = __uint_as_float(sh.far2);
+                    lsd_mark_rays<T>(px, py, F, n_listed, sh);
+                    __syncthreads();
+                    n_rays = (int)lsd_build_ray_list<T>(px, py, F, sh);
+                    if (n_rays == 0) {  // uniform: no ray can exceed the minimum length
+                        pruned++;
+                        // every white pixel is within sqrt(near2) of the seed or beyond dfar: a seed at distance
+                        // t < rho sees none of them in its first ring either
+                        const float k1 = (float)F.k1;
+                        const float dfar = fminf(sqrtf(far2), (float)(F.radius - 1));
+                        const float rho = fminf(k1 - 0.75f - sqrtf(near2), dfar - (2.0f * k1 - 0.25f)) - 0.05f;
+                        if (dead_ok && rho > 0.5f) {  // uniform
+                            const float raw = fmaxf(rho - 3.6f, 0.0f);  // radius for raw (un-centred) seed pixels
+                            if (tid == 0) {
+                                sh.dead[sh.n_dead % (uint32_t)LSD_DEAD] = make_float4(px, py, rho * rho, raw * raw);
+                                sh.n_dead = sh.n_dead + 1u;  // read by the other threads only after the next barrier
+                            }
+                            if (!STATS && raw > 0.0f) {  // strike the disc off this tile-row right away
+                                const int r = tid;  // one row per thread
+                                if (r < 32) {
+                                    const float dy = (float)(row0 + r) - py, r2 = raw * raw - dy * dy;
+                                    if (r2 > 0.0f) {
+                                        const float hw = sqrtf(r2) - 0.01f;
+                                        const int xlo = max((int)ceilf(px - hw), 0), xhi = min((int)floorf(px + hw), (int)W - 1);
+                                        if (xlo <= xhi) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
+                                    }
+                                }
+                                __syncthreads();  // uniform branch: the next seed pick reads the cleared words
+                            }
+                        }
+                        continue;
+                    }
                 }
                 float best[3];
-                if (fast) longest_ray_cta<T, true, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, best, s_keys, s_ends, steps);
-                else longest_ray_cta<T, false, STATS>(im, a.rays, px, py, a.max_gap, a.gap_limit, best, s_keys, s_ends, steps);
+                if (fast)
+                    longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
+                                       [&](float dx, float dy, float& ex, float& ey) { return march_fast<STATS>(im, px, py, a.gap_limit, dx, dy, ex, ey, steps); });
+                else
+                    longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
+                                       [&](float dx, float dy, float& ex, float& ey) { return march(im, px, py, a.max_gap, dx, dy, ex, ey, steps); });
                 if (best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
                     float c1x, c1y;
                     get_centre_warp(im, best[1], best[2], c1x, c1y);
                     const float4 line = make_float4(px, py, c1x, c1y);
                     if (tid == 0) {
-                        s_lines[n] = line;  // read by later chunks only, behind the barriers in between
+                        sh.lines[n] = line;  // read by the others only behind the barriers below
                         out_lines[4 * n + 0] = px; out_lines[4 * n + 1] = py;
                         out_lines[4 * n + 2] = c1x; out_lines[4 * n + 3] = c1y;
                     }
                     n++;
                     if (n == SMH_LSD_MAX_LINES) break;  // `break 'row`
-                    // the new line suppresses pixels for good: strike them off now
-#pragma unroll
-                    for (int k = 0; k < LSD_VPT; k++)
-                        for (uint32_t bits = alive[k]; bits; bits &= bits - 1u) {
-                            const int b = __ffs(bits) - 1;
-                            if (suppressed_by(line, (float)(vx0[k] + (uint32_t)b), (float)vrow[k])) alive[k] &= ~(1u << b);
+                    // the new line suppresses pixels for good: strike them off this tile-row now
+                    if (tid < 32) {
+                        int xlo, xhi;
+                        if (sure_interval(line, (float)(row0 + tid), (int)W, xlo, xhi)) chunk_clear(chunk, TX, PAD, tid, xlo, xhi);
+                    }
+                    __syncthreads();
+                    for (uint32_t i = own0; i < own1; i++) {
+                        uint32_t m = chunk[i];
+                        if (m) {
+                            const uint32_t r = i / TX, wd = i - r * TX;
+                            for (uint32_t bits = m; bits; bits &= bits - 1u) {
+                                const int b = __ffs(bits) - 1;
+                                if (suppressed_by(line, (float)((int)(wd * 32u) + b - (int)PAD), (float)(row0 + (int)r))) m &= ~(1u << b);
+                            }
+                            chunk[i] = m;
                         }
+                    }
                 }
             }
             __syncthreads();
@@ -784,22 +1031,23 @@ __global__ void __launch_bounds__(LSD_THREADS, 4) k_lsd(const LsdArgs a) {
         if (tid == 0) a.n_lines[f] = (uint32_t)n;
         if (STATS) {
             steps = __reduce_add_sync(0xFFFFFFFFu, steps);
-            if ((tid & 31) == 0) atomicAdd(&a.stats[3 * f + 1], (unsigned long long)steps);
+            if (lane == 0) atomicAdd(&a.stats[3 * f + 1], (unsigned long long)steps);
             if (tid == 0) { a.stats[3 * f] = seeds; a.stats[3 * f + 2] = pruned; }
         }
     }
 }
 
-// single find_longest_line call (Vision::find_longest_line); out = {p0x,p0y,p1x,p1y,len}
+// single find_longest_line call (Vision::find_longest_line) on the L8 mask; out = {p0x,p0y,p1x,p1y,len}
 __global__ void __launch_bounds__(LSD_THREADS) k_longest(const uint8_t* lsd, uint32_t pitch, uint32_t pad, uint32_t w,
                                                          uint32_t h, const float2* rays, float px, float py,
                                                          float max_gap, float* out) {
     __shared__ unsigned long long s_keys[LSD_THREADS / 32];
     __shared__ float2 s_ends[LSD_THREADS / 32];
-    Img im{lsd + pad, pitch, w, h};
+    const ImgL8 im{Img{lsd + pad, pitch, w, h}, w, h};
     uint32_t steps = 0;
     float best[3];
-    longest_ray_cta<LSD_THREADS, false, false>(im, rays, px, py, max_gap, 0, best, s_keys, s_ends, steps);
+    longest_ray_cta<LSD_THREADS>(rays, nullptr, -1, px, py, best, s_keys, s_ends,
+                                 [&](float dx, float dy, float& ex, float& ey) { return march(im, px, py, max_gap, dx, dy, ex, ey, steps); });
     if (threadIdx.x == 0) { out[0] = px; out[1] = py; out[2] = best[1]; out[3] = best[2]; out[4] = best[0]; }
 }
 

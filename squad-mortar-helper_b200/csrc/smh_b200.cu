@@ -70,7 +70,11 @@ struct Planes {
     unsigned long long* stats = nullptr;
     uint32_t* start_y = nullptr;
     uint32_t* counter = nullptr;  // frame dispenser of the persistent line-search CTAs
+    uint32_t* bits = nullptr;     // tile-major 1-bit copies of the dilated masks (line-search input)
+    uint64_t bits_stride = 0;     // words per frame
+    smh::BitsGeom bg{};
     void release() {
+        cudaFree(bits);
         cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
         cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y); cudaFree(counter);
         *this = Planes();
@@ -82,7 +86,6 @@ struct Planes {
 struct smh_b200 {
     int device = 0;
     int sm_count = 0;
-    int lsd_ctas_per_sm = 0;
     std::mutex err_mu;
     std::string err;
     std::atomic<uint64_t> launches{0};
@@ -166,6 +169,10 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     CU(h, cudaMalloc(&P->start_y, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMemset(P->start_y, 0, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->counter, sizeof(uint32_t)));
+    P->bg.pad = P->pad; P->bg.w = g.map[2]; P->bg.h = g.map[3];
+    P->bg.tx = (P->pad + g.map[2] + 31u) / 32u; P->bg.ty = (g.map[3] + 31u) / 32u;
+    P->bits_stride = (uint64_t)P->bg.tx * P->bg.ty * 32u;
+    CU(h, cudaMalloc(&P->bits, P->bits_stride * n * sizeof(uint32_t)));
     if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
     P->n = n; P->W = g.W; P->H = g.H;
     return SMH_OK;
@@ -208,9 +215,16 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
 }
 
 int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st) {
+    // 1-bit tile-major copy of the dilated masks (what the search kernel reads)
+    {
+        const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
+        if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
+        smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
     smh::LsdArgs a{};
-    a.lsd = P.lsd.ptr; a.stride = P.lsd.frame_stride; a.pitch = P.lsd.pitch; a.pad = P.lsd.pad;
-    a.w = P.geo.map[2]; a.h = P.geo.map[3];
+    a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
     a.rays = h->d_rays; a.max_gap = max_gap;
     // `gap.0 >= max_gap` on an integer-valued counter <=> counter >= ceil(max_gap)
     a.gap_limit = (max_gap != max_gap || max_gap >= 2147483648.0f) ? 2147483647 : (max_gap <= -2147483648.0f ? -2147483647 : (int)ceilf(max_gap));
@@ -221,18 +235,28 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     a.stats = stats ? P.stats : nullptr;
     CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
     // persistent grid: as many CTAs as stay resident (or one per frame when there are fewer)
-    if (h->lsd_ctas_per_sm == 0) {
-        int nb = 0;
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, 0));
-        h->lsd_ctas_per_sm = nb > 0 ? nb : 1;
+    const size_t dyn = (size_t)P.bg.tx * 32u * sizeof(uint32_t);  // one tile-row of the bitmap
+    {
+        // the limit is a property of the kernel on this device, shared by every handle: only ever raise it
+        static std::mutex mu;
+        static size_t raised[64] = {0};
+        std::lock_guard<std::mutex> g(mu);
+        size_t& cur = raised[h->device & 63];
+        if (dyn > 32768 && dyn > cur) {
+            CU(h, cudaFuncSetAttribute(smh::k_lsd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            CU(h, cudaFuncSetAttribute(smh::k_lsd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            cur = dyn;
+        }
     }
-    const uint32_t resident = (uint32_t)(h->sm_count * h->lsd_ctas_per_sm);
+    int nb = 0;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, dyn));
+    const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
     const uint32_t grid = n < resident ? n : resident;
     if (stats) {
         CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
-        smh::k_lsd<true><<<grid, smh::LSD_THREADS, 0, st>>>(a);
+        smh::k_lsd<true><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
     } else {
-        smh::k_lsd<false><<<grid, smh::LSD_THREADS, 0, st>>>(a);
+        smh::k_lsd<false><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
     }
     h->launches++;
     CU(h, cudaGetLastError());
