@@ -447,6 +447,8 @@ struct LsdArgs {
     const uint32_t* bits; uint64_t bits_stride;  // tile-major bitmaps, words per frame
     BitsGeom g;
     const float2* rays;  // 3600 (cos, sin) pairs built on the host with libm (D11)
+    const float2* ckpt; uint32_t n_ckpt;  // accumulated ray offsets at every LSD_CKPT-th step, [3600][n_ckpt]
+    const uint32_t* span_tab;             // ray span per pixel offset (k_build_span_table)
     float max_gap;
     int gap_limit;        // ceil(max_gap): `gap.0 >= max_gap` on the integer-valued counter
     int prune;            // 1: exact ray filter + dead clusters; 0: march all 3600 rays of every seed
@@ -517,25 +519,33 @@ __device__ __forceinline__ bool suppressed_by(const float4& l, float x, float y)
     return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < SMH_LSD_SUPPRESS_DIST_SQ;
 }
 
-// Columns of row y that line l suppresses FOR SURE: exact distance to the infinite line < 6.99, i.e.
-// squared distance < 48.9, while the float formula above errs by < 0.02 around its threshold of 50.
-// Pixels of the thin fringe in between (and degenerate lines) are left to the exact test.
-// Returns false when the interval is empty.  Integer pixel columns, clamped to [0, w-1].
-__device__ __forceinline__ bool sure_interval(const float4& l, float y, int w, int& xlo, int& xhi) {
+// Columns of row y that line l suppresses FOR SURE / POSSIBLY: exact distance to the infinite line
+// < 6.99 (squared < 48.9) resp. < 7.15 (squared < 51.1), while the float formula above errs by
+// < 0.02 around its threshold of 50.  Pixels outside the outer interval are surely kept, pixels
+// inside the inner one surely struck off; only the thin fringe in between (and every pixel for a
+// degenerate line) takes the exact test.  Integer pixel columns clamped to [0, w-1]; an interval
+// with lo > hi is empty.
+struct Band { int ilo, ihi, olo, ohi; };
+__device__ __forceinline__ Band line_band(const float4& l, float y, int w) {
+    Band b{0, -1, 0, -1};
     const float dx = l.z - l.x, dy = l.w - l.y;
     const float len = sqrtf(dx * dx + dy * dy);
-    if (!(len > 1.0f)) return false;
-    const float c = 6.99f * len, a = (y - l.y) * dx;
-    if (fabsf(dy) < 1.0e-4f * len) {  // (x - p0x) * dy stays below 0.25 * len for |x - p0x| < 2500
-        if (w > 2500 || !(fabsf(a) < c - 0.25f * len)) return false;
-        xlo = 0; xhi = w - 1;
-        return true;
+    if (!(len > 1.0f)) { b.olo = 0; b.ohi = w - 1; return b; }  // degenerate: test everything
+    const float ci = 6.99f * len, co = 7.15f * len, a = (y - l.y) * dx;
+    if (fabsf(dy) < 1.0e-4f * len) {  // |(x - p0x) * dy| < slack over the whole row
+        const float slack = 1.0e-4f * (float)w * len;
+        if (fabsf(a) < ci - slack) { b.ilo = 0; b.ihi = w - 1; }
+        if (fabsf(a) < co + slack) { b.olo = 0; b.ohi = w - 1; }
+        return b;
     }
-    const float t1 = (a - c) / dy, t2 = (a + c) / dy;
-    const float lo = fmaxf(l.x + fminf(t1, t2) + 0.01f, 0.0f), hi = fminf(l.x + fmaxf(t1, t2) - 0.01f, (float)(w - 1));
-    if (!(lo <= hi)) return false;
-    xlo = (int)ceilf(lo); xhi = (int)floorf(hi);
-    return xlo <= xhi;
+    const float inv = 1.0f / dy;
+    const float i1 = (a - ci) * inv, i2 = (a + ci) * inv, o1 = (a - co) * inv, o2 = (a + co) * inv;
+    const float wf = (float)(w - 1);
+    const float ilo = fmaxf(l.x + fminf(i1, i2) + 0.01f, 0.0f), ihi = fminf(l.x + fmaxf(i1, i2) - 0.01f, wf);
+    const float olo = fmaxf(l.x + fminf(o1, o2) - 0.01f, 0.0f), ohi = fminf(l.x + fmaxf(o1, o2) + 0.01f, wf);
+    if (ilo <= ihi) { b.ilo = (int)ceilf(ilo); b.ihi = (int)floorf(ihi); }
+    if (olo <= ohi) { b.olo = (int)floorf(olo); b.ohi = (int)ceilf(ohi); }
+    return b;
 }
 
 // Same automaton for seeds that lie inside the image (all coordinates within (-2^22, 2^22)) and
@@ -600,6 +610,159 @@ __device__ __forceinline__ float march_fast(const Bits& im, float px, float py, 
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
 }
 
+// ---- one ray per WARP -------------------------------------------------------------------------
+// The accumulated offsets xo_n = fl(xo_{n-1} + dx) of a ray do not depend on the seed, so they are
+// tabulated once per handle for every ray direction at every LSD_CKPT-th step (k_build_ray_ckpt).
+// Lane i of a warp then rebuilds step 32c + i of block c with at most LSD_CKPT - 1 adds — the same
+// float sequence as the serial loop — and the 32 samples of a block are fetched and tested in
+// parallel; the gap automaton runs on the two ballot masks with bit tricks.  A ray costs ~2
+// instructions per step instead of ~30, and its latency is one table + one bitmap load per 32 steps.
+constexpr int LSD_CKPT = 4;
+__global__ void k_build_ray_ckpt(const float2* __restrict__ rays, uint32_t n_ckpt, float2* __restrict__ ckpt) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= SMH_LSD_RAYS) return;
+    const float2 d = rays[k];
+    float xo = 0.0f, yo = 0.0f;
+    for (uint32_t c = 0; c < n_ckpt; c++) {
+        ckpt[(uint64_t)k * n_ckpt + c] = make_float2(xo, yo);
+#pragma unroll
+        for (int j = 0; j < LSD_CKPT; j++) { xo = __fadd_rn(xo, d.x); yo = __fadd_rn(yo, d.y); }
+    }
+}
+
+// AND of k consecutive bits ending at each position (k >= 1)
+__device__ __forceinline__ unsigned long long run_and(unsigned long long r, int k) {
+    int len = 1;
+    while (2 * len <= k) { r &= r << len; len *= 2; }
+    if (len < k) r &= r << (k - len);
+    return r;
+}
+
+// One block (32 consecutive samples) of one ray, lane i = sample 32c + i.
+struct RayBlock { float x, y; bool ok; uint32_t word; uint32_t bit; };
+__device__ __forceinline__ RayBlock ray_block_fetch(const Bits& im, float2 ck, int sub, float dx, float dy, float px, float py) {
+    RayBlock b;
+    float xo = ck.x, yo = ck.y;
+#pragma unroll
+    for (int j = 1; j < LSD_CKPT; j++)
+        if (sub >= j) { xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy); }
+    b.x = __fadd_rn(xo, px); b.y = __fadd_rn(yo, py);
+    const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(b.x, 12582912.0f)) - 0x4B400000);
+    const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(b.y, 12582912.0f)) - 0x4B400000);
+    b.ok = ix < im.w && iy < im.h;
+    const uint32_t X = ix + im.pad;
+    b.bit = X & 31u;
+    b.word = 0u;
+    if (b.ok) b.word = im.word(X >> 5, iy);
+    return b;
+}
+// Runs the gap automaton over the block.  Returns true when the ray ends in it: (gx, gy) is then the
+// start of the fatal gap or the first sample outside the image.  Uniform across the warp.
+template <bool STATS>
+__device__ __forceinline__ bool ray_block_decide(const RayBlock& b, float xprev, float yprev, uint32_t& gap_in, int gap_limit,
+                                                 float& gx, float& gy, uint32_t& steps) {
+    const uint32_t inb = __ballot_sync(0xFFFFFFFFu, b.ok), wh = __ballot_sync(0xFFFFFFFFu, (b.word >> b.bit) & 1u);
+    const int first_out = __ffs(~inb) - 1;  // -1: the whole block is inside
+    const uint32_t valid = first_out < 0 ? 0xFFFFFFFFu : ((1u << first_out) - 1u);
+    const uint32_t black = ~wh & valid;
+    // bit 32+i of r: sample i is the (gap_limit+1)-th consecutive non-white one
+    const unsigned long long carry = gap_in ? ((gap_in >= 32u ? 0xFFFFFFFFull : ((1ull << gap_in) - 1ull)) << (32u - min(gap_in, 32u))) : 0ull;
+    const uint32_t stop = (uint32_t)(run_and(((unsigned long long)black << 32) | carry, gap_limit + 1) >> 32);
+    if (stop) {
+        const int i = __ffs(stop) - 1, g = i - gap_limit;  // the gap began at sample g (previous block when negative)
+        if (STATS) steps += (uint32_t)(i + 1);
+        const float cx = __shfl_sync(0xFFFFFFFFu, b.x, g & 31), cy = __shfl_sync(0xFFFFFFFFu, b.y, g & 31);
+        const float qx = __shfl_sync(0xFFFFFFFFu, xprev, g & 31), qy = __shfl_sync(0xFFFFFFFFu, yprev, g & 31);
+        gx = g >= 0 ? cx : qx; gy = g >= 0 ? cy : qy;
+        return true;
+    }
+    if (first_out >= 0) {
+        if (STATS) steps += (uint32_t)first_out;
+        gx = __shfl_sync(0xFFFFFFFFu, b.x, first_out); gy = __shfl_sync(0xFFFFFFFFu, b.y, first_out);
+        return true;
+    }
+    if (STATS) steps += 32u;
+    gap_in = black == 0xFFFFFFFFu ? gap_in + 32u : (uint32_t)__clz((int)~black);  // trailing non-white run
+    return false;
+}
+// end-point rule (vision-cpu/src/lib.rs:426-429, D7) and squared length
+__device__ __forceinline__ float ray_finish(const Bits& im, float gx, float gy, float px, float py, float dx, float dy, float& ex, float& ey) {
+    const uint32_t xi = __float2uint_rz(gx), yi = __float2uint_rz(gy);  // `as u32`: saturating
+    if (xi < im.w && yi < im.h && !im.white(xi, yi)) {
+        ex = __fsub_rn(gx, dx); ey = __fsub_rn(gy, dy);
+    } else {
+        ex = px; ey = py;
+    }
+    const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
+    return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+}
+
+// The listed rays of one seed, LSD_RAYS_PER_WARP rays per warp at a time: the first block of each
+// (where most rays already end) is fetched for all of them before any is tested, so their table
+// and bitmap loads overlap; survivors continue block by block with the next checkpoint prefetched.
+// Same last-index argmax as longest_ray_cta.  Preconditions: 1 <= gap_limit <= 32, seed inside the
+// image, the table covers every step a ray can take inside the image plus two blocks.
+#ifndef LSD_RAYS_PER_WARP
+#define LSD_RAYS_PER_WARP 1
+#endif
+template <int T, bool STATS>
+__device__ __forceinline__ void longest_ray_warps(const Bits& im, const float2* __restrict__ rays, const float2* __restrict__ ckpt, uint32_t n_ckpt,
+                                                  const uint16_t* list, int n_rays, float px, float py, int gap_limit, float (&best)[3],
+                                                  unsigned long long* s_keys, float2* s_ends, uint32_t& steps) {
+    constexpr int R = LSD_RAYS_PER_WARP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & (LSD_CKPT - 1);
+    unsigned long long best_key = 0ull;
+    float bex = px, bey = py;
+    uint32_t st = 0;
+    for (int i0 = warp * R; i0 < n_rays; i0 += (T / 32) * R) {
+        int k[R]; float2 d[R]; const float2* ckp[R]; RayBlock blk[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            k[j] = (int)list[min(i0 + j, n_rays - 1)];
+            ckp[j] = ckpt + (uint64_t)k[j] * n_ckpt + (lane / LSD_CKPT);
+        }
+        float2 ck[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) { d[j] = __ldg(&rays[k[j]]); ck[j] = __ldg(ckp[j]); }
+#pragma unroll
+        for (int j = 0; j < R; j++) blk[j] = ray_block_fetch(im, ck[j], sub, d[j].x, d[j].y, px, py);
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (i0 + j >= n_rays) break;  // uniform
+            uint32_t gap_in = 0;
+            float gx, gy;
+            RayBlock b = blk[j];
+            float xprev = px, yprev = py;
+            if (!ray_block_decide<STATS>(b, xprev, yprev, gap_in, gap_limit, gx, gy, st)) {
+                const float2* cp = ckp[j] + 32 / LSD_CKPT;
+                float2 c1 = __ldg(cp);
+                while (true) {
+                    cp += 32 / LSD_CKPT;
+                    const float2 c2 = __ldg(cp);  // next block's checkpoint, in flight while this block is tested
+                    xprev = b.x; yprev = b.y;
+                    b = ray_block_fetch(im, c1, sub, d[j].x, d[j].y, px, py);
+                    if (ray_block_decide<STATS>(b, xprev, yprev, gap_in, gap_limit, gx, gy, st)) break;
+                    c1 = c2;
+                }
+            }
+            float ex, ey;
+            const float len = ray_finish(im, gx, gy, px, py, d[j].x, d[j].y, ex, ey);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k[j];
+            if (key >= best_key) { best_key = key; bex = ex; bey = ey; }  // ties go to the later ray
+        }
+    }
+    if (STATS && lane == 0) steps += st;  // summed over all threads later: count once per warp
+    if (lane == 0) { s_keys[warp] = best_key; s_ends[warp] = make_float2(bex, bey); }
+    __syncthreads();
+    int bw = 0;
+    unsigned long long bk = s_keys[0];
+#pragma unroll
+    for (int k2 = 1; k2 < T / 32; k2++) { const unsigned long long o = s_keys[k2]; if (o > bk) { bk = o; bw = k2; } }
+    best[0] = __uint_as_float((uint32_t)(bk >> 32));
+    best[1] = s_ends[bw].x;
+    best[2] = s_ends[bw].y;
+}
+
 // get_centre — vision-common/src/lsd.rs:5-44 (indices clamped where the reference is UB, D8) —
 // evaluated by one warp in parallel (every lane returns the result): lane = 8*dir + t tests the
 // loop condition of step t of direction dir (left, right, up, down); the walk stops at the first
@@ -643,8 +806,19 @@ __device__ __forceinline__ void get_centre_warp(const Bits& im, float ptx, float
 #define LSD_MIN_CTAS 4
 #endif
 constexpr int LSD_THREADS = LSD_THREADS_N;
-constexpr int LSD_PX_CAP = 2048;  // ring pixels listed per seed (beyond that every ray is marched)
 constexpr int LSD_DEAD = 16;      // remembered dead clusters per frame
+
+// Optional per-phase cycle accounting of k_lsd (build with -DLSD_PROFILE; tools/lsd_profile.py reads it)
+__device__ unsigned long long g_lsd_prof[16];
+#ifdef LSD_PROFILE
+#define LSD_PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define LSD_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (unsigned long long)(now__ - prof_t); prof_t = now__; } while (0)
+#define LSD_PROF_FLUSH do { if (threadIdx.x == 0) for (int k__ = 0; k__ < 10; k__++) atomicAdd(&g_lsd_prof[k__], prof_acc[k__]); } while (0)
+#else
+#define LSD_PROF_DECL
+#define LSD_PROF(k) do { } while (0)
+#define LSD_PROF_FLUSH do { } while (0)
+#endif
 
 struct LsdShared {
     float4 lines[SMH_LSD_MAX_LINES];
@@ -654,16 +828,43 @@ struct LsdShared {
     uint32_t smin[2][LSD_THREADS / 32];  // double-buffered: a seed may be dismissed without another barrier
     uint32_t wsum[LSD_THREADS / 32];
     uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
-    uint32_t list_n, near2, far2, n_dead, frame;
+    uint32_t pre[SMH_LSD_BITMAP_WORDS + 3];  // rays before each word of the combined bitmap
+    uint32_t grp_n, near2, far2, n_dead, frame;
     union {
-        uint32_t px[LSD_PX_CAP];       // packed (ox + 128) | (oy + 128) << 8 of listed ring pixels
+        uint32_t grp[1024];            // LSD_GRP_CAP non-empty pixel quarters of the window around the seed
         uint16_t rays[SMH_LSD_RAYS];   // compacted indices of the rays to march
     };
 };
 
-// Stage 1: lane group = one bitmap word of a window row; white pixels in a ring are appended to
-// sh.px, and the nearest/farthest white distances around the inner disc are reduced into
-// sh.near2 / sh.far2 (float bits; positive floats order like their bit patterns).
+// Ray spans by pixel offset.  A seed centre is a multiple of 0.5 in each axis (get_centre of an
+// integer pixel), so the ray interval smh_lsd_filter_span() assigns to the pixel at integer offset
+// (ox, oy) from floor(seed) only depends on the offset and on the two half-pixel flags: it is
+// tabulated once per handle ([4][SPAN_N][SPAN_N] x (lo | hi << 16), int16 each) and the per-pixel
+// atan2 / sqrt of the marking step become one 4-byte load.
+constexpr int LSD_SPAN_R = 99;                   // largest window radius (smh_lsd_filter_init: gap_limit <= 48)
+constexpr int LSD_SPAN_N = 2 * LSD_SPAN_R + 1;
+__global__ void k_build_span_table(uint32_t* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * LSD_SPAN_N * LSD_SPAN_N) return;
+    const int v = i / (LSD_SPAN_N * LSD_SPAN_N), rem = i - v * LSD_SPAN_N * LSD_SPAN_N;
+    const int oy = rem / LSD_SPAN_N - LSD_SPAN_R, ox = rem % LSD_SPAN_N - LSD_SPAN_R;
+    const float cx = (float)ox + 0.5f - ((v & 1) ? 0.5f : 0.0f), cy = (float)oy + 0.5f - ((v & 2) ? 0.5f : 0.0f);
+    const float d2 = cx * cx + cy * cy;
+    int lo = 0, hi = SMH_LSD_RAYS - 1;
+    if (d2 >= 1.0f) smh_lsd_filter_span(cx, cy, d2, &lo, &hi);  // lo >= -1803, hi <= 1803 + span
+    tab[i] = (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16);
+}
+
+// OR `m` into a shared bitmap word unless it is already there (most marks of a seed repeat: the
+// pixels of a line all point the same way, and same-address shared atomics serialise)
+__device__ __forceinline__ void or_if_new(uint32_t* w, uint32_t m) {
+    if ((*reinterpret_cast<volatile uint32_t*>(w) & m) != m) atomicOr(w, m);
+}
+
+// Stage 1: scan the (2R+1)^2 window around the seed in the bitmap.  A task is a quarter (8 pixels)
+// of one word of one window row; every non-empty quarter is appended to sh.grp as
+// mask | (x offset of its first pixel + 160) << 8 | (row offset + 128) << 17.
+constexpr int LSD_GRP_CAP = 1024;
 template <int T>
 __device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
     const int fx = (int)px, fy = (int)py, R = F.radius;  // px, py >= 0
@@ -671,32 +872,70 @@ __device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float 
     const int y0 = max(fy - R, 0), y1 = min(fy + R, (int)im.h - 1);
     const int X0 = x0 + (int)im.pad, X1 = x1 + (int)im.pad;
     const int wlo = X0 >> 5, nwords = (X1 >> 5) - wlo + 1;  // <= 8 for R <= 99
-    const float a2 = F.r2_lo[0], z2 = F.r2_hi[F.nw - 1];
-    float near2 = 0.0f, far2 = 3.0e38f;
-    const int sub = threadIdx.x & 7;
-    if (sub < nwords) {
-        const int Xw = (wlo + sub) << 5;
-        uint32_t keep = 0xFFFFFFFFu;  // bits of this word inside [X0, X1]
+    const int lane = threadIdx.x & 31, wi = lane >> 2, q = lane & 3;
+    const int Xw = (wlo + wi) << 5;
+    uint32_t keep = 0u;  // this lane's 8 pixels of the word, inside [X0, X1]
+    if (wi < nwords) {
+        keep = 0xFFu << (8 * q);
         if (Xw < X0) keep &= 0xFFFFFFFFu << (X0 - Xw);
         if (Xw + 31 > X1) keep &= 0xFFFFFFFFu >> (Xw + 31 - X1);
-        for (int y = y0 + (int)(threadIdx.x >> 3); y <= y1; y += T / 8) {
-            uint32_t m = im.word((uint32_t)(wlo + sub), (uint32_t)y) & keep;
-            if (!m) continue;
-            const float cy = __fsub_rn((float)y + 0.5f, py);
-            const float cy2 = __fmul_rn(cy, cy);
-            while (m) {
-                const int x = Xw + __ffs(m) - 1 - (int)im.pad;
-                m &= m - 1u;
-                const float cx = __fsub_rn((float)x + 0.5f, px);
-                const float d2 = __fadd_rn(__fmul_rn(cx, cx), cy2);
-                if (d2 < a2) near2 = fmaxf(near2, d2);
-                else {
-                    far2 = fminf(far2, d2);
-                    if (d2 <= z2) {
-                        const uint32_t i = atomicAdd(&sh.list_n, 1u);
-                        if (i < (uint32_t)LSD_PX_CAP) sh.px[i] = (uint32_t)(x - fx + 128) | ((uint32_t)(y - fy + 128) << 8);
-                    }
-                }
+    }
+    const uint32_t gx = (uint32_t)(Xw + 8 * q - (int)im.pad - fx + 160);
+    constexpr int RS = T / 32;  // rows per pass
+    for (int yb = y0 + (int)(threadIdx.x >> 5); yb <= y1; yb += 4 * RS) {  // warp-uniform trip count
+        uint32_t mm[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // four independent loads in flight
+            const int y = yb + u * RS;
+            mm[u] = (keep && y <= y1) ? im.word((uint32_t)(wlo + wi), (uint32_t)y) & keep : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t m8 = mm[u] >> (8 * q);
+            const uint32_t have = __ballot_sync(0xFFFFFFFFu, m8 != 0u);
+            if (have) {  // one shared-memory atomic per warp and row
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&sh.grp_n, (uint32_t)__popc(have));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0) + (uint32_t)__popc(have & ((1u << lane) - 1u));
+                if (m8 && base < (uint32_t)LSD_GRP_CAP)
+                    sh.grp[base] = m8 | (gx << 8) | ((uint32_t)(yb + u * RS - fy + 128) << 17);
+            }
+        }
+    }
+}
+
+// Stage 2: one pixel per thread (8 threads per listed quarter) -> OR its ray span into the bitmap of
+// each ring it lies in; reduce the nearest / farthest white distances around the inner disc into
+// sh.near2 / sh.far2 (float bits; positive floats order like their bit patterns).
+template <int T>
+__device__ __forceinline__ void lsd_mark_rays(const uint32_t* __restrict__ span_tab, float px, float py, const smh_lsd_filter& F,
+                                              uint32_t n_grp, LsdShared& sh) {
+    if (n_grp > (uint32_t)LSD_GRP_CAP) {  // too many white pixels around: mark everything (uniform)
+        for (int i = threadIdx.x; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0xFFFFFFFFu;
+        if (threadIdx.x == 0) sh.far2 = 0u;  // nothing is known about the surroundings: no dead cluster
+        return;
+    }
+    const int fx = (int)px, fy = (int)py;
+    const float hx = px - (float)fx, hy = py - (float)fy;  // 0 or 0.5
+    const uint32_t* tab = span_tab + ((hx != 0.0f ? 1 : 0) + (hy != 0.0f ? 2 : 0)) * (LSD_SPAN_N * LSD_SPAN_N) + LSD_SPAN_R * LSD_SPAN_N + LSD_SPAN_R;
+    const float a2 = F.r2_lo[0], z2 = F.r2_hi[F.nw - 1];
+    float near2 = 0.0f, far2 = 3.0e38f;
+    const int bit = threadIdx.x & 7;
+    for (uint32_t g = threadIdx.x >> 3; g < n_grp; g += T / 8) {
+        const uint32_t e = sh.grp[g];
+        if (!((e >> bit) & 1u)) continue;
+        const int ox = (int)((e >> 8) & 0x1FFu) - 160 + bit, oy = (int)(e >> 17) - 128;
+        const float cx = __fsub_rn((float)(fx + ox) + 0.5f, px), cy = __fsub_rn((float)(fy + oy) + 0.5f, py);
+        const float d2 = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));
+        if (d2 < a2) near2 = fmaxf(near2, d2);
+        else {
+            far2 = fminf(far2, d2);
+            if (d2 <= z2) {
+                const uint32_t sp = __ldg(tab + oy * LSD_SPAN_N + ox);
+                const int lo = (int)(int16_t)(sp & 0xFFFFu), hi = (int)(int16_t)(sp >> 16);
+#pragma unroll
+                for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+                    if (j < F.nw && d2 >= F.r2_lo[j] && d2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(sh.bits[j], lo, hi, or_if_new);
             }
         }
     }
@@ -708,25 +947,15 @@ __device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float 
     }
 }
 
-// Stage 2: one listed pixel per thread -> OR its ray interval into the bitmap of each ring it lies in.
-template <int T>
-__device__ __forceinline__ void lsd_mark_rays(float px, float py, const smh_lsd_filter& F, uint32_t n_listed, LsdShared& sh) {
-    const int fx = (int)px, fy = (int)py;
-    if (n_listed > (uint32_t)LSD_PX_CAP) {  // too many ring pixels: mark everything (uniform)
-        for (int i = threadIdx.x; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0xFFFFFFFFu;
-        return;
-    }
-    for (uint32_t i = threadIdx.x; i < n_listed; i += T) {
-        const uint32_t e = sh.px[i];
-        const float cx = __fsub_rn((float)(fx + (int)(e & 0xFFu) - 128) + 0.5f, px);
-        const float cy = __fsub_rn((float)(fy + (int)((e >> 8) & 0xFFu) - 128) + 0.5f, py);
-        const float d2 = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));
-        int lo, hi;
-        smh_lsd_filter_span(cx, cy, d2, &lo, &hi);
+// position of the n-th (0-based) set bit of mask (n < popc(mask))
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int n) {
+    int pos = 0;
 #pragma unroll
-        for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
-            if (j < F.nw && d2 >= F.r2_lo[j] && d2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(sh.bits[j], lo, hi, atomicOr);
+    for (int s = 16; s; s >>= 1) {
+        const int c = __popc((mask >> pos) & ((1u << s) - 1u));
+        if (n >= c) { n -= c; pos += s; }
     }
+    return pos;
 }
 
 // Stage 3: AND the usable windows, compact the surviving ray indices into sh.rays (ascending).
@@ -751,18 +980,26 @@ __device__ __forceinline__ uint32_t lsd_build_ray_list(float px, float py, const
         if (lane >= o) incl += up;
     }
     if (lane == 31) sh.wsum[warp] = incl;
-    __syncthreads();  // bitmaps and the pixel list are dead from here on
+    if (tid < SMH_LSD_BITMAP_WORDS) sh.bits[0][tid] = wv;  // window 0's bitmap now holds the AND
+    __syncthreads();
     uint32_t off = incl - c, total = 0;
 #pragma unroll
     for (int k = 0; k < T / 32; k++) { const uint32_t s = sh.wsum[k]; if (k < warp) off += s; total += s; }
-    while (wv) {
-        sh.rays[off++] = (uint16_t)(tid * 32 + __ffs(wv) - 1);
-        wv &= wv - 1u;
-    }
-    for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
-    if (tid == 0) { sh.list_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    if (tid < SMH_LSD_BITMAP_WORDS) sh.pre[tid] = off;  // rays before word tid
     __syncthreads();
-    return total;
+    // slot t of the list: the word whose prefix range holds t, then the (t - prefix)-th set bit of it
+    for (uint32_t t = tid; t < total; t += T) {
+        int lo = 0, hi = SMH_LSD_BITMAP_WORDS - 1;  // last word with pre[word] <= t
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sh.pre[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        sh.rays[t] = (uint16_t)(lo * 32 + nth_set_bit(sh.bits[0][lo], (int)(t - sh.pre[lo])));
+    }
+    __syncthreads();
+    for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
+    if (tid == 0) { sh.grp_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    return total;  // the next writers of bits / near2 / far2 are behind the barrier of the ray search or of the next seed pick
 }
 
 // The rays of one seed, spread over the CTA; the winner is the LAST index among the longest rays
@@ -818,6 +1055,16 @@ __device__ __forceinline__ void chunk_clear(uint32_t* chunk, uint32_t tx, uint32
     }
 }
 
+__device__ __forceinline__ void chunk_set(uint32_t* bm, uint32_t tx, uint32_t pad, int r, int xlo, int xhi) {
+    const int Xlo = xlo + (int)pad, Xhi = xhi + (int)pad;
+    for (int wd = Xlo >> 5; wd <= (Xhi >> 5); wd++) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (wd == (Xlo >> 5)) m &= 0xFFFFFFFFu << (Xlo & 31);
+        if (wd == (Xhi >> 5)) m &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
+        atomicOr(&bm[(uint32_t)r * tx + (uint32_t)wd], m);
+    }
+}
+
 // lsd::find_lines for whole frames (vision-common/src/lsd.rs:60-105).  One CTA works on one frame
 // at a time (persistent CTAs pull frames from a counter).  Per frame the bitmap is walked one
 // tile-row (32 pixel rows) at a time, held row-major in shared memory as the set of pixels that
@@ -833,7 +1080,8 @@ template <bool STATS>
 __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs a) {
     constexpr int T = LSD_THREADS;
     __shared__ LsdShared sh;
-    extern __shared__ uint32_t chunk[];  // [32][tx] current tile-row, row-major
+    extern __shared__ uint32_t chunk[];  // [32][tx] current tile-row, row-major: pixels that can still become seeds
+    uint32_t* fringe = chunk + 32u * a.g.tx;  // [32][tx] pixels inside the uncertain rim of some line's band
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t TX = a.g.tx, W = a.g.w, H = a.g.h, PAD = a.g.pad;
@@ -846,7 +1094,7 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
     const bool dead_ok = F.nw >= 1 && F.border[0] == 0;  // "ring 1 empty => no line" holds for every seed
 
     for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
-    if (tid == 0) { sh.list_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    if (tid == 0) { sh.grp_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
 
     while (true) {
         __syncthreads();
@@ -863,42 +1111,53 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
 
         uint32_t steps = 0, seeds = 0, pruned = 0;
         int n = 0, par = 0;
+        LSD_PROF_DECL
         for (uint32_t tyi = 0; tyi < a.g.ty && n < SMH_LSD_MAX_LINES; tyi++) {
             // ---- load the tile-row (contiguous in memory), transposed to row-major ------------
             {
                 const uint32_t* src = im.p + (uint64_t)tyi * NW;
-                for (uint32_t i = tid; i < NW; i += T) chunk[(i & 31u) * TX + (i >> 5)] = __ldg(src + i);
+                for (uint32_t i = tid; i < NW; i += T) {
+                    const uint32_t o = (i & 31u) * TX + (i >> 5);
+                    chunk[o] = __ldg(src + i);
+                    fringe[o] = 0u;
+                }
                 if (tyi + 1 < a.g.ty)  // pull the next tile-row into L2 while this one is searched
                     for (uint32_t i = tid * 32u; i < NW; i += T * 32u) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + NW + i));
             }
             __syncthreads();
             const int row0 = (int)(tyi * 32u);
             const int nd = STATS ? 0 : (int)min(sh.n_dead, (uint32_t)LSD_DEAD);
-            // ---- strike off what the lines (and dead clusters) found so far cover for sure -----
+            // ---- strike off what the lines (and dead clusters) found so far cover for sure; mark
+            //      the fringe of every line's band for the exact test ------------------------------
             for (int i = tid; i < 32 * (n + nd); i += T) {
                 const int r = i & 31, l = i >> 5, y = row0 + r;
-                int xlo, xhi;
                 if (l < n) {
-                    if (sure_interval(sh.lines[l], (float)y, (int)W, xlo, xhi)) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
+                    const Band b = line_band(sh.lines[l], (float)y, (int)W);
+                    if (b.ilo <= b.ihi) {
+                        chunk_clear(chunk, TX, PAD, r, b.ilo, b.ihi);
+                        if (b.olo < b.ilo) chunk_set(fringe, TX, PAD, r, b.olo, b.ilo - 1);
+                        if (b.ohi > b.ihi) chunk_set(fringe, TX, PAD, r, b.ihi + 1, b.ohi);
+                    } else if (b.olo <= b.ohi) chunk_set(fringe, TX, PAD, r, b.olo, b.ohi);
                 } else {
                     const float4 d = sh.dead[l - n];
                     const float dy = (float)y - d.y, r2 = d.w - dy * dy;
                     if (r2 > 0.0f) {
                         const float hw = sqrtf(r2) - 0.01f;
-                        xlo = max((int)ceilf(d.x - hw), 0); xhi = min((int)floorf(d.x + hw), (int)W - 1);
+                        const int xlo = max((int)ceilf(d.x - hw), 0), xhi = min((int)floorf(d.x + hw), (int)W - 1);
                         if (xlo <= xhi) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
                     }
                 }
             }
             __syncthreads();
-            // ---- the reference's float test for what is left (own words only) ------------------
+            // ---- the reference's float test for the fringe pixels (own words only) -------------
             bool any_white = false;
             for (uint32_t i = own0; i < own1; i++) {
                 uint32_t m = chunk[i];
-                if (m && n > 0) {
+                uint32_t todo = m & fringe[i];
+                if (todo) {
                     const uint32_t r = i / TX, wd = i - r * TX;
-                    for (uint32_t bits = m; bits; bits &= bits - 1u) {
-                        const int b = __ffs(bits) - 1;
+                    for (; todo; todo &= todo - 1u) {
+                        const int b = __ffs(todo) - 1;
                         const float fx = (float)((int)(wd * 32u) + b - (int)PAD), fy = (float)(row0 + (int)r);
                         for (int l = 0; l < n; l++)
                             if (suppressed_by(sh.lines[l], fx, fy)) { m &= ~(1u << b); break; }
@@ -907,7 +1166,9 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                 }
                 any_white |= m != 0u;
             }
-            if (!__syncthreads_or(any_white)) continue;
+            const bool some_white = __syncthreads_or(any_white);
+            LSD_PROF(0);  // tile-row load + strike-off
+            if (!some_white) continue;
 
             // ---- seeds of this tile-row, in raster order ---------------------------------------
             while (true) {
@@ -923,6 +1184,7 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
 #pragma unroll
                 for (int k = 0; k < T / 32; k++) seed = min(seed, sh.smin[par][k]);
                 par ^= 1;
+                LSD_PROF(1);  // seed pick
                 if (seed == 0xFFFFFFFFu) break;  // uniform
                 if (cand == seed) chunk[seed >> 5] &= ~(1u << (seed & 31u));  // the owner takes it off
                 const uint32_t sr = (seed >> 5) / TX, swd = (seed >> 5) - sr * TX;
@@ -938,10 +1200,11 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                         const float ex = sx - d.x, ey = sy - d.y;
                         in = ex * ex + ey * ey < d.w;
                     }
-                    if (__any_sync(0xFFFFFFFFu, in)) { pruned++; continue; }  // uniform: same data in every warp
+                    if (__any_sync(0xFFFFFFFFu, in)) { pruned++; LSD_PROF(2); continue; }  // uniform: same data in every warp
                 }
                 float px, py;
                 get_centre_warp(im, sx, sy, px, py);  // same value in every warp
+                LSD_PROF(3);  // get_centre
                 int n_rays = -1;  // all
                 if (F.nw > 0) {
                     if (dead_ok) {
@@ -951,15 +1214,17 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                             const float ex = px - d.x, ey = py - d.y;
                             in = ex * ex + ey * ey < d.z;
                         }
-                        if (__any_sync(0xFFFFFFFFu, in)) { pruned++; continue; }
+                        if (__any_sync(0xFFFFFFFFu, in)) { pruned++; LSD_PROF(2); continue; }
                     }
                     lsd_scan_window<T>(im, px, py, F, sh);
                     __syncthreads();
-                    const uint32_t n_listed = sh.list_n;
-                    const float near2 = __uint_as_float(sh.near2), far2 = __uint_as_float(sh.far2);
-                    lsd_mark_rays<T>(px, py, F, n_listed, sh);
+                    LSD_PROF(4);  // window scan
+                    lsd_mark_rays<T>(a.span_tab, px, py, F, sh.grp_n, sh);
                     __syncthreads();
+                    LSD_PROF(5);  // ray marking
+                    const float near2 = __uint_as_float(sh.near2), far2 = __uint_as_float(sh.far2);
                     n_rays = (int)lsd_build_ray_list<T>(px, py, F, sh);
+                    LSD_PROF(6);  // ray list
                     if (n_rays == 0) {  // uniform: no ray can exceed the minimum length
                         pruned++;
                         // every white pixel is within sqrt(near2) of the seed or beyond dfar: a seed at distance
@@ -990,12 +1255,15 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                     }
                 }
                 float best[3];
-                if (fast)
+                if (fast && n_rays >= 0 && a.gap_limit <= 32)
+                    longest_ray_warps<T, STATS>(im, a.rays, a.ckpt, a.n_ckpt, sh.rays, n_rays, px, py, a.gap_limit, best, sh.keys, sh.ends, steps);
+                else if (fast)
                     longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
                                        [&](float dx, float dy, float& ex, float& ey) { return march_fast<STATS>(im, px, py, a.gap_limit, dx, dy, ex, ey, steps); });
                 else
                     longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
                                        [&](float dx, float dy, float& ex, float& ey) { return march(im, px, py, a.max_gap, dx, dy, ex, ey, steps); });
+                LSD_PROF(7);  // march
                 if (best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
                     float c1x, c1y;
                     get_centre_warp(im, best[1], best[2], c1x, c1y);
@@ -1007,27 +1275,32 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                     }
                     n++;
                     if (n == SMH_LSD_MAX_LINES) break;  // `break 'row`
-                    // the new line suppresses pixels for good: strike them off this tile-row now
-                    if (tid < 32) {
-                        int xlo, xhi;
-                        if (sure_interval(line, (float)(row0 + tid), (int)W, xlo, xhi)) chunk_clear(chunk, TX, PAD, tid, xlo, xhi);
-                    }
-                    __syncthreads();
-                    for (uint32_t i = own0; i < own1; i++) {
-                        uint32_t m = chunk[i];
-                        if (m) {
-                            const uint32_t r = i / TX, wd = i - r * TX;
-                            for (uint32_t bits = m; bits; bits &= bits - 1u) {
-                                const int b = __ffs(bits) - 1;
-                                if (suppressed_by(line, (float)((int)(wd * 32u) + b - (int)PAD), (float)(row0 + (int)r))) m &= ~(1u << b);
+                    // the new line suppresses pixels for good: strike them off this tile-row now (own words;
+                    // approximate distance first, the reference's float test only in the uncertain rim)
+                    {
+                        const float ldx = line.z - line.x, ldy = line.w - line.y, l2 = ldx * ldx + ldy * ldy;
+                        const float in2 = 48.9f * l2, out2 = 51.1f * l2;
+                        for (uint32_t i = own0; i < own1; i++) {
+                            uint32_t m = chunk[i];
+                            if (m) {
+                                const uint32_t r = i / TX, wd = i - r * TX;
+                                const float fy = (float)(row0 + (int)r);
+                                for (uint32_t bits = m; bits; bits &= bits - 1u) {
+                                    const int b = __ffs(bits) - 1;
+                                    const float fx = (float)((int)(wd * 32u) + b - (int)PAD);
+                                    const float cr = (fx - line.x) * ldy - (fy - line.y) * ldx, c2 = cr * cr;
+                                    if (c2 < in2 || (!(c2 > out2) && suppressed_by(line, fx, fy))) m &= ~(1u << b);
+                                }
+                                chunk[i] = m;
                             }
-                            chunk[i] = m;
                         }
                     }
                 }
             }
             __syncthreads();
+            LSD_PROF(8);  // accept + strike-off of new lines, end of tile-row
         }
+        LSD_PROF_FLUSH;
         if (tid == 0) a.n_lines[f] = (uint32_t)n;
         if (STATS) {
             steps = __reduce_add_sync(0xFFFFFFFFu, steps);

@@ -90,6 +90,9 @@ struct smh_b200 {
     std::string err;
     std::atomic<uint64_t> launches{0};
     float2* d_rays = nullptr;  // 3600 (cos, sin)
+    float2* d_ckpt = nullptr;  // accumulated ray offsets every LSD_CKPT steps, [3600][n_ckpt]
+    uint32_t n_ckpt = 0;
+    uint32_t* d_span = nullptr;  // ray span per pixel offset (line-search filter)
     uint32_t* d_lut = nullptr; // marker predicate bit table, 2^24 bits
 
     // ---- single-frame (trait) state ----
@@ -223,9 +226,24 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
         h->launches++;
         CU(h, cudaGetLastError());
     }
+    // offsets table of the warp-per-ray march: long enough for any ray inside this mask plus two blocks
+    {
+        const double diag = sqrt((double)P.bg.w * P.bg.w + (double)P.bg.h * P.bg.h);
+        const uint32_t need = ((uint32_t)diag / 32u + 4u) * (32u / smh::LSD_CKPT);
+        if (need > h->n_ckpt) {
+            CU(h, cudaDeviceSynchronize());
+            cudaFree(h->d_ckpt); h->d_ckpt = nullptr; h->n_ckpt = 0;
+            CU(h, cudaMalloc(&h->d_ckpt, (size_t)SMH_LSD_RAYS * need * sizeof(float2)));
+            smh::k_build_ray_ckpt<<<(SMH_LSD_RAYS + 127) / 128, 128, 0, st>>>(h->d_rays, need, h->d_ckpt);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            CU(h, cudaStreamSynchronize(st));
+            h->n_ckpt = need;
+        }
+    }
     smh::LsdArgs a{};
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
-    a.rays = h->d_rays; a.max_gap = max_gap;
+    a.rays = h->d_rays; a.ckpt = h->d_ckpt; a.n_ckpt = h->n_ckpt; a.span_tab = h->d_span; a.max_gap = max_gap;
     // `gap.0 >= max_gap` on an integer-valued counter <=> counter >= ceil(max_gap)
     a.gap_limit = (max_gap != max_gap || max_gap >= 2147483648.0f) ? 2147483647 : (max_gap <= -2147483648.0f ? -2147483647 : (int)ceilf(max_gap));
     a.prune = prune ? 1 : 0;
@@ -235,7 +253,7 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     a.stats = stats ? P.stats : nullptr;
     CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
     // persistent grid: as many CTAs as stay resident (or one per frame when there are fewer)
-    const size_t dyn = (size_t)P.bg.tx * 32u * sizeof(uint32_t);  // one tile-row of the bitmap
+    const size_t dyn = (size_t)P.bg.tx * 32u * sizeof(uint32_t) * 2u;  // one tile-row of the bitmap + its fringe map
     {
         // the limit is a property of the kernel on this device, shared by every handle: only ever raise it
         static std::mutex mu;
@@ -361,6 +379,13 @@ int32_t smh_b200_create(int32_t device, smh_b200** out) {
     }
     CUC(cudaMalloc(&h->d_rays, sizeof(float2) * SMH_LSD_RAYS));
     CUC(cudaMemcpy(h->d_rays, rays.data(), sizeof(float2) * SMH_LSD_RAYS, cudaMemcpyHostToDevice));
+    {   // ray spans by pixel offset for the line-search filter
+        const int n_span = 4 * smh::LSD_SPAN_N * smh::LSD_SPAN_N;
+        CUC(cudaMalloc(&h->d_span, (size_t)n_span * sizeof(uint32_t)));
+        smh::k_build_span_table<<<(n_span + 255) / 256, 256, 0, h->s_main>>>(h->d_span);
+        h->launches++;
+        CUC(cudaGetLastError());
+    }
     // exact marker predicate memoised over all 2^24 colours (2 MB, stays in L2)
     CUC(cudaMalloc(&h->d_lut, (1u << 24) / 8));
     smh::k_build_marker_lut<<<(1u << 19) / 256, 256, 0, h->s_main>>>(h->d_lut);
@@ -380,7 +405,7 @@ void smh_b200_destroy(smh_b200* h) {
     cudaDeviceSynchronize();
     free_single(h);
     h->batch.release(); h->pipe[0].release(); h->pipe[1].release();
-    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
+    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
     if (h->s_main) cudaStreamDestroy(h->s_main);
@@ -397,6 +422,16 @@ int32_t smh_b200_bind_thread(smh_b200* h) {
 }
 
 uint64_t smh_b200_launch_count(smh_b200* h) { return h ? h->launches.load() : 0; }
+
+// tuning aid (not in the header): per-phase cycle counters of k_lsd, zero unless built with -DLSD_PROFILE
+int32_t smh_b200_debug_lsd_profile(smh_b200* h, uint64_t out[16], int32_t reset) {
+    if (!h || !out) return SMH_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    CU(h, cudaMemcpyFromSymbol(out, smh::g_lsd_prof, 16 * sizeof(uint64_t)));
+    if (reset) { uint64_t z[16] = {0}; CU(h, cudaMemcpyToSymbol(smh::g_lsd_prof, z, sizeof z)); }
+    return SMH_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // per-frame trait methods
