@@ -610,6 +610,83 @@ __device__ __forceinline__ float march_fast(const Bits& im, float px, float py, 
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
 }
 
+// ---- exact ray filter (smh_lsd_filter.h): per seed, scan the pixel window around it, list the
+//      white pixels that lie in one of the step-window rings, mark the rays each can serve, and
+//      march only the rays marked in every window ---------------------------------------------
+#ifndef LSD_THREADS_N
+#define LSD_THREADS_N 256
+#endif
+#ifndef LSD_MIN_CTAS
+#define LSD_MIN_CTAS 3
+#endif
+constexpr int LSD_THREADS = LSD_THREADS_N;
+constexpr int LSD_DEAD = 16;      // remembered dead clusters per frame
+
+// Optional per-phase cycle accounting of k_lsd (build with -DLSD_PROFILE; tools/lsd_profile.py reads it)
+__device__ unsigned long long g_lsd_prof[16];
+#ifdef LSD_PROFILE
+#define LSD_PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define LSD_CNT(k, v) do { prof_acc[k] += (unsigned long long)(v); } while (0)
+#define LSD_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (unsigned long long)(now__ - prof_t); prof_t = now__; } while (0)
+#define LSD_PROF_FLUSH do { if (threadIdx.x == 0) for (int k__ = 0; k__ < 16; k__++) atomicAdd(&g_lsd_prof[k__], prof_acc[k__]); } while (0)
+#else
+#define LSD_PROF_DECL
+#define LSD_CNT(k, v) do { } while (0)
+#define LSD_PROF(k) do { } while (0)
+#define LSD_PROF_FLUSH do { } while (0)
+#endif
+
+struct LsdShared {
+    float4 lines[SMH_LSD_MAX_LINES];
+    float4 dead[LSD_DEAD];  // (x, y, rho^2, raw^2): centred seeds closer than rho to (x, y) cannot yield a line
+    unsigned long long keys[LSD_THREADS / 32];
+    float2 ends[LSD_THREADS / 32];
+    uint32_t smin[2][LSD_THREADS / 32];  // double-buffered: a seed may be dismissed without another barrier
+    uint32_t wsum[LSD_THREADS / 32];
+    uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
+    uint32_t pre[SMH_LSD_BITMAP_WORDS + 3];  // rays before each word of the combined bitmap
+    uint32_t grp_cnt[LSD_THREADS / 32];  // entries per warp segment of grp[]
+    uint32_t near2, far2, n_dead, frame, surv_n;
+    uint32_t surv[LSD_THREADS];    // rays still alive after the in-window march: k | gap << 16
+    union {
+        uint32_t grp[1024];            // LSD_GRP_CAP non-empty pixel quarters of the window around the seed
+        uint16_t rays[SMH_LSD_RAYS];   // compacted indices of the rays to march
+    };
+};
+
+constexpr int LSD_SPAN_R = 99;                   // largest window radius (smh_lsd_filter_init: gap_limit <= 48)
+constexpr int LSD_SPAN_N = 2 * LSD_SPAN_R + 1;
+
+// The neighbourhood of a seed, copied once from the bitmap into shared memory: rows [y0, y1], 8 words
+// per row starting at bitmap word wlo.  get_centre of the seed, the ring scan and the first
+// LSD_WIN_STEPS samples of every ray read it instead of global memory.
+constexpr int LSD_WIN_EXTRA = 3;                                   // get_centre moves the seed by < 3 px
+constexpr int LSD_WIN_ROWS = 2 * (LSD_SPAN_R + LSD_WIN_EXTRA) + 1;  // 205
+struct WinView {
+    const uint32_t* p;
+    int x0, y0, x1, y1, wlo;
+    uint32_t pad, w, h;  // image geometry (w, h: for get_centre's clamping)
+    __device__ __forceinline__ bool white(uint32_t x, uint32_t y) const {
+        const uint32_t X = x + pad;
+        return (p[((int)y - y0) * 8 + (int)(X >> 5) - wlo] >> (X & 31u)) & 1u;
+    }
+};
+template <int T>
+__device__ __forceinline__ WinView lsd_load_window(const Bits& im, uint32_t* win, int sx, int sy, int radius) {
+    WinView v;
+    v.p = win; v.pad = im.pad; v.w = im.w; v.h = im.h;
+    v.x0 = max(sx - radius, 0); v.x1 = min(sx + radius, (int)im.w - 1);
+    v.y0 = max(sy - radius, 0); v.y1 = min(sy + radius, (int)im.h - 1);
+    v.wlo = (v.x0 + (int)im.pad) >> 5;
+    const int nwords = ((v.x1 + (int)im.pad) >> 5) - v.wlo + 1;  // <= 8 for radius <= 102
+    const int total = (v.y1 - v.y0 + 1) * 8;
+    for (int i = threadIdx.x; i < total; i += T) {  // independent loads: one memory round trip
+        const int r = i >> 3, wi = i & 7;
+        win[i] = wi < nwords ? im.word((uint32_t)(v.wlo + wi), (uint32_t)(v.y0 + r)) : 0u;
+    }
+    return v;
+}
+
 // ---- one ray per WARP -------------------------------------------------------------------------
 // The accumulated offsets xo_n = fl(xo_{n-1} + dx) of a ray do not depend on the seed, so they are
 // tabulated once per handle for every ray direction at every LSD_CKPT-th step (k_build_ray_ckpt).
@@ -662,6 +739,11 @@ template <bool STATS>
 __device__ __forceinline__ bool ray_block_decide(const RayBlock& b, float xprev, float yprev, uint32_t& gap_in, int gap_limit,
                                                  float& gx, float& gy, uint32_t& steps) {
     const uint32_t inb = __ballot_sync(0xFFFFFFFFu, b.ok), wh = __ballot_sync(0xFFFFFFFFu, (b.word >> b.bit) & 1u);
+    if ((inb & wh) == 0xFFFFFFFFu) {  // all inside, all white (the body of a marker line)
+        if (STATS) steps += 32u;
+        gap_in = 0u;
+        return false;
+    }
     const int first_out = __ffs(~inb) - 1;  // -1: the whole block is inside
     const uint32_t valid = first_out < 0 ? 0xFFFFFFFFu : ((1u << first_out) - 1u);
     const uint32_t black = ~wh & valid;
@@ -697,70 +779,155 @@ __device__ __forceinline__ float ray_finish(const Bits& im, float gx, float gy, 
     return __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
 }
 
-// The listed rays of one seed, LSD_RAYS_PER_WARP rays per warp at a time: the first block of each
-// (where most rays already end) is fetched for all of them before any is tested, so their table
-// and bitmap loads overlap; survivors continue block by block with the next checkpoint prefetched.
-// Same last-index argmax as longest_ray_cta.  Preconditions: 1 <= gap_limit <= 32, seed inside the
-// image, the table covers every step a ray can take inside the image plus two blocks.
-#ifndef LSD_RAYS_PER_WARP
-#define LSD_RAYS_PER_WARP 1
-#endif
+// First `limit` samples (a multiple of LSD_BATCH) of one ray per LANE, read from the seed's window in
+// shared memory (all of them lie inside it).  Returns 0: still marching (gap = current run of
+// non-white samples), 1: stopped on a gap that began at (gx, gy), 2: (gx, gy) is the first sample
+// outside the image.  Same arithmetic as march_fast.
+template <bool STATS, typename WIN>
+__device__ __forceinline__ int march_window(const WIN& wv, int limit, float px, float py, int gap_limit, float dx, float dy,
+                                            float& gx, float& gy, int& gap, uint32_t& steps) {
+    float x = px, y = py, xo = 0.0f, yo = 0.0f;
+    gx = px; gy = py; gap = 0;
+    int state = 0;
+    for (int n0 = 0; n0 < limit && state == 0; n0 += LSD_BATCH) {
+        float xs[LSD_BATCH], ys[LSD_BATCH];
+        uint32_t wh = 0, inb = 0;  // bit u: sample u is white / inside the image
+#pragma unroll
+        for (int u = 0; u < LSD_BATCH; u++) {
+            xs[u] = x; ys[u] = y;
+            const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000);
+            const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000);
+            if (ix < wv.w && iy < wv.h) {
+                inb |= 1u << u;
+                wh |= (wv.white(ix, iy) ? 1u : 0u) << u;
+            }
+            xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
+            x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
+        }
+#pragma unroll
+        for (int u = 0; u < LSD_BATCH; u++) {
+            if (state == 0) {
+                if (!((inb >> u) & 1u)) { state = 2; gx = xs[u]; gy = ys[u]; }
+                else {
+                    if (STATS) steps++;
+                    const bool black = !((wh >> u) & 1u);
+                    if (black && gap >= gap_limit) state = 1;
+                    else {
+                        if (black && gap == 0) { gx = xs[u]; gy = ys[u]; }
+                        gap = black ? gap + 1 : 0;
+                    }
+                }
+            }
+        }
+    }
+    return state;
+}
+
+// The listed rays of one seed.  Phase 1, one ray per lane: the first `win_steps` samples from the
+// window in shared memory — most rays end there.  Phase 2, one ray per warp: the survivors continue
+// block by block on the global bitmap (ray_block_*), the next checkpoint prefetched.  Same
+// last-index argmax as longest_ray_cta.  Preconditions: 1 <= gap_limit <= 32, seed inside the
+// image, the offsets table covers every step a ray can take inside the image plus two blocks,
+// win_steps a multiple of 32 whose samples all fall inside the window.
 template <int T, bool STATS>
-__device__ __forceinline__ void longest_ray_warps(const Bits& im, const float2* __restrict__ rays, const float2* __restrict__ ckpt, uint32_t n_ckpt,
-                                                  const uint16_t* list, int n_rays, float px, float py, int gap_limit, float (&best)[3],
-                                                  unsigned long long* s_keys, float2* s_ends, uint32_t& steps) {
-    constexpr int R = LSD_RAYS_PER_WARP;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & (LSD_CKPT - 1);
+__device__ __forceinline__ void longest_ray_hybrid(const Bits& im, const WinView& wv, int win_steps, const float2* __restrict__ rays,
+                                                   const float2* __restrict__ ckpt, uint32_t n_ckpt, const uint16_t* list, int n_rays,
+                                                   float px, float py, int gap_limit, float (&best)[3], LsdShared& sh, uint32_t& steps) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & (LSD_CKPT - 1);
     unsigned long long best_key = 0ull;
     float bex = px, bey = py;
     uint32_t st = 0;
-    for (int i0 = warp * R; i0 < n_rays; i0 += (T / 32) * R) {
-        int k[R]; float2 d[R]; const float2* ckp[R]; RayBlock blk[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            k[j] = (int)list[min(i0 + j, n_rays - 1)];
-            ckp[j] = ckpt + (uint64_t)k[j] * n_ckpt + (lane / LSD_CKPT);
-        }
-        float2 ck[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) { d[j] = __ldg(&rays[k[j]]); ck[j] = __ldg(ckp[j]); }
-#pragma unroll
-        for (int j = 0; j < R; j++) blk[j] = ray_block_fetch(im, ck[j], sub, d[j].x, d[j].y, px, py);
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            if (i0 + j >= n_rays) break;  // uniform
-            uint32_t gap_in = 0;
+    for (int base = 0; base < n_rays; base += T) {
+        // ---- phase 1 ---------------------------------------------------------------------------
+        const int i = base + tid;
+        bool alive = false;
+        int k = 0, gap = 0;
+        if (i < n_rays) {
+            k = (int)list[i];
+            const float2 d = __ldg(&rays[k]);
             float gx, gy;
-            RayBlock b = blk[j];
+            const int state = win_steps > 0 ? march_window<STATS>(wv, win_steps, px, py, gap_limit, d.x, d.y, gx, gy, gap, steps) : 0;
+            if (state == 0) alive = true;
+            else {
+                float ex, ey, len;
+                if (state == 1) {  // the gap's first sample is inside the image and not white: lib.rs:426-429 holds
+                    ex = __fsub_rn(gx, d.x); ey = __fsub_rn(gy, d.y);
+                    const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
+                    len = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                } else len = ray_finish(im, gx, gy, px, py, d.x, d.y, ex, ey);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k;
+                if (key >= best_key) { best_key = key; bex = ex; bey = ey; }
+            }
+        }
+        const uint32_t am = __ballot_sync(0xFFFFFFFFu, alive);
+        if (am) {
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(&sh.surv_n, (uint32_t)__popc(am));
+            slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + (uint32_t)__popc(am & ((1u << lane) - 1u));
+            if (alive) sh.surv[slot] = (uint32_t)k | ((uint32_t)gap << 16);
+        }
+        __syncthreads();
+        // ---- phase 2 ---------------------------------------------------------------------------
+        const int n_surv = (int)sh.surv_n;
+        const int c0 = win_steps / 32;
+        for (int j = warp; j < n_surv; j += T / 32) {
+            const uint32_t e = sh.surv[j];
+            const int k2 = (int)(e & 0xFFFFu);
+            uint32_t gap_in = e >> 16;
+            const float2 d = __ldg(&rays[k2]);
+            const float2* cp = ckpt + (uint64_t)k2 * n_ckpt + (lane / LSD_CKPT) + c0 * (32 / LSD_CKPT);
+            float2 c1 = __ldg(cp);
             float xprev = px, yprev = py;
-            if (!ray_block_decide<STATS>(b, xprev, yprev, gap_in, gap_limit, gx, gy, st)) {
-                const float2* cp = ckp[j] + 32 / LSD_CKPT;
-                float2 c1 = __ldg(cp);
-                while (true) {
-                    cp += 32 / LSD_CKPT;
-                    const float2 c2 = __ldg(cp);  // next block's checkpoint, in flight while this block is tested
-                    xprev = b.x; yprev = b.y;
-                    b = ray_block_fetch(im, c1, sub, d[j].x, d[j].y, px, py);
-                    if (ray_block_decide<STATS>(b, xprev, yprev, gap_in, gap_limit, gx, gy, st)) break;
-                    c1 = c2;
-                }
+            if (c0 > 0) {  // this lane's sample of block c0 - 1 (a gap may have begun there)
+                const float2 cq = __ldg(cp - 32 / LSD_CKPT);
+                float xo = cq.x, yo = cq.y;
+#pragma unroll
+                for (int q = 1; q < LSD_CKPT; q++)
+                    if (sub >= q) { xo = __fadd_rn(xo, d.x); yo = __fadd_rn(yo, d.y); }
+                xprev = __fadd_rn(xo, px); yprev = __fadd_rn(yo, py);
+            }
+            // two blocks in flight: block c+1 is fetched (table value loaded one iteration earlier) before
+            // block c is decided, so bitmap and table latencies overlap; what is fetched beyond the
+            // block where the ray ends is dropped
+            float gx, gy;
+            cp += 32 / LSD_CKPT;
+            float2 c2 = __ldg(cp);
+            RayBlock b = ray_block_fetch(im, c1, sub, d.x, d.y, px, py);
+            while (true) {
+                cp += 32 / LSD_CKPT;
+                const float2 c3 = __ldg(cp);
+                const RayBlock bn = ray_block_fetch(im, c2, sub, d.x, d.y, px, py);
+                if (ray_block_decide<STATS>(b, xprev, yprev, gap_in, gap_limit, gx, gy, st)) break;
+                xprev = b.x; yprev = b.y; b = bn; c2 = c3;
             }
             float ex, ey;
-            const float len = ray_finish(im, gx, gy, px, py, d[j].x, d[j].y, ex, ey);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k[j];
-            if (key >= best_key) { best_key = key; bex = ex; bey = ey; }  // ties go to the later ray
+            const float len = ray_finish(im, gx, gy, px, py, d.x, d.y, ex, ey);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k2;
+            if (key >= best_key) { best_key = key; bex = ex; bey = ey; }  // same in every lane
         }
+        __syncthreads();
+        if (tid == 0) sh.surv_n = 0u;  // next appended to behind another barrier (next round / next seed)
+        if (base + T < n_rays) __syncthreads();
     }
-    if (STATS && lane == 0) steps += st;  // summed over all threads later: count once per warp
-    if (lane == 0) { s_keys[warp] = best_key; s_ends[warp] = make_float2(bex, bey); }
+    if (STATS && lane == 0) steps += st;  // phase-2 samples: once per warp (steps are summed over all threads later)
+    // warp argmax of (len, k), then across the warps
+    unsigned long long wkey = best_key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, wkey, o);
+        wkey = other > wkey ? other : wkey;
+    }
+    const int src = __ffs(__ballot_sync(0xFFFFFFFFu, best_key == wkey)) - 1;
+    bex = __shfl_sync(0xFFFFFFFFu, bex, src); bey = __shfl_sync(0xFFFFFFFFu, bey, src);
+    if (lane == 0) { sh.keys[warp] = wkey; sh.ends[warp] = make_float2(bex, bey); }
     __syncthreads();
     int bw = 0;
-    unsigned long long bk = s_keys[0];
+    unsigned long long bk = sh.keys[0];
 #pragma unroll
-    for (int k2 = 1; k2 < T / 32; k2++) { const unsigned long long o = s_keys[k2]; if (o > bk) { bk = o; bw = k2; } }
+    for (int k2 = 1; k2 < T / 32; k2++) { const unsigned long long o = sh.keys[k2]; if (o > bk) { bk = o; bw = k2; } }
     best[0] = __uint_as_float((uint32_t)(bk >> 32));
-    best[1] = s_ends[bw].x;
-    best[2] = s_ends[bw].y;
+    best[1] = sh.ends[bw].x;
+    best[2] = sh.ends[bw].y;
 }
 
 // get_centre — vision-common/src/lsd.rs:5-44 (indices clamped where the reference is UB, D8) —
@@ -770,12 +937,14 @@ __device__ __forceinline__ void longest_ray_warps(const Bits& im, const float2* 
 // rebuilds its v by t successive +-1.0 adds, because the reference's `(v - pt).abs() < 5` sees the
 // accumulated rounding: across a binade boundary (e.g. 511.6 -> 512.6) five increments can leave
 // |v - pt| just below 5 and the walk takes a sixth step.
-__device__ __forceinline__ bool white_clamped(const Bits& im, float fx, float fy) {
+template <typename IMG>
+__device__ __forceinline__ bool white_clamped(const IMG& im, float fx, float fy) {
     uint32_t x = __float2uint_rz(fx), y = __float2uint_rz(fy);
     x = min(x, im.w - 1u); y = min(y, im.h - 1u);
     return im.white(x, y);
 }
-__device__ __forceinline__ void get_centre_warp(const Bits& im, float ptx, float pty, float& cx, float& cy) {
+template <typename IMG>
+__device__ __forceinline__ void get_centre_warp(const IMG& im, float ptx, float pty, float& cx, float& cy) {
     const int lane = threadIdx.x & 31, dir = lane >> 3, t = lane & 7;
     const float pt = dir < 2 ? ptx : pty;
     const float step = (dir & 1) ? 1.0f : -1.0f;
@@ -796,53 +965,11 @@ __device__ __forceinline__ void get_centre_warp(const Bits& im, float ptx, float
     cy = __fdiv_rn(__fadd_rn(up, down), 2.0f);
 }
 
-// ---- exact ray filter (smh_lsd_filter.h): per seed, scan the pixel window around it, list the
-//      white pixels that lie in one of the step-window rings, mark the rays each can serve, and
-//      march only the rays marked in every window ---------------------------------------------
-#ifndef LSD_THREADS_N
-#define LSD_THREADS_N 256
-#endif
-#ifndef LSD_MIN_CTAS
-#define LSD_MIN_CTAS 4
-#endif
-constexpr int LSD_THREADS = LSD_THREADS_N;
-constexpr int LSD_DEAD = 16;      // remembered dead clusters per frame
-
-// Optional per-phase cycle accounting of k_lsd (build with -DLSD_PROFILE; tools/lsd_profile.py reads it)
-__device__ unsigned long long g_lsd_prof[16];
-#ifdef LSD_PROFILE
-#define LSD_PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define LSD_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (unsigned long long)(now__ - prof_t); prof_t = now__; } while (0)
-#define LSD_PROF_FLUSH do { if (threadIdx.x == 0) for (int k__ = 0; k__ < 10; k__++) atomicAdd(&g_lsd_prof[k__], prof_acc[k__]); } while (0)
-#else
-#define LSD_PROF_DECL
-#define LSD_PROF(k) do { } while (0)
-#define LSD_PROF_FLUSH do { } while (0)
-#endif
-
-struct LsdShared {
-    float4 lines[SMH_LSD_MAX_LINES];
-    float4 dead[LSD_DEAD];  // (x, y, rho^2, raw^2): centred seeds closer than rho to (x, y) cannot yield a line
-    unsigned long long keys[LSD_THREADS / 32];
-    float2 ends[LSD_THREADS / 32];
-    uint32_t smin[2][LSD_THREADS / 32];  // double-buffered: a seed may be dismissed without another barrier
-    uint32_t wsum[LSD_THREADS / 32];
-    uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
-    uint32_t pre[SMH_LSD_BITMAP_WORDS + 3];  // rays before each word of the combined bitmap
-    uint32_t grp_n, near2, far2, n_dead, frame;
-    union {
-        uint32_t grp[1024];            // LSD_GRP_CAP non-empty pixel quarters of the window around the seed
-        uint16_t rays[SMH_LSD_RAYS];   // compacted indices of the rays to march
-    };
-};
-
 // Ray spans by pixel offset.  A seed centre is a multiple of 0.5 in each axis (get_centre of an
 // integer pixel), so the ray interval smh_lsd_filter_span() assigns to the pixel at integer offset
 // (ox, oy) from floor(seed) only depends on the offset and on the two half-pixel flags: it is
 // tabulated once per handle ([4][SPAN_N][SPAN_N] x (lo | hi << 16), int16 each) and the per-pixel
 // atan2 / sqrt of the marking step become one 4-byte load.
-constexpr int LSD_SPAN_R = 99;                   // largest window radius (smh_lsd_filter_init: gap_limit <= 48)
-constexpr int LSD_SPAN_N = 2 * LSD_SPAN_R + 1;
 __global__ void k_build_span_table(uint32_t* __restrict__ tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4 * LSD_SPAN_N * LSD_SPAN_N) return;
@@ -861,17 +988,17 @@ __device__ __forceinline__ void or_if_new(uint32_t* w, uint32_t m) {
     if ((*reinterpret_cast<volatile uint32_t*>(w) & m) != m) atomicOr(w, m);
 }
 
-// Stage 1: scan the (2R+1)^2 window around the seed in the bitmap.  A task is a quarter (8 pixels)
-// of one word of one window row; every non-empty quarter is appended to sh.grp as
-// mask | (x offset of its first pixel + 160) << 8 | (row offset + 128) << 17.
-constexpr int LSD_GRP_CAP = 1024;
+// Stage 1: list the non-empty pixel quarters (8 pixels of one word of one row) of the (2R+1)^2 window
+// around the centred seed: sh.grp[] = mask | (x offset of the quarter's first pixel + 160) << 8 |
+// (row offset + 128) << 17, offsets relative to floor(seed).
+constexpr int LSD_GRP_SEG = 1024 / (LSD_THREADS / 32);  // entries per warp segment of sh.grp
 template <int T>
-__device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
+__device__ __forceinline__ void lsd_scan_window(const WinView& wv, float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
     const int fx = (int)px, fy = (int)py, R = F.radius;  // px, py >= 0
-    const int x0 = max(fx - R, 0), x1 = min(fx + R, (int)im.w - 1);
-    const int y0 = max(fy - R, 0), y1 = min(fy + R, (int)im.h - 1);
-    const int X0 = x0 + (int)im.pad, X1 = x1 + (int)im.pad;
-    const int wlo = X0 >> 5, nwords = (X1 >> 5) - wlo + 1;  // <= 8 for R <= 99
+    const int x0 = max(fx - R, wv.x0), x1 = min(fx + R, wv.x1);
+    const int y0 = max(fy - R, wv.y0), y1 = min(fy + R, wv.y1);
+    const int X0 = x0 + (int)wv.pad, X1 = x1 + (int)wv.pad;
+    const int wlo = X0 >> 5, nwords = (X1 >> 5) - wlo + 1;
     const int lane = threadIdx.x & 31, wi = lane >> 2, q = lane & 3;
     const int Xw = (wlo + wi) << 5;
     uint32_t keep = 0u;  // this lane's 8 pixels of the word, inside [X0, X1]
@@ -880,68 +1007,113 @@ __device__ __forceinline__ void lsd_scan_window(const Bits& im, float px, float 
         if (Xw < X0) keep &= 0xFFFFFFFFu << (X0 - Xw);
         if (Xw + 31 > X1) keep &= 0xFFFFFFFFu >> (Xw + 31 - X1);
     }
-    const uint32_t gx = (uint32_t)(Xw + 8 * q - (int)im.pad - fx + 160);
-    constexpr int RS = T / 32;  // rows per pass
-    for (int yb = y0 + (int)(threadIdx.x >> 5); yb <= y1; yb += 4 * RS) {  // warp-uniform trip count
-        uint32_t mm[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {  // four independent loads in flight
-            const int y = yb + u * RS;
-            mm[u] = (keep && y <= y1) ? im.word((uint32_t)(wlo + wi), (uint32_t)y) & keep : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t m8 = mm[u] >> (8 * q);
-            const uint32_t have = __ballot_sync(0xFFFFFFFFu, m8 != 0u);
-            if (have) {  // one shared-memory atomic per warp and row
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&sh.grp_n, (uint32_t)__popc(have));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0) + (uint32_t)__popc(have & ((1u << lane) - 1u));
-                if (m8 && base < (uint32_t)LSD_GRP_CAP)
-                    sh.grp[base] = m8 | (gx << 8) | ((uint32_t)(yb + u * RS - fy + 128) << 17);
-            }
-        }
+    const uint32_t gx = (uint32_t)(Xw + 8 * q - (int)wv.pad - fx + 160);
+    const uint32_t* col = wv.p + (wlo + wi - wv.wlo);
+    const int warp = threadIdx.x >> 5;
+    uint32_t cnt = 0;  // entries of this warp's segment so far (uniform)
+    for (int y = y0 + warp; y <= y1; y += T / 32) {  // warp-uniform trip count
+        const uint32_t m8 = keep ? (col[(y - wv.y0) * 8] & keep) >> (8 * q) : 0u;
+        const uint32_t have = __ballot_sync(0xFFFFFFFFu, m8 != 0u);
+        const uint32_t slot = cnt + (uint32_t)__popc(have & ((1u << lane) - 1u));
+        if (m8 && slot < (uint32_t)LSD_GRP_SEG) sh.grp[warp * LSD_GRP_SEG + (int)slot] = m8 | (gx << 8) | ((uint32_t)(y - fy + 128) << 17);
+        cnt += (uint32_t)__popc(have);
     }
+    if (lane == 0) sh.grp_cnt[warp] = cnt;  // > LSD_GRP_SEG: overflow
 }
 
-// Stage 2: one pixel per thread (8 threads per listed quarter) -> OR its ray span into the bitmap of
-// each ring it lies in; reduce the nearest / farthest white distances around the inner disc into
-// sh.near2 / sh.far2 (float bits; positive floats order like their bit patterns).
+// bits lo..hi (any integers) that fall into word w of a bitmap
+__device__ __forceinline__ uint32_t range_mask(int w, int lo, int hi) {
+    const int s = max(lo - 32 * w, 0), e = min(hi - 32 * w, 31);
+    return s <= e ? ((0xFFFFFFFFu << s) & (0xFFFFFFFFu >> (31 - e))) : 0u;
+}
+
+// Stage 2: every warp marks the quarters it listed.  The ray spans of horizontally adjacent pixels
+// overlap, so a quarter is marked as a whole: the union of the spans of its first and last white
+// pixel, in every ring that the distance range of the pixels between them meets (a superset of the
+// per-pixel marks).  Lanes first work out the quarters' parameters in parallel (one each), then the
+// warp walks through them with every lane OR-ing the broadcast span into the bitmap words it owns
+// IN REGISTERS (word lane + 32 i of each ring) — no shared-memory atomics in the loop; the
+// accumulated words are merged into sh.bits at the end.  Also reduces, conservatively, the nearest /
+// farthest white distances around the inner disc into sh.near2 / sh.far2 (float bits; positive
+// floats order like their bit patterns).
 template <int T>
-__device__ __forceinline__ void lsd_mark_rays(const uint32_t* __restrict__ span_tab, float px, float py, const smh_lsd_filter& F,
-                                              uint32_t n_grp, LsdShared& sh) {
-    if (n_grp > (uint32_t)LSD_GRP_CAP) {  // too many white pixels around: mark everything (uniform)
+__device__ __forceinline__ void lsd_mark_rays(const uint32_t* __restrict__ span_tab, float px, float py, const smh_lsd_filter& F, LsdShared& sh) {
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < T / 32; k++) overflow |= sh.grp_cnt[k] > (uint32_t)LSD_GRP_SEG;
+    if (overflow) {  // too many white pixels around: mark everything (uniform)
         for (int i = threadIdx.x; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0xFFFFFFFFu;
         if (threadIdx.x == 0) sh.far2 = 0u;  // nothing is known about the surroundings: no dead cluster
         return;
     }
-    const int fx = (int)px, fy = (int)py;
+    const int fx = (int)px, fy = (int)py, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float hx = px - (float)fx, hy = py - (float)fy;  // 0 or 0.5
     const uint32_t* tab = span_tab + ((hx != 0.0f ? 1 : 0) + (hy != 0.0f ? 2 : 0)) * (LSD_SPAN_N * LSD_SPAN_N) + LSD_SPAN_R * LSD_SPAN_N + LSD_SPAN_R;
-    const float a2 = F.r2_lo[0], z2 = F.r2_hi[F.nw - 1];
+    const float a2 = F.r2_lo[0];
     float near2 = 0.0f, far2 = 3.0e38f;
-    const int bit = threadIdx.x & 7;
-    for (uint32_t g = threadIdx.x >> 3; g < n_grp; g += T / 8) {
-        const uint32_t e = sh.grp[g];
-        if (!((e >> bit) & 1u)) continue;
-        const int ox = (int)((e >> 8) & 0x1FFu) - 160 + bit, oy = (int)(e >> 17) - 128;
-        const float cx = __fsub_rn((float)(fx + ox) + 0.5f, px), cy = __fsub_rn((float)(fy + oy) + 0.5f, py);
-        const float d2 = __fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy));
-        if (d2 < a2) near2 = fmaxf(near2, d2);
-        else {
-            far2 = fminf(far2, d2);
-            if (d2 <= z2) {
-                const uint32_t sp = __ldg(tab + oy * LSD_SPAN_N + ox);
-                const int lo = (int)(int16_t)(sp & 0xFFFFu), hi = (int)(int16_t)(sp >> 16);
+    uint32_t acc[SMH_LSD_FILTER_MAX_WINDOWS][4];
+#pragma unroll
+    for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[j][i] = 0u;
+    const int cnt = (int)sh.grp_cnt[warp];
+    for (int base = 0; base < cnt; base += 32) {
+        // ---- this lane's quarter: span [lo, hi] with 0 <= lo < 3600 (hi may run past 3599), rings -----
+        int lo = 0, hi = -1;
+        uint32_t rings = 0;
+        if (base + lane < cnt) {
+            const uint32_t e = sh.grp[warp * LSD_GRP_SEG + base + lane], m8 = e & 0xFFu;
+            const int oxa = (int)((e >> 8) & 0x1FFu) - 160 + (__ffs(m8) - 1), oxb = (int)((e >> 8) & 0x1FFu) - 160 + (31 - __clz((int)m8));
+            const int oy = (int)(e >> 17) - 128;
+            const float cy = (float)oy + 0.5f - hy, cxa = (float)oxa + 0.5f - hx, cxb = (float)oxb + 0.5f - hx;  // exact
+            const float cy2 = cy * cy, da = cxa * cxa + cy2, db = cxb * cxb + cy2;
+            const float dmax = fmaxf(da, db), dmin = (cxa < 0.0f && cxb > 0.0f) ? cy2 : fminf(da, db);  // over [cxa, cxb]
+            if (dmax < a2) near2 = fmaxf(near2, dmax);
+            else {
+                if (dmin < a2) near2 = fmaxf(near2, a2);  // straddles the inner disc's rim: no dead cluster from this seed
+                far2 = fminf(far2, fmaxf(dmin, a2));
 #pragma unroll
                 for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
-                    if (j < F.nw && d2 >= F.r2_lo[j] && d2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(sh.bits[j], lo, hi, or_if_new);
+                    if (j < F.nw && dmax >= F.r2_lo[j] && dmin <= F.r2_hi[j]) rings |= 1u << j;
+                if (rings) {
+                    const uint32_t sa = __ldg(tab + oy * LSD_SPAN_N + oxa), sb = __ldg(tab + oy * LSD_SPAN_N + oxb);
+                    // direction is monotonic along the row between the two pixels, the half-width is not: take the
+                    // range of the centres (sum / 2, +-0.5 from the integer rounding) widened by the larger width
+                    const int loa = (int)(int16_t)(sa & 0xFFFFu), hia = (int)(int16_t)(sa >> 16);
+                    const int lob = (int)(int16_t)(sb & 0xFFFFu), hib = (int)(int16_t)(sb >> 16);
+                    const int wide = max(hia - loa, hib - lob);
+                    lo = ((min(loa + hia, lob + hib) - wide) >> 1) - 1; hi = ((max(loa + hia, lob + hib) + wide + 1) >> 1) + 1;
+                    if (hi - lo >= SMH_LSD_RAYS - 1) { lo = 0; hi = SMH_LSD_RAYS - 1; }
+                    else {
+                        if (lo < 0) { lo += SMH_LSD_RAYS; hi += SMH_LSD_RAYS; }
+                        if (lo >= SMH_LSD_RAYS) { lo -= SMH_LSD_RAYS; hi -= SMH_LSD_RAYS; }
+                    }
+                }
+            }
+        }
+        // ---- every lane ORs each quarter's span into the words it owns ---------------------------------
+        for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, rings != 0u); todo; todo &= todo - 1u) {
+            const int src = __ffs(todo) - 1;
+            const int l = __shfl_sync(0xFFFFFFFFu, lo, src), h = __shfl_sync(0xFFFFFFFFu, hi, src);
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, rings, src);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t mk = range_mask(lane + 32 * i, l, h);
+                if (h >= SMH_LSD_RAYS) mk |= range_mask(lane + 32 * i, l - SMH_LSD_RAYS, h - SMH_LSD_RAYS);  // uniform
+#pragma unroll
+                for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+                    if ((r >> j) & 1u) acc[j][i] |= mk;
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (acc[j][i] && lane + 32 * i < SMH_LSD_BITMAP_WORDS) atomicOr(&sh.bits[j][lane + 32 * i], acc[j][i]);
     const uint32_t n2 = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(near2));
     const uint32_t f2 = __reduce_min_sync(0xFFFFFFFFu, __float_as_uint(far2));
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (n2) atomicMax(&sh.near2, n2);
         if (f2 != __float_as_uint(3.0e38f)) atomicMin(&sh.far2, f2);
     }
@@ -998,7 +1170,7 @@ __device__ __forceinline__ uint32_t lsd_build_ray_list(float px, float py, const
     }
     __syncthreads();
     for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
-    if (tid == 0) { sh.grp_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    if (tid == 0) { sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
     return total;  // the next writers of bits / near2 / far2 are behind the barrier of the ray search or of the next seed pick
 }
 
@@ -1082,6 +1254,7 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
     __shared__ LsdShared sh;
     extern __shared__ uint32_t chunk[];  // [32][tx] current tile-row, row-major: pixels that can still become seeds
     uint32_t* fringe = chunk + 32u * a.g.tx;  // [32][tx] pixels inside the uncertain rim of some line's band
+    uint32_t* win = fringe + 32u * a.g.tx;    // [LSD_WIN_ROWS][8] neighbourhood of the current seed
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t TX = a.g.tx, W = a.g.w, H = a.g.h, PAD = a.g.pad;
@@ -1092,9 +1265,12 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
     smh_lsd_filter F;
     smh_lsd_filter_init(&F, a.prune ? a.gap_limit : 0);
     const bool dead_ok = F.nw >= 1 && F.border[0] == 0;  // "ring 1 empty => no line" holds for every seed
+    const bool hybrid = F.nw > 0 && a.gap_limit <= 32;   // filtered search (march_window / ray_block_* preconditions)
+    // samples 0 .. win_steps-1 of any ray stay inside the seed's window (|P_n - seed| < n + 1)
+    const int win_steps = F.radius >= 65 ? 64 : (F.radius >= 33 ? 32 : 0);
 
     for (int i = tid; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += T) (&sh.bits[0][0])[i] = 0u;
-    if (tid == 0) { sh.grp_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
+    if (tid == 0) { sh.surv_n = 0u; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); }
 
     while (true) {
         __syncthreads();
@@ -1188,7 +1364,8 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                 if (seed == 0xFFFFFFFFu) break;  // uniform
                 if (cand == seed) chunk[seed >> 5] &= ~(1u << (seed & 31u));  // the owner takes it off
                 const uint32_t sr = (seed >> 5) / TX, swd = (seed >> 5) - sr * TX;
-                const float sx = (float)((int)(swd * 32u + (seed & 31u)) - (int)PAD), sy = (float)(row0 + (int)sr);
+                const int isx = (int)(swd * 32u + (seed & 31u)) - (int)PAD, isy = row0 + (int)sr;
+                const float sx = (float)isx, sy = (float)isy;
                 seeds++;
                 const bool have_dead = dead_ok && lane < (int)min(sh.n_dead, (uint32_t)LSD_DEAD);
                 if (dead_ok) {
@@ -1203,10 +1380,15 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                     if (__any_sync(0xFFFFFFFFu, in)) { pruned++; LSD_PROF(2); continue; }  // uniform: same data in every warp
                 }
                 float px, py;
-                get_centre_warp(im, sx, sy, px, py);  // same value in every warp
-                LSD_PROF(3);  // get_centre
-                int n_rays = -1;  // all
-                if (F.nw > 0) {
+                float best[3];
+                if (hybrid) {
+                    // ---- the seed's neighbourhood into shared memory: one memory round trip -----------
+                    const WinView wv = lsd_load_window<T>(im, win, isx, isy, F.radius + LSD_WIN_EXTRA);
+                    __syncthreads();
+                    LSD_PROF(4);  // window load
+                    LSD_CNT(10, 1);
+                    get_centre_warp(wv, sx, sy, px, py);  // same value in every warp
+                    LSD_PROF(9);  // get_centre
                     if (dead_ok) {
                         bool in = false;
                         if (have_dead) {
@@ -1214,17 +1396,19 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                             const float ex = px - d.x, ey = py - d.y;
                             in = ex * ex + ey * ey < d.z;
                         }
-                        if (__any_sync(0xFFFFFFFFu, in)) { pruned++; LSD_PROF(2); continue; }
+                        if (__any_sync(0xFFFFFFFFu, in)) { pruned++; LSD_PROF(2); continue; }  // (win is rewritten behind the next seed-pick barrier)
                     }
-                    lsd_scan_window<T>(im, px, py, F, sh);
+                    lsd_scan_window<T>(wv, px, py, F, sh);
+                    LSD_PROF(3);  // ring scan
                     __syncthreads();
-                    LSD_PROF(4);  // window scan
-                    lsd_mark_rays<T>(a.span_tab, px, py, F, sh.grp_n, sh);
+                    LSD_PROF(15);  // barrier after the ring scan
+                    lsd_mark_rays<T>(a.span_tab, px, py, F, sh);
                     __syncthreads();
                     LSD_PROF(5);  // ray marking
                     const float near2 = __uint_as_float(sh.near2), far2 = __uint_as_float(sh.far2);
-                    n_rays = (int)lsd_build_ray_list<T>(px, py, F, sh);
+                    const int n_rays = (int)lsd_build_ray_list<T>(px, py, F, sh);
                     LSD_PROF(6);  // ray list
+                    LSD_CNT(11, n_rays);
                     if (n_rays == 0) {  // uniform: no ray can exceed the minimum length
                         pruned++;
                         // every white pixel is within sqrt(near2) of the seed or beyond dfar: a seed at distance
@@ -1248,21 +1432,22 @@ __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs
                                         if (xlo <= xhi) chunk_clear(chunk, TX, PAD, r, xlo, xhi);
                                     }
                                 }
-                                __syncthreads();  // uniform branch: the next seed pick reads the cleared words
                             }
                         }
+                        __syncthreads();  // uniform branch: the next seed pick reads the cleared words, the next window load rewrites win
                         continue;
                     }
+                    longest_ray_hybrid<T, STATS>(im, wv, win_steps, a.rays, a.ckpt, a.n_ckpt, sh.rays, n_rays, px, py, a.gap_limit, best, sh, steps);
+                } else {
+                    get_centre_warp(im, sx, sy, px, py);  // same value in every warp
+                    LSD_PROF(3);
+                    if (fast)
+                        longest_ray_cta<T>(a.rays, nullptr, -1, px, py, best, sh.keys, sh.ends,
+                                           [&](float dx, float dy, float& ex, float& ey) { return march_fast<STATS>(im, px, py, a.gap_limit, dx, dy, ex, ey, steps); });
+                    else
+                        longest_ray_cta<T>(a.rays, nullptr, -1, px, py, best, sh.keys, sh.ends,
+                                           [&](float dx, float dy, float& ex, float& ey) { return march(im, px, py, a.max_gap, dx, dy, ex, ey, steps); });
                 }
-                float best[3];
-                if (fast && n_rays >= 0 && a.gap_limit <= 32)
-                    longest_ray_warps<T, STATS>(im, a.rays, a.ckpt, a.n_ckpt, sh.rays, n_rays, px, py, a.gap_limit, best, sh.keys, sh.ends, steps);
-                else if (fast)
-                    longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
-                                       [&](float dx, float dy, float& ex, float& ey) { return march_fast<STATS>(im, px, py, a.gap_limit, dx, dy, ex, ey, steps); });
-                else
-                    longest_ray_cta<T>(a.rays, sh.rays, n_rays, px, py, best, sh.keys, sh.ends,
-                                       [&](float dx, float dy, float& ex, float& ey) { return march(im, px, py, a.max_gap, dx, dy, ex, ey, steps); });
                 LSD_PROF(7);  // march
                 if (best[0] > SMH_LSD_MIN_LEN_SQ) {  // uniform
                     float c1x, c1y;

@@ -229,7 +229,7 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     // offsets table of the warp-per-ray march: long enough for any ray inside this mask plus two blocks
     {
         const double diag = sqrt((double)P.bg.w * P.bg.w + (double)P.bg.h * P.bg.h);
-        const uint32_t need = ((uint32_t)diag / 32u + 4u) * (32u / smh::LSD_CKPT);
+        const uint32_t need = ((uint32_t)diag / 32u + 5u) * (32u / smh::LSD_CKPT);
         if (need > h->n_ckpt) {
             CU(h, cudaDeviceSynchronize());
             cudaFree(h->d_ckpt); h->d_ckpt = nullptr; h->n_ckpt = 0;
@@ -253,7 +253,8 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     a.stats = stats ? P.stats : nullptr;
     CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
     // persistent grid: as many CTAs as stay resident (or one per frame when there are fewer)
-    const size_t dyn = (size_t)P.bg.tx * 32u * sizeof(uint32_t) * 2u;  // one tile-row of the bitmap + its fringe map
+    // one tile-row of the bitmap + its fringe map + the window around the current seed
+    const size_t dyn = ((size_t)P.bg.tx * 32u * 2u + (size_t)smh::LSD_WIN_ROWS * 8u) * sizeof(uint32_t);
     {
         // the limit is a property of the kernel on this device, shared by every handle: only ever raise it
         static std::mutex mu;

@@ -24,9 +24,10 @@ for it in range(3):
     v.process_batch(frames.data_ptr(), n, W, H, stream=st)
     torch.cuda.synchronize()
     L.smh_b200_debug_lsd_profile(v.handle, out, 1)
-names = ["tile-row load+strike", "seed pick", "dismissed (dead cluster)", "get_centre", "window scan", "ray marking",
-         "ray list", "march", "accept+restrike+row end"]
-tot = sum(out[:9]) or 1
-for k, nm in enumerate(names):
+names = {0: "tile-row load+strike", 1: "seed pick", 2: "dismissed (dead cluster)", 3: "ring scan", 4: "window load",
+         5: "ray marking", 6: "ray list", 7: "march", 8: "accept+restrike+row end", 9: "get_centre", 15: "barrier after ring scan"}
+tot = sum(out[k] for k in names) or 1
+for k, nm in names.items():
     print(f"{nm:28s} {out[k] / tot * 100:5.1f}%  {out[k] / n / 1.965e3:9.1f} us/frame")
 print(f"total {tot / n / 1.965e3:.1f} us/frame (cycles of thread 0 at 1.965 GHz)")
+print(f"per frame: {out[10] / n:.1f} seeds reach the window load, {out[11] / n:.0f} rays listed")
