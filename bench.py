@@ -215,7 +215,7 @@ def main() -> None:
     import torch.distributed as dist
 
     import smh_b200  # noqa: F401
-    from squad_mortar_helper_b200 import synth
+    from squad_mortar_helper_b200 import shard, synth
     from squad_mortar_helper_b200.vision import B200Vision, roi as roi_of
 
     if not torch.cuda.is_available():
@@ -235,8 +235,9 @@ def main() -> None:
     vision = B200Vision.init(local_rank)
     p = synth.SynthParams(W, H)  # DENSE scene
     # frame-wise shard: rank r owns frames [r*n, (r+1)*n) of the global batch (no data-path collective)
+    first, _last = shard.weak_shard(rank, n)
     frames = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")
-    synth.frames_device(vision, p, rank * n, n, frames.data_ptr())
+    synth.frames_device(vision, p, first, n, frames.data_ptr())
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
     fp = frames.data_ptr()
@@ -299,6 +300,12 @@ def main() -> None:
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = bpf * n / (px_ms * 1e-3) / 1e9
+        # DRAM bytes of k_pixels from the committed `ncu --set full` capture (per frame; scaled to this launch)
+        traffic, traffic_src = None, None
+        tpath = ROOT / "profiles" / "k_pixels_traffic.json"
+        if tpath.exists():
+            tj = json.loads(tpath.read_text())
+            traffic, traffic_src = tj["dram_bytes_per_frame_1440p"] * n, tj["source"]
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -316,7 +323,7 @@ def main() -> None:
                        "l2": f"inputs {n * W * H * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "parallelism": f"frame-sharded x{world}, no collectives"},
             "roofline": {"kernel": "k_pixels", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpf * n, "kernel_ms": px_ms,
                          "note": "of measured copy bandwidth; HBM-bound pixel pass. k_lsd is not HBM-bound (see kernels)"},
             "kernels": {"dominant_by_time": dominant,

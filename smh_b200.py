@@ -19,4 +19,4 @@ if _NAME not in sys.modules:
     _spec.loader.exec_module(_mod)
 
 pkg = sys.modules[_NAME]
-from squad_mortar_helper_b200 import build, vision, capi, synth  # noqa: E402,F401
+from squad_mortar_helper_b200 import build, vision, capi, synth, shard  # noqa: E402,F401

@@ -5,7 +5,8 @@ map-analysis vision path (the `vision-common::Vision` trait).  See DESIGN.md / I
     capi.py    ctypes declarations of that ABI
     vision.py  host-side mirror of `trait Vision` (B200Vision)
     synth.py   deterministic synthetic captures
+    shard.py   frame-wise sharding across GPUs (no collectives on the data path)
     build.py   in-tree nvcc build
 """
-from . import build, capi, synth, vision  # noqa: F401
+from . import build, capi, shard, synth, vision  # noqa: F401
 from .vision import B200Vision, DebugView, VisionError  # noqa: F401
