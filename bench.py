@@ -147,7 +147,7 @@ def run_e2e(args, vision, frames, roi, n, world, barrier):
     """Same metric through smh_b200_process_host_batch: pinned HOST frames in, host results out."""
     import torch
     import torch.distributed as dist
-    ne = min(args.e2e_frames, n)
+    ne = min(args.e2e_frames or (n if world <= 2 else 512), n)
     host_frames = torch.empty((ne, H, W, 4), dtype=torch.uint8).pin_memory()
     host_frames.copy_(frames[:ne])
     _, _, mw, mh = roi["map"]; _, _, qw, qh = roi["brq"]
@@ -168,7 +168,7 @@ def run_e2e(args, vision, frames, roi, n, world, barrier):
     for _ in range(2):
         e2e_step()
     barrier()
-    e_steps = max(3, min(args.steps, 10))
+    e_steps = max(3, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e_steps):
         e2e_step()
@@ -179,15 +179,17 @@ def run_e2e(args, vision, frames, roi, n, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_dt = float(t.cpu()[0])
     e2e_fps = world * ne * e_steps / e_dt
-    ux0 = min(roi["map"][0], roi["button"][0]) & ~3
-    rows = max(roi["button"][1] + roi["button"][3], roi["map"][1] + roi["map"][3]) - min(roi["map"][1], roi["button"][1])
-    h2d = ne * rows * (W - ux0) * 4
+    # what smh_b200_process_host_batch uploads per frame: the map rows as wide as the pixel pass's
+    # 16-byte vector grid, plus the button rectangle
+    gx0 = roi["map"][0] & ~3
+    nvec = (roi["map"][0] - gx0 + mw + 3) // 4
+    h2d = ne * (min(4 * nvec, W - gx0) * 4 * mh + roi["button"][2] * roi["button"][3] * 4)
     d2h = ne * (mw * mh * 4 + 2 * qw * qh + 512 + 9)
     e2e_check = int(outs["n_lines"].sum())
 
     return {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "frames_per_step": ne, "steps": e_steps, "lines_checksum": e2e_check,
-            "note": "smh_b200_process_host_batch: pinned host frames -> ROI upload -> kernels -> ui_map/ocr/scales/lines back"}
+            "note": "smh_b200_process_host_batch: pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines back, 3 chunks in flight"}
 
 
 def main() -> None:
@@ -197,7 +199,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--e2e-frames", type=int, default=0,
+                    help="host frames per e2e step (default: the whole batch; 512 per rank beyond 2 GPUs to bound pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     args = ap.parse_args()

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -22,6 +23,11 @@
 namespace {
 
 thread_local std::string g_create_error;
+
+// chunks in flight in smh_b200_process_host_batch: upload of chunk c+2, kernels of c+1, download of c
+#ifndef SMH_PIPE_DEPTH
+#define SMH_PIPE_DEPTH 3
+#endif
 
 struct Geometry {
     uint32_t W = 0, H = 0;
@@ -118,9 +124,11 @@ struct smh_b200 {
 
     // ---- batch state ----
     Planes batch;
-    std::vector<cudaStream_t> pipe_streams;
+    std::vector<cudaStream_t> pipe_streams;   // host-batch pipeline: [0] upload, [1],[2] compute, [3] download
+    std::vector<cudaEvent_t> pipe_events;     // [3 * SMH_PIPE_DEPTH]: uploaded / computed / downloaded per slot
     uint8_t* d_stage = nullptr; size_t stage_cap = 0;   // host-batch upload staging (device)
-    Planes pipe[2];
+    uint8_t* d_pack = nullptr; size_t pack_cap = 0;     // host-batch download staging: planes without pitch padding
+    Planes pipe[SMH_PIPE_DEPTH];
 };
 
 namespace {
@@ -405,10 +413,11 @@ void smh_b200_destroy(smh_b200* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_single(h);
-    h->batch.release(); h->pipe[0].release(); h->pipe[1].release();
-    cudaFree(h->d_stage); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
+    h->batch.release(); for (auto& P : h->pipe) P.release();
+    cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
+    for (auto e : h->pipe_events) cudaEventDestroy(e);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_markers) cudaStreamDestroy(h->s_markers);
     if (h->s_scales) cudaStreamDestroy(h->s_scales);
@@ -729,56 +738,170 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
     if (rc) return fail(h, rc, "process_host_batch: %ux%u is a frame size the reference panics on", W, H);
     if (chunk == 0) chunk = 32;
     if (chunk > n) chunk = n;
-    if (h->pipe_streams.size() < 2) {
-        h->pipe_streams.resize(2);
-        for (auto& s : h->pipe_streams) CU(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    constexpr int DEPTH = SMH_PIPE_DEPTH;
+    // Three stages on three streams — upload, compute (kernels + row packing), download — chained by
+    // events per slot, so the bus is busy in both directions all the time: chunk k+1 goes up and chunk
+    // k-1 comes down while chunk k is computed.  A slot's upload staging is free again once its kernels
+    // ran, its planes once they were packed, its packed rows once they were downloaded.
+    if (h->pipe_streams.size() < 4) {
+        const size_t have = h->pipe_streams.size();
+        h->pipe_streams.resize(4);
+        for (size_t i = have; i < 4; i++) CU(h, cudaStreamCreateWithFlags(&h->pipe_streams[i], cudaStreamNonBlocking));
     }
-    // device staging: per frame only the region the path reads (columns [x0&~3, W), rows [map_y, y1))
+    if (h->pipe_events.size() < (size_t)(3 * DEPTH)) {
+        const size_t have = h->pipe_events.size();
+        h->pipe_events.resize(3 * DEPTH);
+        for (size_t i = have; i < (size_t)(3 * DEPTH); i++) CU(h, cudaEventCreateWithFlags(&h->pipe_events[i], cudaEventDisableTiming));
+    }
+    // (two compute streams, taken in turn: the line search of a chunk is latency-bound — one CTA per frame —
+    // and leaves most SMs idle, so consecutive chunks' kernels may overlap)
+    cudaStream_t s_up = h->pipe_streams[0], s_run[2] = {h->pipe_streams[1], h->pipe_streams[2]}, s_down = h->pipe_streams[3];
+    // Device staging keeps the capture's geometry for the region the path reads (columns [x0&~3, W),
+    // rows [map_y, y1)), but only the two rectangles that are read cross the bus: the map rows, as wide
+    // as the pixel pass's vector grid, and the button.
     const uint32_t ux0 = (g.map[0] < g.btn[0] ? g.map[0] : g.btn[0]) & ~3u;
     const uint32_t uy0 = g.map[1] < g.btn[1] ? g.map[1] : g.btn[1];
     const uint32_t yb = g.btn[1] + g.btn[3], ym = g.map[1] + g.map[3];
     const uint32_t uy1 = yb > ym ? yb : ym, rows = uy1 - uy0;
     const uint32_t upitch = round_up((W - ux0) * 4u, 128u);
     const uint64_t ustride = (uint64_t)upitch * rows;
-    const size_t need = (size_t)ustride * chunk * 2;
+    const size_t need = (size_t)ustride * chunk * DEPTH;
     if (h->stage_cap < need) {
         CU(h, cudaDeviceSynchronize());
         cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_cap = 0;
         CU(h, cudaMalloc(&h->d_stage, need));
+        CU(h, cudaMemset(h->d_stage, 0, need));
         h->stage_cap = need;
     }
     const size_t npx = (size_t)g.map[2] * g.map[3], nq = (size_t)g.brq[2] * g.brq[3];
-    for (int b = 0; b < 2; b++)
+    // Download staging: the planes' rows carry pitch padding on the device; a strided copy over the bus
+    // pays per row (the quadrant planes' rows are a few hundred bytes), so the rows are first packed on the
+    // device and each plane of a chunk then crosses the bus as ONE contiguous copy.
+    const size_t pack_frame = (res->ui_map ? npx * 4 : 0) + (res->ocr_out ? nq : 0) + (res->scales ? nq : 0) + (res->lsd_image ? npx : 0);
+    const size_t pack_need = pack_frame * chunk * DEPTH;
+    if (h->pack_cap < pack_need) {
+        CU(h, cudaDeviceSynchronize());
+        cudaFree(h->d_pack); h->d_pack = nullptr; h->pack_cap = 0;
+        CU(h, cudaMalloc(&h->d_pack, pack_need));
+        h->pack_cap = pack_need;
+    }
+    for (int b = 0; b < DEPTH; b++)
         if ((rc = ensure_planes(h, &h->pipe[b], chunk, g, false))) return rc;
+    // map rectangle in frame coordinates: columns of the vector grid [gx0, gx0 + 4*nvec) clipped to the frame
+    const uint32_t gx0 = g.map[0] & ~3u;
+    const uint32_t mcols = (gx0 + 4u * h->pipe[0].nvec <= W ? 4u * h->pipe[0].nvec : W - gx0);
+    // How the rectangles cross the bus: 1 = one 3-D copy per rectangle and chunk (depth = frames; needs
+    // tightly stacked frames), 0 = one 2-D copy per frame.  Measured on B200/PCIe 5 with downloads running
+    // the other way: 47 GB/s against 31 GB/s (and 46 GB/s for SM zero-copy loads, which however idle the
+    // link while they wait for a slot's kernels).
+    int h2d_mode = 1;
+    if (const char* e = getenv("SMH_B200_H2D_MODE")) h2d_mode = atoi(e);
+    // SMH_B200_PIPE_TRACE=1: event-stamp every chunk's upload / kernels / download and print the timeline
+    static const bool trace = getenv("SMH_B200_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     uint32_t done = 0;
     int b = 0;
+    uint32_t kth = 0;
     while (done < n) {
-        const uint32_t c = n - done < chunk ? n - done : chunk;
-        cudaStream_t st = h->pipe_streams[b];
+        // chunk schedule: a short first and second chunk so that kernels and downloads start early, full
+        // chunks in between, halving chunks at the end so that little is left to drain after the last upload
+        const uint32_t left = n - done, quarter = chunk / 4u > 0u ? chunk / 4u : 1u;
+        uint32_t c = kth == 0 ? quarter : (kth == 1 ? (chunk / 2u > 0u ? chunk / 2u : 1u) : chunk);
+        if (left < 2u * chunk) { const uint32_t half = (left + 1u) / 2u; c = half > quarter ? half : quarter; }
+        if (c > chunk) c = chunk;
+        if (c > left) c = left;
+        kth++;
         Planes& P = h->pipe[b];
         uint8_t* stage = h->d_stage + (size_t)b * ustride * chunk;
-        // (stream order makes reuse of pipe[b]/stage safe: the previous work on this stream is done first)
-        for (uint32_t i = 0; i < c; i++) {
-            const uint8_t* src = frames + (uint64_t)(done + i) * frame_stride + (size_t)uy0 * pitch_bytes + (size_t)ux0 * 4u;
-            CU(h, cudaMemcpy2DAsync(stage + (uint64_t)i * ustride, upitch, src, pitch_bytes, (size_t)(W - ux0) * 4u, rows,
-                                    cudaMemcpyHostToDevice, st));
+        cudaEvent_t ev_up = h->pipe_events[3 * b], ev_run = h->pipe_events[3 * b + 1], ev_down = h->pipe_events[3 * b + 2];
+        const bool reused = kth > (uint32_t)DEPTH;  // the slot carried chunk k - DEPTH
+        // ---- upload: the staging slot is free once the previous occupant's kernels have run --------
+        cudaStream_t st = s_up;
+        if (reused) CU(h, cudaStreamWaitEvent(st, ev_run, 0));
+        stamp(st);
+        const uint8_t* src0 = frames + (uint64_t)done * frame_stride;
+        if (h2d_mode == 1 && frame_stride == (uint64_t)pitch_bytes * H) {
+            // one 3-D copy per rectangle for the whole chunk (depth = frames)
+            cudaMemcpy3DParms mp{};
+            mp.srcPtr = make_cudaPitchedPtr((void*)src0, pitch_bytes, (size_t)W * 4u, H);
+            mp.dstPtr = make_cudaPitchedPtr(stage, upitch, upitch, rows);
+            mp.kind = cudaMemcpyHostToDevice;
+            mp.srcPos = make_cudaPos((size_t)gx0 * 4u, g.map[1], 0);
+            mp.dstPos = make_cudaPos((size_t)(gx0 - ux0) * 4u, g.map[1] - uy0, 0);
+            mp.extent = make_cudaExtent((size_t)mcols * 4u, g.map[3], c);
+            CU(h, cudaMemcpy3DAsync(&mp, st));
+            mp.srcPos = make_cudaPos((size_t)g.btn[0] * 4u, g.btn[1], 0);
+            mp.dstPos = make_cudaPos((size_t)(g.btn[0] - ux0) * 4u, g.btn[1] - uy0, 0);
+            mp.extent = make_cudaExtent((size_t)g.btn[2] * 4u, g.btn[3], c);
+            CU(h, cudaMemcpy3DAsync(&mp, st));
+        } else {
+            for (uint32_t i = 0; i < c; i++) {
+                const uint8_t* src = src0 + (uint64_t)i * frame_stride;
+                uint8_t* dst = stage + (uint64_t)i * ustride;
+                CU(h, cudaMemcpy2DAsync(dst + (size_t)(g.map[1] - uy0) * upitch + (size_t)(gx0 - ux0) * 4u, upitch,
+                                        src + (size_t)g.map[1] * pitch_bytes + (size_t)gx0 * 4u, pitch_bytes,
+                                        (size_t)mcols * 4u, g.map[3], cudaMemcpyHostToDevice, st));
+                CU(h, cudaMemcpy2DAsync(dst + (size_t)(g.btn[1] - uy0) * upitch + (size_t)(g.btn[0] - ux0) * 4u, upitch,
+                                        src + (size_t)g.btn[1] * pitch_bytes + (size_t)g.btn[0] * 4u, pitch_bytes,
+                                        (size_t)g.btn[2] * 4u, g.btn[3], cudaMemcpyHostToDevice, st));
+            }
         }
+        stamp(st);
+        CU(h, cudaEventRecord(ev_up, st));
+        // ---- compute: needs the upload; the packed rows of the slot must have gone down ---------------
+        st = s_run[kth & 1u];
+        CU(h, cudaStreamWaitEvent(st, ev_up, 0));
+        if (reused) CU(h, cudaStreamWaitEvent(st, ev_down, 0));
         if (start_y) CU(h, cudaMemcpyAsync(P.start_y, start_y + done, (size_t)c * 4, cudaMemcpyHostToDevice, st));
         if ((rc = launch_pixels(h, P, stage, ustride, upitch, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
                                 pick_rows_per_band(h, c, g.map[3]), st)))
             return rc;
         if (!(flags & SMH_BATCH_SKIP_LSD))
             if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st))) return rc;
-        if (res->ui_map && (rc = download_plane(h, &P.ui, 0, c, res->ui_map + (size_t)done * npx * 4, st))) return rc;
-        if (res->ocr_out && (rc = download_plane(h, &P.ocr, 0, c, res->ocr_out + (size_t)done * nq, st))) return rc;
-        if (res->scales && (rc = download_plane(h, &P.scales, 0, c, res->scales + (size_t)done * nq, st))) return rc;
-        if (res->lsd_image && (rc = download_plane(h, &P.lsd, 0, c, res->lsd_image + (size_t)done * npx, st))) return rc;
+        uint8_t* const pack0 = h->d_pack + (size_t)b * pack_frame * chunk;
+        struct Want { const smh_b200_plane* pl; uint8_t* host; };
+        const Want wants[4] = {{res->ui_map ? &P.ui : nullptr, res->ui_map ? res->ui_map + (size_t)done * npx * 4 : nullptr},
+                               {res->ocr_out ? &P.ocr : nullptr, res->ocr_out ? res->ocr_out + (size_t)done * nq : nullptr},
+                               {res->scales ? &P.scales : nullptr, res->scales ? res->scales + (size_t)done * nq : nullptr},
+                               {res->lsd_image ? &P.lsd : nullptr, res->lsd_image ? res->lsd_image + (size_t)done * npx : nullptr}};
+        uint8_t* cursor = pack0;
+        for (const Want& wnt : wants) {  // rows without their pitch padding, plane after plane
+            if (!wnt.pl) continue;
+            const size_t row = (size_t)wnt.pl->width * wnt.pl->bytes_per_pixel;
+            CU(h, cudaMemcpy2DAsync(cursor, row, wnt.pl->ptr + (size_t)wnt.pl->pad * wnt.pl->bytes_per_pixel, wnt.pl->pitch, row,
+                                    (size_t)wnt.pl->height * c, cudaMemcpyDeviceToDevice, st));
+            cursor += row * wnt.pl->height * c;
+        }
+        stamp(st);
+        CU(h, cudaEventRecord(ev_run, st));
+        // ---- download: every plane of the chunk as one contiguous copy ------------------------------
+        st = s_down;
+        CU(h, cudaStreamWaitEvent(st, ev_run, 0));
+        cursor = pack0;
+        for (const Want& wnt : wants) {
+            if (!wnt.pl) continue;
+            const size_t bytes = (size_t)wnt.pl->width * wnt.pl->bytes_per_pixel * wnt.pl->height * c;
+            CU(h, cudaMemcpyAsync(wnt.host, cursor, bytes, cudaMemcpyDeviceToHost, st));
+            cursor += bytes;
+        }
         CU(h, cudaMemcpyAsync(res->lines + (size_t)done * 128, P.lines, (size_t)c * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(res->n_lines + done, P.n_lines, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(res->red_pixels + done, P.red, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(res->map_open + done, P.open, (size_t)c, cudaMemcpyDeviceToHost, st));
+        stamp(st);
+        CU(h, cudaEventRecord(ev_down, st));
         done += c;
-        b ^= 1;
+        b = (b + 1) % DEPTH;
+    }
+    if (trace) {
+        for (auto s : h->pipe_streams) cudaStreamSynchronize(s);
+        for (size_t k = 0; k + 3 < tev.size(); k += 4) {
+            float t[4];
+            for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], tev[0], tev[k + j]);
+            fprintf(stderr, "[pipe] chunk %2zu  up %7.3f-%7.3f  kernels -%7.3f  down -%7.3f ms\n", k / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : tev) cudaEventDestroy(e);
     }
     for (auto s : h->pipe_streams) CU(h, cudaStreamSynchronize(s));
     return SMH_OK;
