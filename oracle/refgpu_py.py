@@ -1,0 +1,111 @@
+"""ctypes binding of oracle/_ref/libsmh_refgpu.so — the REFERENCE's own CUDA kernels behind a
+restatement of vision-gpu's launch sequence (oracle/ref_gpu_harness.cu).  TEST INFRASTRUCTURE ONLY.
+
+The library is built from the reference sources where they lie (`make -C oracle refgpu`, only where
+/root/reference is mounted) and travels to the GPU box as a prebuilt file; `available()` says
+whether it is there.  Used to pin the CPU oracle against outputs of the reference itself and as the
+"GPU kernel to beat" timing of bench.py's baseline leg.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+SO = _HERE / "_ref" / "libsmh_refgpu.so"
+_LIB = None
+
+
+def available() -> bool:
+    return SO.exists()
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        from . import oracle_py
+        oracle_py.lib()  # the harness links the oracle's host-side find_lines
+        L = C.CDLL(str(SO))
+        vp = C.c_void_p
+        L.refgpu_last_error.restype = C.c_char_p
+        L.refgpu_create.argtypes = [C.POINTER(vp)]
+        L.refgpu_destroy.argtypes = [vp]
+        L.refgpu_process_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                           C.POINTER(C.c_int), C.POINTER(C.c_uint32)] + [vp] * 7 + \
+                                          [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.refgpu_find_longest_line_in.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float,
+                                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.refgpu_time_frames.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _LIB = L
+    return _LIB
+
+
+class RefGpu:
+    """The reference's GPU backend (its kernels, its launch order) for one frame at a time."""
+
+    def __init__(self):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.refgpu_create(C.byref(h))
+        if rc:
+            raise RuntimeError(f"refgpu_create rc={rc}: {self.L.refgpu_last_error().decode()}")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.refgpu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def process_frame(self, bgra: np.ndarray, grayscale=True, start_y=0, max_gap=15) -> dict:
+        from . import oracle_py as O
+        bgra = np.ascontiguousarray(bgra)
+        H, W = bgra.shape[:2]
+        roi = O.roi(W, H)
+        _, _, w, h = roi["map"]
+        _, _, qw, qh = roi["brq"]
+        out = {"ui_map": np.zeros((h, w, 4), np.uint8), "cropped_map_isolated": np.zeros((h, w, 3), np.uint8),
+               "cropped_brq": np.zeros((qh, qw, 3), np.uint8), "raw_mask": np.zeros((h, w), np.uint8),
+               "lsd_image": np.zeros((h, w), np.uint8), "ocr_out": np.zeros((qh, qw), np.uint8),
+               "scales": np.zeros((qh, qw), np.uint8)}
+        lines = np.zeros((32, 4), np.float32)
+        mo, red, n, seeds = C.c_int(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        rc = self.L.refgpu_process_frame(self.h, bgra.ctypes.data, W, H, int(grayscale), start_y, max_gap, C.byref(mo),
+                                         C.byref(red), *[out[k].ctypes.data for k in
+                                                         ("ui_map", "cropped_map_isolated", "cropped_brq", "raw_mask",
+                                                          "lsd_image", "ocr_out", "scales")],
+                                         lines.ctypes.data, C.byref(n), C.byref(seeds))
+        if rc:
+            raise RuntimeError(f"refgpu_process_frame rc={rc}: {self.L.refgpu_last_error().decode()}")
+        out.update(map_open=bool(mo.value), red_pixels=red.value, lines=lines[: n.value].copy(), seeds=seeds.value, roi=roi)
+        return out
+
+    def find_longest_line_in(self, img: np.ndarray, x: float, y: float, max_gap: float):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        line = (C.c_float * 4)()
+        ln = C.c_float()
+        rc = self.L.refgpu_find_longest_line_in(self.h, img.ctypes.data, w, h, x, y, max_gap, line, C.byref(ln))
+        if rc:
+            raise RuntimeError(f"refgpu_find_longest_line_in rc={rc}: {self.L.refgpu_last_error().decode()}")
+        return np.array(list(line), np.float32), np.float32(ln.value)
+
+    def time_frames(self, frames: np.ndarray, grayscale=True, max_gap=15, reps=1) -> dict:
+        """frames: [n, H, W, 4] host BGRA.  Wall-clock frames/s of the reference's per-frame sequence."""
+        frames = np.ascontiguousarray(frames)
+        n, H, W = frames.shape[:3]
+        fps, seeds, launches = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        rc = self.L.refgpu_time_frames(self.h, frames.ctypes.data, n, W, H, int(grayscale), max_gap, reps, C.byref(fps),
+                                       C.byref(seeds), C.byref(launches))
+        if rc:
+            raise RuntimeError(f"refgpu_time_frames rc={rc}: {self.L.refgpu_last_error().decode()}")
+        return {"frames_per_s": fps.value, "seeds_per_frame": seeds.value / (n * reps),
+                "launches_per_frame": launches.value / (n * reps)}

@@ -540,9 +540,16 @@ static inline void nearest_point_on_line(float ptx, float pty, const float l[4],
     out[1] = l[1] + u * dy;
 }
 
-int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap_u,
-                             float lines[32][4], uint32_t *n_out) {
-    /* vision-common/src/lsd.rs:60-105 with N = 32 (vision-common/src/lib.rs:58) */
+static int default_longest_cb(void *user, const uint8_t *img, uint32_t w, uint32_t h, float x, float y,
+                             float max_gap, float line[4], float *len_sq) {
+    (void)user;
+    return smh_oracle_find_longest_line_in(img, w, h, x, y, max_gap, line, len_sq);
+}
+
+int smh_oracle_find_lines_cb(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap_u,
+                             smh_oracle_longest_fn cb, void *user, float lines[32][4], uint32_t *n_out) {
+    /* vision-common/src/lsd.rs:60-105 with N = 32 (vision-common/src/lib.rs:58); `cb` plays the
+     * backend's find_longest_line closure (lsd.rs:63, vision-gpu/src/lib.rs:481-486) */
     const float max_gap = (float)max_gap_u;
     uint32_t n = 0;
     t_seeds = 0; t_steps = 0;
@@ -562,7 +569,8 @@ int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_
             get_centre(img, w, h, x, y, c);
             float longest[4], len;
             t_seeds++;
-            smh_oracle_find_longest_line_in(img, w, h, c[0], c[1], max_gap, longest, &len);
+            int rc = cb(user, img, w, h, c[0], c[1], max_gap, longest, &len);
+            if (rc) { *n_out = n; return rc; }
             if (len > SMH_LSD_MIN_LEN_SQ) {
                 float c1[2];
                 get_centre(img, w, h, longest[2], longest[3], c1);
@@ -575,6 +583,11 @@ int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_
     }
     *n_out = n;
     return 0;
+}
+
+int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap_u,
+                             float lines[32][4], uint32_t *n_out) {
+    return smh_oracle_find_lines_cb(img, w, h, max_gap_u, default_longest_cb, NULL, lines, n_out);
 }
 
 int smh_oracle_find_marker_lines(smh_oracle *o, uint32_t max_gap, float lines[32][4], uint32_t *n) {

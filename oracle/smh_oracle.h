@@ -86,6 +86,13 @@ int smh_oracle_find_marker_lines(smh_oracle *o, uint32_t max_gap, float lines[32
 /* lsd::find_lines on a caller-supplied L8 image */
 int smh_oracle_find_lines_in(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap,
                              float lines[32][4], uint32_t *n);
+/* lsd::find_lines with the backend's find_longest_line supplied by the caller (the closure of
+ * vision-common/src/lsd.rs:63; how vision-gpu plugs its per-seed kernel launch in,
+ * vision-gpu/src/lib.rs:477-487).  A non-zero return of `cb` aborts the scan and is passed on. */
+typedef int (*smh_oracle_longest_fn)(void *user, const uint8_t *img, uint32_t w, uint32_t h, float x, float y,
+                                     float max_gap, float line[4], float *len_sq);
+int smh_oracle_find_lines_cb(const uint8_t *img, uint32_t w, uint32_t h, uint32_t max_gap,
+                             smh_oracle_longest_fn cb, void *user, float lines[32][4], uint32_t *n);
 /* vision-cpu/src/lib.rs:451-460; which = DebugView discriminant (vision-common/src/debug.rs:31-40).
  * Fills rgba (w*h*4 of that view) if non-NULL; always writes wh. Returns 1 for None. */
 int smh_oracle_debug_view(smh_oracle *o, uint8_t which, uint8_t *rgba, uint32_t wh[2]);
