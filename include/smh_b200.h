@@ -105,6 +105,53 @@ int32_t smh_b200_lsd_image(smh_b200 *h, const uint8_t **l8, uint32_t wh[2]);
 /* red-pixel count of the last crop_to_map's button test (vision-gpu/src/lib.rs:236-243) */
 int32_t smh_b200_red_pixels(smh_b200 *h, uint32_t *count);
 
+/* ---- the callers either side of the trait ----------------------- */
+
+/* find_minimap — src/vision/find_minimap.rs:51-146, called by the orchestrator on
+ * `vision.get_cpu_frame().view(x, y, w, h)` (src/vision/mod.rs:85).  Here it runs on the device copy of
+ * the loaded frame, so the host frame is never needed again.  rect = {left, right, top, bottom} in map
+ * ROI coordinates; *found = 0 mirrors None (view smaller than 3x3).  Needs load_frame. */
+int32_t smh_b200_find_minimap(smh_b200 *h, int32_t *found, uint32_t rect[4]);
+
+/* One "NNNm" label the OCR found: (meters, (x, y)) with x = (left + right) / 2, y = bottom of the text,
+ * in bottom-right-quadrant coordinates — src/vision/mod.rs:183 */
+typedef struct { uint32_t meters, x, y; } smh_b200_scale;
+
+/* calc_meters_to_px_ratio — src/vision/mpx_ratio.rs:3-133, on the device copy of the image
+ * find_scales_preprocess last returned (including its stale rows, D9).  n_scales = 0..3.
+ * *found = 0 mirrors None.  debug_lines[k] = {meters, left, right, y} of each bar found (the reference's
+ * scales_debug, before the brq offset is added), may be NULL.  D16: where the reference reads outside
+ * the image (unchecked in release builds, a panic in debug builds) the pixel counts as non-black. */
+int32_t smh_b200_calc_meters_to_px_ratio(smh_b200 *h, const smh_b200_scale *scales, uint32_t n_scales, int32_t *found,
+                                         double *ratio, uint32_t debug_lines[3][4], uint32_t *n_debug);
+
+/* VisionState::process — src/vision/mod.rs:36-240 — as one call: load_frame, crop_to_map, find_minimap,
+ * then the marker branch {isolate, mask, find_marker_lines(max_gap)} overlapped with the scales branch
+ * {ocr_preprocess, `ocr` callback (Tesseract's place: src/vision/mod.rs:127-190), find_scales_preprocess,
+ * calc_meters_to_px_ratio}.  The callback receives the preprocessed L8 quadrant and reports up to 3
+ * scales and scales_start_y (the smallest `bottom` of the labels); returning 0 scales mirrors
+ * `return Ok(None)`.  ocr = NULL skips the scales branch (a heightmap is set, mod.rs:120-122);
+ * detect_markers = 0 skips the marker branch (mod.rs:88,116-118). */
+typedef int32_t (*smh_b200_ocr_fn)(void *user, const uint8_t *ocr_l8, uint32_t w, uint32_t h, smh_b200_scale scales[3],
+                                   uint32_t *n_scales, uint32_t *scales_start_y);
+typedef struct {
+    int32_t map_open;               /* 0: process() returned Ok(None); nothing else is valid */
+    uint32_t xywh[4];               /* map ROI */
+    const uint8_t *ui_map_rgba;     /* VisionResults::map (borrowed, w*h*4) */
+    float markers[32][4];           /* VisionResults::markers */
+    uint32_t n_markers;
+    int32_t has_ratio;              /* VisionResults::meters_to_px_ratio: Option<f64> */
+    double meters_to_px_ratio;
+    int32_t has_minimap;            /* VisionResults::minimap_bounds: Option<Rect<u32>> */
+    uint32_t minimap[4];            /* left, right, top, bottom */
+    uint32_t scales_debug[3][4];    /* meters, left, right, y */
+    uint32_t n_scales_debug;
+    uint32_t reserved;
+} smh_b200_vision_results;
+int32_t smh_b200_process(smh_b200 *h, const uint8_t *bgra, uint32_t W, uint32_t H, uint32_t pitch_bytes, int32_t grayscale,
+                         int32_t detect_markers, uint32_t max_gap, smh_b200_ocr_fn ocr, void *user,
+                         smh_b200_vision_results *out);
+
 /* ---- batch extension (not in the trait): N independent frames per launch ------------------ */
 
 /* A device image plane: pixel (i,j) of frame f lives at
@@ -132,12 +179,15 @@ typedef struct {
     uint32_t *red_pixels;      /* device, [n] */
     uint8_t *map_open;         /* device, [n]: 0 = map closed (n_lines = 0, images still written) */
     uint64_t *lsd_stats;       /* device, [n][3] = {seeds, ray_steps, pruned seeds} when stats were requested, else NULL */
+    uint32_t *minimap;         /* device, [n][4] = left, right, top, bottom (SMH_BATCH_MINIMAP), else NULL */
+    uint8_t *minimap_found;    /* device, [n] */
 } smh_b200_batch;
 
 #define SMH_BATCH_GRAYSCALE 1u /* ui_map = (L,L,L,255) — settings default, src/settings.rs:135 */
 #define SMH_BATCH_LSD_STATS 2u /* count seeds / ray steps per frame (slower; for reporting) */
 #define SMH_BATCH_SKIP_LSD 4u  /* pixel pass only */
 #define SMH_BATCH_SKIP_PIXELS 8u /* line search only, on the planes of the previous call */
+#define SMH_BATCH_MINIMAP 32u   /* also run find_minimap on every open frame (src/vision/find_minimap.rs) */
 #define SMH_BATCH_LSD_EXHAUSTIVE 16u /* march all 3600 rays of every seed (no isolated-blob pruning): makes
                                         the ray-step counter comparable with the CPU oracle's */
 
@@ -160,6 +210,8 @@ typedef struct {
     uint32_t *n_lines;    /* n */
     uint32_t *red_pixels; /* n */
     uint8_t *map_open;    /* n */
+    uint32_t *minimap;    /* n * 4, with SMH_BATCH_MINIMAP (may be NULL) */
+    uint8_t *minimap_found; /* n (may be NULL) */
 } smh_b200_host_results;
 
 /* End-to-end batch from HOST frames (pinned memory recommended): uploads each frame's ROI band,
@@ -169,6 +221,12 @@ int32_t smh_b200_process_host_batch(smh_b200 *h, const uint8_t *frames, uint32_t
                                     uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
                                     uint32_t max_gap, uint32_t flags, uint32_t chunk,
                                     const smh_b200_host_results *res);
+
+/* calc_meters_to_px_ratio for every frame of the last smh_b200_process_batch on this handle, reading its
+ * device-resident `scales` planes.  scales: HOST [n][3], n_scales: HOST [n] (0..3 each); results land in
+ * the HOST arrays ratio[n], found[n] after the call (it synchronises `stream`). */
+int32_t smh_b200_batch_meters_to_px_ratio(smh_b200 *h, const smh_b200_scale *scales, const uint8_t *n_scales, uint32_t n,
+                                          void *stream, double *ratio, uint8_t *found);
 
 /* Copy plane `p` of frames [first, first+count) to tightly packed host memory. */
 int32_t smh_b200_download_plane(smh_b200 *h, const smh_b200_plane *p, uint32_t first, uint32_t count,

@@ -60,6 +60,14 @@
 #define SMH_LSD_SUPPRESS_DIST_SQ 50.0f
 #define SMH_LSD_MIN_LEN_SQ 2500.0f
 
+/* Scale bars — src/vision/mpx_ratio.rs:5-6,12 */
+#define SMH_SCALE_MIN_WIDTH 10u
+#define SMH_SCALE_MIN_VBAR_HEIGHT 4u
+/* Minimap edge search — src/vision/find_minimap.rs:66 (f32); `max as f32 / 765.0 <= 0.01` holds exactly
+ * for max <= 7 (tests/test_next_rows_cpu.py checks all 766 values) */
+#define SMH_MINIMAP_EDGINESS_THRESHOLD 0.01f
+#define SMH_MINIMAP_EDGINESS_MAX_SUM 7u
+
 /* image 0.23.14 rgb_to_luma weights (f32) */
 #define SMH_LUMA_R 0.2126f
 #define SMH_LUMA_G 0.7152f

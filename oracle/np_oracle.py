@@ -266,3 +266,99 @@ def find_lines(img: np.ndarray, max_gap: int, stats: dict | None = None):
     if stats is not None:
         stats["seeds"] = seeds
     return np.array(lines, F).reshape(-1, 4)
+
+
+# ---- next rows: independent restatements, written from the reference source with a
+#      different structure than oracle/smh_oracle.c (vectorised lookups instead of pixel walks) ----------
+
+def calc_meters_to_px_ratio(img: np.ndarray, scales):
+    """src/vision/mpx_ratio.rs:3-133.  img: L8 [h, w]; scales: [(meters, (x, y))].  -> None | float."""
+    h, w = img.shape
+    black = np.zeros((h + 4, w), bool)          # D16: rows past the image are non-black
+    black[:h] = img == 0
+    # vbar[y, x]: (x, y) .. (x, y + 3) all black (the chained `(y..y - 4).rev()` range is empty)
+    vbar = black[:h] & black[1:h + 1] & black[2:h + 2] & black[3:h + 3]
+    found = []
+    for meters, (x, y0) in scales:
+        if y0 < 4 or x >= w:
+            continue
+        max_off = _round_half_away((20.0 / 640.0) * w)
+        for y in range(y0, min(h, y0 + max_off)):
+            if not black[y, x]:
+                continue
+            rs = np.flatnonzero(vbar[y, x:])
+            if rs.size == 0 or x + rs[0] == 0:
+                continue
+            right = x + int(rs[0]) - 1
+            ls = np.flatnonzero(vbar[y, :x])
+            if ls.size == 0 or ls[-1] == 0:
+                continue
+            left = int(ls[-1]) + 1
+            width = (right - left) & 0xFFFFFFFF
+            if width < 10:
+                continue
+            found.append(float(meters) / float(width))
+            break
+    if not found:
+        return None
+    if len(found) == 1:
+        return found[0]
+    s = found[0]
+    for v in found[1:]:
+        s = s + v
+    return s / float(len(found))
+
+
+def low_edginess_map(view_bgra: np.ndarray) -> np.ndarray:
+    """bool [h, w]: get_edginess(x, y) <= 0.01 (src/vision/find_minimap.rs:8-46,66) for interior pixels,
+    through the literal f32 expression `max as f32 / 765.0 <= 0.01`."""
+    v = view_bgra[..., :3].astype(np.int32)
+    h, w = v.shape[:2]
+    mx = np.zeros((h, w), np.int32)
+    c = v[1:-1, 1:-1]
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dx == 0 and dy == 0:
+                continue
+            q = v[1 + dy:h - 1 + dy, 1 + dx:w - 1 + dx]
+            mx[1:-1, 1:-1] = np.maximum(mx[1:-1, 1:-1], np.abs(c - q).sum(axis=2))
+    low = (mx.astype(np.float32) / np.float32(765.0)) <= np.float32(0.01)
+    low[0, :] = low[-1, :] = False
+    low[:, 0] = low[:, -1] = False
+    return low
+
+
+def find_minimap(view_bgra: np.ndarray):
+    """src/vision/find_minimap.rs:51-146 on an already cropped view.  -> None | (left, right, top, bottom)."""
+    h, w = view_bgra.shape[:2]
+    if w < 3 or h < 3:
+        return None
+    low = low_edginess_map(view_bgra)
+    sx, sy = w // 2, h // 2
+
+    def edge(horizontal: bool, cod: int) -> int:
+        c_max = (w if horizontal else h) - 3
+        oc_full = h if horizontal else w
+        s_c, s_oc = (sx, sy) if horizontal else (sy, sx)
+        need = (oc_full - s_oc) // 2 - 1
+        oc_max = oc_full - 3
+        pos = s_c
+        while True:
+            pos += cod
+            if pos > c_max or pos < 0:
+                return c_max + 2
+            if pos < 3:
+                return 0
+            if not (low[s_oc, pos] if horizontal else low[pos, s_oc]):
+                continue
+            # the run goes against the search direction along the other axis
+            lo, hi = (s_oc + 1, s_oc + need) if cod < 0 else (s_oc - need, s_oc - 1)
+            if need > 0:
+                if lo < 3 or hi > oc_max:
+                    continue
+                run = low[lo:hi + 1, pos] if horizontal else low[pos, lo:hi + 1]
+                if not run.all():
+                    continue
+            return pos - cod
+
+    return edge(True, -1), edge(True, 1), edge(False, -1), edge(False, 1)

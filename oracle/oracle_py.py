@@ -68,6 +68,9 @@ def lib() -> C.CDLL:
     L.smh_oracle_lsd_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.smh_oracle_process_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                            C.c_uint32, vp, u32p]
+    L.smh_oracle_calc_meters_to_px_ratio.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_double), vp, u32p]
+    L.smh_oracle_find_minimap_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+    L.smh_oracle_find_minimap.argtypes = [vp, u32p]
     _LIB = L
     return L
 
@@ -228,6 +231,34 @@ class Oracle:
         self.W, self.H = W, H
         self.roi = roi(W, H)
         return bool(rc), lines[: n.value].copy()
+
+
+def calc_meters_to_px_ratio(img: np.ndarray, scales, with_debug: bool = False):
+    """src/vision/mpx_ratio.rs:3-133.  scales: [(meters, (x, y)), ...] -> None | float (f64)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    arr = np.zeros((3, 3), np.uint32)
+    for k, (m, (x, y)) in enumerate(scales):
+        arr[k] = (m, x, y)
+    ratio = C.c_double()
+    dbg = np.zeros((3, 4), np.uint32)
+    nd = C.c_uint32()
+    ok = lib().smh_oracle_calc_meters_to_px_ratio(img.ctypes.data, w, h, arr.ctypes.data, len(scales), C.byref(ratio),
+                                                  dbg.ctypes.data, C.byref(nd))
+    r = ratio.value if ok else None
+    if with_debug:
+        return r, [tuple(int(v) for v in dbg[k]) for k in range(nd.value)]
+    return r
+
+
+def find_minimap_in(bgra: np.ndarray, view):
+    """src/vision/find_minimap.rs:51-146 on frame.view(x, y, w, h) -> None | dict(left, right, top, bottom)."""
+    bgra = np.ascontiguousarray(bgra)
+    H, W = bgra.shape[:2]
+    x, y, w, h = view
+    rect = (C.c_uint32 * 4)()
+    ok = lib().smh_oracle_find_minimap_in(bgra.ctypes.data, W, x, y, w, h, rect)
+    return dict(zip(("left", "right", "top", "bottom"), list(rect))) if ok else None
 
 
 def find_lines_in(img: np.ndarray, max_gap: int) -> np.ndarray:

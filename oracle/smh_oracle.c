@@ -634,6 +634,142 @@ GETTER(lsd_image, lsd_image, 6, 7)
 GETTER(scales, scales, 10, 11)
 GETTER(raw_mask, raw_mask, 6, 7)
 
+/* ---------------------------------------------------------------- meters-per-pixel ratio (N2) */
+
+/* image.get_pixel_fast(x, y).0[0] — unchecked in release builds (util/src/image.rs:136-140), a panic in
+ * debug builds.  D16: a pixel outside the image reads as non-black, i.e. it never belongs to a bar. */
+static inline uint8_t gray_at(const uint8_t *img, uint32_t w, uint32_t h, uint32_t x, uint32_t y) {
+    return (x < w && y < h) ? img[(size_t)y * w + x] : 255;
+}
+
+/* "Make sure this is the vertical line upwards": `(y..y + 4).chain((y..y - 4).rev())` — the second
+ * range is empty (end < start), so the test is the four pixels (x, y) .. (x, y + 3) —
+ * src/vision/mpx_ratio.rs:24-29,45-50 */
+static inline int vertical_bar(const uint8_t *img, uint32_t w, uint32_t h, uint32_t x, uint32_t y) {
+    for (uint32_t yy = y; yy < y + SMH_SCALE_MIN_VBAR_HEIGHT; yy++)
+        if (gray_at(img, w, h, x, yy) != 0) return 0;
+    return 1;
+}
+
+/* find_scale_width — src/vision/mpx_ratio.rs:4-77.  Returns 1 (Some) and fills *ratio and
+ * line = {left, right, y}, or 0 (None). */
+static int find_scale_width(uint32_t meters, uint32_t x, uint32_t y0, const uint8_t *img, uint32_t w, uint32_t h,
+                            double *ratio, uint32_t line[3]) {
+    if (y0 < SMH_SCALE_MIN_VBAR_HEIGHT) return 0;
+    if (x >= w) return 0; /* D16: the reference reads out of bounds here */
+    const uint32_t max_off = (uint32_t)llround((20.0 / 640.0) * (double)w);
+    const uint64_t y_end64 = (uint64_t)y0 + max_off;
+    const uint32_t y_end = y_end64 < h ? (uint32_t)y_end64 : h;
+    for (uint32_t y = y0; y < y_end; y++) {
+        if (img[(size_t)y * w + x] != 0) continue;
+        /* go right */
+        uint32_t right = 0;
+        for (uint32_t xr = x; xr < w; xr++)
+            if (vertical_bar(img, w, h, xr, y)) { right = xr; break; }
+        if (right == 0) continue;
+        right -= 1;
+        /* go left */
+        uint32_t left = 0;
+        for (uint32_t xl = x; xl-- > 0;)
+            if (vertical_bar(img, w, h, xl, y)) { left = xl; break; }
+        if (left == 0) continue;
+        left += 1;
+        const uint32_t width = right - left; /* wraps like the release build when right < left */
+        if (width < SMH_SCALE_MIN_WIDTH) continue;
+        line[0] = left; line[1] = right; line[2] = y;
+        *ratio = (double)meters / (double)width;
+        return 1;
+    }
+    return 0;
+}
+
+int smh_oracle_calc_meters_to_px_ratio(const uint8_t *img, uint32_t w, uint32_t h, const uint32_t (*scales)[3],
+                                       uint32_t n_scales, double *ratio, uint32_t debug[3][4], uint32_t *n_debug) {
+    /* src/vision/mpx_ratio.rs:79-133: the mean of the scales that were found, summed in order */
+    if (n_debug) *n_debug = 0;
+    if (n_scales == 0 || n_scales > 3) return 0;
+    double sum = 0.0;
+    uint32_t found = 0;
+    for (uint32_t k = 0; k < n_scales; k++) {
+        double r;
+        uint32_t line[3];
+        if (find_scale_width(scales[k][0], scales[k][1], scales[k][2], img, w, h, &r, line)) {
+            sum = found ? sum + r : r;
+            if (debug && n_debug) {
+                debug[*n_debug][0] = scales[k][0]; debug[*n_debug][1] = line[0]; debug[*n_debug][2] = line[1]; debug[*n_debug][3] = line[2];
+                (*n_debug)++;
+            }
+            found++;
+        }
+    }
+    if (!found) return 0;
+    *ratio = found == 1 ? sum : sum / (double)found;
+    return 1;
+}
+
+/* ---------------------------------------------------------------- find_minimap (N3) */
+
+/* get_edginess — src/vision/find_minimap.rs:8-46: max over the 8 neighbours of the summed absolute
+ * B,G,R differences, as f32 / 765.0.  (x, y) relative to the view; needs a 1-px margin. */
+static float edginess(const uint8_t *bgra, uint32_t pitch_px, uint32_t vx, uint32_t vy, uint32_t x, uint32_t y) {
+    static const int off[8][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}};
+    const uint8_t *p = bgra + ((size_t)(vy + y) * pitch_px + (vx + x)) * 4;
+    uint16_t mx = 0;
+    for (int k = 0; k < 8; k++) {
+        const uint8_t *q = bgra + ((size_t)(vy + y + off[k][1]) * pitch_px + (vx + x + off[k][0])) * 4;
+        uint16_t s = 0;
+        for (int c = 0; c < 3; c++) s += (uint16_t)abs((int)p[c] - (int)q[c]);
+        if (s > mx) mx = s;
+    }
+    return (float)mx / 765.0f;
+}
+
+/* find_edge — src/vision/find_minimap.rs:65-129.  dir: 0 Left, 1 Right, 2 Up, 3 Down. */
+static uint32_t find_edge(const uint8_t *bgra, uint32_t pitch_px, uint32_t vx, uint32_t vy, uint32_t w, uint32_t h,
+                          uint32_t x, uint32_t y, int dir) {
+    const float THRESHOLD = SMH_MINIMAP_EDGINESS_THRESHOLD;
+    uint32_t xy[2] = {x, y};
+    const int c = dir < 2 ? 0 : 1, oc = 1 - c;
+    const int cod = (dir & 1) ? 1 : -1;
+    uint32_t c_max = c == 0 ? w : h, oc_max = c == 0 ? h : w;
+    const uint32_t d = oc_max > xy[oc] ? oc_max - xy[oc] : xy[oc] - oc_max;
+    const uint32_t min_line_length = d / 2 - 1;
+    c_max -= 3; oc_max -= 3;
+    for (;;) {
+        xy[c] = (uint32_t)((int32_t)xy[c] + cod);
+        if (xy[c] > c_max) return c_max + 2;
+        else if (xy[c] < 3) return 0;
+        if (edginess(bgra, pitch_px, vx, vy, xy[0], xy[1]) <= THRESHOLD) {
+            const uint32_t ret = xy[c];
+            uint32_t q[2] = {xy[0], xy[1]};
+            uint32_t left = min_line_length;
+            int ok = 1;
+            while (left > 0) {
+                q[oc] = (uint32_t)((int32_t)q[oc] - cod);
+                if (q[oc] < 3 || q[oc] > oc_max) { ok = 0; break; }
+                if (edginess(bgra, pitch_px, vx, vy, q[0], q[1]) <= THRESHOLD) left--;
+                else { ok = 0; break; }
+            }
+            if (ok) return (uint32_t)((int32_t)ret - cod);
+        }
+    }
+}
+
+int smh_oracle_find_minimap_in(const uint8_t *bgra, uint32_t pitch_px, uint32_t vx, uint32_t vy, uint32_t w, uint32_t h,
+                               uint32_t rect[4]) {
+    /* src/vision/find_minimap.rs:51-146 -> Rect { left, right, top, bottom } */
+    if (w < 3 || h < 3) return 0;
+    const uint32_t x = w / 2, y = h / 2;
+    for (int dir = 0; dir < 4; dir++) rect[dir] = find_edge(bgra, pitch_px, vx, vy, w, h, x, y, dir);
+    return 1;
+}
+
+int smh_oracle_find_minimap(smh_oracle *o, uint32_t rect[4]) {
+    /* src/vision/mod.rs:85: find_minimap(vision.get_cpu_frame().view(x, y, w, h)) */
+    if (!o || !o->frame) return -2;
+    return smh_oracle_find_minimap_in(o->frame, o->W, o->roi[4], o->roi[5], o->roi[6], o->roi[7], rect);
+}
+
 int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uint32_t H,
                              int grayscale, uint32_t start_y, uint32_t max_gap,
                              float lines[32][4], uint32_t *n_lines) {

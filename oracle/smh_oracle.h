@@ -108,6 +108,20 @@ const uint8_t *smh_oracle_raw_mask(smh_oracle *o, uint32_t wh[2]);
 /* work counters of the last find_marker_lines / find_lines_in call on this thread */
 void smh_oracle_lsd_stats(uint64_t *seeds, uint64_t *ray_steps);
 
+/* calc_meters_to_px_ratio — src/vision/mpx_ratio.rs:3-133 on a caller-supplied `scales_preprocessed`
+ * image.  scales[k] = {meters, x, y} (<= 3).  Returns 1 (Some: *ratio set) or 0 (None).
+ * debug[k] = {meters, left, right, y} of each scale bar found (the scales_debug lines), may be NULL.
+ * D16: where the reference reads outside the image (unchecked in release, panic in debug) the
+ * pixel counts as non-black. */
+int smh_oracle_calc_meters_to_px_ratio(const uint8_t *img, uint32_t w, uint32_t h, const uint32_t (*scales)[3],
+                                       uint32_t n_scales, double *ratio, uint32_t debug[3][4], uint32_t *n_debug);
+/* find_minimap — src/vision/find_minimap.rs:51-146 on the view (vx, vy, w, h) of a BGRA image with
+ * `pitch_px` pixels per row.  rect = {left, right, top, bottom}.  Returns 1 (Some) or 0 (None). */
+int smh_oracle_find_minimap_in(const uint8_t *bgra, uint32_t pitch_px, uint32_t vx, uint32_t vy, uint32_t w, uint32_t h,
+                               uint32_t rect[4]);
+/* same on the loaded frame's map ROI (src/vision/mod.rs:85) */
+int smh_oracle_find_minimap(smh_oracle *o, uint32_t rect[4]);
+
 /* Whole per-frame pipeline in the orchestrator's order (src/vision/mod.rs:66-223):
  * load_frame, crop_to_map, isolate, mask, find_marker_lines(max_gap), ocr_preprocess,
  * find_scales_preprocess(start_y).  Used by the CPU-baseline timing. Returns map_open. */

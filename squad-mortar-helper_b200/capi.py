@@ -13,7 +13,7 @@ import os
 LIB_PATH = Path(os.environ.get("SMH_B200_LIB", PKG / "libsmh_b200.so"))
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
-BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE = 1, 2, 4, 8, 16
+BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP = 1, 2, 4, 8, 16, 32
 
 # every symbol include/smh_b200.h declares (tests assert the library exports all of them)
 SYMBOLS = [
@@ -23,6 +23,7 @@ SYMBOLS = [
     "smh_b200_find_marker_lines", "smh_b200_debug_view", "smh_b200_lsd_image", "smh_b200_red_pixels",
     "smh_b200_process_batch", "smh_b200_process_host_batch", "smh_b200_download_plane", "smh_b200_stream_synchronize", "smh_b200_launch_count",
     "smh_b200_synth_frames_host", "smh_b200_synth_frames_device", "smh_b200_colour_table",
+    "smh_b200_find_minimap", "smh_b200_calc_meters_to_px_ratio", "smh_b200_process", "smh_b200_batch_meters_to_px_ratio",
 ]
 
 
@@ -37,12 +38,33 @@ class Batch(C.Structure):
                 ("roi", C.c_uint32 * 12),
                 ("ui_map", Plane), ("lsd_image", Plane), ("ocr_out", Plane), ("scales", Plane),
                 ("lines", C.c_void_p), ("n_lines", C.c_void_p), ("red_pixels", C.c_void_p),
-                ("map_open", C.c_void_p), ("lsd_stats", C.c_void_p)]
+                ("map_open", C.c_void_p), ("lsd_stats", C.c_void_p),
+                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p)]
 
 
 class HostResults(C.Structure):
     _fields_ = [("ui_map", C.c_void_p), ("ocr_out", C.c_void_p), ("scales", C.c_void_p), ("lsd_image", C.c_void_p),
-                ("lines", C.c_void_p), ("n_lines", C.c_void_p), ("red_pixels", C.c_void_p), ("map_open", C.c_void_p)]
+                ("lines", C.c_void_p), ("n_lines", C.c_void_p), ("red_pixels", C.c_void_p), ("map_open", C.c_void_p),
+                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p)]
+
+
+class Scale(C.Structure):
+    """(meters, (x, y)) of one OCR'd scale label — src/vision/mod.rs:183"""
+    _fields_ = [("meters", C.c_uint32), ("x", C.c_uint32), ("y", C.c_uint32)]
+
+
+class VisionResults(C.Structure):
+    """VisionResults — src/vision/mod.rs:22-29 (plus the map ROI and the scales_debug lines)"""
+    _fields_ = [("map_open", C.c_int32), ("xywh", C.c_uint32 * 4), ("ui_map_rgba", C.c_void_p),
+                ("markers", (C.c_float * 4) * 32), ("n_markers", C.c_uint32),
+                ("has_ratio", C.c_int32), ("meters_to_px_ratio", C.c_double),
+                ("has_minimap", C.c_int32), ("minimap", C.c_uint32 * 4),
+                ("scales_debug", (C.c_uint32 * 4) * 3), ("n_scales_debug", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+# int32_t (*)(void *user, const uint8_t *ocr_l8, uint32_t w, uint32_t h, smh_b200_scale scales[3], uint32_t *n, uint32_t *start_y)
+OCR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Scale), C.POINTER(C.c_uint32),
+                     C.POINTER(C.c_uint32))
 
 
 class SynthParams(C.Structure):
@@ -89,6 +111,10 @@ def lib() -> C.CDLL:
         "smh_b200_synth_frames_host": (i32, [P(SynthParams), u32, u32, vp]),
         "smh_b200_synth_frames_device": (i32, [vp, P(SynthParams), u32, u32, vp, vp]),
         "smh_b200_colour_table": (i32, [vp, u32, vp]),
+        "smh_b200_find_minimap": (i32, [vp, P(i32), P(u32)]),
+        "smh_b200_calc_meters_to_px_ratio": (i32, [vp, P(Scale), u32, P(i32), P(C.c_double), vp, P(u32)]),
+        "smh_b200_process": (i32, [vp, vp, u32, u32, u32, i32, i32, u32, OCR_FN, vp, P(VisionResults)]),
+        "smh_b200_batch_meters_to_px_ratio": (i32, [vp, vp, vp, u32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

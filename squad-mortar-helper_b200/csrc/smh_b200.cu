@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "kernels_next.cuh"
 
 namespace {
 
@@ -76,11 +77,17 @@ struct Planes {
     unsigned long long* stats = nullptr;
     uint32_t* start_y = nullptr;
     uint32_t* counter = nullptr;  // frame dispenser of the persistent line-search CTAs
+    uint32_t* minimap = nullptr;  // [n][4] find_minimap rectangles
+    uint8_t* minimap_found = nullptr;
+    uint32_t* mpx_in = nullptr;   // [n][3][3] scales of calc_meters_to_px_ratio
+    uint8_t* mpx_n = nullptr; double* mpx_ratio = nullptr; uint8_t* mpx_found = nullptr;
+    uint32_t* mpx_debug = nullptr; uint8_t* mpx_ndebug = nullptr;
     uint32_t* bits = nullptr;     // tile-major 1-bit copies of the dilated masks (line-search input)
     uint64_t bits_stride = 0;     // words per frame
     smh::BitsGeom bg{};
     void release() {
-        cudaFree(bits);
+        cudaFree(bits); cudaFree(minimap); cudaFree(minimap_found);
+        cudaFree(mpx_in); cudaFree(mpx_n); cudaFree(mpx_ratio); cudaFree(mpx_found); cudaFree(mpx_debug); cudaFree(mpx_ndebug);
         cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
         cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y); cudaFree(counter);
         *this = Planes();
@@ -117,6 +124,7 @@ struct smh_b200 {
     size_t view_cap = 0;
     float* h_small = nullptr;     // pinned scratch: lines[32][4], n, longest[5]
     float* d_longest = nullptr;
+    uint8_t* d_scales_keep = nullptr;  // device twin of h_scales (tight rows): what calc_meters_to_px_ratio reads
     bool ocr_fetched = false, lsd_fetched = false;
     cudaStream_t s_main = nullptr, s_markers = nullptr, s_scales = nullptr;
     cudaEvent_t ev_pixels = nullptr;
@@ -180,6 +188,16 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     CU(h, cudaMalloc(&P->start_y, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMemset(P->start_y, 0, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->counter, sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->minimap, (size_t)n * 4 * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->minimap, 0, (size_t)n * 4 * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->minimap_found, (size_t)n));
+    CU(h, cudaMemset(P->minimap_found, 0, (size_t)n));
+    CU(h, cudaMalloc(&P->mpx_in, (size_t)n * 9 * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->mpx_n, (size_t)n));
+    CU(h, cudaMalloc(&P->mpx_ratio, (size_t)n * sizeof(double)));
+    CU(h, cudaMalloc(&P->mpx_found, (size_t)n));
+    CU(h, cudaMalloc(&P->mpx_debug, (size_t)n * 12 * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->mpx_ndebug, (size_t)n));
     P->bg.pad = P->pad; P->bg.w = g.map[2]; P->bg.h = g.map[3];
     P->bg.tx = (P->pad + g.map[2] + 31u) / 32u; P->bg.ty = (g.map[3] + 31u) / 32u;
     P->bits_stride = (uint64_t)P->bg.tx * P->bg.ty * 32u;
@@ -290,6 +308,35 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     return SMH_OK;
 }
 
+// find_minimap over n frames: one CTA per (direction, frame)
+int launch_minimap(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t ox, uint32_t oy,
+                   uint32_t n, bool use_open, cudaStream_t st) {
+    const Geometry& g = P.geo;
+    smh::MinimapArgs a{};
+    a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
+    a.map_x = g.map[0] - ox; a.map_y = g.map[1] - oy; a.w = g.map[2]; a.h = g.map[3];
+    a.n_frames = n; a.open = use_open ? P.open : nullptr;
+    a.rect = P.minimap; a.found = P.minimap_found;
+    if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
+    smh::k_minimap<<<dim3(4, n), smh::MM_THREADS, 0, st>>>(a);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+// calc_meters_to_px_ratio over n frames; the scales were already copied to P.mpx_in / P.mpx_n
+int launch_mpx(smh_b200* h, const Planes& P, const uint8_t* img, uint64_t stride, uint32_t pitch, uint32_t pad, uint32_t n,
+               cudaStream_t st) {
+    smh::MpxArgs a{};
+    a.scales = img; a.stride = stride; a.pitch = pitch; a.pad = pad; a.w = P.geo.brq[2]; a.h = P.geo.brq[3];
+    a.n_frames = n; a.in = P.mpx_in; a.n_in = P.mpx_n; a.ratio = P.mpx_ratio; a.found = P.mpx_found;
+    a.debug = P.mpx_debug; a.n_debug = P.mpx_ndebug;
+    smh::k_mpx_ratio<<<n, 96, 0, st>>>(a);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
 uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
     // batches: 128-row bands (halo re-reads <= 5 %, few generic groups); a lone frame: enough
     // bands to cover the SMs
@@ -301,13 +348,15 @@ uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
     return rows;
 }
 
-void fill_batch_out(const Planes& P, bool stats, smh_b200_batch* out) {
+void fill_batch_out(const Planes& P, bool stats, bool minimap, smh_b200_batch* out) {
     memset(out, 0, sizeof *out);
     out->n_frames = P.n; out->W = P.W; out->H = P.H;
     memcpy(out->roi, P.geo.btn, 16); memcpy(out->roi + 4, P.geo.map, 16); memcpy(out->roi + 8, P.geo.brq, 16);
     out->ui_map = P.ui; out->lsd_image = P.lsd; out->ocr_out = P.ocr; out->scales = P.scales;
     out->lines = P.lines; out->n_lines = P.n_lines; out->red_pixels = P.red; out->map_open = P.open;
     out->lsd_stats = stats ? (uint64_t*)P.stats : nullptr;
+    out->minimap = minimap ? P.minimap : nullptr;
+    out->minimap_found = minimap ? P.minimap_found : nullptr;
 }
 
 int download_plane(smh_b200* h, const smh_b200_plane* p, uint32_t first, uint32_t count, uint8_t* host_out, cudaStream_t st) {
@@ -320,6 +369,7 @@ int download_plane(smh_b200* h, const smh_b200_plane* p, uint32_t first, uint32_
 
 void free_single(smh_b200* h) {
     cudaFree(h->d_frame); h->d_frame = nullptr;
+    cudaFree(h->d_scales_keep); h->d_scales_keep = nullptr;
     h->one.release();
     cudaFreeHost(h->h_ui); cudaFreeHost(h->h_ocr); cudaFreeHost(h->h_scales);
     cudaFreeHost(h->h_lsd);
@@ -474,6 +524,8 @@ int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32
         CU(h, cudaMallocHost(&h->h_ocr, nq));
         CU(h, cudaMallocHost(&h->h_scales, nq));
         memset(h->h_scales, 0, nq);
+        CU(h, cudaMalloc(&h->d_scales_keep, nq));
+        CU(h, cudaMemset(h->d_scales_keep, 0, nq));
     }
     const Geometry& g = h->geo;
     CU(h, cudaMemcpy2DAsync(h->d_frame, h->upitch, bgra + (size_t)h->uy0 * pitch_bytes + (size_t)h->ux0 * 4u, pitch_bytes,
@@ -553,6 +605,8 @@ int32_t smh_b200_find_scales_preprocess(smh_b200* h, uint32_t start_y, const uin
         CU(h, cudaStreamWaitEvent(h->s_scales, h->ev_pixels, 0));
         CU(h, cudaMemcpy2DAsync(h->h_scales + (size_t)start_y * qw, qw, p.ptr + (size_t)start_y * p.pitch + p.pad, p.pitch,
                                 qw, qh - start_y, cudaMemcpyDeviceToHost, h->s_scales));
+        CU(h, cudaMemcpy2DAsync(h->d_scales_keep + (size_t)start_y * qw, qw, p.ptr + (size_t)start_y * p.pitch + p.pad, p.pitch,
+                                qw, qh - start_y, cudaMemcpyDeviceToDevice, h->s_scales));
         CU(h, cudaStreamSynchronize(h->s_scales));
     }
     if (out) *out = h->h_scales;
@@ -612,21 +666,124 @@ int32_t smh_b200_find_longest_line(smh_b200* h, float x, float y, float max_gap,
     return SMH_OK;
 }
 
+// the line search of the single-frame path in two halves, so that the orchestrator can overlap the
+// scales branch with it: enqueue on s_markers (no wait), then collect
+static int marker_lines_enqueue(smh_b200* h, uint32_t max_gap) {
+    int rc;
+    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, true, h->s_markers))) return rc;
+    CU(h, cudaMemcpyAsync(h->h_small, h->one.lines, 128 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaMemcpyAsync(h->h_small + 128, h->one.n_lines, 4, cudaMemcpyDeviceToHost, h->s_markers));
+    return SMH_OK;
+}
+static int marker_lines_collect(smh_b200* h, float lines[32][4], uint32_t* n) {
+    CU(h, cudaStreamSynchronize(h->s_markers));
+    const uint32_t cnt = *reinterpret_cast<uint32_t*>(h->h_small + 128);
+    *n = cnt;
+    memcpy(lines, h->h_small, (size_t)cnt * 16);
+    return SMH_OK;
+}
+
 int32_t smh_b200_find_marker_lines(smh_b200* h, uint32_t max_gap, float lines[32][4], uint32_t* n) {
     int rc = need_open_map(h, "find_marker_lines");
     if (rc) return rc;
     if (!lines || !n) return fail(h, SMH_E_ARG, "find_marker_lines: null output");
     std::lock_guard<std::mutex> g(h->markers_mu);
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
-    if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, true, h->s_markers))) return rc;
-    CU(h, cudaMemcpyAsync(h->h_small, h->one.lines, 128 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
-    CU(h, cudaMemcpyAsync(h->h_small + 128, h->one.n_lines, 4, cudaMemcpyDeviceToHost, h->s_markers));
-    CU(h, cudaStreamSynchronize(h->s_markers));
-    const uint32_t cnt = *reinterpret_cast<uint32_t*>(h->h_small + 128);
-    *n = cnt;
-    memcpy(lines, h->h_small, (size_t)cnt * 16);
+    if ((rc = marker_lines_enqueue(h, max_gap))) return rc;
+    return marker_lines_collect(h, lines, n);
+}
+
+int32_t smh_b200_find_minimap(smh_b200* h, int32_t* found, uint32_t rect[4]) {
+    if (!h || !found || !rect) return fail(h, SMH_E_ARG, "find_minimap: bad argument");
+    if (!h->have_frame) return fail(h, SMH_E_STATE, "find_minimap before load_frame");
+    CU(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = launch_minimap(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, h->s_main))) return rc;
+    uint32_t* hs = reinterpret_cast<uint32_t*>(h->h_small + 208);
+    CU(h, cudaMemcpyAsync(hs, h->one.minimap, 16, cudaMemcpyDeviceToHost, h->s_main));
+    CU(h, cudaMemcpyAsync(hs + 4, h->one.minimap_found, 1, cudaMemcpyDeviceToHost, h->s_main));
+    CU(h, cudaStreamSynchronize(h->s_main));
+    *found = reinterpret_cast<uint8_t*>(hs + 4)[0] ? 1 : 0;
+    memcpy(rect, hs, 16);
     return SMH_OK;
+}
+
+int32_t smh_b200_calc_meters_to_px_ratio(smh_b200* h, const smh_b200_scale* scales, uint32_t n_scales, int32_t* found,
+                                         double* ratio, uint32_t debug_lines[3][4], uint32_t* n_debug) {
+    int rc = need_open_map(h, "calc_meters_to_px_ratio");
+    if (rc) return rc;
+    if (!found || !ratio || (n_scales && !scales) || n_scales > 3) return fail(h, SMH_E_ARG, "calc_meters_to_px_ratio: bad argument");
+    std::lock_guard<std::mutex> g(h->scales_mu);
+    CU(h, cudaSetDevice(h->device));
+    *found = 0;
+    if (n_debug) *n_debug = 0;
+    if (n_scales == 0) return SMH_OK;  // `if scales.is_empty() { return None }`
+    // pinned scratch: [216..225) scales in, then the results
+    uint32_t* in = reinterpret_cast<uint32_t*>(h->h_small + 216);
+    for (uint32_t k = 0; k < n_scales; k++) { in[3 * k] = scales[k].meters; in[3 * k + 1] = scales[k].x; in[3 * k + 2] = scales[k].y; }
+    uint8_t* nin = reinterpret_cast<uint8_t*>(h->h_small + 226);
+    nin[0] = (uint8_t)n_scales;
+    CU(h, cudaMemcpyAsync(h->one.mpx_in, in, 36, cudaMemcpyHostToDevice, h->s_scales));
+    CU(h, cudaMemcpyAsync(h->one.mpx_n, nin, 1, cudaMemcpyHostToDevice, h->s_scales));
+    const uint32_t qw = h->geo.brq[2];
+    if ((rc = launch_mpx(h, h->one, h->d_scales_keep, 0, qw, 0, 1, h->s_scales))) return rc;
+    double* hr = reinterpret_cast<double*>(h->h_small + 228);
+    uint32_t* hd = reinterpret_cast<uint32_t*>(h->h_small + 230);
+    uint8_t* hf = reinterpret_cast<uint8_t*>(h->h_small + 242);
+    CU(h, cudaMemcpyAsync(hr, h->one.mpx_ratio, 8, cudaMemcpyDeviceToHost, h->s_scales));
+    CU(h, cudaMemcpyAsync(hd, h->one.mpx_debug, 48, cudaMemcpyDeviceToHost, h->s_scales));
+    CU(h, cudaMemcpyAsync(hf, h->one.mpx_found, 1, cudaMemcpyDeviceToHost, h->s_scales));
+    CU(h, cudaMemcpyAsync(hf + 1, h->one.mpx_ndebug, 1, cudaMemcpyDeviceToHost, h->s_scales));
+    CU(h, cudaStreamSynchronize(h->s_scales));
+    *found = hf[0] ? 1 : 0;
+    *ratio = hr[0];
+    if (debug_lines) memcpy(debug_lines, hd, (size_t)hf[1] * 16);
+    if (n_debug) *n_debug = hf[1];
+    return SMH_OK;
+}
+
+int32_t smh_b200_process(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t H, uint32_t pitch_bytes, int32_t grayscale,
+                         int32_t detect_markers, uint32_t max_gap, smh_b200_ocr_fn ocr, void* user, smh_b200_vision_results* out) {
+    if (!h || !out) return fail(h, SMH_E_ARG, "process: bad argument");
+    memset(out, 0, sizeof *out);
+    int rc;
+    if ((rc = smh_b200_load_frame(h, bgra, W, H, pitch_bytes))) return rc;                        // mod.rs:66
+    if ((rc = smh_b200_crop_to_map(h, grayscale, &out->map_open, out->xywh, &out->ui_map_rgba))) return rc;  // mod.rs:69-75
+    if (!out->map_open) return SMH_OK;                                                             // Ok(None)
+    if ((rc = smh_b200_find_minimap(h, &out->has_minimap, out->minimap))) return rc;               // mod.rs:85
+    // marker branch (mod.rs:87-118): the search is enqueued now and collected after the scales branch,
+    // which is how the two rayon workers of the reference overlap (mod.rs:219-223)
+    if (detect_markers) {
+        if ((rc = smh_b200_isolate_map_markers(h))) return rc;
+        if ((rc = smh_b200_mask_marker_lines(h))) return rc;
+        std::lock_guard<std::mutex> g(h->markers_mu);
+        if ((rc = marker_lines_enqueue(h, max_gap))) return rc;
+    }
+    int scales_rc = SMH_OK;
+    if (ocr) {                                                                                     // mod.rs:124-216
+        const uint8_t* ocr_img = nullptr; size_t len = 0;
+        scales_rc = smh_b200_ocr_preprocess(h, &ocr_img, &len);
+        if (!scales_rc) {
+            smh_b200_scale sc[3]; uint32_t ns = 0, start_y = 0xFFFFFFFFu;
+            memset(sc, 0, sizeof sc);
+            const int32_t orc = ocr(user, ocr_img, h->geo.brq[2], h->geo.brq[3], sc, &ns, &start_y);
+            if (orc) scales_rc = fail(h, orc, "process: the ocr callback failed with %d", orc);
+            else if (ns > 0 && start_y != 0xFFFFFFFFu) {
+                if (ns > 3) ns = 3;
+                const uint8_t* simg = nullptr; uint32_t wh[2];
+                scales_rc = smh_b200_find_scales_preprocess(h, start_y, &simg, wh);
+                if (!scales_rc)
+                    scales_rc = smh_b200_calc_meters_to_px_ratio(h, sc, ns, &out->has_ratio, &out->meters_to_px_ratio,
+                                                                 out->scales_debug, &out->n_scales_debug);
+            }
+        }
+    }
+    if (detect_markers) {
+        std::lock_guard<std::mutex> g(h->markers_mu);
+        if ((rc = marker_lines_collect(h, out->markers, &out->n_markers))) return rc;
+    }
+    return scales_rc;
 }
 
 int32_t smh_b200_debug_view(smh_b200* h, uint8_t which, const uint8_t** rgba, uint32_t wh[2]) {
@@ -708,9 +865,28 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
                                 flags & SMH_BATCH_GRAYSCALE, pick_rows_per_band(h, n, g.map[3]), st)))
             return rc;
     }
+    if ((flags & SMH_BATCH_MINIMAP) && !(flags & SMH_BATCH_SKIP_PIXELS))
+        if ((rc = launch_minimap(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
     if (!(flags & SMH_BATCH_SKIP_LSD))
         if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
-    fill_batch_out(h->batch, stats, out);
+    fill_batch_out(h->batch, stats, (flags & SMH_BATCH_MINIMAP) != 0, out);
+    return SMH_OK;
+}
+
+int32_t smh_b200_batch_meters_to_px_ratio(smh_b200* h, const smh_b200_scale* scales, const uint8_t* n_scales, uint32_t n,
+                                          void* stream, double* ratio, uint8_t* found) {
+    if (!h || !scales || !n_scales || !ratio || !found || n == 0) return fail(h, SMH_E_ARG, "batch_meters_to_px_ratio: bad argument");
+    if (h->batch.n != n) return fail(h, SMH_E_STATE, "batch_meters_to_px_ratio: needs a previous process_batch of %u frames", n);
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Planes& P = h->batch;
+    CU(h, cudaMemcpyAsync(P.mpx_in, scales, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(P.mpx_n, n_scales, (size_t)n, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = launch_mpx(h, P, P.scales.ptr, P.scales.frame_stride, P.scales.pitch, P.scales.pad, n, st))) return rc;
+    CU(h, cudaMemcpyAsync(ratio, P.mpx_ratio, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(found, P.mpx_found, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
     return SMH_OK;
 }
 
@@ -857,6 +1033,8 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         if ((rc = launch_pixels(h, P, stage, ustride, upitch, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
                                 pick_rows_per_band(h, c, g.map[3]), st)))
             return rc;
+        if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found)
+            if ((rc = launch_minimap(h, P, stage, ustride, upitch, ux0, uy0, c, true, st))) return rc;
         if (!(flags & SMH_BATCH_SKIP_LSD))
             if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st))) return rc;
         uint8_t* const pack0 = h->d_pack + (size_t)b * pack_frame * chunk;
@@ -889,6 +1067,10 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         CU(h, cudaMemcpyAsync(res->n_lines + done, P.n_lines, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(res->red_pixels + done, P.red, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(res->map_open + done, P.open, (size_t)c, cudaMemcpyDeviceToHost, st));
+        if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found) {
+            CU(h, cudaMemcpyAsync(res->minimap + (size_t)done * 4, P.minimap, (size_t)c * 16, cudaMemcpyDeviceToHost, st));
+            CU(h, cudaMemcpyAsync(res->minimap_found + done, P.minimap_found, (size_t)c, cudaMemcpyDeviceToHost, st));
+        }
         stamp(st);
         CU(h, cudaEventRecord(ev_down, st));
         done += c;

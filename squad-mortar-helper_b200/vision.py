@@ -184,18 +184,101 @@ class B200Vision:
             return None
         return _borrow(p.value, (wh[1], wh[0], 4)).copy()
 
+    # -- the callers either side of the trait -------------------------
+    def find_minimap(self):
+        """find_minimap(vision.get_cpu_frame().view(x, y, w, h)) — src/vision/find_minimap.rs:51-146, on the
+        device copy of the loaded frame.  -> None | dict(left, right, top, bottom)"""
+        found = C.c_int32()
+        rect = (C.c_uint32 * 4)()
+        check(self._h, self._L.smh_b200_find_minimap(self._h, C.byref(found), rect))
+        if not found.value:
+            return None
+        return dict(zip(("left", "right", "top", "bottom"), list(rect)))
+
+    def calc_meters_to_px_ratio(self, scales, with_debug: bool = False):
+        """calc_meters_to_px_ratio(scales, image) — src/vision/mpx_ratio.rs:3-133 — on the device copy of
+        what find_scales_preprocess last returned.  scales: [(meters, (x, y)), ...] (<= 3).
+        -> Option<f64> as None | float; with_debug also returns the scales_debug lines [(meters, left, right, y)]."""
+        arr = (capi.Scale * 3)()
+        for k, (m, (x, y)) in enumerate(scales):
+            arr[k] = capi.Scale(int(m), int(x), int(y))
+        found, ratio = C.c_int32(), C.c_double()
+        dbg = ((C.c_uint32 * 4) * 3)()
+        nd = C.c_uint32()
+        check(self._h, self._L.smh_b200_calc_meters_to_px_ratio(self._h, arr, len(scales), C.byref(found), C.byref(ratio),
+                                                                C.cast(dbg, C.c_void_p), C.byref(nd)))
+        r = ratio.value if found.value else None
+        if with_debug:
+            return r, [tuple(dbg[k]) for k in range(nd.value)]
+        return r
+
+    def process(self, bgra: np.ndarray, *, grayscale: bool = True, detect_markers: bool = True, max_gap: int = 15, ocr=None):
+        """VisionState::process — src/vision/mod.rs:36-240 — as one call into the C ABI.
+        ocr: None (a heightmap is set: no scales branch) or callable(ocr_l8[h,w]) -> ([(meters, (x, y))...], scales_start_y)
+        standing where Tesseract does.  -> None (map closed) | dict of VisionResults."""
+        if bgra.strides[2] != 1 or bgra.strides[1] != 4:
+            bgra = np.ascontiguousarray(bgra)
+        H, W = bgra.shape[:2]
+        err = []
+
+        def _cb(user, img, w, h, scales, n, start_y):
+            try:
+                got, sy = ocr(_borrow(img, (h, w)))
+                got = list(got)[:3]
+                for k, (m, (x, y)) in enumerate(got):
+                    scales[k].meters, scales[k].x, scales[k].y = int(m), int(x), int(y)
+                n[0] = len(got)
+                start_y[0] = int(sy) if got else 0xFFFFFFFF
+                return 0
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+                return -100
+
+        cb = capi.OCR_FN(_cb) if ocr is not None else capi.OCR_FN()
+        res = capi.VisionResults()
+        rc = self._L.smh_b200_process(self._h, bgra.ctypes.data, W, H, bgra.strides[0], int(bool(grayscale)),
+                                      int(bool(detect_markers)), int(max_gap), cb, None, C.byref(res))
+        if err:
+            raise err[0]
+        check(self._h, rc)
+        self._frame = bgra
+        if not res.map_open:
+            return None
+        x, y, w, h = list(res.xywh)
+        lines = np.array([list(res.markers[k]) for k in range(res.n_markers)], np.float32).reshape(-1, 4)
+        return {"map": _borrow(res.ui_map_rgba, (h, w, 4)).copy(), "xywh": [x, y, w, h], "markers": lines,
+                "meters_to_px_ratio": res.meters_to_px_ratio if res.has_ratio else None,
+                "minimap_bounds": dict(zip(("left", "right", "top", "bottom"), list(res.minimap))) if res.has_minimap else None,
+                "scales_debug": [tuple(res.scales_debug[k]) for k in range(res.n_scales_debug)]}
+
+    def batch_meters_to_px_ratio(self, scales, stream: int = 0):
+        """calc_meters_to_px_ratio for every frame of the last process_batch.  scales: per frame a list of
+        (meters, (x, y)) (<= 3).  -> (ratio[n] float64, found[n] bool)"""
+        n = len(scales)
+        arr = np.zeros((n, 3, 3), np.uint32)
+        cnt = np.zeros(n, np.uint8)
+        for f, sc in enumerate(scales):
+            cnt[f] = len(sc)
+            for k, (m, (x, y)) in enumerate(sc):
+                arr[f, k] = (m, x, y)
+        ratio = np.zeros(n, np.float64)
+        found = np.zeros(n, np.uint8)
+        check(self._h, self._L.smh_b200_batch_meters_to_px_ratio(self._h, arr.ctypes.data, cnt.ctypes.data, n, stream,
+                                                                 ratio.ctypes.data, found.ctypes.data))
+        return ratio, found.astype(bool)
+
     # -- batch extension (not in the trait) ------------------------------------------------
     def process_batch(self, d_frames: int, n: int, W: int, H: int, *, pitch: int | None = None,
                       frame_stride: int | None = None, start_y=None, max_gap: int = 15, grayscale: bool = True,
                       lsd_stats: bool = False, skip_lsd: bool = False, skip_pixels: bool = False,
-                      lsd_exhaustive: bool = False,
+                      lsd_exhaustive: bool = False, minimap: bool = False,
                       stream: int = 0) -> capi.Batch:
         """Enqueue the whole path for n device-resident frames on `stream`; returns the plane table."""
         pitch = W * 4 if pitch is None else pitch
         frame_stride = pitch * H if frame_stride is None else frame_stride
         flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_LSD_STATS if lsd_stats else 0) | \
                 (capi.BATCH_SKIP_LSD if skip_lsd else 0) | (capi.BATCH_SKIP_PIXELS if skip_pixels else 0) | \
-                (capi.BATCH_LSD_EXHAUSTIVE if lsd_exhaustive else 0)
+                (capi.BATCH_LSD_EXHAUSTIVE if lsd_exhaustive else 0) | (capi.BATCH_MINIMAP if minimap else 0)
         sy = None
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)
@@ -233,10 +316,15 @@ class B200Vision:
             if k not in out:
                 out[k] = np.zeros(shp, dt)
             setattr(res, k, out[k].ctypes.data if isinstance(out[k], np.ndarray) else int(out[k]))
+        if "minimap" in want:
+            out.setdefault("minimap", np.zeros((n, 4), np.uint32))
+            out.setdefault("minimap_found", np.zeros((n,), np.uint8))
+            res.minimap = out["minimap"].ctypes.data if isinstance(out["minimap"], np.ndarray) else int(out["minimap"])
+            res.minimap_found = out["minimap_found"].ctypes.data if isinstance(out["minimap_found"], np.ndarray) else int(out["minimap_found"])
         sy = None
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)
-        flags = capi.BATCH_GRAYSCALE if grayscale else 0
+        flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_MINIMAP if "minimap" in want else 0)
         check(self._h, self._L.smh_b200_process_host_batch(self._h, frames_ptr, n, W, H, W * 4, W * H * 4,
                                                            sy.ctypes.data if sy is not None else None, max_gap, flags,
                                                            chunk, C.byref(res)))

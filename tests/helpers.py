@@ -72,3 +72,28 @@ def assert_same(got: dict, want: dict, what="", scales_from=0):
     assert gl.shape == wl.shape, f"{what}: {gl.shape[0]} lines, oracle has {wl.shape[0]}\n{gl}\n{wl}"
     # bit-exact: compare the raw f32 bit patterns
     assert np.array_equal(gl.view(np.uint32), wl.view(np.uint32)), f"{what}: line endpoints differ\n{gl}\n{wl}"
+
+
+def oracle_process(frame, grayscale=True, detect_markers=True, max_gap=15, ocr=None, oracle=None):
+    """VisionState::process (src/vision/mod.rs:36-240) composed from the oracle's pieces.
+    ocr: None | callable(ocr_l8) -> ([(meters, (x, y))], scales_start_y).  -> None | dict like B200Vision.process"""
+    from oracle import oracle_py as O
+    o = oracle or O.Oracle()
+    o.load_frame(frame)
+    got = o.crop_to_map(grayscale)
+    if got is None:
+        return None
+    ui, xywh = got
+    res = {"map": ui, "xywh": xywh, "markers": np.zeros((0, 4), np.float32), "meters_to_px_ratio": None, "scales_debug": []}
+    res["minimap_bounds"] = O.find_minimap_in(frame, xywh)
+    if detect_markers:
+        o.isolate_map_markers()
+        o.mask_marker_lines()
+        res["markers"] = o.find_marker_lines(max_gap)
+    if ocr is not None:
+        scales, start_y = ocr(o.ocr_preprocess())
+        scales = list(scales)[:3]
+        if scales:
+            img = o.find_scales_preprocess(start_y)
+            res["meters_to_px_ratio"], res["scales_debug"] = O.calc_meters_to_px_ratio(img, scales, with_debug=True)
+    return res
