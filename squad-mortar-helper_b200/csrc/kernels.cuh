@@ -129,8 +129,17 @@ __device__ __forceinline__ uint32_t luma_biased_i2f(uint32_t w) {
     return __float_as_uint(__fadd_rd(l, 8388608.0f));
 }
 
-// rare path shared by both vector kinds: exact marker bits of the 4 pixels
+// Marker fast-reject for a whole vector: a marker colour has max(r,g,b) >= 178, i.e. some colour
+// byte with bit 7 set and low 7 bits >= 50; SIMD-in-register test over the three colour bytes.
+__device__ __forceinline__ uint32_t bright_bytes(uint32_t w) {  // nonzero iff some of b,g,r is >= 178
+    return ((w & 0x007F7F7Fu) + 0x004E4E4Eu) & w & 0x00808080u;
+}
+
+// rare path shared by both vector kinds: exact marker bits of the 4 pixels.  Entered when the OR of
+// the four words has a colour byte >= 178 (necessary, not sufficient), so the exact per-word test
+// comes first.
 __device__ __noinline__ uint32_t marker_nibble(uint4 v, const uint32_t* __restrict__ lut) {
+    if (!(bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w))) return 0u;
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     uint32_t m4 = 0;
 #pragma unroll
@@ -142,15 +151,19 @@ __device__ __noinline__ uint32_t marker_nibble(uint4 v, const uint32_t* __restri
 }
 
 // ---- vector with no pixel inside the OCR quadrant (flags: marker only), owned row -------------
-// Marker fast-reject for the whole vector: a marker colour has max(r,g,b) >= 178, i.e. some colour
-// byte with bit 7 set and low 7 bits >= 50; SIMD-in-register test over the three colour bytes.
-__device__ __forceinline__ uint32_t bright_bytes(uint32_t w) {  // nonzero iff some of b,g,r is >= 178
-    return ((w & 0x007F7F7Fu) + 0x004E4E4Eu) & w & 0x00808080u;
-}
+// Vector-level fast rejects work on the OR of the four BGRA words (2 instructions, shared by both
+// tests): a byte of the OR is >= any of the four bytes it combines and keeps their bit 7, so
+//   some colour byte >= 178  =>  bright_bytes(or4) != 0          (marker colours: max(r,g,b) >= 178)
+//   some pixel with b,g,r all >= 130  =>  bit 7 of all three colour bytes of or4   (OCR classes)
+__device__ __forceinline__ uint32_t or4(const uint4& v) { return v.x | v.y | v.z | v.w; }
 
 template <bool GRAY>
 __device__ __forceinline__ void vec_plain(const uint4& v, const uint32_t* __restrict__ lut, uint32_t alpha, PxOut& o) {
+#if defined(PX_EXP) && PX_EXP >= 1
+    if (false) {
+#else
     if (GRAY) {  // (L,L,L,255) — vision-cpu/src/lib.rs:150-157
+#endif
         o.ui.x = __byte_perm(luma_biased_i2f(v.x), alpha, 0x7000);
         o.ui.y = __byte_perm(luma_biased_i2f(v.y), alpha, 0x7000);
         o.ui.z = __byte_perm(luma_biased_i2f(v.z), alpha, 0x7000);
@@ -162,12 +175,14 @@ __device__ __forceinline__ void vec_plain(const uint4& v, const uint32_t* __rest
         o.ui.w = __byte_perm(v.w, alpha, 0x7012);
     }
     o.m4 = 0;
-    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) o.m4 = marker_nibble(v, lut);  // rare
+#if !defined(PX_EXP) || PX_EXP < 2
+    if (bright_bytes(or4(v))) o.m4 = marker_nibble(v, lut);  // rare
+#endif
 }
 
 // marker flags only (halo rows: nothing is stored)
 __device__ __forceinline__ uint32_t vec_marker_only(const uint4& v, const uint32_t* __restrict__ lut) {
-    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) return marker_nibble(v, lut);
+    if (bright_bytes(or4(v))) return marker_nibble(v, lut);
     return 0u;
 }
 
@@ -176,21 +191,22 @@ __device__ __forceinline__ uint32_t vec_marker_only(const uint4& v, const uint32
 template <bool GRAY>
 __device__ __forceinline__ void vec_quadrant(const uint4& v, bool owned, const uint32_t* __restrict__ lut, uint32_t alpha, PxOut& o) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-    uint32_t uo[4], dmin = 0xFFFFFFFFu, lmin = 0xFFFFFFFFu;
+    uint32_t uo[4], lmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-        const uint32_t cb = chan<0>(wd[e]), cg = chan<1>(wd[e]), cr = chan<2>(wd[e]);
-        dmin = min(dmin, max(cr, max(cg, cb)) - min(cr, min(cg, cb)));
-        const uint32_t lb = owned ? luma_biased(cr, cg, cb) : BIAS + 1u;
+        const uint32_t lb = owned ? luma_biased_i2f(wd[e]) : BIAS + 1u;
         lmin = min(lmin, lb);
         if (GRAY) uo[e] = __byte_perm(lb, alpha, 0x7000);
         else uo[e] = __byte_perm(wd[e], alpha, 0x7012);
     }
     o.ui = make_uint4(uo[0], uo[1], uo[2], uo[3]);
     o.m4 = 0; o.c4 = 0; o.e4 = 0; o.ocrw = 0xFFFFFFFFu; o.scw = 0xFFFFFFFFu;
-    if (bright_bytes(v.x) | bright_bytes(v.y) | bright_bytes(v.z) | bright_bytes(v.w)) o.m4 = marker_nibble(v, lut);  // rare
-    // OCR classes — vision-cpu/src/lib.rs:39-53,188-193; mono = sum |ci-cj| = 4*(max-min)
-    if (dmin <= SMH_OCR_MONO_EDGE / 4u) {  // rare: a near-grey pixel
+    const uint32_t any = or4(v);
+    if (bright_bytes(any)) o.m4 = marker_nibble(v, lut);  // rare
+    // OCR classes — vision-cpu/src/lib.rs:39-53,188-193; mono = sum |ci-cj| = 4*(max-min).  Both
+    // classes need every channel >= SMH_OCR_BRIGHT_EDGE (130 > 128): bit 7 of b, g and r.
+    static_assert(SMH_OCR_BRIGHT_EDGE >= 128u && SMH_OCR_BRIGHT >= SMH_OCR_BRIGHT_EDGE, "fast reject assumes min channel >= 128");
+    if ((any & 0x00808080u) == 0x00808080u) {  // rare: possibly a bright near-grey pixel
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
@@ -229,9 +245,12 @@ constexpr int PX_STRIP = 30;  // inner vector columns per warp
 #define PX_MIN_BLOCKS 8  // register cap 64/thread -> 32 warps per SM
 #endif
 #ifndef PX_DEPTH
-#define PX_DEPTH 3       // rows of 128-bit copies in flight per lane (3 measured best on B200; 5-7 are ~4% slower)
+#define PX_DEPTH 2       // rows of 128-bit copies in flight per lane (B200, 32-row bands: 1 -> 3.07 ms, 2 -> 2.91, 3 -> 3.05 per 1024 frames)
 #endif
-constexpr int PX_SLOTS = 8;  // ring slots per warp (power of two > PX_DEPTH), 512 B each
+#ifndef PX_SLOTS_N
+#define PX_SLOTS_N 8
+#endif
+constexpr int PX_SLOTS = PX_SLOTS_N;  // ring slots per warp (power of two > PX_DEPTH), 512 B each
 constexpr int PX_SMEM_BYTES = PX_WARPS * PX_SLOTS * 512;
 
 template <bool GRAY>
@@ -267,7 +286,6 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
     const int r0 = (int)(band * a.rows_per_band);
     const int r1 = min(r0 + (int)a.rows_per_band, (int)a.h);
     const int bqh = (int)a.bqh, bqw = (int)a.bqw;
-    const int halo = (r1 > bqh && r0 < 2 * bqh) ? SMH_OCR_RADIUS : 1;
     const uint32_t start_y = a.start_y ? a.start_y[f] : a.start_y_uniform;
     const uint32_t* __restrict__ lut = a.lut;
     const uint32_t alpha = opaque_alpha();
@@ -290,6 +308,8 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
     }
     const bool col_brq = em4 != 0u;  // some pixel inside the quadrant columns
     const bool brq_strip = __any_sync(0xFFFFFFFFu, col_brq && inner);
+    // rows of halo: 3 where the strip and band meet the OCR quadrant (7x7 search), else 1 (3x3 cross)
+    const int halo = (brq_strip && r1 > bqh && r0 < 2 * bqh) ? SMH_OCR_RADIUS : 1;
     const uint32_t qo = active ? (uint32_t)q : 0u;
     const uint32_t qpos = (uint32_t)((int)a.qpad - (int)a.pad - bqw + 4 * (int)qo);  // byte position in a quadrant row (used when col_brq)
     uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
@@ -307,6 +327,28 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
     uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
 
     auto row = [&](const uint4& cur, int jn) {
+#if defined(PX_EXP) && PX_EXP >= 3  // memory pattern only (timing experiment; 4: reads only, 5: writes only)
+#if PX_EXP == 8  // lsd plane only, 32 lanes x 4 B = one aligned 128-byte line per warp-row
+        if (jn >= r0 && jn < r1 && strip * 128u + 128u <= a.lsd_pitch)
+            stg_u32(a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)jn * (int64_t)a.lsd_pitch + strip * 128u + lane * 4u, cur.x);
+#endif
+#if PX_EXP == 4  // reads only: keep the value alive without storing
+        if (cur.x == 0x12345678u && cur.y == 0x9ABCDEF0u) stg_u32(lsd_p + 3 * a.lsd_pitch, cur.z);
+        else if (false) {
+#else
+        if (active && jn >= r0 && jn < r1 && inner) {
+#endif
+            if (PX_EXP != 7 && PX_EXP < 8) stg_v4(ui_p, cur);
+            if (PX_EXP != 6 && PX_EXP != 8) stg_u32(lsd_p + 3 * a.lsd_pitch, cur.x);
+            const int jq = jn - bqh;
+            if (PX_EXP != 6 && PX_EXP < 8 && (uint32_t)jq < (uint32_t)bqh && col_brq) {
+                stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), cur.y);
+                stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), cur.z);
+            }
+        }
+        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
+        return;
+#endif
         // ---------------- phase 1: row jn -------------------------------------------------------
         uint32_t m4 = 0, c4 = 0, e4 = 0;
         if (active && jn >= j_lo && jn < j_hi) {
@@ -390,12 +432,18 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
     for (int jn = j_first; jn - SMH_OCR_RADIUS < r1; jn++) {
         {
             const int j = jn + PX_DEPTH;
+#if !defined(PX_EXP) || PX_EXP < 5
             if (active && j >= j_lo && j < j_hi) cp_async16(ring0 + ((slot + PX_DEPTH) & (PX_SLOTS - 1)) * 512u, fetch_p);
+#endif
             cp_async_commit();
             fetch_p += a.pitch;
         }
         cp_async_wait<PX_DEPTH>();  // the group of row jn has landed
+#if defined(PX_EXP) && PX_EXP >= 5
+        const uint4 cur = make_uint4(jn, slot, lane, 0);
+#else
         const uint4 cur = lds_v4(ring0 + slot * 512u);
+#endif
         slot = (slot + 1) & (PX_SLOTS - 1);
         row(cur, jn);
     }

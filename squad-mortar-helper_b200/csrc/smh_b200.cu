@@ -338,13 +338,18 @@ int launch_mpx(smh_b200* h, const Planes& P, const uint8_t* img, uint64_t stride
 }
 
 uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
-    // batches: 128-row bands (halo re-reads <= 5 %, few generic groups); a lone frame: enough
-    // bands to cover the SMs
-    if (n >= 16) return 128;
+    // batches: 32-row bands.  The pass is bound by how DRAM takes its stores, not by instructions or
+    // by the halo re-reads: with short bands all bands of a frame are in flight together and each
+    // output row is completed within a short window (measured on B200, 1024 frames 1440p: 8 rows
+    // 3.57 ms, 16 -> 3.05, 32 -> 2.91, 64 -> 2.98, 128 -> 3.19, 274 -> 3.63, whole map -> 4.27;
+    // profiles/r1g_variants.txt).  A lone frame: enough bands to cover the SMs
+    static const int forced = [] { const char* e = getenv("SMH_B200_ROWS_PER_BAND"); return e ? atoi(e) : 0; }();  // tuning knob
+    if (forced >= 8) return (uint32_t)forced;
+    if (n >= 16) return 32;
     uint32_t want = (uint32_t)h->sm_count * 2u / (n ? n : 1u);
     uint32_t rows = want ? (map_h + want - 1) / want : map_h;
     if (rows < 8) rows = 8;
-    if (rows > 128) rows = 128;
+    if (rows > 32) rows = 32;
     return rows;
 }
 
