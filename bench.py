@@ -203,6 +203,8 @@ def main() -> None:
                     help="host frames per e2e step (default: the whole batch; 512 per rank beyond 2 GPUs to bound pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--serial", action="store_true",
+                    help="one launch per kernel on one stream (no chunk overlap): the form the ncu launch list is taken on")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,17 +247,21 @@ def main() -> None:
     stream = torch.cuda.current_stream().cuda_stream
     fp = frames.data_ptr()
 
-    def step(ev=None):
-        # one launch of each kernel; split only so that events can sit between them
+    def step():
+        # the product call: one smh_b200_process_batch over the whole batch.  Large batches run as chunks
+        # on the library's internal streams (pixel pass of one chunk under the line search of another);
+        # --serial forces one launch per kernel on this stream (what the ncu launch list is taken on)
+        vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, serial=args.serial, stream=stream)
+
+    def step_split(ev):
+        # per-kernel durations: one launch of each kernel over the whole batch, each timed alone
         vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, skip_lsd=True, stream=stream)
-        if ev is not None:
-            ev[1].record()
+        ev[1].record()
         vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, skip_pixels=True, stream=stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = vision.launch_count()
@@ -263,14 +269,21 @@ def main() -> None:
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
     for k in range(args.steps):
-        evs[k][0].record()
-        step(evs[k])
-        evs[k][2].record()
+        step()
     t_end.record()
     barrier()
-    clocks = sampler.stop()
     launches = vision.launch_count() - launches0
     total_ms = t_start.elapsed_time(t_end)
+    # second timed pass, same inputs, kernels one after the other with events between them
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    step_split(evs[0])
+    barrier()
+    for k in range(args.steps):
+        evs[k][0].record()
+        step_split(evs[k])
+        evs[k][2].record()
+    barrier()
+    clocks = sampler.stop()
     px_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     lsd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
     if world > 1:
@@ -328,8 +341,14 @@ def main() -> None:
             "roofline": {"kernel": "k_pixels", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpf * n, "kernel_ms": px_ms,
-                         "note": "of measured copy bandwidth; HBM-bound pixel pass. k_lsd is not HBM-bound (see kernels)"},
+                         "note": "of measured copy bandwidth; HBM-bound pixel pass, one launch over the whole batch timed alone "
+                                 "with CUDA events (second timed pass). k_lsd is not HBM-bound (see kernels)"},
             "kernels": {"dominant_by_time": dominant,
+                        "timing": "second timed pass of the same steps: one launch per kernel over the whole batch, events between",
+                        "serial_ms_per_step": px_ms + lsd_ms,
+                        "step_form": "serial (one launch per kernel)" if args.serial else
+                                     "chunks on internal streams: pixel pass of one chunk overlaps the line search of another",
+                        "overlap_speedup": (px_ms + lsd_ms) / ms_per_step,
                         "k_pixels": {"ms": px_ms, "share": px_ms / (px_ms + lsd_ms)},
                         "k_lsd": {"ms": lsd_ms, "share": lsd_ms / (px_ms + lsd_ms), "bound": "instruction issue / L1 latency",
                                   "seeds_per_frame": seeds_pf, "seeds_pruned_per_frame": pruned_pf, "ray_steps_per_frame": steps_pf,

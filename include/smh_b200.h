@@ -187,6 +187,7 @@ typedef struct {
 #define SMH_BATCH_LSD_STATS 2u /* count seeds / ray steps per frame (slower; for reporting) */
 #define SMH_BATCH_SKIP_LSD 4u  /* pixel pass only */
 #define SMH_BATCH_SKIP_PIXELS 8u /* line search only, on the planes of the previous call */
+#define SMH_BATCH_SERIAL 64u   /* one launch per kernel on the caller's stream (profiling: no chunk overlap) */
 #define SMH_BATCH_MINIMAP 32u   /* also run find_minimap on every open frame (src/vision/find_minimap.rs) */
 #define SMH_BATCH_LSD_EXHAUSTIVE 16u /* march all 3600 rays of every seed (no isolated-blob pruning): makes
                                         the ray-step counter comparable with the CPU oracle's */

@@ -13,7 +13,7 @@ import os
 LIB_PATH = Path(os.environ.get("SMH_B200_LIB", PKG / "libsmh_b200.so"))
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
-BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP = 1, 2, 4, 8, 16, 32
+BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP, BATCH_SERIAL = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/smh_b200.h declares (tests assert the library exports all of them)
 SYMBOLS = [

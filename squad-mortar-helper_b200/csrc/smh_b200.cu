@@ -29,6 +29,8 @@ thread_local std::string g_create_error;
 #ifndef SMH_PIPE_DEPTH
 #define SMH_PIPE_DEPTH 3
 #endif
+// smh_b200_process_batch splits a large batch into chunks that run on up to this many internal streams
+#define SMH_BATCH_LANES_MAX 8
 
 struct Geometry {
     uint32_t W = 0, H = 0;
@@ -137,6 +139,8 @@ struct smh_b200 {
     uint8_t* d_stage = nullptr; size_t stage_cap = 0;   // host-batch upload staging (device)
     uint8_t* d_pack = nullptr; size_t pack_cap = 0;     // host-batch download staging: planes without pitch padding
     Planes pipe[SMH_PIPE_DEPTH];
+    std::vector<cudaStream_t> lane_streams;   // process_batch: chunks of a large batch, taken in turn
+    std::vector<cudaEvent_t> lane_events;     // [0] fork, [1 + lane] join
 };
 
 namespace {
@@ -187,7 +191,7 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     CU(h, cudaMalloc(&P->open, (size_t)n));
     CU(h, cudaMalloc(&P->start_y, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMemset(P->start_y, 0, (size_t)n * sizeof(uint32_t)));
-    CU(h, cudaMalloc(&P->counter, sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->counter, SMH_BATCH_LANES_MAX * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->minimap, (size_t)n * 4 * sizeof(uint32_t)));
     CU(h, cudaMemset(P->minimap, 0, (size_t)n * 4 * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->minimap_found, (size_t)n));
@@ -243,6 +247,38 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     return SMH_OK;
 }
 
+// offsets table of the warp-per-ray march: long enough for any ray inside this mask plus two blocks
+int ensure_ray_ckpt(smh_b200* h, const Planes& P, cudaStream_t st) {
+    const double diag = sqrt((double)P.bg.w * P.bg.w + (double)P.bg.h * P.bg.h);
+    const uint32_t need = ((uint32_t)diag / 32u + 5u) * (32u / smh::LSD_CKPT);
+    if (need > h->n_ckpt) {
+        CU(h, cudaDeviceSynchronize());
+        cudaFree(h->d_ckpt); h->d_ckpt = nullptr; h->n_ckpt = 0;
+        CU(h, cudaMalloc(&h->d_ckpt, (size_t)SMH_LSD_RAYS * need * sizeof(float2)));
+        smh::k_build_ray_ckpt<<<(SMH_LSD_RAYS + 127) / 128, 128, 0, st>>>(h->d_rays, need, h->d_ckpt);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        CU(h, cudaStreamSynchronize(st));
+        h->n_ckpt = need;
+    }
+    return SMH_OK;
+}
+
+// Frames [f0, f0 + cn) of a batch's planes as a batch of their own (shallow: never release()d);
+// `lane` picks the frame dispenser the line search of this view uses.
+Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
+    Planes V = P;
+    V.n = cn;
+    V.ui.ptr += (uint64_t)f0 * P.ui.frame_stride; V.lsd.ptr += (uint64_t)f0 * P.lsd.frame_stride;
+    V.ocr.ptr += (uint64_t)f0 * P.ocr.frame_stride; V.scales.ptr += (uint64_t)f0 * P.scales.frame_stride;
+    V.lines += (size_t)f0 * 128; V.n_lines += f0; V.red += f0; V.open += f0; V.start_y += f0;
+    if (V.stats) V.stats += (size_t)f0 * 3;
+    V.counter += lane;
+    V.minimap += (size_t)f0 * 4; V.minimap_found += f0;
+    V.bits += (uint64_t)f0 * P.bits_stride;
+    return V;
+}
+
 int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st) {
     // 1-bit tile-major copy of the dilated masks (what the search kernel reads)
     {
@@ -252,21 +288,7 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
         h->launches++;
         CU(h, cudaGetLastError());
     }
-    // offsets table of the warp-per-ray march: long enough for any ray inside this mask plus two blocks
-    {
-        const double diag = sqrt((double)P.bg.w * P.bg.w + (double)P.bg.h * P.bg.h);
-        const uint32_t need = ((uint32_t)diag / 32u + 5u) * (32u / smh::LSD_CKPT);
-        if (need > h->n_ckpt) {
-            CU(h, cudaDeviceSynchronize());
-            cudaFree(h->d_ckpt); h->d_ckpt = nullptr; h->n_ckpt = 0;
-            CU(h, cudaMalloc(&h->d_ckpt, (size_t)SMH_LSD_RAYS * need * sizeof(float2)));
-            smh::k_build_ray_ckpt<<<(SMH_LSD_RAYS + 127) / 128, 128, 0, st>>>(h->d_rays, need, h->d_ckpt);
-            h->launches++;
-            CU(h, cudaGetLastError());
-            CU(h, cudaStreamSynchronize(st));
-            h->n_ckpt = need;
-        }
-    }
+    { int rc = ensure_ray_ckpt(h, P, st); if (rc) return rc; }
     smh::LsdArgs a{};
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
     a.rays = h->d_rays; a.ckpt = h->d_ckpt; a.n_ckpt = h->n_ckpt; a.span_tab = h->d_span; a.max_gap = max_gap;
@@ -335,6 +357,17 @@ int launch_mpx(smh_b200* h, const Planes& P, const uint8_t* img, uint64_t stride
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
+}
+
+// chunk size / stream count of the chunked form of smh_b200_process_batch (environment = tuning knobs)
+void batch_tuning(const smh_b200* h, uint32_t* chunk, uint32_t* lanes) {
+    const char* ec = getenv("SMH_B200_BATCH_CHUNK");
+    const char* el = getenv("SMH_B200_BATCH_LANES");
+    int c = ec ? atoi(ec) : 0, l = el ? atoi(el) : 0;
+    if (c <= 0) c = h->sm_count;           // one line-search CTA per SM and chunk
+    if (l <= 0) l = 3;
+    if (l > SMH_BATCH_LANES_MAX) l = SMH_BATCH_LANES_MAX;
+    *chunk = (uint32_t)c; *lanes = (uint32_t)l;
 }
 
 uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
@@ -473,6 +506,8 @@ void smh_b200_destroy(smh_b200* h) {
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
     for (auto e : h->pipe_events) cudaEventDestroy(e);
+    for (auto s : h->lane_streams) cudaStreamDestroy(s);
+    for (auto e : h->lane_events) cudaEventDestroy(e);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     if (h->s_markers) cudaStreamDestroy(h->s_markers);
     if (h->s_scales) cudaStreamDestroy(h->s_scales);
@@ -860,20 +895,63 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
     if ((flags & SMH_BATCH_SKIP_PIXELS) && (h->batch.n != n || h->batch.W != W || h->batch.H != H))
         return fail(h, SMH_E_STATE, "process_batch: SKIP_PIXELS needs a previous batch of the same shape");
     if ((rc = ensure_planes(h, &h->batch, n, g, stats))) return rc;
-    if (!(flags & SMH_BATCH_SKIP_PIXELS)) {
-        if (start_y) {
-            for (uint32_t i = 0; i < n; i++)
-                if (start_y[i] > g.brq[3]) return fail(h, SMH_E_RANGE, "process_batch: start_y[%u]=%u > %u", i, start_y[i], g.brq[3]);
-            CU(h, cudaMemcpyAsync(h->batch.start_y, start_y, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        }
-        if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, start_y != nullptr, 0,
-                                flags & SMH_BATCH_GRAYSCALE, pick_rows_per_band(h, n, g.map[3]), st)))
-            return rc;
+    if (!(flags & SMH_BATCH_SKIP_PIXELS) && start_y) {
+        for (uint32_t i = 0; i < n; i++)
+            if (start_y[i] > g.brq[3]) return fail(h, SMH_E_RANGE, "process_batch: start_y[%u]=%u > %u", i, start_y[i], g.brq[3]);
+        CU(h, cudaMemcpyAsync(h->batch.start_y, start_y, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     }
-    if ((flags & SMH_BATCH_MINIMAP) && !(flags & SMH_BATCH_SKIP_PIXELS))
-        if ((rc = launch_minimap(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
-    if (!(flags & SMH_BATCH_SKIP_LSD))
-        if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
+    const uint32_t rows_per_band = pick_rows_per_band(h, n, g.map[3]);
+    // Large batches: frames are independent, so the batch runs as chunks taken in turn by a few internal
+    // streams (pixel pass -> bitmap -> line search per chunk).  The line search is latency-bound and its
+    // persistent CTAs leave issue slots and, in the tail of every wave, whole SMs idle; the HBM-bound
+    // pixel pass of the following chunks fills them.  Same kernels, same results; the caller's stream
+    // is forked and joined with events, so the call stays asynchronous and stream-ordered.
+    uint32_t chunk = 0, lanes = 0;
+    batch_tuning(h, &chunk, &lanes);
+    const bool whole = (flags & (SMH_BATCH_SKIP_PIXELS | SMH_BATCH_SKIP_LSD | SMH_BATCH_SERIAL)) || n < 2u * chunk || lanes < 2;
+    if (whole) {
+        if (!(flags & SMH_BATCH_SKIP_PIXELS)) {
+            if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, start_y != nullptr, 0,
+                                    flags & SMH_BATCH_GRAYSCALE, rows_per_band, st)))
+                return rc;
+            if (flags & SMH_BATCH_MINIMAP)
+                if ((rc = launch_minimap(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
+        }
+        if (!(flags & SMH_BATCH_SKIP_LSD))
+            if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
+    } else {
+        if ((rc = ensure_ray_ckpt(h, h->batch, st))) return rc;
+        if (stats) CU(h, cudaMemsetAsync(h->batch.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
+        while (h->lane_streams.size() < lanes) {
+            cudaStream_t s;
+            CU(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            h->lane_streams.push_back(s);
+        }
+        while (h->lane_events.size() < 1u + lanes) {
+            cudaEvent_t e;
+            CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->lane_events.push_back(e);
+        }
+        CU(h, cudaEventRecord(h->lane_events[0], st));
+        for (uint32_t l = 0; l < lanes; l++) CU(h, cudaStreamWaitEvent(h->lane_streams[l], h->lane_events[0], 0));
+        uint32_t c = 0;
+        for (uint32_t f0 = 0; f0 < n; f0 += chunk, c++) {
+            const uint32_t cn = n - f0 < chunk ? n - f0 : chunk, lane = c % lanes;
+            cudaStream_t ls = h->lane_streams[lane];
+            const Planes V = planes_view(h->batch, f0, cn, lane);
+            const uint8_t* fr = d_frames + (uint64_t)f0 * frame_stride;
+            if ((rc = launch_pixels(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, start_y != nullptr, 0,
+                                    flags & SMH_BATCH_GRAYSCALE, rows_per_band, ls)))
+                return rc;
+            if (flags & SMH_BATCH_MINIMAP)
+                if ((rc = launch_minimap(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, true, ls))) return rc;
+            if ((rc = launch_lsd(h, V, cn, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), ls))) return rc;
+        }
+        for (uint32_t l = 0; l < lanes; l++) {
+            CU(h, cudaEventRecord(h->lane_events[1 + l], h->lane_streams[l]));
+            CU(h, cudaStreamWaitEvent(st, h->lane_events[1 + l], 0));
+        }
+    }
     fill_batch_out(h->batch, stats, (flags & SMH_BATCH_MINIMAP) != 0, out);
     return SMH_OK;
 }

@@ -271,14 +271,15 @@ class B200Vision:
     def process_batch(self, d_frames: int, n: int, W: int, H: int, *, pitch: int | None = None,
                       frame_stride: int | None = None, start_y=None, max_gap: int = 15, grayscale: bool = True,
                       lsd_stats: bool = False, skip_lsd: bool = False, skip_pixels: bool = False,
-                      lsd_exhaustive: bool = False, minimap: bool = False,
+                      lsd_exhaustive: bool = False, minimap: bool = False, serial: bool = False,
                       stream: int = 0) -> capi.Batch:
         """Enqueue the whole path for n device-resident frames on `stream`; returns the plane table."""
         pitch = W * 4 if pitch is None else pitch
         frame_stride = pitch * H if frame_stride is None else frame_stride
         flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_LSD_STATS if lsd_stats else 0) | \
                 (capi.BATCH_SKIP_LSD if skip_lsd else 0) | (capi.BATCH_SKIP_PIXELS if skip_pixels else 0) | \
-                (capi.BATCH_LSD_EXHAUSTIVE if lsd_exhaustive else 0) | (capi.BATCH_MINIMAP if minimap else 0)
+                (capi.BATCH_LSD_EXHAUSTIVE if lsd_exhaustive else 0) | (capi.BATCH_MINIMAP if minimap else 0) | \
+                (capi.BATCH_SERIAL if serial else 0)
         sy = None
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)

@@ -156,6 +156,38 @@ def test_full_size_properties_1440p(vision):
         assert_same(gpu_run(vision, host[k], True, 0, 15), want, f"trait path frame {i}")
 
 
+@pytest.mark.parametrize("chunk,lanes", [(16, 3), (40, 2), (7, 8)])
+def test_chunked_streams_equal_one_launch(vision, monkeypatch, chunk, lanes):
+    """smh_b200_process_batch runs a large batch as chunks on internal streams (pixel pass of one chunk
+    under the line search of another); every plane, line, flag and counter must equal the
+    one-launch-per-kernel form (SMH_BATCH_SERIAL), with ragged last chunks and per-frame start_y."""
+    W, H, n = 1280, 720, 101
+    frames = np.concatenate([synth.frames_host(synth.SynthParams(W, H, map_open=(i % 5 != 3)), 300 + i, 1) for i in range(n)])
+    dev = torch.from_numpy(frames).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    start_y = (np.arange(n, dtype=np.uint32) * 11) % 60
+    a = vision.process_batch(dev.data_ptr(), n, W, H, start_y=start_y, max_gap=15, lsd_stats=True, minimap=True, serial=True, stream=st)
+    ra = _results(vision, a, n)
+    mm_a = _device_array(a.minimap, n * 16).cpu().numpy().copy(), _device_array(a.minimap_found, n).cpu().numpy().copy()
+    ra = {k: v.copy() for k, v in ra.items()}
+    monkeypatch.setenv("SMH_B200_BATCH_CHUNK", str(chunk))
+    monkeypatch.setenv("SMH_B200_BATCH_LANES", str(lanes))
+    l0 = vision.launch_count()
+    b = vision.process_batch(dev.data_ptr(), n, W, H, start_y=start_y, max_gap=15, lsd_stats=True, minimap=True, stream=st)
+    assert vision.launch_count() - l0 == 4 * ((n + chunk - 1) // chunk), "expected one launch of each kernel per chunk"
+    rb = _results(vision, b, n)
+    mm_b = _device_array(b.minimap, n * 16).cpu().numpy(), _device_array(b.minimap_found, n).cpu().numpy()
+    for k in ra:
+        if k == "lines":
+            for i in range(n):
+                m = int(ra["n_lines"][i])
+                assert np.array_equal(ra[k][i, :m].view(np.uint32), rb[k][i, :m].view(np.uint32)), (k, i)
+        else:
+            assert np.array_equal(ra[k], rb[k]), k
+    assert np.array_equal(mm_a[1], mm_b[1]) and np.array_equal(mm_a[0], mm_b[0])
+    assert (ra["map_open"] == (np.arange(n) % 5 != 3)).all()
+
+
 def test_4k_frame_and_lsd_stress(vision):
     """BASELINE config 4 frame size and config 5 (LSD stress) scenes, checked against the oracle."""
     for W, H, kw, n in ((3840, 2160, synth.DENSE, 2), (2560, 1440, synth.STRESS_SEGMENTS, 1),
