@@ -84,6 +84,26 @@ int32_t smh_b200_find_scales_preprocess(smh_b200 *h, uint32_t scales_start_y, co
 int32_t smh_b200_isolate_map_markers(smh_b200 *h);
 int32_t smh_b200_mask_marker_lines(smh_b200 *h);
 
+/* Vision::load_map_markers / filter_map_marker_icons — the marker icon template match the reference
+ * carries COMMENTED OUT (trait: vision-common/src/lib.rs:46,53; CPU vision-cpu/src/lib.rs:101-108,
+ * 270-277,282-355; GPU vision-gpu/src/lib.rs:129-137,202-204,373-430 + cuda.cu:548-614; orchestrator
+ * src/vision/mod.rs:48-49,95-107).  Off unless the host calls it.
+ *
+ * load_map_markers: n_markers (<= 8) templates of size x size RGBA pixels, tightly packed, in the
+ * layout vision-gpu uploads (`load_markers::<UnfilteredMarkers>(size)`, vision-gpu/src/gpumarkers.rs:24-52;
+ * the TGA decode / Gaussian resize / colour isolation / corner mask of
+ * vision-common/src/markers/mod.rs:96-119 stay host-side `image`-crate work).  n_markers*size*size <= 8192.
+ *
+ * filter_map_marker_icons: call between isolate_map_markers and mask_marker_lines, at most once per frame.
+ * Scores every candidate pixel (marker-coloured, size <= x < w-size-1, size <= y < h-size-1) against every
+ * template — sum over opaque template pixels of u32(f32(|dr|+|dg|+|db|) * (f32(alpha)/255)) on the isolated
+ * crop — takes the global minimum (ties: first in raster order, D17; the reference's order is
+ * nondeterministic), blacks the icon's size x size square out of the crop and leaves the 4x4 green square at
+ * its tip, so that the mask, the line search and the LSDPreprocess / LSDInput debug views see the edit.
+ * *found = 0 when the map holds no candidate (or is smaller than the template). */
+int32_t smh_b200_load_map_markers(smh_b200 *h, const uint8_t *rgba, uint32_t n_markers, uint32_t size);
+int32_t smh_b200_filter_map_marker_icons(smh_b200 *h, int32_t *found, uint32_t xy[2], uint32_t *sad);
+
 /* Vision::find_longest_line — lib.rs:55; CPU :387-449; GPU :489-538 (+K10).  Searches the
  * handle's current dilated mask (the trait's `image` argument is the backend's own LSDImage).
  * line = {p0.x,p0.y,p1.x,p1.y} — layout of #[repr(C)] Line<f32>, util/src/geometry.rs:168-173. */
@@ -181,6 +201,9 @@ typedef struct {
     uint64_t *lsd_stats;       /* device, [n][3] = {seeds, ray_steps, pruned seeds} when stats were requested, else NULL */
     uint32_t *minimap;         /* device, [n][4] = left, right, top, bottom (SMH_BATCH_MINIMAP), else NULL */
     uint8_t *minimap_found;    /* device, [n] */
+    uint8_t *icon_found;       /* device, [n]: template match found (SMH_BATCH_FILTER_ICONS), else NULL */
+    uint32_t *icon_xy;         /* device, [n][2] = x, y of the matched icon's window in the map crop */
+    uint32_t *icon_sad;        /* device, [n] */
 } smh_b200_batch;
 
 #define SMH_BATCH_GRAYSCALE 1u /* ui_map = (L,L,L,255) — settings default, src/settings.rs:135 */
@@ -188,6 +211,8 @@ typedef struct {
 #define SMH_BATCH_SKIP_LSD 4u  /* pixel pass only */
 #define SMH_BATCH_SKIP_PIXELS 8u /* line search only, on the planes of the previous call */
 #define SMH_BATCH_SERIAL 64u   /* one launch per kernel on the caller's stream (profiling: no chunk overlap) */
+#define SMH_BATCH_FILTER_ICONS 128u /* run the (reference-disabled) icon template match between the mask and the
+                                       line search; needs smh_b200_load_map_markers */
 #define SMH_BATCH_MINIMAP 32u   /* also run find_minimap on every open frame (src/vision/find_minimap.rs) */
 #define SMH_BATCH_LSD_EXHAUSTIVE 16u /* march all 3600 rays of every seed (no isolated-blob pruning): makes
                                         the ray-step counter comparable with the CPU oracle's */

@@ -362,3 +362,40 @@ def find_minimap(view_bgra: np.ndarray):
             return pos - cod
 
     return edge(True, -1), edge(True, 1), edge(False, -1), edge(False, 1)
+
+
+# ---- marker icon template match (A20 / N4; the reference carries this stage commented out) -------------
+
+def filter_map_marker_icons(cropped_map: np.ndarray, templates: np.ndarray):
+    """vision-cpu/src/lib.rs:270-277 (candidates) + 282-355 on the ISOLATED cropped_map [h,w,3]; templates
+    [n,size,size,4] RGBA.  -> (None | (x, y, sad), cropped_map after erase + stamp).  Vectorised over the
+    candidates: an independent restatement of oracle/smh_oracle.c's loops (ties: raster-first, D17)."""
+    h, w = cropped_map.shape[:2]
+    n, size = templates.shape[:2]
+    out = cropped_map.copy()
+    if w < size + 2 or h < size + 2:
+        return None, out
+    cand = is_marker(cropped_map)
+    cand[:size] = False; cand[h - size - 1:] = False
+    cand[:, :size] = False; cand[:, w - size - 1:] = False
+    ys, xs = np.nonzero(cand)  # raster order
+    if len(ys) == 0:
+        return None, out
+    m16 = cropped_map.astype(np.int32)
+    sad = np.zeros((len(ys), n), np.uint32)
+    for my in range(size):
+        for mx in range(size):
+            t = templates[:, my, mx].astype(np.int32)  # [n, 4]
+            if not t[:, 3].any():
+                continue
+            q = m16[ys + my, xs + mx]  # [c, 3]
+            ad = np.abs(q[:, None, :] - t[None, :, :3]).sum(axis=2).astype(np.float32)  # [c, n]
+            a = (t[:, 3].astype(np.float32) / np.float32(255.0)).astype(np.float32)
+            sad += (ad * a[None, :]).astype(np.float32).astype(np.uint32)  # alpha == 0 contributes 0
+    best = sad.min(axis=1)
+    k = int(np.argmin(best))  # first minimum in raster order
+    x, y, s = int(xs[k]), int(ys[k]), int(best[k])
+    out[y:min(y + size, h - 1), x:min(x + size, w - 1)] = 0
+    px, py = x + size // 2, y + _round_half_away(float(np.float32(size) * np.float32(0.70)))
+    out[max(py - 2, 0):py + 2, max(px - 2, 0):px + 2] = (0, 255, 0)
+    return (x, y, s), out

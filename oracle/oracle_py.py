@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
     L.smh_oracle_find_scales_preprocess.argtypes = [vp, C.c_uint32, C.POINTER(vp), u32p]
     L.smh_oracle_isolate_map_markers.argtypes = [vp]
     L.smh_oracle_mask_marker_lines.argtypes = [vp]
+    L.smh_oracle_load_map_markers.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    L.smh_oracle_filter_map_marker_icons.argtypes = [vp, C.POINTER(C.c_int), u32p, u32p]
     L.smh_oracle_find_longest_line.argtypes = [vp, C.c_float, C.c_float, C.c_float, f32p, f32p]
     L.smh_oracle_find_longest_line_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float,
                                                   C.c_float, f32p, f32p]
@@ -178,6 +180,20 @@ class Oracle:
 
     def mask_marker_lines(self) -> None:
         assert self.L.smh_oracle_mask_marker_lines(self.h) == 0
+
+    def load_map_markers(self, templates: np.ndarray) -> None:
+        """templates: [n, size, size, 4] RGBA (UnfilteredMarkers layout, markers/mod.rs:142-152)."""
+        t = np.ascontiguousarray(templates, np.uint8)
+        assert t.ndim == 4 and t.shape[1] == t.shape[2] and t.shape[3] == 4
+        assert self.L.smh_oracle_load_map_markers(self.h, t.ctypes.data, t.shape[0], t.shape[1]) == 0
+
+    def filter_map_marker_icons(self):
+        """The disabled template-match stage (vision-cpu/src/lib.rs:282-355) -> None | (x, y, sad)."""
+        found = C.c_int()
+        xy = (C.c_uint32 * 2)()
+        sad = C.c_uint32()
+        assert self.L.smh_oracle_filter_map_marker_icons(self.h, C.byref(found), xy, C.byref(sad)) == 0
+        return (int(xy[0]), int(xy[1]), int(sad.value)) if found.value else None
 
     def find_longest_line(self, x: float, y: float, max_gap: float):
         line = (C.c_float * 4)()

@@ -167,6 +167,8 @@ struct smh_oracle {
     uint8_t *raw_mask;     /* L8 w*h (oracle-only view of the mask before dilation) */
     uint8_t *ui_map;       /* RGBA w*h, owned by the oracle, refreshed by crop_to_map */
     uint16_t *dist;        /* scratch for the distance transform */
+    /* disabled template-match stage (A20): UnfilteredMarkers layout, n * size*size RGBA */
+    uint8_t *markers; uint32_t n_markers, marker_size;
 };
 
 smh_oracle *smh_oracle_new(void) { return (smh_oracle *)calloc(1, sizeof(smh_oracle)); }
@@ -182,6 +184,7 @@ void smh_oracle_free(smh_oracle *o) {
     if (!o) return;
     free_buffers(o);
     free(o->frame);
+    free(o->markers);
     free(o);
 }
 
@@ -619,6 +622,78 @@ int smh_oracle_debug_view(smh_oracle *o, uint8_t which, uint8_t *rgba, uint32_t 
             rgba[4 * i + 3] = 255;
         }
     }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- marker icon template match (A20 / N4)
+ * The stage is commented out everywhere in the reference (F2); this restates the commented code. */
+
+int smh_oracle_load_map_markers(smh_oracle *o, const uint8_t *rgba, uint32_t n, uint32_t size) {
+    /* vision-cpu/src/lib.rs:101-108; the templates themselves come from
+     * vision-common/src/markers/mod.rs:111-119 (host-side `image` crate work: TGA decode, Gaussian
+     * resize, colour isolation, corner mask) and are passed in as data. */
+    if (!o || !rgba || n == 0 || size == 0) return -2;
+    free(o->markers);
+    o->markers = (uint8_t *)malloc((size_t)n * size * size * 4);
+    memcpy(o->markers, rgba, (size_t)n * size * size * 4);
+    o->n_markers = n; o->marker_size = size;
+    return 0;
+}
+
+int smh_oracle_filter_map_marker_icons(smh_oracle *o, int *found, uint32_t xy[2], uint32_t *sad_out) {
+    /* vision-cpu/src/lib.rs:282-355 on cropped_map AFTER isolate_map_markers, with the candidate list
+     * of lib.rs:270-277.  The reference's candidate order is whatever order its rayon workers' fetch_add
+     * produced, and min_by_key keeps the first minimum of that order, so ties are nondeterministic
+     * there; D17: candidates in raster order, markers in order, first minimum wins. */
+    if (!o || !o->frame || !o->markers) return -2;
+    const uint32_t w = o->roi[6], h = o->roi[7], size = o->marker_size;
+    if (found) *found = 0;
+    /* `if w >= map_marker_size && h >= map_marker_size` (src/vision/mod.rs:104); the u32 bounds
+     * `w - size - 1` of lib.rs:272-273 must not wrap for the candidate rule to mean anything */
+    if (w < size + 2 || h < size + 2) return 0;
+    uint8_t *map = o->cropped_map;
+    uint64_t best = UINT64_MAX;
+#pragma omp parallel for schedule(dynamic, 8) reduction(min : best)
+    for (uint32_t y = size; y < h - size - 1; y++)
+        for (uint32_t x = size; x < w - size - 1; x++) {
+            const uint8_t *c = map + ((size_t)y * w + x) * 3;
+            /* a candidate is a pixel that survived isolate (lib.rs:269-277) */
+            if (!smh_oracle_is_marker(c[0], c[1], c[2])) continue;
+            for (uint32_t m = 0; m < o->n_markers; m++) {
+                const uint8_t *tpl = o->markers + (size_t)m * size * size * 4;
+                uint32_t sad = 0;
+                for (uint32_t my = 0; my < size; my++)
+                    for (uint32_t mx = 0; mx < size; mx++) {
+                        const uint8_t *t = tpl + ((size_t)my * size + mx) * 4;
+                        if (t[3] == 0) continue; /* FilteredMarkers drops alpha == 0 (markers/mod.rs:135) */
+                        const uint8_t *q = map + ((size_t)(y + my) * w + (x + mx)) * 3;
+                        uint32_t ad = 0;
+                        for (int k = 0; k < 3; k++) ad += (uint32_t)(q[k] > t[k] ? q[k] - t[k] : t[k] - q[k]);
+                        /* ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323 */
+                        const float a = (float)t[3] / 255.0f;
+                        const float v = (float)ad * a;
+                        sad += (uint32_t)v;
+                    }
+                const uint64_t key = ((uint64_t)sad << 32) | ((uint64_t)y << 16) | x;
+                if (key < best) best = key;
+            }
+        }
+    if (best == UINT64_MAX) return 0;
+    const uint32_t x = (uint32_t)(best & 0xFFFFu), y = (uint32_t)((best >> 16) & 0xFFFFu);
+    if (found) *found = 1;
+    if (xy) { xy[0] = x; xy[1] = y; }
+    if (sad_out) *sad_out = (uint32_t)(best >> 32);
+    /* erase the icon — lib.rs:335-340 */
+    const uint32_t ex = x + size < w - 1 ? x + size : w - 1, ey = y + size < h - 1 ? y + size : h - 1;
+    for (uint32_t cx = x; cx < ex; cx++)
+        for (uint32_t cy = y; cy < ey; cy++) { uint8_t *q = map + ((size_t)cy * w + cx) * 3; q[0] = q[1] = q[2] = 0; }
+    /* leave a 4x4 square where the icon points — lib.rs:344-351 */
+    const uint32_t px = x + size / 2, py = y + (uint32_t)roundf((float)size * SMH_MAP_MARKER_POI_LOCATION);
+    for (uint32_t cx = px >= 2 ? px - 2 : 0; cx < px + 2; cx++)
+        for (uint32_t cy = py >= 2 ? py - 2 : 0; cy < py + 2; cy++) {
+            if (cx >= w || cy >= h) continue; /* put_pixel_fast is unchecked; unreachable for candidates of lib.rs:270-273 */
+            uint8_t *q = map + ((size_t)cy * w + cx) * 3; q[0] = 0; q[1] = 255; q[2] = 0;
+        }
     return 0;
 }
 

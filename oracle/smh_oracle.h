@@ -69,6 +69,13 @@ int smh_oracle_find_scales_preprocess(smh_oracle *o, uint32_t scales_start_y, co
                                       uint32_t wh[2]);
 /* vision-cpu/src/lib.rs:253-280 */
 int smh_oracle_isolate_map_markers(smh_oracle *o);
+/* The template-match stage the reference carries commented out (A20; vision-cpu/src/lib.rs:101-108,
+ * 270-277, 282-355).  Templates: n * size*size RGBA in the UnfilteredMarkers layout
+ * (vision-common/src/markers/mod.rs:142-152).  Call between isolate_map_markers and mask_marker_lines
+ * (src/vision/mod.rs:96-107): erases the best-matching icon from cropped_map and leaves the 4x4 green
+ * square.  D17: ties go to the first candidate in raster order. */
+int smh_oracle_load_map_markers(smh_oracle *o, const uint8_t *rgba, uint32_t n, uint32_t size);
+int smh_oracle_filter_map_marker_icons(smh_oracle *o, int *found, uint32_t xy[2], uint32_t *sad);
 /* vision-cpu/src/lib.rs:357-375 (+ imageproc dilate L1,k=1) */
 int smh_oracle_mask_marker_lines(smh_oracle *o);
 /* vision-cpu/src/lib.rs:387-449 on the oracle's own lsd_image */

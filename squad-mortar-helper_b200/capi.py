@@ -13,7 +13,7 @@ import os
 LIB_PATH = Path(os.environ.get("SMH_B200_LIB", PKG / "libsmh_b200.so"))
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
-BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP, BATCH_SERIAL = 1, 2, 4, 8, 16, 32, 64
+BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP, BATCH_SERIAL, BATCH_FILTER_ICONS = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/smh_b200.h declares (tests assert the library exports all of them)
 SYMBOLS = [
@@ -24,6 +24,7 @@ SYMBOLS = [
     "smh_b200_process_batch", "smh_b200_process_host_batch", "smh_b200_download_plane", "smh_b200_stream_synchronize", "smh_b200_launch_count",
     "smh_b200_synth_frames_host", "smh_b200_synth_frames_device", "smh_b200_colour_table",
     "smh_b200_find_minimap", "smh_b200_calc_meters_to_px_ratio", "smh_b200_process", "smh_b200_batch_meters_to_px_ratio",
+    "smh_b200_load_map_markers", "smh_b200_filter_map_marker_icons",
 ]
 
 
@@ -39,7 +40,8 @@ class Batch(C.Structure):
                 ("ui_map", Plane), ("lsd_image", Plane), ("ocr_out", Plane), ("scales", Plane),
                 ("lines", C.c_void_p), ("n_lines", C.c_void_p), ("red_pixels", C.c_void_p),
                 ("map_open", C.c_void_p), ("lsd_stats", C.c_void_p),
-                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p)]
+                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p),
+                ("icon_found", C.c_void_p), ("icon_xy", C.c_void_p), ("icon_sad", C.c_void_p)]
 
 
 class HostResults(C.Structure):
@@ -115,6 +117,8 @@ def lib() -> C.CDLL:
         "smh_b200_calc_meters_to_px_ratio": (i32, [vp, P(Scale), u32, P(i32), P(C.c_double), vp, P(u32)]),
         "smh_b200_process": (i32, [vp, vp, u32, u32, u32, i32, i32, u32, OCR_FN, vp, P(VisionResults)]),
         "smh_b200_batch_meters_to_px_ratio": (i32, [vp, vp, vp, u32, vp, vp, vp]),
+        "smh_b200_load_map_markers": (i32, [vp, vp, u32, u32]),
+        "smh_b200_filter_map_marker_icons": (i32, [vp, P(i32), P(u32), P(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -1,0 +1,261 @@
+// kernels_icons.cuh — marker icon template match.
+//
+// The reference carries this stage commented out in both backends (vision-cpu/src/lib.rs:270-277,
+// 282-355; vision-gpu/src/lib.rs:373-430 + cuda.cu:548-614) and in the orchestrator
+// (src/vision/mod.rs:95-107).  Semantics restated here (the CPU backend's flavour):
+//
+//   candidates   marker-coloured pixels (x, y) of the map crop with size <= x < w-size-1 and
+//                size <= y < h-size-1 (lib.rs:269-277)
+//   score        for every candidate and every template t:  sum over template pixels with alpha != 0 of
+//                u32( f32(|r-tr| + |g-tg| + |b-tb|) * (f32(alpha) / 255) )  against the ISOLATED crop
+//                (non-marker pixels are black), the window's top-left corner at the candidate (lib.rs:307-331)
+//   pick         the global minimum; D17: ties -> first candidate in raster order
+//   edit         black out [x, min(x+size, w-1)) x [y, min(y+size, h-1)), then a 4x4 pure-green square at
+//                (x + size/2 - 2, y + round(0.70*size) - 2) (lib.rs:333-352) — so mask_marker_lines sees
+//                the icon gone and its tip kept.
+//
+// B200 design: the isolated crop is never materialised (the fused pixel pass writes only the dilated
+// mask), so k_icons rebuilds it tile by tile in shared memory from the resident capture and the 2^24-bit
+// predicate table, and only for tiles whose dilated-mask bitmap has a set bit (~90 % of the tiles of a
+// map have none: one 128-byte read each).  Candidates of a tile are compacted with ballots; one warp
+// scores one candidate, lanes over the template pixels that are opaque in at least one template; a
+// window pixel that is black (the common case) costs nothing — its contribution is precomputed per
+// template and added up front.  k_icon_apply then edits the dilated mask and its bitmap in place.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/smh_consts.h"
+#include "kernels.cuh"
+
+namespace smh {
+
+constexpr int ICON_THREADS = 256;
+constexpr int ICON_MAX_TEMPLATES = 8;
+constexpr uint32_t ICON_TILE = 32;
+constexpr unsigned long long ICON_NONE = 0xFFFFFFFFFFFFFFFFull;
+
+// Per-handle template table (built on the host by smh_b200_load_map_markers):
+//   act[j]            = mx | my << 8 for the j-th template pixel that is opaque in some template
+//   rgb/af/c0[j*n+t]  = packed b|g<<8|r<<16, alpha/255 (f32), contribution against a black pixel
+//   base[t]           = sum_j c0[j*n+t]
+struct IconTable {
+    const uint32_t* act; const uint32_t* rgb; const float* af; const uint32_t* c0; const uint32_t* base;
+    uint32_t n_act, n, size;
+};
+
+struct IconArgs {
+    const uint8_t* frames; uint64_t frame_stride; uint32_t pitch;  // BGRA captures
+    uint32_t map_x, map_y, w, h;                                    // map crop, relative to `frames`
+    const uint32_t* lut;                                            // marker predicate bit table
+    const uint32_t* bits; uint64_t bits_stride; BitsGeom g;         // dilated mask, tile-major bitmap
+    const uint8_t* open;                                            // nullptr: every frame
+    IconTable t;
+    uint32_t n_frames;
+    unsigned long long* best;                                       // [n] sad << 32 | y << 16 | x, ICON_NONE-initialised
+};
+
+__device__ __forceinline__ uint32_t icon_pixel(const IconArgs& a, const uint8_t* frame, uint32_t x, uint32_t y) {
+    // pixel (x, y) of the isolated crop as b|g<<8|r<<16, or 0 (vision-cpu/src/lib.rs:266-268)
+    if (x >= a.w || y >= a.h) return 0u;
+    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(frame + (uint64_t)(a.map_y + y) * a.pitch + (uint64_t)(a.map_x + x) * 4u));
+    const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
+    return marker_bit(word, max(r, max(g, b)), min(r, min(g, b)), a.lut) ? (word & 0x00FFFFFFu) : 0u;
+}
+
+// Persistent CTAs over (frame, tile) items.  Dynamic shared memory: window [(32+size-1)^2] words,
+// candidate list [1024] halves, template table.
+__global__ void __launch_bounds__(ICON_THREADS) k_icons(const IconArgs a) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t size = a.t.size, n = a.t.n, n_act = a.t.n_act;
+    const uint32_t WIN = ICON_TILE + size - 1u, WP = WIN | 1u;  // odd pitch: rows fall in different banks
+    uint32_t* win = sm;                                  // [WIN][WP]
+    uint32_t* cand = win + WIN * WP;                     // [1024] cx | cy << 8 (tile coordinates)
+    uint32_t* s_act = cand + ICON_TILE * ICON_TILE;      // [n_act] offset into win | j-independent
+    uint32_t* s_rgb = s_act + n_act;                     // [n_act * n]
+    float* s_af = reinterpret_cast<float*>(s_rgb + n_act * n);
+    uint32_t* s_c0 = reinterpret_cast<uint32_t*>(s_af + n_act * n);
+    __shared__ uint32_t s_any, s_ncand;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    for (uint32_t j = tid; j < n_act; j += ICON_THREADS) {
+        const uint32_t v = a.t.act[j];
+        s_act[j] = (v >> 8) * WP + (v & 0xFFu);
+    }
+    for (uint32_t j = tid; j < n_act * n; j += ICON_THREADS) { s_rgb[j] = a.t.rgb[j]; s_af[j] = a.t.af[j]; s_c0[j] = a.t.c0[j]; }
+    uint32_t base[ICON_MAX_TEMPLATES];
+#pragma unroll
+    for (int t = 0; t < ICON_MAX_TEMPLATES; t++) base[t] = (uint32_t)t < n ? a.t.base[t] : 0u;
+
+    // candidate bounds (lib.rs:270-273)
+    const uint32_t x_lo = size, y_lo = size, x_hi = a.w - size - 1u, y_hi = a.h - size - 1u;  // [lo, hi)
+    // tiles are aligned to the crop (not to the padded bitmap grid): tile (i, j) = pixels [32i, 32i+32) x [32j, ..)
+    const uint32_t ntx = (a.w + ICON_TILE - 1u) / ICON_TILE, nty = (a.h + ICON_TILE - 1u) / ICON_TILE;
+    const uint64_t per_frame = (uint64_t)ntx * nty, items = per_frame * a.n_frames;
+
+    uint32_t cur_frame = 0xFFFFFFFFu;
+    unsigned long long my_best = ICON_NONE;  // thread 0 of each warp keeps the warp's best of the current frame
+    for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const uint32_t f = (uint32_t)(it / per_frame), tile = (uint32_t)(it % per_frame);
+        const uint32_t tx0 = (tile % ntx) * ICON_TILE, ty0 = (tile / ntx) * ICON_TILE;
+        if (f != cur_frame) {
+            if (cur_frame != 0xFFFFFFFFu && lane == 0 && my_best != ICON_NONE) atomicMin(a.best + cur_frame, my_best);
+            my_best = ICON_NONE;
+            cur_frame = f;
+        }
+        __syncthreads();  // previous item's shared state is dead (also orders the table fill on the first pass)
+        if (tid == 0) { s_any = 0u; s_ncand = 0u; }
+        __syncthreads();
+        // does the tile hold any white pixel of the dilated mask?  (dilated >= raw: no bit, no candidate)
+        const bool rows_ok = ty0 < y_hi && ty0 + ICON_TILE > y_lo && tx0 < x_hi && tx0 + ICON_TILE > x_lo &&
+                             !(a.open && !a.open[f]);
+        if (rows_ok && warp == 0) {
+            const uint32_t y = ty0 + lane;
+            uint32_t any = 0u;
+            if (y < a.h) {
+                const uint32_t X0 = tx0 + a.g.pad;  // padded column of the tile's first pixel
+                const uint32_t* fb = a.bits + (uint64_t)f * a.bits_stride;
+                const uint32_t w0 = __ldg(fb + ((((y >> 5) * a.g.tx + (X0 >> 5)) << 5) + (y & 31u)));
+                uint32_t w1 = 0u;
+                if ((X0 & 31u) && (X0 >> 5) + 1u < a.g.tx) w1 = __ldg(fb + ((((y >> 5) * a.g.tx + (X0 >> 5) + 1u) << 5) + (y & 31u)));
+                any = (uint32_t)(((unsigned long long)w1 << 32 | w0) >> (X0 & 31u));
+            }
+            any = __reduce_or_sync(0xFFFFFFFFu, any);
+            if (lane == 0) s_any = any;
+        }
+        __syncthreads();
+        if (!s_any) continue;
+        const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
+        // isolated crop of the tile plus the template's reach, and the tile's candidates
+        for (uint32_t i0 = 0; i0 < WIN * WIN; i0 += ICON_THREADS) {  // whole warps iterate: the ballot is full-mask
+            const uint32_t i = i0 + tid;
+            bool is_cand = false;
+            uint32_t r = 0, c = 0;
+            if (i < WIN * WIN) {
+                r = i / WIN; c = i - r * WIN;
+                const uint32_t x = tx0 + c, y = ty0 + r;
+                const uint32_t v = icon_pixel(a, frame, x, y);
+                win[r * WP + c] = v;
+                is_cand = v != 0u && r < ICON_TILE && c < ICON_TILE && x >= x_lo && x < x_hi && y >= y_lo && y < y_hi;
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_cand);
+            if (m) {
+                // raster order inside the tile is not needed: the key carries (y, x)
+                uint32_t pos = 0;
+                const uint32_t leader = __ffs(m) - 1u;
+                if (lane == leader) pos = atomicAdd(&s_ncand, (uint32_t)__popc(m));
+                pos = __shfl_sync(0xFFFFFFFFu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+                if (is_cand) cand[pos] = c | (r << 8);
+            }
+        }
+        __syncthreads();
+        const uint32_t nc = s_ncand;
+        for (uint32_t k = warp; k < nc; k += ICON_THREADS / 32) {
+            const uint32_t cv = cand[k], cx = cv & 0xFFu, cy = cv >> 8;
+            const uint32_t* wp = win + cy * WP + cx;
+            uint32_t sad[ICON_MAX_TEMPLATES];
+#pragma unroll
+            for (int t = 0; t < ICON_MAX_TEMPLATES; t++) sad[t] = 0u;
+            for (uint32_t j = lane; j < n_act; j += 32u) {
+                const uint32_t m = wp[s_act[j]];
+                if (m) {
+#pragma unroll
+                    for (int t = 0; t < ICON_MAX_TEMPLATES; t++)
+                        if ((uint32_t)t < n) {
+                            const uint32_t e = j * n + t;
+                            // ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323; minus what a black pixel gives
+                            const uint32_t ad = __vsadu4(m, s_rgb[e]);
+                            sad[t] += (uint32_t)__fmul_rn((float)ad, s_af[e]) - s_c0[e];
+                        }
+                }
+            }
+            uint32_t best_sad = 0xFFFFFFFFu;
+#pragma unroll
+            for (int t = 0; t < ICON_MAX_TEMPLATES; t++)
+                if ((uint32_t)t < n) {
+                    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, sad[t]) + base[t];
+                    best_sad = min(best_sad, s);
+                }
+            const unsigned long long key = ((unsigned long long)best_sad << 32) | ((unsigned long long)(ty0 + cy) << 16) | (tx0 + cx);
+            my_best = key < my_best ? key : my_best;
+        }
+    }
+    if (cur_frame != 0xFFFFFFFFu && lane == 0 && my_best != ICON_NONE) atomicMin(a.best + cur_frame, my_best);
+}
+
+struct IconApplyArgs {
+    const uint8_t* frames; uint64_t frame_stride; uint32_t pitch;
+    uint32_t map_x, map_y, w, h;
+    const uint32_t* lut;
+    uint8_t* lsd; uint64_t lsd_stride; uint32_t lsd_pitch, pad;   // dilated mask, L8 (pixel x at byte pad + x)
+    uint32_t* bits; uint64_t bits_stride; BitsGeom g;              // and its bitmap (may be nullptr)
+    uint32_t size;
+    const unsigned long long* best;   // [n]
+    uint8_t* found; uint32_t* xy; uint32_t* sad;   // [n], [n][2], [n]
+};
+
+// One CTA per frame: decode the winner, then rewrite the dilated mask where the edit can change it.
+__global__ void __launch_bounds__(ICON_THREADS) k_icon_apply(const IconApplyArgs a) {
+    const uint32_t f = blockIdx.x;
+    const unsigned long long key = a.best[f];
+    if (key == ICON_NONE) {
+        if (threadIdx.x == 0) { a.found[f] = 0; a.xy[2 * f] = a.xy[2 * f + 1] = 0u; a.sad[f] = 0u; }
+        return;
+    }
+    const uint32_t x0 = (uint32_t)(key & 0xFFFFu), y0 = (uint32_t)((key >> 16) & 0xFFFFu);
+    if (threadIdx.x == 0) { a.found[f] = 1; a.xy[2 * f] = x0; a.xy[2 * f + 1] = y0; a.sad[f] = (uint32_t)(key >> 32); }
+    const uint32_t size = a.size;
+    // erased rectangle [x0, ex) x [y0, ey) and the green square [sx0, sx1) x [sy0, sy1)
+    const uint32_t ex = min(x0 + size, a.w - 1u), ey = min(y0 + size, a.h - 1u);
+    const uint32_t px = x0 + size / 2u, py = y0 + (uint32_t)roundf(__fmul_rn((float)size, SMH_MAP_MARKER_POI_LOCATION));
+    const uint32_t sx0 = px >= 2u ? px - 2u : 0u, sy0 = py >= 2u ? py - 2u : 0u, sx1 = min(px + 2u, a.w), sy1 = min(py + 2u, a.h);
+    // is pure green a marker colour?  (it is — Alpha's hue; asked of the table rather than assumed)
+    const uint32_t green = 0x0000FF00u;
+    const bool green_on = (__ldg(a.lut + (green >> 5)) >> (green & 31u)) & 1u;
+    // every mask pixel within one step of an edited pixel
+    const uint32_t bx0 = min(x0, sx0), by0 = min(y0, sy0), bx1 = max(ex, sx1), by1 = max(ey, sy1);
+    const uint32_t rx0 = bx0 ? bx0 - 1u : 0u, ry0 = by0 ? by0 - 1u : 0u, rx1 = min(bx1 + 1u, a.w), ry1 = min(by1 + 1u, a.h);
+    const uint32_t rw = rx1 - rx0, rh = ry1 - ry0;
+    const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
+    auto raw = [&](int x, int y) -> bool {  // predicate on the edited, isolated crop
+        if (x < 0 || y < 0 || (uint32_t)x >= a.w || (uint32_t)y >= a.h) return false;
+        const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
+        if (ux >= sx0 && ux < sx1 && uy >= sy0 && uy < sy1) return green_on;
+        if (ux >= x0 && ux < ex && uy >= y0 && uy < ey) return false;
+        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(frame + (uint64_t)(a.map_y + uy) * a.pitch + (uint64_t)(a.map_x + ux) * 4u));
+        const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
+        return marker_bit(word, max(r, max(g, b)), min(r, min(g, b)), a.lut) != 0u;
+    };
+    for (uint32_t i = threadIdx.x; i < rw * rh; i += ICON_THREADS) {
+        const int x = (int)(rx0 + i % rw), y = (int)(ry0 + i / rw);
+        // 3x3 cross dilation — vision-cpu/src/lib.rs:372 (imageproc L1, k = 1)
+        const bool on = raw(x, y) || raw(x - 1, y) || raw(x + 1, y) || raw(x, y - 1) || raw(x, y + 1);
+        a.lsd[(uint64_t)f * a.lsd_stride + (uint64_t)y * a.lsd_pitch + a.pad + (uint32_t)x] = on ? 255 : 0;
+        if (a.bits) {
+            const uint32_t X = (uint32_t)x + a.g.pad;
+            uint32_t* wd = a.bits + (uint64_t)f * a.bits_stride + (((((uint32_t)y >> 5) * a.g.tx + (X >> 5)) << 5) + ((uint32_t)y & 31u));
+            if (on) atomicOr(wd, 1u << (X & 31u)); else atomicAnd(wd, ~(1u << (X & 31u)));
+        }
+    }
+}
+
+// debug view LSDPreprocess after the edit: black rectangle, green square (RGBA words, w pixels per row)
+__global__ void k_icon_overlay(uint32_t* rgba, uint32_t w, uint32_t h, uint32_t x0, uint32_t y0, uint32_t size) {
+    const uint32_t ex = min(x0 + size, w - 1u), ey = min(y0 + size, h - 1u);
+    const uint32_t px = x0 + size / 2u, py = y0 + (uint32_t)roundf(__fmul_rn((float)size, SMH_MAP_MARKER_POI_LOCATION));
+    const uint32_t sx0 = px >= 2u ? px - 2u : 0u, sy0 = py >= 2u ? py - 2u : 0u, sx1 = min(px + 2u, w), sy1 = min(py + 2u, h);
+    const uint32_t bx1 = max(ex, sx1), by1 = max(ey, sy1), bx0 = min(x0, sx0), by0 = min(y0, sy0);
+    const uint32_t rw = bx1 - bx0, rh = by1 - by0;
+    for (uint32_t i = threadIdx.x; i < rw * rh; i += blockDim.x) {
+        const uint32_t x = bx0 + i % rw, y = by0 + i / rw;
+        if (x >= sx0 && x < sx1 && y >= sy0 && y < sy1) rgba[(uint64_t)y * w + x] = 0xFF00FF00u;   // (0,255,0,255)
+        else if (x >= x0 && x < ex && y >= y0 && y < ey) rgba[(uint64_t)y * w + x] = 0xFF000000u;  // (0,0,0,255)
+    }
+}
+
+__global__ void k_fill_u64(unsigned long long* p, uint32_t n, unsigned long long v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace smh

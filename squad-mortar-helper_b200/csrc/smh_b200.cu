@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "kernels_next.cuh"
+#include "kernels_icons.cuh"
 
 namespace {
 
@@ -84,11 +85,14 @@ struct Planes {
     uint32_t* mpx_in = nullptr;   // [n][3][3] scales of calc_meters_to_px_ratio
     uint8_t* mpx_n = nullptr; double* mpx_ratio = nullptr; uint8_t* mpx_found = nullptr;
     uint32_t* mpx_debug = nullptr; uint8_t* mpx_ndebug = nullptr;
+    unsigned long long* icon_best = nullptr;  // [n] template-match keys
+    uint8_t* icon_found = nullptr; uint32_t* icon_xy = nullptr; uint32_t* icon_sad = nullptr;
     uint32_t* bits = nullptr;     // tile-major 1-bit copies of the dilated masks (line-search input)
     uint64_t bits_stride = 0;     // words per frame
     smh::BitsGeom bg{};
     void release() {
         cudaFree(bits); cudaFree(minimap); cudaFree(minimap_found);
+        cudaFree(icon_best); cudaFree(icon_found); cudaFree(icon_xy); cudaFree(icon_sad);
         cudaFree(mpx_in); cudaFree(mpx_n); cudaFree(mpx_ratio); cudaFree(mpx_found); cudaFree(mpx_debug); cudaFree(mpx_ndebug);
         cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
         cudaFree(lines); cudaFree(n_lines); cudaFree(red); cudaFree(open); cudaFree(stats); cudaFree(start_y); cudaFree(counter);
@@ -109,6 +113,10 @@ struct smh_b200 {
     uint32_t n_ckpt = 0;
     uint32_t* d_span = nullptr;  // ray span per pixel offset (line-search filter)
     uint32_t* d_lut = nullptr; // marker predicate bit table, 2^24 bits
+    // marker icon templates (smh_b200_load_map_markers): one allocation, see smh::IconTable
+    uint32_t* d_icons = nullptr;
+    smh::IconTable icons{};
+    bool icons_applied = false; int icon_found = 0; uint32_t icon_xy[2] = {0, 0};
 
     // ---- single-frame (trait) state ----
     Geometry geo;                 // of the loaded frame
@@ -196,6 +204,13 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     CU(h, cudaMemset(P->minimap, 0, (size_t)n * 4 * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->minimap_found, (size_t)n));
     CU(h, cudaMemset(P->minimap_found, 0, (size_t)n));
+    CU(h, cudaMalloc(&P->icon_best, (size_t)n * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&P->icon_found, (size_t)n));
+    CU(h, cudaMemset(P->icon_found, 0, (size_t)n));
+    CU(h, cudaMalloc(&P->icon_xy, (size_t)n * 2 * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->icon_xy, 0, (size_t)n * 2 * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&P->icon_sad, (size_t)n * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->icon_sad, 0, (size_t)n * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->mpx_in, (size_t)n * 9 * sizeof(uint32_t)));
     CU(h, cudaMalloc(&P->mpx_n, (size_t)n));
     CU(h, cudaMalloc(&P->mpx_ratio, (size_t)n * sizeof(double)));
@@ -275,19 +290,76 @@ Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
     if (V.stats) V.stats += (size_t)f0 * 3;
     V.counter += lane;
     V.minimap += (size_t)f0 * 4; V.minimap_found += f0;
+    V.icon_best += f0; V.icon_found += f0; V.icon_xy += (size_t)f0 * 2; V.icon_sad += f0;
     V.bits += (uint64_t)f0 * P.bits_stride;
     return V;
 }
 
-int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st) {
-    // 1-bit tile-major copy of the dilated masks (what the search kernel reads)
-    {
-        const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
-        if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
-        smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
+// 1-bit tile-major copy of the dilated masks (what the line search and the icon match read)
+int launch_pack(smh_b200* h, const Planes& P, uint32_t n, cudaStream_t st) {
+    const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
+    if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
+    smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+// Marker icon template match over n frames (after launch_pack): scores, then edits mask + bitmap.
+int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t ox, uint32_t oy,
+                 uint32_t n, bool use_open, cudaStream_t st) {
+    if (!h->d_icons) return fail(h, SMH_E_STATE, "filter_map_marker_icons before load_map_markers");
+    const Geometry& g = P.geo;
+    const uint32_t size = h->icons.size;
+    smh::k_fill_u64<<<(n + 255u) / 256u, 256, 0, st>>>(P.icon_best, n, smh::ICON_NONE);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    // `if w >= map_marker_size && h >= map_marker_size` (src/vision/mod.rs:104); the candidate bounds
+    // w - size - 1 of vision-cpu/src/lib.rs:272-273 must not wrap
+    if (g.map[2] >= size + 2u && g.map[3] >= size + 2u) {
+        smh::IconArgs a{};
+        a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
+        a.map_x = g.map[0] - ox; a.map_y = g.map[1] - oy; a.w = g.map[2]; a.h = g.map[3];
+        a.lut = h->d_lut; a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
+        a.open = use_open ? P.open : nullptr;
+        a.t = h->icons; a.n_frames = n; a.best = P.icon_best;
+        const uint32_t WIN = smh::ICON_TILE + size - 1u, WP = WIN | 1u;
+        const size_t dyn = ((size_t)WIN * WP + smh::ICON_TILE * smh::ICON_TILE + h->icons.n_act + 3u * (size_t)h->icons.n_act * h->icons.n) * 4u;
+        {
+            static std::mutex mu;
+            static size_t raised[64] = {0};
+            std::lock_guard<std::mutex> lk(mu);
+            size_t& cur = raised[h->device & 63];
+            if (dyn > 32768 && dyn > cur) {
+                CU(h, cudaFuncSetAttribute(smh::k_icons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                cur = dyn;
+            }
+        }
+        int nb = 0;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_icons, smh::ICON_THREADS, dyn));
+        const uint64_t ntiles = (uint64_t)((g.map[2] + 31u) / 32u) * ((g.map[3] + 31u) / 32u) * n;
+        uint64_t grid = (uint64_t)h->sm_count * (nb > 0 ? nb : 1);
+        if (grid > ntiles) grid = ntiles;
+        smh::k_icons<<<(unsigned)grid, smh::ICON_THREADS, dyn, st>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
     }
+    smh::IconApplyArgs b{};
+    b.frames = frames; b.frame_stride = frame_stride; b.pitch = pitch;
+    b.map_x = g.map[0] - ox; b.map_y = g.map[1] - oy; b.w = g.map[2]; b.h = g.map[3];
+    b.lut = h->d_lut;
+    b.lsd = P.lsd.ptr; b.lsd_stride = P.lsd.frame_stride; b.lsd_pitch = P.lsd.pitch; b.pad = P.pad;
+    b.bits = P.bits; b.bits_stride = P.bits_stride; b.g = P.bg;
+    b.size = size; b.best = P.icon_best; b.found = P.icon_found; b.xy = P.icon_xy; b.sad = P.icon_sad;
+    smh::k_icon_apply<<<n, smh::ICON_THREADS, 0, st>>>(b);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st,
+               bool pack = true) {
+    if (pack) { int rc = launch_pack(h, P, n, st); if (rc) return rc; }
     { int rc = ensure_ray_ckpt(h, P, st); if (rc) return rc; }
     smh::LsdArgs a{};
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
@@ -364,8 +436,12 @@ void batch_tuning(const smh_b200* h, uint32_t* chunk, uint32_t* lanes) {
     const char* ec = getenv("SMH_B200_BATCH_CHUNK");
     const char* el = getenv("SMH_B200_BATCH_LANES");
     int c = ec ? atoi(ec) : 0, l = el ? atoi(el) : 0;
-    if (c <= 0) c = h->sm_count;           // one line-search CTA per SM and chunk
-    if (l <= 0) l = 3;
+    // Measured on B200 (1024 dense 1440p frames, profiles/r1h_sweep_overlap.txt): one launch per kernel
+    // 7.54 ms; best chunked form (6 streams x 222 frames) 7.80 ms, 3 x 148 10.8 ms.  The line search is
+    // bound by the per-frame latency of its sequential seed chain, so splitting it into more, smaller
+    // waves costs more than the overlap returns: the chunked form is opt-in (SMH_B200_BATCH_LANES >= 2).
+    if (c <= 0) c = 2 * h->sm_count;
+    if (l <= 0) l = 1;
     if (l > SMH_BATCH_LANES_MAX) l = SMH_BATCH_LANES_MAX;
     *chunk = (uint32_t)c; *lanes = (uint32_t)l;
 }
@@ -386,7 +462,7 @@ uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
     return rows;
 }
 
-void fill_batch_out(const Planes& P, bool stats, bool minimap, smh_b200_batch* out) {
+void fill_batch_out(const Planes& P, bool stats, bool minimap, bool icons, smh_b200_batch* out) {
     memset(out, 0, sizeof *out);
     out->n_frames = P.n; out->W = P.W; out->H = P.H;
     memcpy(out->roi, P.geo.btn, 16); memcpy(out->roi + 4, P.geo.map, 16); memcpy(out->roi + 8, P.geo.brq, 16);
@@ -395,6 +471,7 @@ void fill_batch_out(const Planes& P, bool stats, bool minimap, smh_b200_batch* o
     out->lsd_stats = stats ? (uint64_t*)P.stats : nullptr;
     out->minimap = minimap ? P.minimap : nullptr;
     out->minimap_found = minimap ? P.minimap_found : nullptr;
+    out->icon_found = icons ? P.icon_found : nullptr; out->icon_xy = icons ? P.icon_xy : nullptr; out->icon_sad = icons ? P.icon_sad : nullptr;
 }
 
 int download_plane(smh_b200* h, const smh_b200_plane* p, uint32_t first, uint32_t count, uint8_t* host_out, cudaStream_t st) {
@@ -502,7 +579,7 @@ void smh_b200_destroy(smh_b200* h) {
     cudaDeviceSynchronize();
     free_single(h);
     h->batch.release(); for (auto& P : h->pipe) P.release();
-    cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_longest); cudaFree(h->d_view);
+    cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_icons); cudaFree(h->d_longest); cudaFree(h->d_view);
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
     for (auto e : h->pipe_events) cudaEventDestroy(e);
@@ -595,7 +672,7 @@ int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, 
     h->red_pixels = h_red[0];
     h->map_open = (reinterpret_cast<uint8_t*>(h_red + 1))[0] != 0;
     h->grayscale = grayscale;
-    h->cropped = true; h->ocr_fetched = h->lsd_fetched = false;
+    h->cropped = true; h->ocr_fetched = h->lsd_fetched = false; h->icons_applied = false;
     *map_open = h->map_open ? 1 : 0;
     if (xywh) memcpy(xywh, g.map, 16);
     if (ui_map_rgba) *ui_map_rgba = h->map_open ? h->h_ui : nullptr;
@@ -658,6 +735,76 @@ int32_t smh_b200_isolate_map_markers(smh_b200* h) {
     int rc = need_open_map(h, "isolate_map_markers");
     if (rc) return rc;
     // the marker predicate was evaluated inside the fused pixel pass; nothing left to launch
+    return SMH_OK;
+}
+
+int32_t smh_b200_load_map_markers(smh_b200* h, const uint8_t* rgba, uint32_t n_markers, uint32_t size) {
+    if (!h || !rgba) return fail(h, SMH_E_ARG, "load_map_markers: bad argument");
+    if (n_markers == 0 || n_markers > (uint32_t)smh::ICON_MAX_TEMPLATES || size < 4 || size > 96 ||
+        (uint64_t)n_markers * size * size > 8192u)
+        return fail(h, SMH_E_RANGE, "load_map_markers: %u templates of %ux%u (at most %d templates, 4 <= size <= 96, n*size*size <= 8192)",
+                    n_markers, size, size, smh::ICON_MAX_TEMPLATES);
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    CU(h, cudaSetDevice(h->device));
+    // template pixels opaque in at least one template, and per (pixel, template): colour, alpha/255 and the
+    // score against a black pixel — ((ad as f32) * (alpha as f32 / 255.0)) as u32, vision-cpu/src/lib.rs:323
+    std::vector<uint32_t> act;
+    for (uint32_t my = 0; my < size; my++)
+        for (uint32_t mx = 0; mx < size; mx++) {
+            bool any = false;
+            for (uint32_t t = 0; t < n_markers; t++) any = any || rgba[(((size_t)t * size + my) * size + mx) * 4 + 3] != 0;
+            if (any) act.push_back(mx | (my << 8));
+        }
+    const size_t na = act.size(), ne = na * n_markers;
+    std::vector<uint32_t> blob(na + 3 * ne + n_markers, 0u);
+    uint32_t* rgb = blob.data() + na; float* af = reinterpret_cast<float*>(rgb + ne);
+    uint32_t* c0 = reinterpret_cast<uint32_t*>(af + ne); uint32_t* base = c0 + ne;
+    for (size_t j = 0; j < na; j++) {
+        blob[j] = act[j];
+        const uint32_t mx = act[j] & 0xFFu, my = act[j] >> 8;
+        for (uint32_t t = 0; t < n_markers; t++) {
+            const uint8_t* px = rgba + (((size_t)t * size + my) * size + mx) * 4;
+            const volatile float a = (float)px[3] / 255.0f;
+            const volatile float v = (float)((uint32_t)px[0] + px[1] + px[2]) * a;
+            rgb[j * n_markers + t] = (uint32_t)px[2] | ((uint32_t)px[1] << 8) | ((uint32_t)px[0] << 16);  // b | g<<8 | r<<16
+            af[j * n_markers + t] = a;
+            c0[j * n_markers + t] = (uint32_t)v;
+            base[t] += (uint32_t)v;
+        }
+    }
+    CU(h, cudaDeviceSynchronize());  // no kernel may still read the previous table
+    cudaFree(h->d_icons); h->d_icons = nullptr;
+    CU(h, cudaMalloc(&h->d_icons, blob.size() * 4));
+    CU(h, cudaMemcpy(h->d_icons, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    h->icons.act = h->d_icons; h->icons.rgb = h->d_icons + na;
+    h->icons.af = reinterpret_cast<const float*>(h->d_icons + na + ne);
+    h->icons.c0 = h->d_icons + na + 2 * ne; h->icons.base = h->d_icons + na + 3 * ne;
+    h->icons.n_act = (uint32_t)na; h->icons.n = n_markers; h->icons.size = size;
+    return SMH_OK;
+}
+
+int32_t smh_b200_filter_map_marker_icons(smh_b200* h, int32_t* found, uint32_t xy[2], uint32_t* sad) {
+    int rc = need_open_map(h, "filter_map_marker_icons");
+    if (rc) return rc;
+    if (!found) return fail(h, SMH_E_ARG, "filter_map_marker_icons: null output");
+    std::lock_guard<std::mutex> g(h->markers_mu);
+    if (!h->d_icons) return fail(h, SMH_E_STATE, "filter_map_marker_icons before load_map_markers");
+    if (h->icons_applied) return fail(h, SMH_E_STATE, "filter_map_marker_icons: already applied to this frame");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    if ((rc = launch_pack(h, h->one, 1, h->s_markers))) return rc;
+    if ((rc = launch_icons(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, h->s_markers))) return rc;
+    uint32_t* hs = reinterpret_cast<uint32_t*>(h->h_small + 248);  // (the scales branch owns 216..243)
+    CU(h, cudaMemcpyAsync(hs, h->one.icon_xy, 8, cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaMemcpyAsync(hs + 2, h->one.icon_sad, 4, cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaMemcpyAsync(hs + 3, h->one.icon_found, 1, cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaStreamSynchronize(h->s_markers));
+    h->icons_applied = true; h->lsd_fetched = false;
+    h->icon_found = reinterpret_cast<uint8_t*>(hs + 3)[0] ? 1 : 0;
+    h->icon_xy[0] = hs[0]; h->icon_xy[1] = hs[1];
+    *found = h->icon_found;
+    if (xy) { xy[0] = hs[0]; xy[1] = hs[1]; }
+    if (sad) *sad = hs[2];
     return SMH_OK;
 }
 
@@ -854,6 +1001,11 @@ int32_t smh_b200_debug_view(smh_b200* h, uint8_t which, const uint8_t** rgba, ui
         smh::k_debug_rgb<<<grid, 256, 0, h->s_main>>>(h->d_frame, h->upitch, x0, y0, w, hh, full ? 1 : 0, h->d_view);
         h->launches++;
         CU(h, cudaGetLastError());
+        if (full && h->icons_applied && h->icon_found) {  // the crop after filter_map_marker_icons (vision-cpu/src/lib.rs:333-352)
+            smh::k_icon_overlay<<<1, 256, 0, h->s_main>>>(reinterpret_cast<uint32_t*>(h->d_view), w, hh, h->icon_xy[0], h->icon_xy[1], h->icons.size);
+            h->launches++;
+            CU(h, cudaGetLastError());
+        }
         CU(h, cudaMemcpyAsync(h->h_view, h->d_view, need, cudaMemcpyDeviceToHost, h->s_main));
         CU(h, cudaStreamSynchronize(h->s_main));
     } else {
@@ -892,6 +1044,10 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
     if (rc) return fail(h, rc, "process_batch: %ux%u is a frame size the reference panics on", W, H);
     cudaStream_t st = (cudaStream_t)stream;
     const bool stats = flags & SMH_BATCH_LSD_STATS;
+    const bool icons = flags & SMH_BATCH_FILTER_ICONS;
+    if (icons && (flags & SMH_BATCH_SKIP_PIXELS))
+        return fail(h, SMH_E_ARG, "process_batch: FILTER_ICONS edits the mask of this call's pixel pass; not with SKIP_PIXELS");
+    if (icons && !h->d_icons) return fail(h, SMH_E_STATE, "process_batch: FILTER_ICONS before load_map_markers");
     if ((flags & SMH_BATCH_SKIP_PIXELS) && (h->batch.n != n || h->batch.W != W || h->batch.H != H))
         return fail(h, SMH_E_STATE, "process_batch: SKIP_PIXELS needs a previous batch of the same shape");
     if ((rc = ensure_planes(h, &h->batch, n, g, stats))) return rc;
@@ -917,8 +1073,12 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
             if (flags & SMH_BATCH_MINIMAP)
                 if ((rc = launch_minimap(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
         }
+        if (icons) {
+            if ((rc = launch_pack(h, h->batch, n, st))) return rc;
+            if ((rc = launch_icons(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
+        }
         if (!(flags & SMH_BATCH_SKIP_LSD))
-            if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
+            if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st, !icons))) return rc;
     } else {
         if ((rc = ensure_ray_ckpt(h, h->batch, st))) return rc;
         if (stats) CU(h, cudaMemsetAsync(h->batch.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
@@ -945,14 +1105,18 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
                 return rc;
             if (flags & SMH_BATCH_MINIMAP)
                 if ((rc = launch_minimap(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, true, ls))) return rc;
-            if ((rc = launch_lsd(h, V, cn, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), ls))) return rc;
+            if (icons) {
+                if ((rc = launch_pack(h, V, cn, ls))) return rc;
+                if ((rc = launch_icons(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, true, ls))) return rc;
+            }
+            if ((rc = launch_lsd(h, V, cn, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), ls, !icons))) return rc;
         }
         for (uint32_t l = 0; l < lanes; l++) {
             CU(h, cudaEventRecord(h->lane_events[1 + l], h->lane_streams[l]));
             CU(h, cudaStreamWaitEvent(st, h->lane_events[1 + l], 0));
         }
     }
-    fill_batch_out(h->batch, stats, (flags & SMH_BATCH_MINIMAP) != 0, out);
+    fill_batch_out(h->batch, stats, (flags & SMH_BATCH_MINIMAP) != 0, icons, out);
     return SMH_OK;
 }
 

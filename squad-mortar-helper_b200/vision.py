@@ -157,6 +157,24 @@ class B200Vision:
     def mask_marker_lines(self) -> None:
         check(self._h, self._L.smh_b200_mask_marker_lines(self._h))
 
+    def load_map_markers(self, templates: np.ndarray) -> None:
+        """load_map_markers(map_marker_size) — vision-common/src/lib.rs:46 (commented out in the reference).
+        templates: [n, size, size, 4] RGBA as `markers::load_markers::<UnfilteredMarkers>(size)` returns them
+        (vision-common/src/markers/mod.rs:111-119; host-side `image`-crate work)."""
+        t = np.ascontiguousarray(templates, np.uint8)
+        if t.ndim != 4 or t.shape[1] != t.shape[2] or t.shape[3] != 4:
+            raise ValueError("load_map_markers expects [n, size, size, 4] uint8 RGBA templates")
+        check(self._h, self._L.smh_b200_load_map_markers(self._h, t.ctypes.data, t.shape[0], t.shape[1]))
+
+    def filter_map_marker_icons(self):
+        """filter_map_marker_icons() — vision-common/src/lib.rs:53 (commented out in the reference), between
+        isolate_map_markers and mask_marker_lines.  -> None | (x, y, sad) of the erased icon."""
+        found = C.c_int32()
+        xy = (C.c_uint32 * 2)()
+        sad = C.c_uint32()
+        check(self._h, self._L.smh_b200_filter_map_marker_icons(self._h, C.byref(found), xy, C.byref(sad)))
+        return (int(xy[0]), int(xy[1]), int(sad.value)) if found.value else None
+
     def lsd_image(self) -> np.ndarray:
         p = C.c_void_p()
         wh = (C.c_uint32 * 2)()
@@ -272,6 +290,7 @@ class B200Vision:
                       frame_stride: int | None = None, start_y=None, max_gap: int = 15, grayscale: bool = True,
                       lsd_stats: bool = False, skip_lsd: bool = False, skip_pixels: bool = False,
                       lsd_exhaustive: bool = False, minimap: bool = False, serial: bool = False,
+                      filter_icons: bool = False,
                       stream: int = 0) -> capi.Batch:
         """Enqueue the whole path for n device-resident frames on `stream`; returns the plane table."""
         pitch = W * 4 if pitch is None else pitch
@@ -279,7 +298,7 @@ class B200Vision:
         flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_LSD_STATS if lsd_stats else 0) | \
                 (capi.BATCH_SKIP_LSD if skip_lsd else 0) | (capi.BATCH_SKIP_PIXELS if skip_pixels else 0) | \
                 (capi.BATCH_LSD_EXHAUSTIVE if lsd_exhaustive else 0) | (capi.BATCH_MINIMAP if minimap else 0) | \
-                (capi.BATCH_SERIAL if serial else 0)
+                (capi.BATCH_SERIAL if serial else 0) | (capi.BATCH_FILTER_ICONS if filter_icons else 0)
         sy = None
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)

@@ -97,3 +97,19 @@ def oracle_process(frame, grayscale=True, detect_markers=True, max_gap=15, ocr=N
             img = o.find_scales_preprocess(start_y)
             res["meters_to_px_ratio"], res["scales_debug"] = O.calc_meters_to_px_ratio(img, scales, with_debug=True)
     return res
+
+
+def marker_templates(size=22):
+    """The committed fixture of `load_markers(22)` (tests/golden/make_marker_templates.py)."""
+    from pathlib import Path
+    return np.load(Path(__file__).with_name("golden") / f"marker_templates_{size}.npy")
+
+
+def stamp_icon(frame, map_xywh, template, x, y):
+    """Draw a marker icon into a BGRA frame: template pixels with alpha != 0 replace the map pixel at
+    map coordinates (x + mx, y + my)."""
+    mx0, my0 = map_xywh[0], map_xywh[1]
+    s = template.shape[0]
+    sel = template[..., 3] != 0
+    patch = frame[my0 + y:my0 + y + s, mx0 + x:mx0 + x + s]
+    patch[sel] = np.concatenate([template[..., 2::-1], np.full((s, s, 1), 255, np.uint8)], axis=2)[sel]
