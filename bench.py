@@ -346,8 +346,9 @@ def main() -> None:
             "kernels": {"dominant_by_time": dominant,
                         "timing": "second timed pass of the same steps: one launch per kernel over the whole batch, events between",
                         "serial_ms_per_step": px_ms + lsd_ms,
-                        "step_form": "serial (one launch per kernel)" if args.serial else
-                                     "chunks on internal streams: pixel pass of one chunk overlaps the line search of another",
+                        "step_form": "chunks on internal streams (SMH_B200_BATCH_LANES): pixel pass of one chunk overlaps the line search of another"
+                                     if (not args.serial and int(os.environ.get("SMH_B200_BATCH_LANES", "1") or 1) >= 2) else
+                                     "one smh_b200_process_batch call: one launch per kernel on the caller's stream",
                         "overlap_speedup": (px_ms + lsd_ms) / ms_per_step,
                         "k_pixels": {"ms": px_ms, "share": px_ms / (px_ms + lsd_ms)},
                         "k_lsd": {"ms": lsd_ms, "share": lsd_ms / (px_ms + lsd_ms), "bound": "instruction issue / L1 latency",

@@ -22,6 +22,8 @@ extern "C" {
     pub fn smh_b200_find_scales_preprocess(h: *mut smh_b200, scales_start_y: u32, out: *mut *const u8, wh: *mut u32) -> i32;
     pub fn smh_b200_isolate_map_markers(h: *mut smh_b200) -> i32;
     pub fn smh_b200_mask_marker_lines(h: *mut smh_b200) -> i32;
+    pub fn smh_b200_load_map_markers(h: *mut smh_b200, rgba: *const u8, n_markers: u32, size: u32) -> i32;
+    pub fn smh_b200_filter_map_marker_icons(h: *mut smh_b200, found: *mut i32, xy: *mut u32, sad: *mut u32) -> i32;
     pub fn smh_b200_find_longest_line(h: *mut smh_b200, x: f32, y: f32, max_gap: f32, line: *mut f32, len_sq: *mut f32) -> i32;
     pub fn smh_b200_find_marker_lines(h: *mut smh_b200, max_gap: u32, lines: *mut [f32; 4], n: *mut u32) -> i32;
     pub fn smh_b200_debug_view(h: *mut smh_b200, which: u8, rgba: *mut *const u8, wh: *mut u32) -> i32;

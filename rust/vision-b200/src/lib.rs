@@ -45,6 +45,25 @@ impl B200Vision {
     }
 }
 
+impl B200Vision {
+    /// `load_map_markers` — vision-gpu/src/lib.rs:129-137,202-204: the templates are prepared on the host by
+    /// `markers::load_markers::<UnfilteredMarkers>` (vision-common/src/markers/mod.rs:111-119, once that
+    /// module is un-commented) and handed to the library as one packed RGBA block.
+    #[allow(dead_code)]
+    pub fn load_map_markers_rgba(&mut self, rgba: &[u8], n_markers: u32, map_marker_size: u32) -> Result<(), AnyError> {
+        assert_eq!(rgba.len(), (n_markers * map_marker_size * map_marker_size * 4) as usize);
+        self.check(unsafe { ffi::smh_b200_load_map_markers(self.h, rgba.as_ptr(), n_markers, map_marker_size) })
+    }
+
+    /// `filter_map_marker_icons` — vision-cpu/src/lib.rs:282-355; `Ok(Some((x, y, sad)))` of the erased icon.
+    #[allow(dead_code)]
+    pub fn filter_map_marker_icons(&self) -> Result<Option<(u32, u32, u32)>, AnyError> {
+        let (mut found, mut xy, mut sad) = (0i32, [0u32; 2], 0u32);
+        self.check(unsafe { ffi::smh_b200_filter_map_marker_icons(self.h, &mut found, xy.as_mut_ptr(), &mut sad) })?;
+        Ok(if found != 0 { Some((xy[0], xy[1], sad)) } else { None })
+    }
+}
+
 impl Drop for B200Vision {
     fn drop(&mut self) {
         unsafe { ffi::smh_b200_destroy(self.h) }
@@ -124,6 +143,17 @@ impl Vision for B200Vision {
     fn mask_marker_lines(&self) -> Result<(), Self::Error> {
         self.check(unsafe { ffi::smh_b200_mask_marker_lines(self.h) })
     }
+
+    // The two trait methods the reference carries commented out (vision-common/src/lib.rs:46,53).  They are
+    // written as they would read with the trait lines restored; until then they are inherent methods below.
+    /*
+    fn load_map_markers(&mut self, map_marker_size: u32) -> Result<(), Self::Error> {
+        B200Vision::load_map_markers(self, map_marker_size)
+    }
+    fn filter_map_marker_icons(&self) -> Result<(), Self::Error> {
+        B200Vision::filter_map_marker_icons(self).map(|_| ())
+    }
+    */
 
     fn find_longest_line(&self, _image: &Self::LSDImage, pt: Point<f32>, max_gap: f32) -> Result<(Line<f32>, f32), Self::Error> {
         let (mut line, mut len) = ([0f32; 4], 0f32);

@@ -53,6 +53,7 @@ struct IconArgs {
     IconTable t;
     uint32_t n_frames;
     unsigned long long* best;                                       // [n] sad << 32 | y << 16 | x, ICON_NONE-initialised
+    uint32_t* counter;                                              // item dispenser, zeroed before the launch
 };
 
 __device__ __forceinline__ uint32_t icon_pixel(const IconArgs& a, const uint8_t* frame, uint32_t x, uint32_t y) {
@@ -63,121 +64,129 @@ __device__ __forceinline__ uint32_t icon_pixel(const IconArgs& a, const uint8_t*
     return marker_bit(word, max(r, max(g, b)), min(r, min(g, b)), a.lut) ? (word & 0x00FFFFFFu) : 0u;
 }
 
-// Persistent CTAs over (frame, tile) items.  Dynamic shared memory: window [(32+size-1)^2] words,
-// candidate list [1024] halves, template table.
+// Persistent CTAs over (frame, tile-row) items handed out by an atomic counter.  A tile is one 32 x 32
+// tile of the dilated-mask bitmap (padded columns X = x + pad), so "any white pixel?" is one coalesced
+// 128-byte read per warp.  Dynamic shared memory: window [(32+size-1)^2] words, candidate list [1024],
+// queue of the row's live tiles, per-warp lists of non-black window pixels, template table.
 __global__ void __launch_bounds__(ICON_THREADS) k_icons(const IconArgs a) {
     extern __shared__ uint32_t sm[];
+    constexpr uint32_t NW = ICON_THREADS / 32;
     const uint32_t size = a.t.size, n = a.t.n, n_act = a.t.n_act;
     const uint32_t WIN = ICON_TILE + size - 1u, WP = WIN | 1u;  // odd pitch: rows fall in different banks
     uint32_t* win = sm;                                  // [WIN][WP]
     uint32_t* cand = win + WIN * WP;                     // [1024] cx | cy << 8 (tile coordinates)
-    uint32_t* s_act = cand + ICON_TILE * ICON_TILE;      // [n_act] offset into win | j-independent
+    uint32_t* s_act = cand + ICON_TILE * ICON_TILE;      // [n_act] offset into win
     uint32_t* s_rgb = s_act + n_act;                     // [n_act * n]
     float* s_af = reinterpret_cast<float*>(s_rgb + n_act * n);
     uint32_t* s_c0 = reinterpret_cast<uint32_t*>(s_af + n_act * n);
-    __shared__ uint32_t s_any, s_ncand;
+    uint32_t* queue = s_c0 + n_act * n;                  // [g.tx] live tiles of the current tile-row
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(queue + a.g.tx);  // [NW][n_act rounded up to even]
+    __shared__ uint32_t s_item, s_nq, s_ncand;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint16_t* list = s_list + warp * ((n_act + 1u) & ~1u);
 
     for (uint32_t j = tid; j < n_act; j += ICON_THREADS) {
         const uint32_t v = a.t.act[j];
         s_act[j] = (v >> 8) * WP + (v & 0xFFu);
     }
     for (uint32_t j = tid; j < n_act * n; j += ICON_THREADS) { s_rgb[j] = a.t.rgb[j]; s_af[j] = a.t.af[j]; s_c0[j] = a.t.c0[j]; }
-    uint32_t base[ICON_MAX_TEMPLATES];
-#pragma unroll
-    for (int t = 0; t < ICON_MAX_TEMPLATES; t++) base[t] = (uint32_t)t < n ? a.t.base[t] : 0u;
+    // scoring: G lanes per template, each lane sums its template over a share of the non-black pixels
+    const uint32_t G = 32u / n, my_t = lane / G, sub = lane - my_t * G;
+    const bool scorer = my_t < n;
+    const uint32_t my_base = scorer ? a.t.base[my_t] : 0u;
 
-    // candidate bounds (lib.rs:270-273)
-    const uint32_t x_lo = size, y_lo = size, x_hi = a.w - size - 1u, y_hi = a.h - size - 1u;  // [lo, hi)
-    // tiles are aligned to the crop (not to the padded bitmap grid): tile (i, j) = pixels [32i, 32i+32) x [32j, ..)
-    const uint32_t ntx = (a.w + ICON_TILE - 1u) / ICON_TILE, nty = (a.h + ICON_TILE - 1u) / ICON_TILE;
-    const uint64_t per_frame = (uint64_t)ntx * nty, items = per_frame * a.n_frames;
+    // candidate bounds (lib.rs:270-273), [lo, hi)
+    const int x_lo = (int)size, y_lo = (int)size, x_hi = (int)(a.w - size - 1u), y_hi = (int)(a.h - size - 1u);
+    const uint32_t items = a.g.ty * a.n_frames;
 
     uint32_t cur_frame = 0xFFFFFFFFu;
-    unsigned long long my_best = ICON_NONE;  // thread 0 of each warp keeps the warp's best of the current frame
-    for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const uint32_t f = (uint32_t)(it / per_frame), tile = (uint32_t)(it % per_frame);
-        const uint32_t tx0 = (tile % ntx) * ICON_TILE, ty0 = (tile / ntx) * ICON_TILE;
+    unsigned long long my_best = ICON_NONE;  // every lane of a warp tracks the warp's best of the current frame
+    for (;;) {
+        __syncthreads();  // previous item's shared state is dead (also orders the table fill on the first pass)
+        if (tid == 0) { s_item = atomicAdd(a.counter, 1u); s_nq = 0u; }
+        __syncthreads();
+        const uint32_t it = s_item;
+        if (it >= items) break;
+        const uint32_t f = it / a.g.ty, tyi = it - f * a.g.ty;
         if (f != cur_frame) {
             if (cur_frame != 0xFFFFFFFFu && lane == 0 && my_best != ICON_NONE) atomicMin(a.best + cur_frame, my_best);
             my_best = ICON_NONE;
             cur_frame = f;
         }
-        __syncthreads();  // previous item's shared state is dead (also orders the table fill on the first pass)
-        if (tid == 0) { s_any = 0u; s_ncand = 0u; }
-        __syncthreads();
-        // does the tile hold any white pixel of the dilated mask?  (dilated >= raw: no bit, no candidate)
-        const bool rows_ok = ty0 < y_hi && ty0 + ICON_TILE > y_lo && tx0 < x_hi && tx0 + ICON_TILE > x_lo &&
-                             !(a.open && !a.open[f]);
-        if (rows_ok && warp == 0) {
-            const uint32_t y = ty0 + lane;
+        const int ty0 = (int)(tyi * ICON_TILE);
+        if ((a.open && !a.open[f]) || ty0 >= y_hi || ty0 + (int)ICON_TILE <= y_lo) continue;
+        // live tiles of this tile-row: a tile without a white pixel in the dilated mask has no candidate
+        const uint32_t* fb = a.bits + (uint64_t)f * a.bits_stride + (((uint64_t)tyi * a.g.tx) << 5);
+        for (uint32_t t0 = 0; t0 < a.g.tx; t0 += NW) {
+            const uint32_t ti = t0 + warp;
             uint32_t any = 0u;
-            if (y < a.h) {
-                const uint32_t X0 = tx0 + a.g.pad;  // padded column of the tile's first pixel
-                const uint32_t* fb = a.bits + (uint64_t)f * a.bits_stride;
-                const uint32_t w0 = __ldg(fb + ((((y >> 5) * a.g.tx + (X0 >> 5)) << 5) + (y & 31u)));
-                uint32_t w1 = 0u;
-                if ((X0 & 31u) && (X0 >> 5) + 1u < a.g.tx) w1 = __ldg(fb + ((((y >> 5) * a.g.tx + (X0 >> 5) + 1u) << 5) + (y & 31u)));
-                any = (uint32_t)(((unsigned long long)w1 << 32 | w0) >> (X0 & 31u));
-            }
+            if (ti < a.g.tx) any = __ldg(fb + (ti << 5) + lane);
             any = __reduce_or_sync(0xFFFFFFFFu, any);
-            if (lane == 0) s_any = any;
+            const int tx0 = (int)(ti * ICON_TILE) - (int)a.g.pad;
+            if (any && lane == 0 && tx0 < x_hi && tx0 + (int)ICON_TILE > x_lo) queue[atomicAdd(&s_nq, 1u)] = ti;
         }
         __syncthreads();
-        if (!s_any) continue;
+        const uint32_t nq = s_nq;
         const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
-        // isolated crop of the tile plus the template's reach, and the tile's candidates
-        for (uint32_t i0 = 0; i0 < WIN * WIN; i0 += ICON_THREADS) {  // whole warps iterate: the ballot is full-mask
-            const uint32_t i = i0 + tid;
-            bool is_cand = false;
-            uint32_t r = 0, c = 0;
-            if (i < WIN * WIN) {
-                r = i / WIN; c = i - r * WIN;
-                const uint32_t x = tx0 + c, y = ty0 + r;
-                const uint32_t v = icon_pixel(a, frame, x, y);
-                win[r * WP + c] = v;
-                is_cand = v != 0u && r < ICON_TILE && c < ICON_TILE && x >= x_lo && x < x_hi && y >= y_lo && y < y_hi;
-            }
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_cand);
-            if (m) {
-                // raster order inside the tile is not needed: the key carries (y, x)
-                uint32_t pos = 0;
-                const uint32_t leader = __ffs(m) - 1u;
-                if (lane == leader) pos = atomicAdd(&s_ncand, (uint32_t)__popc(m));
-                pos = __shfl_sync(0xFFFFFFFFu, pos, leader) + __popc(m & ((1u << lane) - 1u));
-                if (is_cand) cand[pos] = c | (r << 8);
-            }
-        }
-        __syncthreads();
-        const uint32_t nc = s_ncand;
-        for (uint32_t k = warp; k < nc; k += ICON_THREADS / 32) {
-            const uint32_t cv = cand[k], cx = cv & 0xFFu, cy = cv >> 8;
-            const uint32_t* wp = win + cy * WP + cx;
-            uint32_t sad[ICON_MAX_TEMPLATES];
-#pragma unroll
-            for (int t = 0; t < ICON_MAX_TEMPLATES; t++) sad[t] = 0u;
-            for (uint32_t j = lane; j < n_act; j += 32u) {
-                const uint32_t m = wp[s_act[j]];
-                if (m) {
-#pragma unroll
-                    for (int t = 0; t < ICON_MAX_TEMPLATES; t++)
-                        if ((uint32_t)t < n) {
-                            const uint32_t e = j * n + t;
-                            // ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323; minus what a black pixel gives
-                            const uint32_t ad = __vsadu4(m, s_rgb[e]);
-                            sad[t] += (uint32_t)__fmul_rn((float)ad, s_af[e]) - s_c0[e];
-                        }
+        for (uint32_t q = 0; q < nq; q++) {
+            const int tx0 = (int)(queue[q] * ICON_TILE) - (int)a.g.pad;  // crop x of the tile's first column (may be < 0)
+            if (tid == 0) s_ncand = 0u;
+            __syncthreads();
+            // isolated crop of the tile plus the template's reach, and the tile's candidates
+            for (uint32_t r0 = 0; r0 < WIN; r0 += NW) {
+                const uint32_t r = r0 + warp;
+                for (uint32_t c0 = 0; c0 < WIN; c0 += 32u) {  // whole warps iterate: the ballot is full-mask
+                    const uint32_t c = c0 + lane;
+                    bool is_cand = false;
+                    if (r < WIN && c < WIN) {
+                        const int x = tx0 + (int)c, y = ty0 + (int)r;
+                        const uint32_t v = x >= 0 ? icon_pixel(a, frame, (uint32_t)x, (uint32_t)y) : 0u;
+                        win[r * WP + c] = v;
+                        is_cand = v != 0u && r < ICON_TILE && c < ICON_TILE && x >= x_lo && x < x_hi && y >= y_lo && y < y_hi;
+                    }
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_cand);
+                    if (m) {
+                        // raster order inside the tile is not needed: the key carries (y, x)
+                        uint32_t pos = 0;
+                        const uint32_t leader = __ffs(m) - 1u;
+                        if (lane == leader) pos = atomicAdd(&s_ncand, (uint32_t)__popc(m));
+                        pos = __shfl_sync(0xFFFFFFFFu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+                        if (is_cand) cand[pos] = c | (r << 8);
+                    }
                 }
             }
-            uint32_t best_sad = 0xFFFFFFFFu;
-#pragma unroll
-            for (int t = 0; t < ICON_MAX_TEMPLATES; t++)
-                if ((uint32_t)t < n) {
-                    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, sad[t]) + base[t];
-                    best_sad = min(best_sad, s);
+            __syncthreads();
+            const uint32_t nc = s_ncand;
+            for (uint32_t k = warp; k < nc; k += NW) {
+                const uint32_t cv = cand[k], cx = cv & 0xFFu, cy = cv >> 8;
+                const uint32_t* wp = win + cy * WP + cx;
+                // 1. the template pixels that see a non-black pixel of the crop (the rest is in `base`)
+                uint32_t cnt = 0;
+                for (uint32_t j0 = 0; j0 < n_act; j0 += 32u) {
+                    const uint32_t j = j0 + lane;
+                    const bool nz = j < n_act && wp[s_act[j]] != 0u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, nz);
+                    if (nz) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+                    cnt += __popc(m);
                 }
-            const unsigned long long key = ((unsigned long long)best_sad << 32) | ((unsigned long long)(ty0 + cy) << 16) | (tx0 + cx);
-            my_best = key < my_best ? key : my_best;
+                __syncwarp();
+                // 2. ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323 — minus what a black pixel gives
+                uint32_t acc = 0u;
+                if (scorer)
+                    for (uint32_t e = sub; e < cnt; e += G) {
+                        const uint32_t j = list[e], idx = j * n + my_t;
+                        const uint32_t ad = __vsadu4(wp[s_act[j]], s_rgb[idx]);
+                        acc += (uint32_t)__fmul_rn((float)ad, s_af[idx]) - s_c0[idx];
+                    }
+                uint32_t tot = 0u;
+                for (uint32_t d = 0; d < G; d++) tot += __shfl_sync(0xFFFFFFFFu, acc, scorer ? my_t * G + d : lane);
+                const uint32_t best_sad = __reduce_min_sync(0xFFFFFFFFu, scorer ? tot + my_base : 0xFFFFFFFFu);
+                const unsigned long long key = ((unsigned long long)best_sad << 32) | ((unsigned long long)(uint32_t)(ty0 + (int)cy) << 16) |
+                                               (uint32_t)(tx0 + (int)cx);
+                my_best = key < my_best ? key : my_best;
+                __syncwarp();  // the list is rewritten by the next candidate
+            }
+            __syncthreads();  // window and candidate list are rewritten by the next tile
         }
     }
     if (cur_frame != 0xFFFFFFFFu && lane == 0 && my_best != ICON_NONE) atomicMin(a.best + cur_frame, my_best);

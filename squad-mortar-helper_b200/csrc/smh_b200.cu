@@ -323,8 +323,12 @@ int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t f
         a.lut = h->d_lut; a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
         a.open = use_open ? P.open : nullptr;
         a.t = h->icons; a.n_frames = n; a.best = P.icon_best;
+        a.counter = P.counter;  // this lane's dispenser; the line search zeroes it again before its own launch
+        CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
         const uint32_t WIN = smh::ICON_TILE + size - 1u, WP = WIN | 1u;
-        const size_t dyn = ((size_t)WIN * WP + smh::ICON_TILE * smh::ICON_TILE + h->icons.n_act + 3u * (size_t)h->icons.n_act * h->icons.n) * 4u;
+        const size_t na = h->icons.n_act;
+        const size_t dyn = ((size_t)WIN * WP + smh::ICON_TILE * smh::ICON_TILE + na + 3u * na * h->icons.n + P.bg.tx) * 4u +
+                           (size_t)(smh::ICON_THREADS / 32) * ((na + 1u) & ~(size_t)1u) * 2u;
         {
             static std::mutex mu;
             static size_t raised[64] = {0};
@@ -337,9 +341,9 @@ int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t f
         }
         int nb = 0;
         CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_icons, smh::ICON_THREADS, dyn));
-        const uint64_t ntiles = (uint64_t)((g.map[2] + 31u) / 32u) * ((g.map[3] + 31u) / 32u) * n;
+        const uint64_t nitems = (uint64_t)P.bg.ty * n;
         uint64_t grid = (uint64_t)h->sm_count * (nb > 0 ? nb : 1);
-        if (grid > ntiles) grid = ntiles;
+        if (grid > nitems) grid = nitems;
         smh::k_icons<<<(unsigned)grid, smh::ICON_THREADS, dyn, st>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
