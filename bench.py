@@ -203,6 +203,8 @@ def main() -> None:
                     help="host frames per e2e step (default: the whole batch; 512 per rank beyond 2 GPUs to bound pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="batches in flight: steps alternate between this many handles/streams (1 = one stream)")
     ap.add_argument("--serial", action="store_true",
                     help="one launch per kernel on one stream (no chunk overlap): the form the ncu launch list is taken on")
     args = ap.parse_args()
@@ -247,11 +249,35 @@ def main() -> None:
     stream = torch.cuda.current_stream().cuda_stream
     fp = frames.data_ptr()
 
+    # Batches in flight: consecutive steps alternate between `--in-flight` handles, each with its own output
+    # planes and its own CUDA stream (double buffering): the line search of a batch is a couple of waves of
+    # long sequential per-frame chains, and its tail leaves most SMs idle — the next batch's pixel pass and
+    # line search fill them.  Every step is still one smh_b200_process_batch call over the whole batch, all
+    # K steps complete inside the timed region, and a step's results stay valid until its handle's next call.
+    n_fly = 1 if args.serial else max(1, args.in_flight)
+    handles = [vision] + [B200Vision.init(local_rank) for _ in range(n_fly - 1)]
+    fly_streams = [torch.cuda.Stream() for _ in range(n_fly)] if n_fly > 1 else [torch.cuda.current_stream()]
+    step_no = [0]
+    last = [None] * n_fly
+
     def step():
-        # the product call: one smh_b200_process_batch over the whole batch.  Large batches run as chunks
-        # on the library's internal streams (pixel pass of one chunk under the line search of another);
-        # --serial forces one launch per kernel on this stream (what the ncu launch list is taken on)
-        vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, serial=args.serial, stream=stream)
+        # the product call: one smh_b200_process_batch over the whole batch; --serial forces one handle,
+        # one stream (what the ncu launch list is taken on)
+        k = step_no[0] % n_fly
+        step_no[0] += 1
+        last[k] = handles[k].process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, serial=args.serial,
+                                           stream=fly_streams[k].cuda_stream)
+
+    def fork():
+        if n_fly > 1:
+            ev = torch.cuda.Event(); ev.record()
+            for s_ in fly_streams:
+                s_.wait_event(ev)
+
+    def join():
+        if n_fly > 1:
+            for s_ in fly_streams:
+                torch.cuda.current_stream().wait_stream(s_)
 
     def step_split(ev):
         # per-kernel durations: one launch of each kernel over the whole batch, each timed alone
@@ -261,18 +287,33 @@ def main() -> None:
 
     for _ in range(max(args.warmup, 3)):
         step()
+    join()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = vision.launch_count()
+    launches0 = sum(h_.launch_count() for h_ in handles)
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
+    fork()
     for k in range(args.steps):
         step()
+    join()
     t_end.record()
     barrier()
-    launches = vision.launch_count() - launches0
+    launches = sum(h_.launch_count() for h_ in handles) - launches0
+
+    def dev_u32(ptr, count):
+        class _H:
+            pass
+        hd = _H()
+        hd.__cuda_array_interface__ = {"shape": (count * 4,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(hd, device="cuda").cpu().numpy().view(np.uint32)
+    # every handle processed the same frames: their results must agree (guards the in-flight scheme)
+    sums = [int(dev_u32(b_.n_lines, n).sum()) for b_ in last if b_ is not None]
+    if len(set(sums)) != 1:
+        raise SystemExit(f"bench: handles disagree on the number of lines found: {sums}")
+    lines_checksum = sums[0]
     total_ms = t_start.elapsed_time(t_end)
     # second timed pass, same inputs, kernels one after the other with events between them
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -337,7 +378,8 @@ def main() -> None:
             "config": {"workload": WORKLOAD, "frames_per_gpu": n, "resolution": [W, H], "max_gap": MAX_GAP,
                        "grayscale": True, "synth": p.as_dict(),
                        "l2": f"inputs {n * W * H * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "parallelism": f"frame-sharded x{world}, no collectives"},
+                       "parallelism": f"frame-sharded x{world}, no collectives",
+                       "batches_in_flight": n_fly},
             "roofline": {"kernel": "k_pixels", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpf * n, "kernel_ms": px_ms,
@@ -346,15 +388,17 @@ def main() -> None:
             "kernels": {"dominant_by_time": dominant,
                         "timing": "second timed pass of the same steps: one launch per kernel over the whole batch, events between",
                         "serial_ms_per_step": px_ms + lsd_ms,
-                        "step_form": "chunks on internal streams (SMH_B200_BATCH_LANES): pixel pass of one chunk overlaps the line search of another"
-                                     if (not args.serial and int(os.environ.get("SMH_B200_BATCH_LANES", "1") or 1) >= 2) else
-                                     "one smh_b200_process_batch call: one launch per kernel on the caller's stream",
+                        "step_form": "one smh_b200_process_batch call per step (one launch per kernel); "
+                                     + (f"{n_fly} batches in flight: steps alternate between {n_fly} handles, each with its own planes and CUDA stream"
+                                        if n_fly > 1 else "one handle, one stream"),
+                        "in_flight": n_fly,
                         "overlap_speedup": (px_ms + lsd_ms) / ms_per_step,
                         "k_pixels": {"ms": px_ms, "share": px_ms / (px_ms + lsd_ms)},
                         "k_lsd": {"ms": lsd_ms, "share": lsd_ms / (px_ms + lsd_ms), "bound": "instruction issue / L1 latency",
                                   "seeds_per_frame": seeds_pf, "seeds_pruned_per_frame": pruned_pf, "ray_steps_per_frame": steps_pf,
                                   "ray_steps_per_s": steps_pf * n / (lsd_ms * 1e-3)}},
             "frames_per_s_pixels_only": n / (px_ms * 1e-3),
+            "lines_checksum": lines_checksum,
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -363,7 +407,8 @@ def main() -> None:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    vision.close()
+    for h_ in handles:
+        h_.close()
 
 
 if __name__ == "__main__":

@@ -204,3 +204,31 @@ def test_4k_frame_and_lsd_stress(vision):
             got = _frame_result(res, i); got["xywh"] = want["xywh"]
             assert_same(got, want, f"{W}x{H} {kw} frame {i}")
             assert tuple(int(x) for x in res["stats"][i][:2]) == tuple(want["lsd_stats"])
+
+
+def test_two_handles_two_streams_in_flight(vision):
+    """bench.py keeps two batches in flight: steps alternate between two handles on two CUDA streams.
+    Interleaved calls must give each handle exactly the single-stream result."""
+    W, H, n = 1280, 720, 64
+    p = synth.SynthParams(W, H)
+    dev = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda")
+    synth.frames_device(vision, p, 900, n, dev.data_ptr())
+    torch.cuda.synchronize()
+    ref = _results(vision, vision.process_batch(dev.data_ptr(), n, W, H, max_gap=15, stream=torch.cuda.current_stream().cuda_stream), n)
+    ref = {k: v.copy() for k, v in ref.items()}
+    other = B200Vision.init(0)
+    try:
+        hs, ss = [vision, other], [torch.cuda.Stream(), torch.cuda.Stream()]
+        last = [None, None]
+        for i in range(6):
+            last[i % 2] = hs[i % 2].process_batch(dev.data_ptr(), n, W, H, max_gap=15, stream=ss[i % 2].cuda_stream)
+        torch.cuda.synchronize()
+        for k in range(2):
+            got = _results(hs[k], last[k], n)
+            for key in ("ui_map", "lsd_image", "ocr_out", "scales", "n_lines", "red_pixels", "map_open"):
+                assert np.array_equal(got[key], ref[key]), (k, key)
+            for i in range(n):
+                m = int(ref["n_lines"][i])
+                assert np.array_equal(got["lines"][i, :m].view(np.uint32), ref["lines"][i, :m].view(np.uint32))
+    finally:
+        other.close()
