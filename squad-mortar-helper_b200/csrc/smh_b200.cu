@@ -393,6 +393,9 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     }
     int nb = 0;
     CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, dyn));
+    // tuning knob: cap the persistent CTAs per SM (leaves registers for a pixel pass running beside the search)
+    static const int cap = [] { const char* e = getenv("SMH_B200_LSD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (cap >= 1 && nb > cap) nb = cap;
     const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
     const uint32_t grid = n < resident ? n : resident;
     if (stats) {
