@@ -371,6 +371,20 @@ def main() -> None:
             cpu = {"value": fps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{done} frames of the same workload, C oracle (restated vision-cpu) with {cores} OpenMP threads"}
         dominant = "k_lsd" if lsd_ms > px_ms else "k_pixels"
+        # k_lsd is bound by instruction issue / latency, not by HBM or the tensor pipes: its roofline is the
+        # SMs' issue rate (4 schedulers x 1 warp instruction per clock per SM).  Instructions per frame come from
+        # the committed ncu capture of the same workload, the duration is this run's.
+        lsd_issue = None
+        ipath = ROOT / "profiles" / "k_lsd_instructions.json"
+        if ipath.exists():
+            ij = json.loads(ipath.read_text())
+            props = torch.cuda.get_device_properties(local_rank)
+            sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+            peak_ginst = props.multi_processor_count * 4 * sm_clock_ghz
+            ach_ginst = ij["warp_instructions_per_frame_1440p_dense"] * n / (lsd_ms * 1e-3) / 1e9
+            lsd_issue = {"bound": "issue", "achieved": ach_ginst, "peak": peak_ginst, "unit": "G warp-inst/s",
+                         "frac": ach_ginst / peak_ginst, "instructions_source": ij["source"],
+                         "note": "duration includes k_pack_bits (~8 % of it); peak = SMs x 4 schedulers x SM clock under load"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -396,7 +410,7 @@ def main() -> None:
                         "k_pixels": {"ms": px_ms, "share": px_ms / (px_ms + lsd_ms)},
                         "k_lsd": {"ms": lsd_ms, "share": lsd_ms / (px_ms + lsd_ms), "bound": "instruction issue / L1 latency",
                                   "seeds_per_frame": seeds_pf, "seeds_pruned_per_frame": pruned_pf, "ray_steps_per_frame": steps_pf,
-                                  "ray_steps_per_s": steps_pf * n / (lsd_ms * 1e-3)}},
+                                  "ray_steps_per_s": steps_pf * n / (lsd_ms * 1e-3), "issue_roofline": lsd_issue}},
             "frames_per_s_pixels_only": n / (px_ms * 1e-3),
             "lines_checksum": lines_checksum,
             "clocks": clocks,
