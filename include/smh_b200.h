@@ -92,7 +92,7 @@ int32_t smh_b200_mask_marker_lines(smh_b200 *h);
  * load_map_markers: n_markers (<= 8) templates of size x size RGBA pixels, tightly packed, in the
  * layout vision-gpu uploads (`load_markers::<UnfilteredMarkers>(size)`, vision-gpu/src/gpumarkers.rs:24-52;
  * the TGA decode / Gaussian resize / colour isolation / corner mask of
- * vision-common/src/markers/mod.rs:96-119 stay host-side `image`-crate work).  n_markers*size*size <= 8192.
+ * vision-common/src/markers/mod.rs:96-119 stay host-side `image`-crate work).  size <= 32, n_markers*size*size <= 8192.
  *
  * filter_map_marker_icons: call between isolate_map_markers and mask_marker_lines, at most once per frame.
  * Scores every candidate pixel (marker-coloured, size <= x < w-size-1, size <= y < h-size-1) against every

@@ -18,9 +18,10 @@
 // mask), so k_icons rebuilds it tile by tile in shared memory from the resident capture and the 2^24-bit
 // predicate table, and only for tiles whose dilated-mask bitmap has a set bit (~90 % of the tiles of a
 // map have none: one 128-byte read each).  Candidates of a tile are compacted with ballots; one warp
-// scores one candidate, lanes over the template pixels that are opaque in at least one template; a
-// window pixel that is black (the common case) costs nothing — its contribution is precomputed per
-// template and added up front.  k_icon_apply then edits the dilated mask and its bitmap in place.
+// scores one candidate, lanes grouped by template and split over the template's rows; a window pixel that
+// is black (the common case) costs nothing — its contribution is precomputed per template and added up
+// front, and the pixels that do count are found with one AND of the row's non-black mask and the
+// template's opaque mask.  k_icon_apply then edits the dilated mask and its bitmap in place.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,13 +36,13 @@ constexpr int ICON_MAX_TEMPLATES = 8;
 constexpr uint32_t ICON_TILE = 32;
 constexpr unsigned long long ICON_NONE = 0xFFFFFFFFFFFFFFFFull;
 
-// Per-handle template table (built on the host by smh_b200_load_map_markers):
-//   act[j]            = mx | my << 8 for the j-th template pixel that is opaque in some template
-//   rgb/af/c0[j*n+t]  = packed b|g<<8|r<<16, alpha/255 (f32), contribution against a black pixel
-//   base[t]           = sum_j c0[j*n+t]
+// Per-handle template table (built on the host by smh_b200_load_map_markers), p = my*size + mx:
+//   rgb/af/c0[p*n+t]  = packed b|g<<8|r<<16, alpha/255 (f32), contribution against a black pixel
+//   base[t]           = sum_p c0[p*n+t]
+//   opq[t*size+my]    = bit mx set where template t is opaque (alpha != 0) at (mx, my); size <= 32
 struct IconTable {
-    const uint32_t* act; const uint32_t* rgb; const float* af; const uint32_t* c0; const uint32_t* base;
-    uint32_t n_act, n, size;
+    const uint32_t* rgb; const float* af; const uint32_t* c0; const uint32_t* base; const uint32_t* opq;
+    uint32_t n, size;
 };
 
 struct IconArgs {
@@ -56,44 +57,41 @@ struct IconArgs {
     uint32_t* counter;                                              // item dispenser, zeroed before the launch
 };
 
-__device__ __forceinline__ uint32_t icon_pixel(const IconArgs& a, const uint8_t* frame, uint32_t x, uint32_t y) {
-    // pixel (x, y) of the isolated crop as b|g<<8|r<<16, or 0 (vision-cpu/src/lib.rs:266-268)
-    if (x >= a.w || y >= a.h) return 0u;
-    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(frame + (uint64_t)(a.map_y + y) * a.pitch + (uint64_t)(a.map_x + x) * 4u));
+// a BGRA word of the capture as the isolated crop holds it: b|g<<8|r<<16, or 0 when the colour is not a
+// marker colour (vision-cpu/src/lib.rs:266-268)
+__device__ __forceinline__ uint32_t icon_isolate(uint32_t word, const uint32_t* __restrict__ lut) {
     const uint32_t b = word & 0xFFu, g = (word >> 8) & 0xFFu, r = (word >> 16) & 0xFFu;
-    return marker_bit(word, max(r, max(g, b)), min(r, min(g, b)), a.lut) ? (word & 0x00FFFFFFu) : 0u;
+    return marker_bit(word, max(r, max(g, b)), min(r, min(g, b)), lut) ? (word & 0x00FFFFFFu) : 0u;
 }
 
 // Persistent CTAs over (frame, tile-row) items handed out by an atomic counter.  A tile is one 32 x 32
 // tile of the dilated-mask bitmap (padded columns X = x + pad), so "any white pixel?" is one coalesced
-// 128-byte read per warp.  Dynamic shared memory: window [(32+size-1)^2] words, candidate list [1024],
-// queue of the row's live tiles, per-warp lists of non-black window pixels, template table.
-__global__ void __launch_bounds__(ICON_THREADS) k_icons(const IconArgs a) {
-    extern __shared__ uint32_t sm[];
+// 128-byte read per warp.  Dynamic shared memory: window [(32+size-1)^2] words and one 64-bit row mask of
+// its non-black pixels per row, candidate list [1024], queue of the row's live tiles, template table.
+__global__ void __launch_bounds__(ICON_THREADS, 5) k_icons(const IconArgs a) {
+    extern __shared__ __align__(16) uint32_t sm[];
     constexpr uint32_t NW = ICON_THREADS / 32;
-    const uint32_t size = a.t.size, n = a.t.n, n_act = a.t.n_act;
-    const uint32_t WIN = ICON_TILE + size - 1u, WP = WIN | 1u;  // odd pitch: rows fall in different banks
-    uint32_t* win = sm;                                  // [WIN][WP]
+    const uint32_t size = a.t.size, n = a.t.n, np = size * size;
+    const uint32_t WIN = ICON_TILE + size - 1u, WP = WIN | 1u;  // <= 63 columns; odd pitch: rows fall in different banks
+    unsigned long long* rowbits = reinterpret_cast<unsigned long long*>(sm);  // [64] bit c of row r: win[r][c] != 0
+    uint32_t* win = sm + 128;                            // [WIN][WP]
     uint32_t* cand = win + WIN * WP;                     // [1024] cx | cy << 8 (tile coordinates)
-    uint32_t* s_act = cand + ICON_TILE * ICON_TILE;      // [n_act] offset into win
-    uint32_t* s_rgb = s_act + n_act;                     // [n_act * n]
-    float* s_af = reinterpret_cast<float*>(s_rgb + n_act * n);
-    uint32_t* s_c0 = reinterpret_cast<uint32_t*>(s_af + n_act * n);
-    uint32_t* queue = s_c0 + n_act * n;                  // [g.tx] live tiles of the current tile-row
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(queue + a.g.tx);  // [NW][n_act rounded up to even]
+    uint32_t* s_rgb = cand + ICON_TILE * ICON_TILE;      // [np * n]
+    float* s_af = reinterpret_cast<float*>(s_rgb + np * n);
+    uint32_t* s_c0 = reinterpret_cast<uint32_t*>(s_af + np * n);
+    uint32_t* s_opq = s_c0 + np * n;                     // [n][size]
+    uint32_t* queue = s_opq + n * size;                  // [g.tx] live tiles of the current tile-row
     __shared__ uint32_t s_item, s_nq, s_ncand;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint16_t* list = s_list + warp * ((n_act + 1u) & ~1u);
 
-    for (uint32_t j = tid; j < n_act; j += ICON_THREADS) {
-        const uint32_t v = a.t.act[j];
-        s_act[j] = (v >> 8) * WP + (v & 0xFFu);
-    }
-    for (uint32_t j = tid; j < n_act * n; j += ICON_THREADS) { s_rgb[j] = a.t.rgb[j]; s_af[j] = a.t.af[j]; s_c0[j] = a.t.c0[j]; }
-    // scoring: G lanes per template, each lane sums its template over a share of the non-black pixels
+    for (uint32_t j = tid; j < np * n; j += ICON_THREADS) { s_rgb[j] = a.t.rgb[j]; s_af[j] = a.t.af[j]; s_c0[j] = a.t.c0[j]; }
+    // scoring: G lanes per template, each lane takes every G-th row of its template
     const uint32_t G = 32u / n, my_t = lane / G, sub = lane - my_t * G;
     const bool scorer = my_t < n;
     const uint32_t my_base = scorer ? a.t.base[my_t] : 0u;
+    for (uint32_t j = tid; j < n * size; j += ICON_THREADS) s_opq[j] = a.t.opq[j];
+    const uint32_t* my_opq = s_opq + (scorer ? my_t : 0u) * size;
+    const uint32_t my_rows = scorer ? size : 0u;
 
     // candidate bounds (lib.rs:270-273), [lo, hi)
     const int x_lo = (int)size, y_lo = (int)size, x_hi = (int)(a.w - size - 1u), y_hi = (int)(a.h - size - 1u);
@@ -132,18 +130,25 @@ __global__ void __launch_bounds__(ICON_THREADS) k_icons(const IconArgs a) {
             const int tx0 = (int)(queue[q] * ICON_TILE) - (int)a.g.pad;  // crop x of the tile's first column (may be < 0)
             if (tid == 0) s_ncand = 0u;
             __syncthreads();
-            // isolated crop of the tile plus the template's reach, and the tile's candidates
+            // isolated crop of the tile plus the template's reach, its non-black row masks, the tile's candidates
             for (uint32_t r0 = 0; r0 < WIN; r0 += NW) {
                 const uint32_t r = r0 + warp;
-                for (uint32_t c0 = 0; c0 < WIN; c0 += 32u) {  // whole warps iterate: the ballot is full-mask
-                    const uint32_t c = c0 + lane;
-                    bool is_cand = false;
+                uint32_t nzw[2] = {0u, 0u};
+#pragma unroll
+                for (uint32_t half = 0; half < 2; half++) {  // whole warps iterate: the ballots are full-mask
+                    const uint32_t c = half * 32u + lane;
+                    bool is_cand = false, nz = false;
                     if (r < WIN && c < WIN) {
                         const int x = tx0 + (int)c, y = ty0 + (int)r;
-                        const uint32_t v = x >= 0 ? icon_pixel(a, frame, (uint32_t)x, (uint32_t)y) : 0u;
+                        uint32_t v = 0u;  // black is not a marker colour: pixels outside the crop stay 0
+                        if (x >= 0 && (uint32_t)x < a.w && (uint32_t)y < a.h)
+                            v = icon_isolate(__ldg(reinterpret_cast<const uint32_t*>(frame + (uint64_t)(a.map_y + (uint32_t)y) * a.pitch +
+                                                                                     (uint64_t)(a.map_x + (uint32_t)x) * 4u)), a.lut);
                         win[r * WP + c] = v;
-                        is_cand = v != 0u && r < ICON_TILE && c < ICON_TILE && x >= x_lo && x < x_hi && y >= y_lo && y < y_hi;
+                        nz = v != 0u;
+                        is_cand = nz && r < ICON_TILE && c < ICON_TILE && x >= x_lo && x < x_hi && y >= y_lo && y < y_hi;
                     }
+                    nzw[half] = __ballot_sync(0xFFFFFFFFu, nz);
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_cand);
                     if (m) {
                         // raster order inside the tile is not needed: the key carries (y, x)
@@ -154,39 +159,36 @@ __global__ void __launch_bounds__(ICON_THREADS) k_icons(const IconArgs a) {
                         if (is_cand) cand[pos] = c | (r << 8);
                     }
                 }
+                if (lane == 0 && r < WIN) rowbits[r] = ((unsigned long long)nzw[1] << 32) | nzw[0];
             }
             __syncthreads();
             const uint32_t nc = s_ncand;
             for (uint32_t k = warp; k < nc; k += NW) {
                 const uint32_t cv = cand[k], cx = cv & 0xFFu, cy = cv >> 8;
                 const uint32_t* wp = win + cy * WP + cx;
-                // 1. the template pixels that see a non-black pixel of the crop (the rest is in `base`)
-                uint32_t cnt = 0;
-                for (uint32_t j0 = 0; j0 < n_act; j0 += 32u) {
-                    const uint32_t j = j0 + lane;
-                    const bool nz = j < n_act && wp[s_act[j]] != 0u;
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, nz);
-                    if (nz) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
-                    cnt += __popc(m);
-                }
-                __syncwarp();
-                // 2. ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323 — minus what a black pixel gives
+                // a black crop pixel scores a per-template constant (summed in `base`); only the template's
+                // opaque pixels that see a non-black crop pixel are evaluated:
+                // ((ad as f32) * (alpha as f32 / 255.0)) as u32 — lib.rs:323 — minus what a black pixel gives
                 uint32_t acc = 0u;
-                if (scorer)
-                    for (uint32_t e = sub; e < cnt; e += G) {
-                        const uint32_t j = list[e], idx = j * n + my_t;
-                        const uint32_t ad = __vsadu4(wp[s_act[j]], s_rgb[idx]);
-                        acc += (uint32_t)__fmul_rn((float)ad, s_af[idx]) - s_c0[idx];
+                for (uint32_t my = sub; my < my_rows; my += G) {
+                    uint32_t bits = (uint32_t)(rowbits[cy + my] >> cx) & my_opq[my];
+                    const uint32_t* wr = wp + my * WP;
+                    const uint32_t e0 = my * size * n + my_t;
+                    while (bits) {
+                        const uint32_t mx = __ffs(bits) - 1u;
+                        bits &= bits - 1u;
+                        const uint32_t idx = e0 + mx * n;
+                        acc += (uint32_t)__fmul_rn((float)__vsadu4(wr[mx], s_rgb[idx]), s_af[idx]) - s_c0[idx];
                     }
-                uint32_t tot = 0u;
+                }
+                uint32_t tot = 0u;  // sum over the template's lanes (a per-group REDUX with six different masks measured slower)
                 for (uint32_t d = 0; d < G; d++) tot += __shfl_sync(0xFFFFFFFFu, acc, scorer ? my_t * G + d : lane);
                 const uint32_t best_sad = __reduce_min_sync(0xFFFFFFFFu, scorer ? tot + my_base : 0xFFFFFFFFu);
                 const unsigned long long key = ((unsigned long long)best_sad << 32) | ((unsigned long long)(uint32_t)(ty0 + (int)cy) << 16) |
                                                (uint32_t)(tx0 + (int)cx);
                 my_best = key < my_best ? key : my_best;
-                __syncwarp();  // the list is rewritten by the next candidate
             }
-            __syncthreads();  // window and candidate list are rewritten by the next tile
+            __syncthreads();  // window, row masks and candidate list are rewritten by the next tile
         }
     }
     if (cur_frame != 0xFFFFFFFFu && lane == 0 && my_best != ICON_NONE) atomicMin(a.best + cur_frame, my_best);

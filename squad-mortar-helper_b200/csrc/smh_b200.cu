@@ -326,9 +326,8 @@ int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t f
         a.counter = P.counter;  // this lane's dispenser; the line search zeroes it again before its own launch
         CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
         const uint32_t WIN = smh::ICON_TILE + size - 1u, WP = WIN | 1u;
-        const size_t na = h->icons.n_act;
-        const size_t dyn = ((size_t)WIN * WP + smh::ICON_TILE * smh::ICON_TILE + na + 3u * na * h->icons.n + P.bg.tx) * 4u +
-                           (size_t)(smh::ICON_THREADS / 32) * ((na + 1u) & ~(size_t)1u) * 2u;
+        const size_t npx = (size_t)size * size;
+        const size_t dyn = (128u + (size_t)WIN * WP + smh::ICON_TILE * smh::ICON_TILE + 3u * npx * h->icons.n + (size_t)h->icons.n * size + P.bg.tx) * 4u;
         {
             static std::mutex mu;
             static size_t raised[64] = {0};
@@ -747,46 +746,36 @@ int32_t smh_b200_isolate_map_markers(smh_b200* h) {
 
 int32_t smh_b200_load_map_markers(smh_b200* h, const uint8_t* rgba, uint32_t n_markers, uint32_t size) {
     if (!h || !rgba) return fail(h, SMH_E_ARG, "load_map_markers: bad argument");
-    if (n_markers == 0 || n_markers > (uint32_t)smh::ICON_MAX_TEMPLATES || size < 4 || size > 96 ||
+    if (n_markers == 0 || n_markers > (uint32_t)smh::ICON_MAX_TEMPLATES || size < 4 || size > 32 ||
         (uint64_t)n_markers * size * size > 8192u)
-        return fail(h, SMH_E_RANGE, "load_map_markers: %u templates of %ux%u (at most %d templates, 4 <= size <= 96, n*size*size <= 8192)",
+        return fail(h, SMH_E_RANGE, "load_map_markers: %u templates of %ux%u (at most %d templates, 4 <= size <= 32, n*size*size <= 8192)",
                     n_markers, size, size, smh::ICON_MAX_TEMPLATES);
     std::lock_guard<std::mutex> g(h->markers_mu);
     CU(h, cudaSetDevice(h->device));
-    // template pixels opaque in at least one template, and per (pixel, template): colour, alpha/255 and the
-    // score against a black pixel — ((ad as f32) * (alpha as f32 / 255.0)) as u32, vision-cpu/src/lib.rs:323
-    std::vector<uint32_t> act;
-    for (uint32_t my = 0; my < size; my++)
-        for (uint32_t mx = 0; mx < size; mx++) {
-            bool any = false;
-            for (uint32_t t = 0; t < n_markers; t++) any = any || rgba[(((size_t)t * size + my) * size + mx) * 4 + 3] != 0;
-            if (any) act.push_back(mx | (my << 8));
-        }
-    const size_t na = act.size(), ne = na * n_markers;
-    std::vector<uint32_t> blob(na + 3 * ne + n_markers, 0u);
-    uint32_t* rgb = blob.data() + na; float* af = reinterpret_cast<float*>(rgb + ne);
-    uint32_t* c0 = reinterpret_cast<uint32_t*>(af + ne); uint32_t* base = c0 + ne;
-    for (size_t j = 0; j < na; j++) {
-        blob[j] = act[j];
-        const uint32_t mx = act[j] & 0xFFu, my = act[j] >> 8;
+    // per (template pixel p = my*size + mx, template t): colour, alpha/255 and the score against a black pixel —
+    // ((ad as f32) * (alpha as f32 / 255.0)) as u32, vision-cpu/src/lib.rs:323; per (t, my) the opaque columns
+    const size_t np = (size_t)size * size, ne = np * n_markers;
+    std::vector<uint32_t> blob(3 * ne + n_markers + (size_t)n_markers * size, 0u);
+    uint32_t* rgb = blob.data(); float* af = reinterpret_cast<float*>(rgb + ne);
+    uint32_t* c0 = reinterpret_cast<uint32_t*>(af + ne); uint32_t* base = c0 + ne; uint32_t* opq = base + n_markers;
+    for (size_t p = 0; p < np; p++)
         for (uint32_t t = 0; t < n_markers; t++) {
-            const uint8_t* px = rgba + (((size_t)t * size + my) * size + mx) * 4;
+            const uint8_t* px = rgba + ((size_t)t * np + p) * 4;
             const volatile float a = (float)px[3] / 255.0f;
             const volatile float v = (float)((uint32_t)px[0] + px[1] + px[2]) * a;
-            rgb[j * n_markers + t] = (uint32_t)px[2] | ((uint32_t)px[1] << 8) | ((uint32_t)px[0] << 16);  // b | g<<8 | r<<16
-            af[j * n_markers + t] = a;
-            c0[j * n_markers + t] = (uint32_t)v;
+            rgb[p * n_markers + t] = (uint32_t)px[2] | ((uint32_t)px[1] << 8) | ((uint32_t)px[0] << 16);  // b | g<<8 | r<<16
+            af[p * n_markers + t] = a;
+            c0[p * n_markers + t] = (uint32_t)v;
             base[t] += (uint32_t)v;
+            if (px[3] != 0) opq[(size_t)t * size + p / size] |= 1u << (p % size);
         }
-    }
     CU(h, cudaDeviceSynchronize());  // no kernel may still read the previous table
     cudaFree(h->d_icons); h->d_icons = nullptr;
     CU(h, cudaMalloc(&h->d_icons, blob.size() * 4));
     CU(h, cudaMemcpy(h->d_icons, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
-    h->icons.act = h->d_icons; h->icons.rgb = h->d_icons + na;
-    h->icons.af = reinterpret_cast<const float*>(h->d_icons + na + ne);
-    h->icons.c0 = h->d_icons + na + 2 * ne; h->icons.base = h->d_icons + na + 3 * ne;
-    h->icons.n_act = (uint32_t)na; h->icons.n = n_markers; h->icons.size = size;
+    h->icons.rgb = h->d_icons; h->icons.af = reinterpret_cast<const float*>(h->d_icons + ne);
+    h->icons.c0 = h->d_icons + 2 * ne; h->icons.base = h->d_icons + 3 * ne; h->icons.opq = h->d_icons + 3 * ne + n_markers;
+    h->icons.n = n_markers; h->icons.size = size;
     return SMH_OK;
 }
 
