@@ -147,7 +147,7 @@ def run_e2e(args, vision, frames, roi, n, world, barrier):
     """Same metric through smh_b200_process_host_batch: pinned HOST frames in, host results out."""
     import torch
     import torch.distributed as dist
-    ne = min(args.e2e_frames or (n if world <= 2 else 512), n)
+    ne = min(args.e2e_frames or (n if world <= 2 else (512 if world <= 4 else 256)), n)
     host_frames = torch.empty((ne, H, W, 4), dtype=torch.uint8).pin_memory()
     host_frames.copy_(frames[:ne])
     _, _, mw, mh = roi["map"]; _, _, qw, qh = roi["brq"]
@@ -200,7 +200,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--e2e-frames", type=int, default=0,
-                    help="host frames per e2e step (default: the whole batch; 512 per rank beyond 2 GPUs to bound pinned host memory)")
+                    help="host frames per e2e step (default: the whole batch; 512 per rank beyond 2 GPUs, 256 beyond 4, to bound pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--in-flight", type=int, default=2,
