@@ -184,12 +184,17 @@ def run_e2e(args, vision, frames, roi, n, world, barrier):
     gx0 = roi["map"][0] & ~3
     nvec = (roi["map"][0] - gx0 + mw + 3) // 4
     h2d = ne * (min(4 * nvec, W - gx0) * 4 * mh + roi["button"][2] * roi["button"][3] * 4)
-    d2h = ne * (mw * mh * 4 + 2 * qw * qh + 512 + 9)
+    # grayscale ui_map: only its L plane crosses the bus (host threads of the library widen it to RGBA)
+    ui_l8 = os.environ.get("SMH_B200_UI_L8", "1") != "0"
+    d2h = ne * (mw * mh * (1 if ui_l8 else 4) + 2 * qw * qh + 512 + 9)
     e2e_check = int(outs["n_lines"].sum())
 
     return {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "frames_per_step": ne, "steps": e_steps, "lines_checksum": e2e_check,
-            "note": "smh_b200_process_host_batch: pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines back, 3 chunks in flight"}
+            "note": "smh_b200_process_host_batch: pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines back, "
+                    "3 chunks in flight; the grayscale ui_map crosses the bus as its L plane and is widened to RGBA in the caller's buffer "
+                    "by the library's host threads inside the timed region" if ui_l8 else
+                    "smh_b200_process_host_batch: pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines back, 3 chunks in flight"}
 
 
 def main() -> None:

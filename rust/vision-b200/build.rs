@@ -10,7 +10,8 @@ fn main() {
     let src = PathBuf::from(env::var("SMH_B200_SRC").unwrap_or_else(|_| "../..".into()));
     let csrc = src.join("squad-mortar-helper_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
-    for f in ["smh_b200.cu", "kernels.cuh", "smh_pixel.h", "smh_synth.h"] {
+    for f in ["smh_b200.cu", "kernels.cuh", "kernels_next.cuh", "kernels_icons.cuh", "smh_host_widen.cpp", "smh_pixel.h", "smh_synth.h",
+              "smh_lsd_filter.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", src.join("include/smh_b200.h").display());
@@ -25,8 +26,15 @@ fn main() {
         .arg("-c").arg(csrc.join("smh_b200.cu")).arg("-o").arg(&obj)
         .status().expect("failed to run nvcc");
     assert!(status.success(), "nvcc failed");
+    // host-only helper (AVX2 widening of the grayscale ui_map rows that cross the bus as L8)
+    let obj2 = out.join("smh_host_widen.o");
+    let status = Command::new(&nvcc)
+        .args(["-O3", "-std=c++17", "-Xcompiler", "-fPIC"])
+        .arg("-c").arg(csrc.join("smh_host_widen.cpp")).arg("-o").arg(&obj2)
+        .status().expect("failed to run nvcc");
+    assert!(status.success(), "nvcc (host file) failed");
     let lib = out.join("libsmh_b200_static.a");
-    assert!(Command::new("ar").arg("crs").arg(&lib).arg(&obj).status().unwrap().success());
+    assert!(Command::new("ar").arg("crs").arg(&lib).arg(&obj).arg(&obj2).status().unwrap().success());
 
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=static=smh_b200_static");

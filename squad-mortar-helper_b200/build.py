@@ -41,14 +41,14 @@ def _stale(target: Path, sources) -> bool:
 
 
 def cuda_sources():
-    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h",
+    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_host_widen.cpp", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h",
             ROOT / "include" / "smh_b200.h", ROOT / "include" / "smh_consts.h"]
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     out = PKG / "libsmh_b200.so"
     if force or _stale(out, cuda_sources()):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _gxx(), "-o", str(out), str(CSRC / "smh_b200.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _gxx(), "-o", str(out), str(CSRC / "smh_b200.cu"), str(CSRC / "smh_host_widen.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True, cwd=str(CSRC))

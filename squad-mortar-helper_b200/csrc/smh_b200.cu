@@ -14,13 +14,18 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "kernels.cuh"
 #include "kernels_next.cuh"
 #include "kernels_icons.cuh"
+
+extern "C" void smh_host_widen_l8_to_rgba(const uint8_t* src, uint32_t* dst, size_t n);  // smh_host_widen.cpp
 
 namespace {
 
@@ -100,6 +105,59 @@ struct Planes {
     }
 };
 
+// Host-side workers of smh_b200_process_host_batch: with a grayscale ui_map every pixel is (L, L, L, 255), so
+// only L crosses the bus (a quarter of the bytes of the largest output) and these threads widen it into the
+// caller's RGBA buffer while later chunks are still in flight.  A task waits for its chunk's download event.
+struct HostPool {
+    struct Task { cudaEvent_t ev; const uint8_t* src; uint32_t* dst; size_t n; std::atomic<int>* pending; };
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<Task> q;
+    bool stop = false;
+    int device = 0;
+    std::atomic<int> failed{0};
+
+    void run() {
+        cudaSetDevice(device);
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;
+                t = q.front(); q.pop_front();
+            }
+            if (cudaEventSynchronize(t.ev) != cudaSuccess) failed = 1;
+            else smh_host_widen_l8_to_rgba(t.src, t.dst, t.n);
+            if (t.pending->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu); cv_done.notify_all(); }
+        }
+    }
+    void start(int dev, unsigned n_threads) {
+        if (!th.empty()) return;
+        device = dev;
+        for (unsigned i = 0; i < n_threads; i++) th.emplace_back([this] { run(); });
+    }
+    void push(const Task& t) { { std::lock_guard<std::mutex> lk(mu); q.push_back(t); } cv.notify_one(); }
+    void wait_zero(std::atomic<int>& pending) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending.load() == 0; });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+
+// first byte of every RGBA pixel of a ui_map plane (its L when the map is grayscale), rows tightly packed
+__global__ void k_pack_gray(const uint8_t* __restrict__ ui, uint32_t pitch, uint32_t pad, uint32_t w, uint32_t rows, uint8_t* __restrict__ out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    for (uint32_t r = blockIdx.y; r < rows; r += gridDim.y)
+        out[(size_t)r * w + x] = (uint8_t)__ldg(reinterpret_cast<const uint32_t*>(ui + (size_t)r * pitch + (size_t)(pad + x) * 4u));
+}
+
 }  // namespace
 
 struct smh_b200 {
@@ -147,6 +205,10 @@ struct smh_b200 {
     uint8_t* d_stage = nullptr; size_t stage_cap = 0;   // host-batch upload staging (device)
     uint8_t* d_pack = nullptr; size_t pack_cap = 0;     // host-batch download staging: planes without pitch padding
     Planes pipe[SMH_PIPE_DEPTH];
+    HostPool pool;                            // host-batch: widens grayscale ui_map rows (L8 over the bus)
+    uint8_t* h_gray = nullptr; size_t gray_cap = 0;   // pinned landing area of the L8 rows, [SMH_PIPE_DEPTH][chunk * w*h]
+    cudaEvent_t ev_gray[SMH_PIPE_DEPTH] = {};
+    std::atomic<int> gray_pending[SMH_PIPE_DEPTH];
     std::vector<cudaStream_t> lane_streams;   // process_batch: chunks of a large batch, taken in turn
     std::vector<cudaEvent_t> lane_events;     // [0] fork, [1 + lane] join
 };
@@ -586,7 +648,8 @@ void smh_b200_destroy(smh_b200* h) {
     free_single(h);
     h->batch.release(); for (auto& P : h->pipe) P.release();
     cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_icons); cudaFree(h->d_longest); cudaFree(h->d_view);
-    cudaFreeHost(h->h_small); cudaFreeHost(h->h_view);
+    cudaFreeHost(h->h_small); cudaFreeHost(h->h_view); cudaFreeHost(h->h_gray);
+    for (auto e : h->ev_gray) if (e) cudaEventDestroy(e);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
     for (auto e : h->pipe_events) cudaEventDestroy(e);
     for (auto s : h->lane_streams) cudaStreamDestroy(s);
@@ -1196,7 +1259,31 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
     // Download staging: the planes' rows carry pitch padding on the device; a strided copy over the bus
     // pays per row (the quadrant planes' rows are a few hundred bytes), so the rows are first packed on the
     // device and each plane of a chunk then crosses the bus as ONE contiguous copy.
-    const size_t pack_frame = (res->ui_map ? npx * 4 : 0) + (res->ocr_out ? nq : 0) + (res->scales ? nq : 0) + (res->lsd_image ? npx : 0);
+    // grayscale ui_map: every pixel is (L, L, L, 255) — only L crosses the bus, host threads widen it (HostPool)
+    static const bool l8_ok = [] { const char* e = getenv("SMH_B200_UI_L8"); return !(e && e[0] == '0'); }();
+    const bool ui_l8 = res->ui_map && (flags & SMH_BATCH_GRAYSCALE) && l8_ok;
+    if (ui_l8) {
+        if (h->pool.th.empty()) {
+            // measured on a 16-core B200 host, 1024 x 1440p frames: 2 threads 6.5 k frames/s, 4 -> 7.8 k, 8 -> 7.5 k, 12 -> 7.4 k
+            // (the RGBA rows over the bus instead: 7.25 k)
+            unsigned hw = std::thread::hardware_concurrency(), nt = hw >= 8 ? 4 : 2;
+            if (const char* e = getenv("SMH_B200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nt = (unsigned)v; }
+            h->pool.start(h->device, nt);
+            for (int i = 0; i < DEPTH; i++) {
+                CU(h, cudaEventCreateWithFlags(&h->ev_gray[i], cudaEventDisableTiming | cudaEventBlockingSync));
+                h->gray_pending[i] = 0;
+            }
+        }
+        const size_t gneed = npx * chunk * DEPTH;
+        if (h->gray_cap < gneed) {
+            for (int i = 0; i < DEPTH; i++) h->pool.wait_zero(h->gray_pending[i]);
+            CU(h, cudaDeviceSynchronize());
+            cudaFreeHost(h->h_gray); h->h_gray = nullptr; h->gray_cap = 0;
+            CU(h, cudaMallocHost(&h->h_gray, gneed));
+            h->gray_cap = gneed;
+        }
+    }
+    const size_t pack_frame = (res->ui_map ? (ui_l8 ? npx : npx * 4) : 0) + (res->ocr_out ? nq : 0) + (res->scales ? nq : 0) + (res->lsd_image ? npx : 0);
     const size_t pack_need = pack_frame * chunk * DEPTH;
     if (h->pack_cap < pack_need) {
         CU(h, cudaDeviceSynchronize());
@@ -1289,6 +1376,14 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         uint8_t* cursor = pack0;
         for (const Want& wnt : wants) {  // rows without their pitch padding, plane after plane
             if (!wnt.pl) continue;
+            if (ui_l8 && wnt.pl == &P.ui) {
+                const uint32_t nrows = P.ui.height * c;
+                k_pack_gray<<<dim3((P.ui.width + 255u) / 256u, nrows < 4096u ? nrows : 4096u), 256, 0, st>>>(P.ui.ptr, P.ui.pitch, P.ui.pad, P.ui.width, nrows, cursor);
+                h->launches++;
+                CU(h, cudaGetLastError());
+                cursor += npx * c;
+                continue;
+            }
             const size_t row = (size_t)wnt.pl->width * wnt.pl->bytes_per_pixel;
             CU(h, cudaMemcpy2DAsync(cursor, row, wnt.pl->ptr + (size_t)wnt.pl->pad * wnt.pl->bytes_per_pixel, wnt.pl->pitch, row,
                                     (size_t)wnt.pl->height * c, cudaMemcpyDeviceToDevice, st));
@@ -1302,6 +1397,22 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         cursor = pack0;
         for (const Want& wnt : wants) {
             if (!wnt.pl) continue;
+            if (ui_l8 && wnt.pl == &P.ui) {
+                // the slot's landing area is free once the workers widened its previous occupant
+                h->pool.wait_zero(h->gray_pending[b]);
+                uint8_t* land = h->h_gray + (size_t)b * npx * chunk;
+                CU(h, cudaMemcpyAsync(land, cursor, npx * c, cudaMemcpyDeviceToHost, st));
+                CU(h, cudaEventRecord(h->ev_gray[b], st));
+                const size_t total = npx * c, nt = h->pool.th.size(), per = (total / nt + 63) & ~(size_t)63;
+                int tasks = 0;
+                for (size_t o = 0; o < total; o += per) tasks++;
+                h->gray_pending[b] = tasks;
+                for (size_t o = 0; o < total; o += per)
+                    h->pool.push({h->ev_gray[b], land + o, reinterpret_cast<uint32_t*>(wnt.host) + o, total - o < per ? total - o : per,
+                                  &h->gray_pending[b]});
+                cursor += npx * c;
+                continue;
+            }
             const size_t bytes = (size_t)wnt.pl->width * wnt.pl->bytes_per_pixel * wnt.pl->height * c;
             CU(h, cudaMemcpyAsync(wnt.host, cursor, bytes, cudaMemcpyDeviceToHost, st));
             cursor += bytes;
@@ -1329,6 +1440,10 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         for (auto e : tev) cudaEventDestroy(e);
     }
     for (auto s : h->pipe_streams) CU(h, cudaStreamSynchronize(s));
+    if (ui_l8) {
+        for (int i = 0; i < DEPTH; i++) h->pool.wait_zero(h->gray_pending[i]);
+        if (h->pool.failed.exchange(0)) return fail(h, SMH_E_STATE, "process_host_batch: a host worker failed to wait for its download");
+    }
     return SMH_OK;
 }
 

@@ -102,15 +102,17 @@ def test_batch_with_closed_maps_and_rgb(vision):
             assert res["n_lines"][i] == 0
 
 
-def test_host_batch_end_to_end(vision):
-    W, H, n = 1920, 1080, 11
+@pytest.mark.parametrize("gray,W,H,n,chunk", [(True, 1920, 1080, 11, 4), (False, 1920, 1080, 7, 3), (True, 1366, 768, 23, 5)])
+def test_host_batch_end_to_end(vision, gray, W, H, n, chunk):
+    """Host frames in, host results out.  With a grayscale ui_map only its L plane crosses the bus and the
+    library's host threads widen it into the caller's RGBA buffer; the colour ui_map crosses as RGBA."""
     p = synth.SynthParams(W, H)
     frames = synth.frames_host(p, 7, n)
     start_y = (np.arange(n, dtype=np.uint32) * 13) % 90
-    out = vision.process_host_batch(frames, start_y=start_y, max_gap=15, grayscale=True, chunk=4,
+    out = vision.process_host_batch(frames, start_y=start_y, max_gap=15, grayscale=gray, chunk=chunk,
                                     want=("ui_map", "ocr_out", "scales", "lsd_image"))
     for i in range(n):
-        want = oracle_run(frames[i], True, int(start_y[i]), 15)
+        want = oracle_run(frames[i], gray, int(start_y[i]), 15)
         got = _frame_result(out, i); got["xywh"] = want["xywh"]
         # pipelined chunks reuse plane buffers: rows above start_y hold an earlier frame's data
         sy = int(start_y[i])
