@@ -234,6 +234,11 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own log (the version banner this image's NCCL_DEBUG setting prints
+        # on the first collective) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # the banner is printf'ed to stdout whatever the log file
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -294,8 +299,11 @@ def main() -> None:
         step()
     join()
     barrier()
+    # one nvidia-smi poller for the whole job (rank 0's GPU): eight of them querying the driver every 100 ms
+    # perturb the launches of all ranks
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     launches0 = sum(h_.launch_count() for h_ in handles)
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
