@@ -238,11 +238,16 @@ typedef struct {
     uint8_t *map_open;    /* n */
     uint32_t *minimap;    /* n * 4, with SMH_BATCH_MINIMAP (may be NULL) */
     uint8_t *minimap_found; /* n (may be NULL) */
+    uint8_t *icon_found;  /* n, with SMH_BATCH_FILTER_ICONS (may be NULL) */
+    uint32_t *icon_xy;    /* n * 2 (may be NULL) */
+    uint32_t *icon_sad;   /* n (may be NULL) */
 } smh_b200_host_results;
 
 /* End-to-end batch from HOST frames (pinned memory recommended): uploads each frame's ROI band,
  * runs the path and copies the results back, pipelined over chunks of `chunk` frames on
- * internal streams; returns after everything has landed in `res`. */
+ * internal streams; returns after everything has landed in `res`.  With SMH_BATCH_GRAYSCALE the
+ * ui_map crosses the bus as its L plane and is widened to (L, L, L, 255) in `res->ui_map` by host
+ * threads of the library.  Flags honoured: GRAYSCALE, SKIP_LSD, MINIMAP, FILTER_ICONS. */
 int32_t smh_b200_process_host_batch(smh_b200 *h, const uint8_t *frames, uint32_t n, uint32_t W, uint32_t H,
                                     uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
                                     uint32_t max_gap, uint32_t flags, uint32_t chunk,

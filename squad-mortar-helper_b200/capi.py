@@ -47,7 +47,8 @@ class Batch(C.Structure):
 class HostResults(C.Structure):
     _fields_ = [("ui_map", C.c_void_p), ("ocr_out", C.c_void_p), ("scales", C.c_void_p), ("lsd_image", C.c_void_p),
                 ("lines", C.c_void_p), ("n_lines", C.c_void_p), ("red_pixels", C.c_void_p), ("map_open", C.c_void_p),
-                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p)]
+                ("minimap", C.c_void_p), ("minimap_found", C.c_void_p),
+                ("icon_found", C.c_void_p), ("icon_xy", C.c_void_p), ("icon_sad", C.c_void_p)]
 
 
 class Scale(C.Structure):

@@ -1220,6 +1220,8 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
     if (rc) return fail(h, rc, "process_host_batch: %ux%u is a frame size the reference panics on", W, H);
     if (chunk == 0) chunk = 32;
     if (chunk > n) chunk = n;
+    const bool icons = flags & SMH_BATCH_FILTER_ICONS;
+    if (icons && !h->d_icons) return fail(h, SMH_E_STATE, "process_host_batch: FILTER_ICONS before load_map_markers");
     constexpr int DEPTH = SMH_PIPE_DEPTH;
     // Three stages on three streams — upload, compute (kernels + row packing), download — chained by
     // events per slot, so the bus is busy in both directions all the time: chunk k+1 goes up and chunk
@@ -1365,8 +1367,12 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
             return rc;
         if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found)
             if ((rc = launch_minimap(h, P, stage, ustride, upitch, ux0, uy0, c, true, st))) return rc;
+        if (icons) {
+            if ((rc = launch_pack(h, P, c, st))) return rc;
+            if ((rc = launch_icons(h, P, stage, ustride, upitch, ux0, uy0, c, true, st))) return rc;
+        }
         if (!(flags & SMH_BATCH_SKIP_LSD))
-            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st))) return rc;
+            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st, !icons))) return rc;
         uint8_t* const pack0 = h->d_pack + (size_t)b * pack_frame * chunk;
         struct Want { const smh_b200_plane* pl; uint8_t* host; };
         const Want wants[4] = {{res->ui_map ? &P.ui : nullptr, res->ui_map ? res->ui_map + (size_t)done * npx * 4 : nullptr},
@@ -1424,6 +1430,11 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found) {
             CU(h, cudaMemcpyAsync(res->minimap + (size_t)done * 4, P.minimap, (size_t)c * 16, cudaMemcpyDeviceToHost, st));
             CU(h, cudaMemcpyAsync(res->minimap_found + done, P.minimap_found, (size_t)c, cudaMemcpyDeviceToHost, st));
+        }
+        if (icons) {
+            if (res->icon_found) CU(h, cudaMemcpyAsync(res->icon_found + done, P.icon_found, (size_t)c, cudaMemcpyDeviceToHost, st));
+            if (res->icon_xy) CU(h, cudaMemcpyAsync(res->icon_xy + (size_t)done * 2, P.icon_xy, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
+            if (res->icon_sad) CU(h, cudaMemcpyAsync(res->icon_sad + done, P.icon_sad, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         }
         stamp(st);
         CU(h, cudaEventRecord(ev_down, st));

@@ -341,10 +341,15 @@ class B200Vision:
             out.setdefault("minimap_found", np.zeros((n,), np.uint8))
             res.minimap = out["minimap"].ctypes.data if isinstance(out["minimap"], np.ndarray) else int(out["minimap"])
             res.minimap_found = out["minimap_found"].ctypes.data if isinstance(out["minimap_found"], np.ndarray) else int(out["minimap_found"])
+        if "icons" in want:  # the reference-disabled template match (needs load_map_markers)
+            for k, shp, dt in (("icon_found", (n,), np.uint8), ("icon_xy", (n, 2), np.uint32), ("icon_sad", (n,), np.uint32)):
+                out.setdefault(k, np.zeros(shp, dt))
+                setattr(res, k, out[k].ctypes.data if isinstance(out[k], np.ndarray) else int(out[k]))
         sy = None
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)
-        flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_MINIMAP if "minimap" in want else 0)
+        flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_MINIMAP if "minimap" in want else 0) | \
+                (capi.BATCH_FILTER_ICONS if "icons" in want else 0)
         check(self._h, self._L.smh_b200_process_host_batch(self._h, frames_ptr, n, W, H, W * 4, W * H * 4,
                                                            sy.ctypes.data if sy is not None else None, max_gap, flags,
                                                            chunk, C.byref(res)))

@@ -73,3 +73,20 @@ def test_synthetic_generator_is_deterministic():
     assert not tm[(rgb[..., 2] << 16) | (rgb[..., 1] << 8) | rgb[..., 0]].any()
     rgb = a[0][y:y + h, x:x + w].astype(np.uint32)
     assert tm[(rgb[..., 2] << 16) | (rgb[..., 1] << 8) | rgb[..., 0]].sum() > 500
+
+
+def test_host_widen_l8_to_rgba_matches_numpy():
+    """The host half of the grayscale ui_map transfer (csrc/smh_host_widen.cpp): (L) -> (L, L, L, 255), any
+    length and alignment (vector body + scalar head and tail)."""
+    L = ctypes.CDLL(str(capi.LIB_PATH))
+    fn = L.smh_host_widen_l8_to_rgba
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    fn.restype = None
+    rng = np.random.default_rng(3)
+    for n, off in [(0, 0), (1, 0), (7, 1), (8, 0), (63, 3), (4096, 0), (100003, 5), (1 << 20, 2)]:
+        src = rng.integers(0, 256, n + 16, dtype=np.uint8)
+        dst = np.zeros(n + 16, np.uint32)
+        fn(src.ctypes.data + off, dst.ctypes.data + 4 * off, n)
+        want = src[off:off + n].astype(np.uint32) * 0x010101 | 0xFF000000
+        assert np.array_equal(dst[off:off + n], want)
+        assert not dst[:off].any() and not dst[off + n:].any()

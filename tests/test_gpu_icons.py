@@ -116,3 +116,16 @@ def test_batch_flag_matches_oracle(vision):
     b = vision.process_batch(dev.data_ptr(), n, W, H, max_gap=15, stream=st)
     torch.cuda.synchronize()
     assert b.icon_found is None
+
+
+def test_host_batch_with_icons(vision):
+    W, H, n = 1280, 720, 9
+    fr, t = _frames(W, H, n, 120)
+    vision.load_map_markers(t)
+    out = vision.process_host_batch(fr, max_gap=15, grayscale=True, chunk=4, want=("ui_map", "lsd_image", "icons"))
+    for i in range(n):
+        want_hit, want_mask, want_lines, _ = _oracle(fr[i], t)
+        assert out["icon_found"][i] and (int(out["icon_xy"][i, 0]), int(out["icon_xy"][i, 1]), int(out["icon_sad"][i])) == want_hit
+        assert np.array_equal(out["lsd_image"][i], want_mask)
+        m = int(out["n_lines"][i])
+        assert m == len(want_lines) and np.array_equal(out["lines"][i, :m].view(np.uint32), want_lines.view(np.uint32))
