@@ -72,6 +72,9 @@ struct PixelArgs {
     uint32_t grayscale;
     uint32_t n_frames, nstrips;  // strips of PX_STRIP vector columns per row
     const uint32_t* lut;  // marker predicate, 1 bit per colour (r<<16|g<<8|b)
+    // 1-bit tile-major copy of the dilated mask (the line search's input, layout: see BitsGeom), written
+    // alongside lsd_image when non-null: words per frame, tiles per tile-row
+    uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;
 };
 
 
@@ -253,7 +256,7 @@ constexpr int PX_STRIP = 30;  // inner vector columns per warp
 constexpr int PX_SLOTS = PX_SLOTS_N;  // ring slots per warp (power of two > PX_DEPTH), 512 B each
 constexpr int PX_SMEM_BYTES = PX_WARPS * PX_SLOTS * 512;
 
-template <bool GRAY>
+template <bool GRAY, bool BITS = false>
 __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const PixelArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * PX_WARPS + (threadIdx.x >> 5);
@@ -387,6 +390,14 @@ __global__ void __launch_bounds__(PX_THREADS, PX_MIN_BLOCKS) k_pixels(const Pixe
         const uint32_t d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> 16) | (mwin >> 8)) & vm4;
         // nibble -> 4 bytes of 0/255 (pixels outside [0, w) stay 0); lsd_p already points one row ahead
         if (inner) stg_u32(lsd_p - a.lsd_pitch, ((d4 * 0x00204081u) & 0x01010101u) * 255u);
+        if (BITS) {
+            // the same nibble into the bitmap: X = 4q + e, so a lane's nibble is half a byte of word q >> 3 of tile
+            // row jc >> 5.  Inner lanes come in pairs (odd lane: even q), the odd one stores the pair's byte.
+            const uint32_t hi = __shfl_down_sync(0xFFFFFFFFu, d4, 1);
+            if (inner && active && (lane & 1))
+                reinterpret_cast<uint8_t*>(a.bits + (uint64_t)f * a.bits_stride)[
+                    (((((uint32_t)jc >> 5) * a.bits_tx + (qo >> 3)) << 5) + ((uint32_t)jc & 31u)) * 4u + ((qo & 7u) >> 1)] = (uint8_t)(d4 | (hi << 4));
+        }
 
         const int jqc = jc - bqh;
         if (!brq_strip || (uint32_t)jqc >= (uint32_t)bqh) return;  // warp-uniform

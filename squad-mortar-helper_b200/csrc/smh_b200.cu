@@ -283,9 +283,20 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     P->bg.tx = (P->pad + g.map[2] + 31u) / 32u; P->bg.ty = (g.map[3] + 31u) / 32u;
     P->bits_stride = (uint64_t)P->bg.tx * P->bg.ty * 32u;
     CU(h, cudaMalloc(&P->bits, P->bits_stride * n * sizeof(uint32_t)));
+    CU(h, cudaMemset(P->bits, 0, P->bits_stride * n * sizeof(uint32_t)));  // the pixel pass never writes rows >= h / columns >= nvec
     if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
     P->n = n; P->W = g.W; P->H = g.H;
     return SMH_OK;
+}
+
+// SMH_B200_FOLD_PACK=1: the pixel pass also writes the line search's bitmap (no k_pack_bits launch).  Measured on
+// B200, 1024 dense 1440p frames, two batches in flight: step 6.50 -> 6.21 ms (+4.7 % frames/s), but the pixel pass
+// itself slows from 2.88 to 3.22 ms (its 15 byte stores per warp row land as 4-byte pieces in 4-5 tiles) and
+// drops from 76 % to 68 % of the measured copy bandwidth.  Off by default: the separate 0.39 ms kernel keeps
+// the HBM-bound pass at its best store pattern.
+bool fold_pack_enabled() {
+    static const bool on = [] { const char* e = getenv("SMH_B200_FOLD_PACK"); return e && e[0] == '1'; }();
+    return on;
 }
 
 // Launch the fused pixel pass over n frames.  `frames` origin may be a cropped view of the
@@ -311,9 +322,12 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.rows_per_band = rows_per_band; a.nbands = (a.h + rows_per_band - 1) / rows_per_band;
     a.grayscale = grayscale ? 1u : 0u;
     a.lut = h->d_lut;
+    // the bitmap of the dilated mask is written by the same pass (SMH_B200_FOLD_PACK=0: by k_pack_bits afterwards)
+    a.bits = fold_pack_enabled() ? P.bits : nullptr; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
     a.n_frames = n;
     a.nstrips = (a.nvec + smh::PX_STRIP - 1) / smh::PX_STRIP;
-    auto kern = grayscale ? smh::k_pixels<true> : smh::k_pixels<false>;
+    auto kern = a.bits ? (grayscale ? smh::k_pixels<true, true> : smh::k_pixels<false, true>)
+                       : (grayscale ? smh::k_pixels<true, false> : smh::k_pixels<false, false>);
     // one warp per (frame, band, strip) item plus one per frame for the button test
     const uint64_t items = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips + 1u);
     const uint64_t blocks = (items + smh::PX_WARPS - 1) / smh::PX_WARPS;
@@ -359,6 +373,7 @@ Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
 
 // 1-bit tile-major copy of the dilated masks (what the line search and the icon match read)
 int launch_pack(smh_b200* h, const Planes& P, uint32_t n, cudaStream_t st) {
+    if (fold_pack_enabled()) return SMH_OK;  // the pixel pass wrote the bitmap
     const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
     if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
     smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
