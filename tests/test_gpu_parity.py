@@ -5,6 +5,7 @@ import threading
 
 import numpy as np
 import pytest
+import torch
 
 import smh_b200  # noqa: F401
 from conftest import GOLDEN, sample_path, load_png_bgra
@@ -92,6 +93,22 @@ def test_real_screenshots(vision, name):
 def test_odd_resolutions(vision, W, H):
     frame = synth.frames_host(synth.SynthParams(W, H, n_segments=5, n_blips=4, n_labels=3), 1, 1)[0]
     assert_same(gpu_run(vision, frame, True, 3, 15), oracle_run(frame, True, 3, 15), f"{W}x{H}", scales_from=3)
+
+
+@pytest.mark.parametrize("W,H", [(160, 120), (200, 150), (320, 240), (640, 480), (7680, 4320), (16384, 2160)])
+def test_extreme_sizes(vision, W, H):
+    """The smallest frames the reference's ROI arithmetic accepts (map 56 x 91: narrower than one strip of the
+    pixel pass, smaller than the line search's window), 8K, and the widest frame the ABI takes."""
+    frame = synth.frames_host(synth.SynthParams(W, H, n_segments=3, n_blips=3, n_labels=2), 2, 1)[0]
+    assert_same(gpu_run(vision, frame, True, 0, 15), oracle_run(frame, True, 0, 15), f"{W}x{H}")
+    # and through the batch form, twice the same frame
+    dev = torch.from_numpy(np.stack([frame, frame])).cuda()
+    b = vision.process_batch(dev.data_ptr(), 2, W, H, max_gap=15, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want = oracle_run(frame, True, 0, 15)
+    for i in range(2):
+        assert np.array_equal(vision.download_plane(b.lsd_image, i, 1)[0], want["lsd_image"])
+        assert np.array_equal(vision.download_plane(b.ui_map, i, 1)[0], want["ui_map"])
 
 
 def test_random_noise_frames(vision):
