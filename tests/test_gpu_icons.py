@@ -129,3 +129,28 @@ def test_host_batch_with_icons(vision):
         assert np.array_equal(out["lsd_image"][i], want_mask)
         m = int(out["n_lines"][i])
         assert m == len(want_lines) and np.array_equal(out["lines"][i, :m].view(np.uint32), want_lines.view(np.uint32))
+
+
+def test_icon_goldens(vision):
+    """The committed goldens of the stage (tests/golden/golden_icons.json) through the trait-order calls."""
+    import importlib.util
+    import json
+    from pathlib import Path
+    from helpers import sha
+    gdir = Path(__file__).with_name("golden")
+    spec = importlib.util.spec_from_file_location("make_golden_icons", gdir / "make_golden_icons.py")
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    gold = json.loads((gdir / "golden_icons.json").read_text())
+    vision.load_map_markers(marker_templates())
+    for case in G.CASES:
+        rec = gold[case[0]]
+        vision.load_frame(G.frame_of(case))
+        assert vision.crop_to_map(True) is not None
+        vision.isolate_map_markers()
+        hit = vision.filter_map_marker_icons()
+        assert (list(hit) if hit else None) == rec["hit"], case[0]
+        vision.mask_marker_lines()
+        assert sha(vision.lsd_image()) == rec["lsd_image_sha"]
+        lines = vision.find_marker_lines(15)
+        assert [[f"{int(b):08x}" for b in row] for row in lines.view(np.uint32)] == rec["lines_bits"]

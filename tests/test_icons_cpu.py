@@ -82,3 +82,19 @@ def test_no_candidates_no_match():
     frame = synth.frames_host(synth.SynthParams(W, H, n_segments=0, n_blips=0), 1, 1)[0]
     _, before, hit, after = _oracle_filter(frame, marker_templates())
     assert hit is None and np.array_equal(before, after)
+
+
+def test_oracle_reproduces_the_icon_goldens():
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_golden_icons", Path(__file__).with_name("golden") / "make_golden_icons.py")
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    gold = json.loads((Path(__file__).with_name("golden") / "golden_icons.json").read_text())
+    from helpers import sha
+    for case in G.CASES:
+        hit, mask, lines = G.run_oracle(G.frame_of(case))
+        rec = gold[case[0]]
+        assert (list(hit) if hit else None) == rec["hit"], case[0]
+        assert sha(mask) == rec["lsd_image_sha"] and int((mask == 255).sum()) == rec["white_px"]
+        assert [[f"{int(b):08x}" for b in row] for row in lines.view(np.uint32)] == rec["lines_bits"]
