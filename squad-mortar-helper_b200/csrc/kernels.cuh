@@ -1155,8 +1155,12 @@ __device__ __forceinline__ void lsd_mark_rays(const uint32_t* __restrict__ span_
             const int src = __ffs(todo) - 1;
             const int l = __shfl_sync(0xFFFFFFFFu, lo, src), h = __shfl_sync(0xFFFFFFFFu, hi, src);
             const uint32_t r = __shfl_sync(0xFFFFFFFFu, rings, src);
+            // the span touches words [l >> 5, h >> 5] (and [0, (h - 3600) >> 5] where it wraps): lanes own words
+            // lane + 32 i, so only the i whose 32 words meet those ranges can change (uniform tests)
+            const int ia = l >> 10, ib = min(h, SMH_LSD_RAYS - 1) >> 10, ic = h >= SMH_LSD_RAYS ? (h - SMH_LSD_RAYS) >> 10 : -1;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
+                if ((i < ia || i > ib) && i > ic) continue;
                 uint32_t mk = range_mask(lane + 32 * i, l, h);
                 if (h >= SMH_LSD_RAYS) mk |= range_mask(lane + 32 * i, l - SMH_LSD_RAYS, h - SMH_LSD_RAYS);  // uniform
 #pragma unroll
