@@ -1073,6 +1073,7 @@ __device__ __forceinline__ void lsd_scan_window(const WinView& wv, float px, flo
     for (int y = y0 + warp; y <= y1; y += T / 32) {  // warp-uniform trip count
         const uint32_t m8 = keep ? (col[(y - wv.y0) * 8] & keep) >> (8 * q) : 0u;
         const uint32_t have = __ballot_sync(0xFFFFFFFFu, m8 != 0u);
+        if (have == 0u) continue;  // nothing white in this row of the window (uniform)
         const uint32_t slot = cnt + (uint32_t)__popc(have & ((1u << lane) - 1u));
         if (m8 && slot < (uint32_t)LSD_GRP_SEG) sh.grp[warp * LSD_GRP_SEG + (int)slot] = m8 | (gx << 8) | ((uint32_t)(y - fy + 128) << 17);
         cnt += (uint32_t)__popc(have);
@@ -1157,10 +1158,11 @@ __device__ __forceinline__ void lsd_mark_rays(const uint32_t* __restrict__ span_
             const uint32_t r = __shfl_sync(0xFFFFFFFFu, rings, src);
             // the span touches words [l >> 5, h >> 5] (and [0, (h - 3600) >> 5] where it wraps): lanes own words
             // lane + 32 i, so only the i whose 32 words meet those ranges can change (uniform tests)
-            const int ia = l >> 10, ib = min(h, SMH_LSD_RAYS - 1) >> 10, ic = h >= SMH_LSD_RAYS ? (h - SMH_LSD_RAYS) >> 10 : -1;
+            const uint32_t need = ((0xFu << (l >> 10)) & (0xFu >> (3 - (min(h, SMH_LSD_RAYS - 1) >> 10)))) |
+                                  (h >= SMH_LSD_RAYS ? 0xFu >> (3 - ((h - SMH_LSD_RAYS) >> 10)) : 0u);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if ((i < ia || i > ib) && i > ic) continue;
+                if (!((need >> i) & 1u)) continue;
                 uint32_t mk = range_mask(lane + 32 * i, l, h);
                 if (h >= SMH_LSD_RAYS) mk |= range_mask(lane + 32 * i, l - SMH_LSD_RAYS, h - SMH_LSD_RAYS);  // uniform
 #pragma unroll
