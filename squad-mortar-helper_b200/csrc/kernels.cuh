@@ -1313,8 +1313,19 @@ __device__ __forceinline__ void chunk_set(uint32_t* bm, uint32_t tx, uint32_t pa
 //     rays with a last-index argmax, get_centre of the far end;
 //   * a seed whose first ring is empty proves a whole disc of seeds hopeless (dead cluster): they
 //     are struck off in bulk (or, when counting seeds for the statistics, dismissed one by one).
+// Registers: capped at 64 (four CTAs per SM).  Alone the search is as fast with 80 registers and three CTAs
+// (4.41 against 4.45 ms per 1024 frames), but with a second batch in flight the smaller footprint lets the next
+// batch's pixel pass and line search move in earlier: 163.9 k -> 170.8 k frames/s (56 / 60 / 64 / 68 / 72 / 80
+// registers: 169.4 / 169.2 / 170.8 / 164.3 / 165.0 / 163.9 k).  LSD_MAXNREG=0 restores __launch_bounds__.
+#ifndef LSD_MAXNREG
+#define LSD_MAXNREG 64
+#endif
 template <bool STATS>
+#if LSD_MAXNREG > 0
+__global__ void __maxnreg__(LSD_MAXNREG) k_lsd(const LsdArgs a) {
+#else
 __global__ void __launch_bounds__(LSD_THREADS, LSD_MIN_CTAS) k_lsd(const LsdArgs a) {
+#endif
     constexpr int T = LSD_THREADS;
     __shared__ LsdShared sh;
     extern __shared__ uint32_t chunk[];  // [32][tx] current tile-row, row-major: pixels that can still become seeds
