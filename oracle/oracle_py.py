@@ -73,6 +73,12 @@ def lib() -> C.CDLL:
     L.smh_oracle_calc_meters_to_px_ratio.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_double), vp, u32p]
     L.smh_oracle_find_minimap_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     L.smh_oracle_find_minimap.argtypes = [vp, u32p]
+    L.smh_oracle_gpuflavour_rays_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    L.smh_oracle_rays_in_dirs.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp]
+    L.smh_oracle_gpuflavour_dilate.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.smh_oracle_gpuflavour_icon_sad.restype = C.c_uint16
+    L.smh_oracle_gpuflavour_icon_sad.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    L.smh_oracle_gpuflavour_icon_clear.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     _LIB = L
     return L
 
@@ -310,3 +316,47 @@ def get_centre_in(img: np.ndarray, x: float, y: float):
     out = (C.c_float * 2)()
     lib().smh_oracle_get_centre_in(img.ctypes.data, w, h, x, y, out)
     return float(out[0]), float(out[1])
+
+
+# ---- vision-gpu flavour (restated reference CUDA kernels; see smh_oracle.h) -------------------------------
+
+def gpuflavour_rays_in(img: np.ndarray, x: float, y: float, max_gap: float, dxdy: np.ndarray):
+    """K10 restated: -> (ends[3600, 2] f32, d5[3600] u8: the gap_count rule decided the ray)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    dxdy = np.ascontiguousarray(dxdy, np.float32)
+    h, w = img.shape
+    ends = np.empty((3600, 2), np.float32)
+    d5 = np.empty(3600, np.uint8)
+    lib().smh_oracle_gpuflavour_rays_in(img.ctypes.data, w, h, x, y, max_gap, dxdy.ctypes.data, ends.ctypes.data, d5.ctypes.data)
+    return ends, d5
+
+
+def rays_in_dirs(img: np.ndarray, x: float, y: float, max_gap: float, dxdy: np.ndarray) -> np.ndarray:
+    """The vision-cpu march over a caller-supplied direction table -> ends[3600, 2]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    dxdy = np.ascontiguousarray(dxdy, np.float32)
+    h, w = img.shape
+    ends = np.empty((3600, 2), np.float32)
+    lib().smh_oracle_rays_in_dirs(img.ctypes.data, w, h, x, y, max_gap, dxdy.ctypes.data, ends.ctypes.data)
+    return ends
+
+
+def gpuflavour_dilate(raw: np.ndarray) -> np.ndarray:
+    """NPP 2x2 dilation as vision-gpu calls it; the 1-px frame stays 0."""
+    raw = np.ascontiguousarray(raw, np.uint8)
+    h, w = raw.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().smh_oracle_gpuflavour_dilate(raw.ctypes.data, w, h, out.ctypes.data)
+    return out
+
+
+def gpuflavour_icon_sad(map_rgb: np.ndarray, x: int, y: int, tpl_rgba: np.ndarray) -> int:
+    map_rgb = np.ascontiguousarray(map_rgb, np.uint8)
+    tpl_rgba = np.ascontiguousarray(tpl_rgba, np.uint8)
+    return int(lib().smh_oracle_gpuflavour_icon_sad(map_rgb.ctypes.data, map_rgb.shape[1], x, y, tpl_rgba.ctypes.data, tpl_rgba.shape[0]))
+
+
+def gpuflavour_icon_clear(map_rgb: np.ndarray, x: int, y: int, size: int) -> np.ndarray:
+    out = np.ascontiguousarray(map_rgb, np.uint8).copy()
+    lib().smh_oracle_gpuflavour_icon_clear(out.ctypes.data, out.shape[1], out.shape[0], x, y, size)
+    return out

@@ -278,3 +278,120 @@ int refgpu_time_frames(refgpu* r, const uint8_t* frames, uint32_t n, uint32_t W,
 }
 
 }  // extern "C"
+
+/* ---- per-ray / per-kernel access to the reference's object code (pins oracle/smh_oracle.c's vision-gpu
+ *      flavour bit for bit; tests/test_gpu_refcuda.py) ------------------------------------------------ */
+
+// The 3600 ray directions exactly as K10 computes them (cuda.cu:654,669-670): the same expression compiled by
+// the same nvcc with the same flags in this translation unit, so CUDA's cosf/sinf expand to the same code.
+// (K10 itself only reveals them for the first quadrant — a seed at (1e-30, 1e-30) of an all-black image ends
+// every ray at exactly (-dx, -dy) — which the test uses to check this table against the kernel.)
+__global__ void harness_ray_dirs(float* out) {
+    const unsigned k = threadIdx.x + blockIdx.x * blockDim.x;
+    if (k >= 3600) return;
+    const float theta = ((float)k / 10.0) * CUDART_PI_F / 180.0;
+    out[2 * k] = cosf(theta);
+    out[2 * k + 1] = sinf(theta);
+}
+
+extern "C" {
+
+int refgpu_ray_dirs(refgpu* r, float* dxdy /* 7200 */) {
+    float* d = nullptr;
+    RCHECK(cudaMalloc(&d, 7200 * sizeof(float)));
+    harness_ray_dirs<<<8, 450, 0, r->markers_stream>>>(d);
+    RCHECK(cudaMemcpyAsync(dxdy, d, 7200 * sizeof(float), cudaMemcpyDeviceToHost, r->markers_stream));
+    RCHECK(cudaStreamSynchronize(r->markers_stream));
+    cudaFree(d);
+    return 0;
+}
+
+/* K10 launched as <<<3600, 1>>>: the kernel indexes its ray by threadIdx.x + blockIdx.x * blockDim.x and writes
+ * one Line per BLOCK (cuda.cu:654,730-738), so with one thread per block the unmodified object code hands back
+ * EVERY ray's line.  img: host L8; seeds: n x (x, y); lines: n x 3600 x 4 floats. */
+int refgpu_rays_per_seed(refgpu* r, const uint8_t* img, uint32_t w, uint32_t h, const float* seeds, uint32_t n, float max_gap,
+                         float* lines) {
+    uint8_t* d = nullptr; Line* dl = nullptr;
+    RCHECK(cudaMalloc(&d, (size_t)w * h));
+    RCHECK(cudaMalloc(&dl, (size_t)n * 3600 * sizeof(Line)));
+    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < n; i++) {
+        find_longest_line<<<3600, 1, 0, r->markers_stream>>>(d, w, h, Point{seeds[2 * i], seeds[2 * i + 1]}, max_gap, dl + (size_t)i * 3600);
+        r->launches++;
+    }
+    RCHECK(cudaGetLastError());
+    RCHECK(cudaMemcpyAsync(lines, dl, (size_t)n * 3600 * sizeof(Line), cudaMemcpyDeviceToHost, r->markers_stream));
+    RCHECK(cudaStreamSynchronize(r->markers_stream));
+    cudaFree(d); cudaFree(dl);
+    return 0;
+}
+
+/* K10 in vision-gpu's own launch shape <<<8, 450>>> (vision-gpu/src/lib.rs:494-510): the 8 block winners of
+ * every seed, before the host fold.  blocks: n x 8 x 4 floats. */
+int refgpu_block_winners(refgpu* r, const uint8_t* img, uint32_t w, uint32_t h, const float* seeds, uint32_t n, float max_gap,
+                         float* blocks) {
+    uint8_t* d = nullptr; Line* dl = nullptr;
+    RCHECK(cudaMalloc(&d, (size_t)w * h));
+    RCHECK(cudaMalloc(&dl, (size_t)n * 8 * sizeof(Line)));
+    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < n; i++)
+        find_longest_line<<<8, 450, 0, r->markers_stream>>>(d, w, h, Point{seeds[2 * i], seeds[2 * i + 1]}, max_gap, dl + (size_t)i * 8);
+    RCHECK(cudaGetLastError());
+    RCHECK(cudaMemcpyAsync(blocks, dl, (size_t)n * 8 * sizeof(Line), cudaMemcpyDeviceToHost, r->markers_stream));
+    RCHECK(cudaStreamSynchronize(r->markers_stream));
+    cudaFree(d); cudaFree(dl);
+    return 0;
+}
+
+/* K8 + K9 on a caller-supplied RGB crop: mask_marker_lines then NPP dilate exactly as
+ * vision-gpu/src/lib.rs:454-472 (lsd_image pre-zeroed so the frame NPP never writes is defined). */
+int refgpu_mask_and_dilate(refgpu* r, const uint8_t* rgb, uint32_t w, uint32_t h, uint8_t* raw_mask, uint8_t* lsd_image) {
+    RGB* d = nullptr; uint8_t *m = nullptr, *o = nullptr, *k = nullptr;
+    RCHECK(cudaMalloc(&d, (size_t)w * h * 3)); RCHECK(cudaMalloc(&m, (size_t)w * h)); RCHECK(cudaMalloc(&o, (size_t)w * h));
+    RCHECK(cudaMalloc(&k, 4)); RCHECK(cudaMemset(k, 255, 4)); RCHECK(cudaMemset(o, 0, (size_t)w * h));
+    RCHECK(cudaMemcpy(d, rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice));
+    mask_marker_lines<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(d, w, h, m);
+    RCHECK(cudaStreamSynchronize(r->markers_stream));
+    const int res = gpu_dilate(m, o, w, h, k, 2, 2);
+    if (res != 0) { snprintf(g_err, sizeof g_err, "nppiDilate_8u_C1R error %d", res); return res; }
+    RCHECK(cudaDeviceSynchronize());
+    if (raw_mask) RCHECK(cudaMemcpy(raw_mask, m, (size_t)w * h, cudaMemcpyDeviceToHost));
+    if (lsd_image) RCHECK(cudaMemcpy(lsd_image, o, (size_t)w * h, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(m); cudaFree(o); cudaFree(k);
+    return 0;
+}
+
+/* The template-match kernels vision-gpu carries but never launches (K11/K12, cuda.cu:548-614), driven as the
+ * commented host code would (vision-gpu/src/lib.rs:373-430): K11 over `n_cand` candidates (xy = y * w + x) with
+ * the templates ONE AT A TIME — with several templates the kernel's threads add into the same u16 without
+ * atomics (cuda.cu:583), a data race; one template per launch makes its arithmetic observable.
+ * sads: n_markers x n_cand (u16).  Then, when clear_xy != UINT32_MAX, K12 on that position; map_out: the crop after it. */
+int refgpu_icons(refgpu* r, const uint8_t* map_rgb, uint32_t w, uint32_t h, const uint8_t* tpl_rgba, uint32_t n_markers, uint32_t size,
+                 const uint32_t* cand_xy, uint32_t n_cand, uint16_t* sads, uint32_t clear_xy, uint8_t* map_out) {
+    RGB* d = nullptr; RGBA* t = nullptr; const RGBA** tp = nullptr; markers::TemplateMatch* c = nullptr;
+    const size_t np = (size_t)size * size;
+    RCHECK(cudaMalloc(&d, (size_t)w * h * 3)); RCHECK(cudaMalloc(&t, np * 4 * n_markers)); RCHECK(cudaMalloc(&tp, sizeof(RGBA*)));
+    RCHECK(cudaMalloc(&c, sizeof(markers::TemplateMatch) * (n_cand ? n_cand : 1)));
+    RCHECK(cudaMemcpy(d, map_rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice));
+    RCHECK(cudaMemcpy(t, tpl_rgba, np * 4 * n_markers, cudaMemcpyHostToDevice));
+    std::vector<markers::TemplateMatch> hc(n_cand);
+    for (uint32_t m = 0; m < n_markers && n_cand; m++) {
+        for (uint32_t i = 0; i < n_cand; i++) hc[i] = markers::TemplateMatch{cand_xy[i], 0};
+        RCHECK(cudaMemcpy(c, hc.data(), sizeof(markers::TemplateMatch) * n_cand, cudaMemcpyHostToDevice));
+        const RGBA* one = t + np * m;
+        RCHECK(cudaMemcpy(tp, &one, sizeof one, cudaMemcpyHostToDevice));
+        filter_map_marker_icons<<<grid2d(1, n_cand, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(d, w, c, tp, size, 1, n_cand);
+        RCHECK(cudaStreamSynchronize(r->markers_stream));
+        RCHECK(cudaMemcpy(hc.data(), c, sizeof(markers::TemplateMatch) * n_cand, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n_cand; i++) sads[(size_t)m * n_cand + i] = hc[i].sad;
+    }
+    if (clear_xy != 0xFFFFFFFFu) {
+        filter_map_marker_icons_clear<<<grid2d(size, size, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(d, w, h, clear_xy, size);
+        RCHECK(cudaStreamSynchronize(r->markers_stream));
+    }
+    if (map_out) RCHECK(cudaMemcpy(map_out, d, (size_t)w * h * 3, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(t); cudaFree(tp); cudaFree(c);
+    return 0;
+}
+
+}  // extern "C"

@@ -39,6 +39,11 @@ def lib() -> C.CDLL:
                                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.refgpu_time_frames.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
                                          C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.refgpu_ray_dirs.argtypes = [vp, vp]
+        L.refgpu_rays_per_seed.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_float, vp]
+        L.refgpu_block_winners.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_float, vp]
+        L.refgpu_mask_and_dilate.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]
+        L.refgpu_icons.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]
         _LIB = L
     return _LIB
 
@@ -109,3 +114,54 @@ class RefGpu:
             raise RuntimeError(f"refgpu_time_frames rc={rc}: {self.L.refgpu_last_error().decode()}")
         return {"frames_per_s": fps.value, "seeds_per_frame": seeds.value / (n * reps),
                 "launches_per_frame": launches.value / (n * reps)}
+
+    def _ck(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what} rc={rc}: {self.L.refgpu_last_error().decode()}")
+
+    def ray_dirs(self) -> np.ndarray:
+        """The 3600 (dx, dy) of K10, computed on the device with the kernel's own expression."""
+        out = np.empty((3600, 2), np.float32)
+        self._ck(self.L.refgpu_ray_dirs(self.h, out.ctypes.data), "refgpu_ray_dirs")
+        return out
+
+    def rays_per_seed(self, img: np.ndarray, seeds: np.ndarray, max_gap: float) -> np.ndarray:
+        """K10 as <<<3600, 1>>>: every ray's Line of every seed -> [n, 3600, 4]."""
+        img = np.ascontiguousarray(img, np.uint8)
+        seeds = np.ascontiguousarray(seeds, np.float32).reshape(-1, 2)
+        h, w = img.shape
+        out = np.empty((len(seeds), 3600, 4), np.float32)
+        self._ck(self.L.refgpu_rays_per_seed(self.h, img.ctypes.data, w, h, seeds.ctypes.data, len(seeds), max_gap, out.ctypes.data),
+                 "refgpu_rays_per_seed")
+        return out
+
+    def block_winners(self, img: np.ndarray, seeds: np.ndarray, max_gap: float) -> np.ndarray:
+        """K10 in vision-gpu's launch shape <<<8, 450>>>: the 8 block winners of every seed -> [n, 8, 4]."""
+        img = np.ascontiguousarray(img, np.uint8)
+        seeds = np.ascontiguousarray(seeds, np.float32).reshape(-1, 2)
+        h, w = img.shape
+        out = np.empty((len(seeds), 8, 4), np.float32)
+        self._ck(self.L.refgpu_block_winners(self.h, img.ctypes.data, w, h, seeds.ctypes.data, len(seeds), max_gap, out.ctypes.data),
+                 "refgpu_block_winners")
+        return out
+
+    def mask_and_dilate(self, rgb: np.ndarray):
+        """K8 + NPP dilate on an RGB crop -> (raw_mask, lsd_image)."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w = rgb.shape[:2]
+        raw = np.empty((h, w), np.uint8); out = np.empty((h, w), np.uint8)
+        self._ck(self.L.refgpu_mask_and_dilate(self.h, rgb.ctypes.data, w, h, raw.ctypes.data, out.ctypes.data), "refgpu_mask_and_dilate")
+        return raw, out
+
+    def icons(self, map_rgb: np.ndarray, templates: np.ndarray, cand_xy: np.ndarray, clear_xy=None):
+        """K11 per (template, candidate) and K12: -> (sads[n_markers, n_cand] u16, crop after the clear or None)."""
+        map_rgb = np.ascontiguousarray(map_rgb, np.uint8)
+        templates = np.ascontiguousarray(templates, np.uint8)
+        cand_xy = np.ascontiguousarray(cand_xy, np.uint32)
+        h, w = map_rgb.shape[:2]
+        n, size = templates.shape[0], templates.shape[1]
+        sads = np.zeros((n, len(cand_xy)), np.uint16)
+        out = np.empty_like(map_rgb)
+        self._ck(self.L.refgpu_icons(self.h, map_rgb.ctypes.data, w, h, templates.ctypes.data, n, size, cand_xy.ctypes.data, len(cand_xy),
+                                     sads.ctypes.data, 0xFFFFFFFF if clear_xy is None else int(clear_xy), out.ctypes.data), "refgpu_icons")
+        return sads, (out if clear_xy is not None else None)

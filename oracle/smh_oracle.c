@@ -863,3 +863,98 @@ int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uin
     smh_oracle_find_scales_preprocess(o, start_y, NULL, NULL);
     return 1;
 }
+
+/* ---------------------------------------------------------------- vision-gpu flavour (see smh_oracle.h)
+ * Restates the reference's CUDA kernels so that their object code can pin this file bit for bit. */
+
+/* CUDA `(uint32_t)f`: cvt.rzi.u32.f32 — truncates, saturates, NaN -> 0: the same as Rust's `as u32` */
+uint32_t smh_oracle_gpuflavour_ray(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                                   float dx, float dy, float end[2]) {
+    /* vision-gpu/cuda/cuda.cu:656-722 */
+    float x = px, y = py;
+    uint32_t gap_count = 0, gap = 0, d5 = 0;
+    float gap_x = 0.0f, gap_y = 0.0f, xo = 0.0f, yo = 0.0f;
+    const float wf = (float)w, hf = (float)h;
+    while (x >= 0.0f && y >= 0.0f && x < wf && y < hf) {
+        const uint8_t v = img[(size_t)f32_as_u32(y) * w + f32_as_u32(x)];
+        if (gap == 0) {
+            if (v != 255) { gap = 1; gap_x = x; gap_y = y; gap_count++; }
+        } else {
+            if (v == 255) { gap = 0; gap_x = 0.0f; gap_y = 0.0f; }
+            else if ((float)gap >= max_gap || (float)gap_count >= max_gap) {
+                if (!((float)gap >= max_gap)) d5 = 1;
+                x = gap_x; y = gap_y;
+                break;
+            } else gap++;
+        }
+        xo += dx; yo += dy;
+        x = xo + px; y = yo + py;
+    }
+    end[0] = px; end[1] = py;
+    const uint32_t xi = f32_as_u32(x), yi = f32_as_u32(y);
+    if (xi < w && yi < h && img[(size_t)yi * w + xi] == 0) { end[0] = x - dx; end[1] = y - dy; }
+    return d5;
+}
+
+int smh_oracle_gpuflavour_rays_in(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                                  const float *dxdy, float *ends, uint8_t *d5) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < SMH_LSD_RAYS; k++) {
+        const uint32_t f = smh_oracle_gpuflavour_ray(img, w, h, px, py, max_gap, dxdy[2 * k], dxdy[2 * k + 1], ends + 2 * k);
+        if (d5) d5[k] = (uint8_t)f;
+    }
+    return 0;
+}
+
+int smh_oracle_rays_in_dirs(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                            const float *dxdy, float *ends) {
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < SMH_LSD_RAYS; k++) march(img, w, h, px, py, max_gap, dxdy[2 * k], dxdy[2 * k + 1], ends + 2 * k);
+    return 0;
+}
+
+void smh_oracle_gpuflavour_dilate(const uint8_t *raw, uint32_t w, uint32_t h, uint8_t *out) {
+    /* dilate.cpp:12-24: src/dst advanced to (1,1), ROI (w-2, h-2), 2x2 mask of 255s anchored (1,1):
+     * dst(x,y) = max over mask(i,j) != 0 of src(x + i - 1, y + j - 1) */
+    if (w < 3 || h < 3) return;
+    for (uint32_t y = 1; y + 1 < h; y++)
+        for (uint32_t x = 1; x + 1 < w; x++) {
+            uint8_t m = raw[(size_t)y * w + x];
+            const uint8_t a = raw[(size_t)(y - 1) * w + x - 1], b = raw[(size_t)(y - 1) * w + x], c = raw[(size_t)y * w + x - 1];
+            if (a > m) m = a;
+            if (b > m) m = b;
+            if (c > m) m = c;
+            out[(size_t)y * w + x] = m;
+        }
+}
+
+uint16_t smh_oracle_gpuflavour_icon_sad(const uint8_t *map_rgb, uint32_t stride, uint32_t x, uint32_t y,
+                                        const uint8_t *tpl_rgba, uint32_t size) {
+    /* cuda.cu:571-583 */
+    uint16_t sad = 0;
+    for (uint32_t my = 0; my < size; my++)
+        for (uint32_t mx = 0; mx < size; mx++) {
+            const uint8_t *t = tpl_rgba + ((size_t)my * size + mx) * 4;
+            const uint8_t *q = map_rgb + ((size_t)(y + my) * stride + (x + mx)) * 3;
+            uint16_t ad = 0;
+            for (int k = 0; k < 3; k++) ad = (uint16_t)(ad + (q[k] > t[k] ? q[k] - t[k] : t[k] - q[k]));
+            const double v = (double)(float)ad * ((double)(float)t[3] / 255.0); /* `(float)ad * ((float)a / 255.0)` */
+            ad = (uint16_t)v; /* cvt.rzi.u16.f64; 0 <= v <= 765 */
+            sad = (uint16_t)(sad + ad);
+        }
+    return sad;
+}
+
+void smh_oracle_gpuflavour_icon_clear(uint8_t *map_rgb, uint32_t w, uint32_t h, uint32_t rx, uint32_t ry, uint32_t size) {
+    /* cuda.cu:594-613 under a grid of ceil(size/8)^2 blocks of (8,8) threads */
+    const uint32_t ext = (size + 7u) / 8u * 8u;
+    const uint32_t sq_x = rx + size / 2u, sq_y = ry + (uint32_t)roundf((float)size * SMH_MAP_MARKER_POI_LOCATION);
+    for (uint32_t j = 0; j < ext; j++)
+        for (uint32_t i = 0; i < ext; i++) {
+            const uint32_t x = rx + i, y = ry + j;
+            if (x >= w || y >= h) continue;
+            uint8_t *q = map_rgb + ((size_t)y * w + x) * 3;
+            q[0] = q[1] = q[2] = 0;
+            if (x >= sq_x - 2u && x <= sq_x + 2u && y >= sq_y - 2u && y <= sq_y + 2u) { q[0] = 0; q[1] = 255; q[2] = 0; }
+        }
+}

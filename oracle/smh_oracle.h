@@ -136,6 +136,44 @@ int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uin
                              int grayscale, uint32_t start_y, uint32_t max_gap,
                              float lines[32][4], uint32_t *n_lines);
 
+
+/* ---- `vision-gpu` flavour: the reference's CUDA kernels restated on the CPU ------------------------
+ * vision-cpu and vision-gpu are two implementations of one specification by one author that differ in
+ * documented details.  vision-cpu cannot be built here (no Rust toolchain) but vision-gpu's
+ * kernels can: these functions restate THEIR arithmetic, so that tests/test_gpu_refcuda.py can demand BIT
+ * equality with the reference's own object code (oracle/_ref/libsmh_refgpu.so) — that pins the march loop,
+ * the end-point rule, the saturating casts and the dilation model against the reference itself.  The
+ * vision-cpu functions above share their code with these wherever the two backends agree (the same `march`
+ * body with the D5 rule switched), so what remains reader-verified is listed explicitly in DESIGN.md §2. */
+
+/* One ray of K10 `find_longest_line` (vision-gpu/cuda/cuda.cu:637-722): directions are INPUTS (the kernel
+ * computes them with CUDA's cosf/sinf on a double-precision theta, D11; the harness exports that table).
+ * D5: besides `gap >= max_gap` the kernel stops on `gap_count >= max_gap` (cuda.cu:664,685,697).
+ * end = the kernel's (x_end, y_end).  Returns bit 0: the ray stopped on the gap_count rule while the
+ * vision-cpu rule would have marched on (D5 decided this ray). */
+uint32_t smh_oracle_gpuflavour_ray(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                                   float dx, float dy, float end[2]);
+/* all 3600 rays of one seed: dxdy[7200] in, ends[7200] out, d5[3600] out (may be NULL) */
+int smh_oracle_gpuflavour_rays_in(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                                  const float *dxdy, float *ends, uint8_t *d5);
+/* the vision-cpu march (vision-cpu/src/lib.rs:388-432 — the SAME code find_longest_line_in runs) over a
+ * caller-supplied direction table: with the kernel's own table it must equal the kernel wherever d5 = 0 */
+int smh_oracle_rays_in_dirs(const uint8_t *img, uint32_t w, uint32_t h, float px, float py, float max_gap,
+                            const float *dxdy, float *ends);
+/* K9: nppiDilate_8u_C1R as vision-gpu calls it (vision-gpu/cuda/dilate.cpp:3-25, vision-gpu/src/lib.rs:465-472):
+ * 2x2 all-ones mask anchored (1,1) over the ROI (1,1)..(w-2,h-2); the outer 1-px frame of `out` is NOT
+ * written (D4) — the caller pre-fills it. */
+void smh_oracle_gpuflavour_dilate(const uint8_t *raw, uint32_t w, uint32_t h, uint8_t *out);
+/* K11 `filter_map_marker_icons` for ONE (template, candidate) pair (cuda.cu:548-585): u16 accumulator, the
+ * alpha scale evaluated in double (`(float)ad * ((float)a / 255.0)`), every template pixel visited.
+ * map: RGB8 with `stride` pixels per row; (x, y): the candidate (window origin). */
+uint16_t smh_oracle_gpuflavour_icon_sad(const uint8_t *map_rgb, uint32_t stride, uint32_t x, uint32_t y,
+                                        const uint8_t *tpl_rgba, uint32_t size);
+/* K12 `filter_map_marker_icons_clear` (cuda.cu:587-614) launched as vision-gpu would
+ * (grid ceil(size/8)^2 x (8,8), vision-gpu/src/lib.rs:413-424): blacks the whole launched square (a multiple
+ * of 8, not `size`), 5x5 green square at the tip. */
+void smh_oracle_gpuflavour_icon_clear(uint8_t *map_rgb, uint32_t w, uint32_t h, uint32_t x, uint32_t y, uint32_t size);
+
 #ifdef __cplusplus
 }
 #endif

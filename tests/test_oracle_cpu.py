@@ -213,3 +213,47 @@ def test_find_lines_small_cases():
         a = O.find_lines_in(img, 15)
         b = N.find_lines(img, 15)
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), trial
+
+
+def test_cross_dilation_against_opencv():
+    """The vision-cpu-only dilation (imageproc L1, k = 1 = 3x3 cross, D4) has no reference object code to run;
+    it is checked against an independent implementation (OpenCV's cross-shaped dilate) instead."""
+    import cv2
+    frame = synth.frames_host(synth.SynthParams(1280, 720, n_segments=6, n_blips=8, n_labels=2), 2, 1)[0]
+    o = O.Oracle()
+    o.load_frame(frame); o.crop_to_map(True); o.isolate_map_markers(); o.mask_marker_lines()
+    want = cv2.dilate(o.raw_mask(), cv2.getStructuringElement(cv2.MORPH_CROSS, (3, 3)), borderType=cv2.BORDER_CONSTANT, borderValue=0)
+    assert np.array_equal(o.lsd_image(), want)
+
+
+def test_vision_cpu_and_vision_gpu_march_flavours_agree_outside_d5():
+    """The restated K10 march (pinned bit for bit against the reference's object code on the GPU box,
+    tests/test_gpu_refcuda.py) and the vision-cpu march differ only in the gap_count rule (D5): on one
+    direction table they must agree on every ray that rule does not decide."""
+    rng = np.random.default_rng(21)
+    dirs = O.ray_table()
+    img = np.where(rng.random((120, 160)) < 0.9, 255, 0).astype(np.uint8)
+    img[:, ::5] = 255
+    n_d5 = 0
+    for _ in range(12):
+        sx, sy = float(rng.integers(0, 160)) + 0.5, float(rng.integers(0, 120))
+        for gap in (15.0, 3.0, 1.0):
+            g, d5 = O.gpuflavour_rays_in(img, sx, sy, gap, dirs)
+            c = O.rays_in_dirs(img, sx, sy, gap, dirs)
+            keep = d5 == 0
+            assert np.array_equal(g.view(np.uint32)[keep], c.view(np.uint32)[keep])
+            n_d5 += int((~keep).sum())
+            # and rays_in_dirs with the host table is find_longest_line's own march
+            lens = O.ray_lengths_in(img, sx, sy, gap)
+            mine = (np.float32(sx) - c[:, 0]) ** 2 + (np.float32(sy) - c[:, 1]) ** 2
+            assert np.array_equal(lens.view(np.uint32), mine.astype(np.float32).view(np.uint32))
+    assert n_d5 > 0
+
+
+def test_gpuflavour_dilate_is_the_2x2_box_model():
+    rng = np.random.default_rng(2)
+    raw = np.where(rng.random((40, 53)) < 0.2, 255, 0).astype(np.uint8)
+    h, w = raw.shape
+    box = np.zeros_like(raw)
+    box[1:h - 1, 1:w - 1] = np.maximum.reduce([raw[0:h - 2, 0:w - 2], raw[0:h - 2, 1:w - 1], raw[1:h - 1, 0:w - 2], raw[1:h - 1, 1:w - 1]])
+    assert np.array_equal(O.gpuflavour_dilate(raw), box)
