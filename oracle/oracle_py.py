@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.smh_oracle_calc_meters_to_px_ratio.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_double), vp, u32p]
     L.smh_oracle_find_minimap_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     L.smh_oracle_find_minimap.argtypes = [vp, u32p]
+    L.smh_oracle_gpuflavour_table_marker.argtypes = [vp]
     L.smh_oracle_gpuflavour_rays_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.smh_oracle_rays_in_dirs.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.smh_oracle_gpuflavour_dilate.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -359,4 +360,11 @@ def gpuflavour_icon_sad(map_rgb: np.ndarray, x: int, y: int, tpl_rgba: np.ndarra
 def gpuflavour_icon_clear(map_rgb: np.ndarray, x: int, y: int, size: int) -> np.ndarray:
     out = np.ascontiguousarray(map_rgb, np.uint8).copy()
     lib().smh_oracle_gpuflavour_icon_clear(out.ctypes.data, out.shape[1], out.shape[0], x, y, size)
+    return out
+
+
+def gpuflavour_table_marker() -> np.ndarray:
+    """K8's marker predicate (vision-gpu's HSV formulas) over all 2^24 colours."""
+    out = np.empty(1 << 24, np.uint8)
+    lib().smh_oracle_gpuflavour_table_marker(out.ctypes.data)
     return out

@@ -314,7 +314,7 @@ int refgpu_rays_per_seed(refgpu* r, const uint8_t* img, uint32_t w, uint32_t h, 
     uint8_t* d = nullptr; Line* dl = nullptr;
     RCHECK(cudaMalloc(&d, (size_t)w * h));
     RCHECK(cudaMalloc(&dl, (size_t)n * 3600 * sizeof(Line)));
-    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice));
+    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
     for (uint32_t i = 0; i < n; i++) {
         find_longest_line<<<3600, 1, 0, r->markers_stream>>>(d, w, h, Point{seeds[2 * i], seeds[2 * i + 1]}, max_gap, dl + (size_t)i * 3600);
         r->launches++;
@@ -333,7 +333,7 @@ int refgpu_block_winners(refgpu* r, const uint8_t* img, uint32_t w, uint32_t h, 
     uint8_t* d = nullptr; Line* dl = nullptr;
     RCHECK(cudaMalloc(&d, (size_t)w * h));
     RCHECK(cudaMalloc(&dl, (size_t)n * 8 * sizeof(Line)));
-    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice));
+    RCHECK(cudaMemcpy(d, img, (size_t)w * h, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
     for (uint32_t i = 0; i < n; i++)
         find_longest_line<<<8, 450, 0, r->markers_stream>>>(d, w, h, Point{seeds[2 * i], seeds[2 * i + 1]}, max_gap, dl + (size_t)i * 8);
     RCHECK(cudaGetLastError());
@@ -349,7 +349,7 @@ int refgpu_mask_and_dilate(refgpu* r, const uint8_t* rgb, uint32_t w, uint32_t h
     RGB* d = nullptr; uint8_t *m = nullptr, *o = nullptr, *k = nullptr;
     RCHECK(cudaMalloc(&d, (size_t)w * h * 3)); RCHECK(cudaMalloc(&m, (size_t)w * h)); RCHECK(cudaMalloc(&o, (size_t)w * h));
     RCHECK(cudaMalloc(&k, 4)); RCHECK(cudaMemset(k, 255, 4)); RCHECK(cudaMemset(o, 0, (size_t)w * h));
-    RCHECK(cudaMemcpy(d, rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice));
+    RCHECK(cudaMemcpy(d, rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
     mask_marker_lines<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(d, w, h, m);
     RCHECK(cudaStreamSynchronize(r->markers_stream));
     const int res = gpu_dilate(m, o, w, h, k, 2, 2);
@@ -372,14 +372,14 @@ int refgpu_icons(refgpu* r, const uint8_t* map_rgb, uint32_t w, uint32_t h, cons
     const size_t np = (size_t)size * size;
     RCHECK(cudaMalloc(&d, (size_t)w * h * 3)); RCHECK(cudaMalloc(&t, np * 4 * n_markers)); RCHECK(cudaMalloc(&tp, sizeof(RGBA*)));
     RCHECK(cudaMalloc(&c, sizeof(markers::TemplateMatch) * (n_cand ? n_cand : 1)));
-    RCHECK(cudaMemcpy(d, map_rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice));
-    RCHECK(cudaMemcpy(t, tpl_rgba, np * 4 * n_markers, cudaMemcpyHostToDevice));
+    RCHECK(cudaMemcpy(d, map_rgb, (size_t)w * h * 3, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
+    RCHECK(cudaMemcpy(t, tpl_rgba, np * 4 * n_markers, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
     std::vector<markers::TemplateMatch> hc(n_cand);
     for (uint32_t m = 0; m < n_markers && n_cand; m++) {
         for (uint32_t i = 0; i < n_cand; i++) hc[i] = markers::TemplateMatch{cand_xy[i], 0};
-        RCHECK(cudaMemcpy(c, hc.data(), sizeof(markers::TemplateMatch) * n_cand, cudaMemcpyHostToDevice));
+        RCHECK(cudaMemcpy(c, hc.data(), sizeof(markers::TemplateMatch) * n_cand, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
         const RGBA* one = t + np * m;
-        RCHECK(cudaMemcpy(tp, &one, sizeof one, cudaMemcpyHostToDevice));
+        RCHECK(cudaMemcpy(tp, &one, sizeof one, cudaMemcpyHostToDevice)); RCHECK(cudaDeviceSynchronize());
         filter_map_marker_icons<<<grid2d(1, n_cand, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(d, w, c, tp, size, 1, n_cand);
         RCHECK(cudaStreamSynchronize(r->markers_stream));
         RCHECK(cudaMemcpy(hc.data(), c, sizeof(markers::TemplateMatch) * n_cand, cudaMemcpyDeviceToHost));

@@ -958,3 +958,33 @@ void smh_oracle_gpuflavour_icon_clear(uint8_t *map_rgb, uint32_t w, uint32_t h, 
             if (x >= sq_x - 2u && x <= sq_x + 2u && y >= sq_y - 2u && y <= sq_y + 2u) { q[0] = 0; q[1] = 255; q[2] = 0; }
         }
 }
+
+int smh_oracle_gpuflavour_is_marker(uint8_t r8, uint8_t g8, uint8_t b8) {
+    /* cuda.cu:191-239 (to_hsv), 277-309 (is_any_map_marker_color); CUDA's (uintN_t)f saturates like Rust's `as` */
+    const float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, b = (float)b8 / 255.0f;
+    const float mx = fmaxf(r, fmaxf(g, b)), mn = fminf(r, fminf(g, b)), diff = mx - mn;
+    float h = 0.0f, s = 0.0f;
+    const float v = mx;
+    if (v != 0.0f) {
+        s = diff / v;
+        if (!(diff < 0.001f)) {
+            if (mx == r) { h = 60.0f * (g - b) / diff; if (h < 0.0f) h += 360.0f; }
+            else if (mx == g) h = 60.0f * (2 + (b - r) / diff);
+            else h = 60.0f * (4 + (r - g) / diff);
+        }
+    }
+    const int H = (int)f32_as_u16(h), S = (int)f32_as_u8(s * 100.f), V = (int)f32_as_u8(v * 100.f);
+    static const int M[3][3] = {{105, 100, 100}, {285, 46, 85}, {158, 60, 91}};  /* consts.toml:33-43 */
+    if (S < SMH_MIN_SAT) return 0;
+    for (int t = 0; t < 3; t++) {
+        const int hue_ok = abs(H - M[t][0]) <= 15, sat_ok = abs(S - M[t][1]) <= 15, light_ok = abs(S - (M[t][1] - 50)) <= 15;
+        const int vib_ok = abs(V - M[t][2]) <= 15;
+        if (hue_ok && (sat_ok || light_ok) && vib_ok) return 1;
+    }
+    return 0;
+}
+
+void smh_oracle_gpuflavour_table_marker(uint8_t *out) {
+#pragma omp parallel for schedule(static)
+    for (uint32_t c = 0; c < (1u << 24); c++) out[c] = (uint8_t)smh_oracle_gpuflavour_is_marker((uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c);
+}

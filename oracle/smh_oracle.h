@@ -146,6 +146,12 @@ int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uin
  * vision-cpu functions above share their code with these wherever the two backends agree (the same `march`
  * body with the D5 rule switched), so what remains reader-verified is listed explicitly in DESIGN.md §2. */
 
+/* K7/K8's marker predicate: RGB::to_hsv + is_any_map_marker_color of vision-gpu (cuda.cu:191-239, 277-309) — differs
+ * from vision-cpu's in how h and s are formed (D1).  Pinned bit for bit over all 2^24 colours against a table the
+ * reference's own K8 object code produced on a B200 (tests/golden/k8_marker_table.npz, tools/k8_table.py). */
+int smh_oracle_gpuflavour_is_marker(uint8_t r, uint8_t g, uint8_t b);
+void smh_oracle_gpuflavour_table_marker(uint8_t *out /* 2^24 */);
+
 /* One ray of K10 `find_longest_line` (vision-gpu/cuda/cuda.cu:637-722): directions are INPUTS (the kernel
  * computes them with CUDA's cosf/sinf on a double-precision theta, D11; the harness exports that table).
  * D5: besides `gap >= max_gap` the kernel stops on `gap_count >= max_gap` (cuda.cu:664,685,697).

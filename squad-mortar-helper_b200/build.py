@@ -41,7 +41,7 @@ def _stale(target: Path, sources) -> bool:
 
 
 def cuda_sources():
-    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_host_widen.cpp", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h",
+    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_lsd.cuh", CSRC / "kernels_px.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_host_widen.cpp", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h",
             ROOT / "include" / "smh_b200.h", ROOT / "include" / "smh_consts.h"]
 
 

@@ -58,4 +58,44 @@ int smh_hostcheck_lsd_filter(const uint8_t* img, uint32_t w, uint32_t h, float p
     }
     return F.nw;
 }
+
+// The QUARTER form of the filter, as k_lsd2 marks it: white pixels are taken 8 at a time (columns 8q .. 8q+7 of a
+// pixel row in the bitmap's padded coordinates X = x + pad), each quarter marks the union span of its first and
+// last white pixel in every ring its distance range meets.
+int smh_hostcheck_lsd_filter_quarters(const uint8_t* img, uint32_t w, uint32_t h, uint32_t pad, float px, float py, int gap_limit,
+                                      uint8_t* marked) {
+    smh_lsd_filter F;
+    smh_lsd_filter_init(&F, gap_limit);
+    if (F.nw == 0) { memset(marked, 1, SMH_LSD_RAYS); return 0; }
+    static uint32_t bits[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
+    memset(bits, 0, sizeof bits);
+    const int fx = (int)px, fy = (int)py, R = F.radius;
+    const float hx = px - (float)fx, hy = py - (float)fy;
+    const int x0 = fx - R < 0 ? 0 : fx - R, x1 = fx + R > (int)w - 1 ? (int)w - 1 : fx + R;
+    const int y0 = fy - R < 0 ? 0 : fy - R, y1 = fy + R > (int)h - 1 ? (int)h - 1 : fy + R;
+    for (int y = y0; y <= y1; y++) {
+        const float cy = (float)(y - fy) + 0.5f - hy;
+        for (int Xq = ((x0 + (int)pad) & ~7); Xq <= x1 + (int)pad; Xq += 8) {
+            int a = -1, b = -1;
+            for (int e = 0; e < 8; e++) {
+                const int x = Xq + e - (int)pad;
+                if (x < x0 || x > x1 || img[(size_t)y * w + x] != 255) continue;
+                if (a < 0) a = x;
+                b = x;
+            }
+            if (a < 0) continue;
+            float dmin2, dmax2; int lo, hi;
+            smh_lsd_filter_quarter(cy, (float)(a - fx) + 0.5f - hx, (float)(b - fx) + 0.5f - hx, &dmin2, &dmax2, &lo, &hi);
+            for (int j = 0; j < F.nw; j++)
+                if (dmax2 >= F.r2_lo[j] && dmin2 <= F.r2_hi[j]) SMH_LSD_FILTER_SET_BITS(bits[j], lo, hi, or_bits);
+        }
+    }
+    for (int k = 0; k < SMH_LSD_RAYS; k++) {
+        int on = 1;
+        for (int j = 0; j < F.nw; j++)
+            if (smh_lsd_filter_window_on(&F, j, px, py) && !((bits[j][k >> 5] >> (k & 31)) & 1u)) on = 0;
+        marked[k] = (uint8_t)on;
+    }
+    return F.nw;
+}
 }

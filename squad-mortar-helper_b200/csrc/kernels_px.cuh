@@ -1,0 +1,393 @@
+// kernels_px.cuh — k_pixels2: the fused pixel pass with TMA tile movement (sm_100a).
+//
+// One read of the captured BGRA map ROI produces ui_map, the dilated marker mask (lsd_image) AND its 1-bit
+// tile-major copy for the line search, ocr_out and scales, plus the close-deployment-button test.  Replaces
+// reference kernels K1-K9 (vision-gpu/cuda/cuda.cu:312-546,616-635 + NPP dilate) and restates the vision-cpu
+// arithmetic (vision-cpu/src/lib.rs:110-280,357-375) bit for bit (vec_plain / vec_quadrant in kernels.cuh).
+//
+// Warp-autonomous, no block barrier.  A work item is (frame, band of 32 map rows = one tile-row of the bitmap,
+// strip of 128 columns = 4 bitmap tiles) or a frame's button test.  Columns are PADDED coordinates X = x + pad,
+// pad = map_x & 3: the map ROI starts at an arbitrary pixel column of the capture (1219 at 1440p) and a TMA box
+// must start on a 16-byte boundary (measured: tools/tma_probe.cu — an odd pixel start raises an illegal
+// instruction), so every plane carries the capture's 16-byte phase as a left pad of 0..3 pixels and strip,
+// vector and bitmap-word boundaries coincide in all of them.  Lane l owns the 4 pixels X = 128 s + 4 l .. of
+// every row: 512 contiguous, 128-byte aligned bytes of ui_map and 128 of lsd_image per warp row.  Lane 0 issues
+// one cp.async.bulk.tensor per chunk of two rows (box = 136 pixels x 2 rows: the strip plus a 4-pixel halo
+// either side, out-of-frame pixels arrive as zeros) into a three-stage ring of the warp's own shared memory and
+// the lanes wait on the stage's mbarrier; nobody computes an address or commits / waits for a copy of its own.
+//   phase 1 (row jn)      classify the lane's 4 pixels, store ui_map / provisional ocr_out / scales, shift the
+//                         row's flag nibbles (marker, OCR core, OCR edge) into window registers; lanes 0 and 31
+//                         also classify the halo vector next to them.
+//   phase 2 (row jn - lag) 3x3-cross dilation (up/down from the window, left/right by shuffle) -> lsd_image bytes
+//                         and, gathered by a 3-step butterfly, the four 32-pixel words of the bitmap; the 7x7
+//                         neighbour search of the rare OCR edge pixels.  lag = 1 outside the OCR quadrant, 3 in it.
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace smh {
+
+struct Pixel2Args {
+    const uint8_t* frames;  // captured BGRA frames; ROI coordinates below are relative to this origin
+    uint64_t frame_stride;
+    uint32_t pitch;
+    uint32_t map_x, map_y, w, h, bqw, bqh;
+    uint32_t pad;           // map_x & 3: plane column X = x + pad
+    uint32_t btn_x, btn_y, btn_w, btn_h;
+    uint8_t* ui; uint64_t ui_stride; uint32_t ui_pitch;
+    uint8_t* lsd; uint64_t lsd_stride; uint32_t lsd_pitch;
+    uint8_t* ocr; uint8_t* scales; uint64_t q_stride; uint32_t q_pitch;
+    uint32_t q_pad;         // left pad of the quadrant planes: (pad + bqw) & 127 (a strip's quadrant bytes start 128-byte aligned)
+    const uint32_t* start_y;  // device [n] or nullptr
+    uint32_t start_y_uniform;
+    uint32_t* red; uint8_t* open;
+    uint32_t nbands, nstrips, n_frames;
+    uint32_t qb0, qb1, qs0, qs1;  // bands x strips that own pixels of the OCR quadrant (the QUAD launch's items)
+    const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
+    uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
+};
+
+constexpr int PX2_THREADS = 128;
+constexpr int PX2_WARPS = PX2_THREADS / 32;
+constexpr int PX2_STAGES = 3;
+constexpr int PX2_ROWS = 2;                      // rows per TMA box
+constexpr int PX2_HALO = 4;                      // halo pixels either side of the strip
+constexpr int PX2_BOX_W = 128 + 2 * PX2_HALO;    // pixels per box row
+constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     // 544
+constexpr int PX2_STAGE_BYTES = 1152;            // 2 x 544 rounded up to a multiple of 128
+constexpr int PX2_WARP_BYTES = PX2_STAGES * PX2_STAGE_BYTES + 128;  // ring + mbarriers
+constexpr int PX2_SMEM_BYTES = PX2_WARPS * PX2_WARP_BYTES;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+// nibble -> 4 bytes of 0/255
+__device__ __forceinline__ uint32_t nibble_bytes(uint32_t d4) { return ((d4 * 0x00204081u) & 0x01010101u) * 255u; }
+
+template <bool GRAY, bool QUAD>
+__device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Args& a, uint32_t f, uint32_t band, uint32_t strip,
+                                         uint32_t ring, uint32_t bars) {
+    constexpr int LAG = QUAD ? SMH_OCR_RADIUS : 1;   // rows phase 2 runs behind phase 1 (= rows of halo above / below)
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int w = (int)a.w, h = (int)a.h, bqw = (int)a.bqw, bqh = (int)a.bqh;
+    const int r0 = (int)band * 32, r1 = min(r0 + 32, h);
+    const int x_base = (int)strip * 128 - (int)a.pad;  // map column of the strip's first pixel (X = 128 strip)
+    const int i_lo = x_base + 4 * lane;              // map column of the lane's first pixel
+    const bool active = i_lo < w;                     // the lane's vector starts left of the map's right edge: it stores
+    const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
+    const uint32_t* __restrict__ lut = a.lut;
+    const uint32_t alpha = opaque_alpha();
+    const uint32_t start_y = a.start_y ? a.start_y[f] : a.start_y_uniform;
+
+    // ---- per-lane column masks: pixel in the image / may carry an OCR core bit / an OCR edge bit -----------
+    uint32_t vm4 = 0, cm4 = 0, em4 = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = i_lo + e;
+        const bool valid = i >= 0 && i < w;
+        const bool inq = QUAD && valid && i >= bqw && i < 2 * bqw;
+        vm4 |= valid ? (1u << e) : 0u;
+        em4 |= inq ? (1u << e) : 0u;
+        // an OCR core pixel is visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
+        cm4 |= (inq && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
+    }
+    // the halo vector next to lanes 0 / 31: columns x_base - 4 .. x_base - 1 / x_base + 128 .. x_base + 131
+    const bool edge = lane == 0 || lane == 31;
+    const int h_lo = lane == 0 ? x_base - PX2_HALO : x_base + 128;
+    uint32_t hvm4 = 0, hcm4 = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = h_lo + e;
+        const bool valid = edge && i >= 0 && i < w;
+        hvm4 |= valid ? (1u << e) : 0u;
+        hcm4 |= (QUAD && valid && i >= bqw && i < 2 * bqw && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
+    }
+    const uint32_t h_off = lane == 0 ? 0u : (uint32_t)(PX2_HALO + 128) * 4u;  // byte offset of the halo vector in a box row
+    const bool col_brq = em4 != 0u;
+    const uint32_t qpos = (uint32_t)(i_lo - bqw + (int)a.q_pad);  // byte position in a quadrant row (used when col_brq)
+
+    // ---- rows: read [j_first, j_end), owned (stored) [r0, r1) -----------------------------------------------
+    const int j_first = r0 - LAG, j_end = r1 + LAG;
+    const int n_chunks = (j_end - j_first + PX2_ROWS - 1) / PX2_ROWS;
+    const int tx = (int)a.map_x + x_base - PX2_HALO, ty = (int)a.map_y + j_first;
+
+    const uint32_t X_lo = strip * 128u + 4u * (uint32_t)lane;  // plane column of the lane's first pixel
+    uint8_t* ui_p = a.ui + (uint64_t)f * a.ui_stride + (int64_t)j_first * (int64_t)a.ui_pitch + X_lo * 4u;
+    uint8_t* lsd_p = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)(j_first - LAG) * (int64_t)a.lsd_pitch + X_lo;
+    uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
+    uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
+    // bitmap: word of tile (band, 4 strip + lane / 8), row jc & 31
+    const uint32_t btile = 4u * strip + (uint32_t)(lane >> 3);
+    uint32_t* bits_p = a.bits + (uint64_t)f * a.bits_stride + (((uint64_t)band * a.bits_tx + btile) << 5);
+    const bool bits_lane = (lane & 7) == 0 && btile < a.bits_tx;
+
+    uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
+    uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo vector
+
+    // ---- prologue: the first PX2_STAGES chunks are requested ------------------------------------------------
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < PX2_STAGES; c++) {
+            if (c < n_chunks) {
+                mbar_expect_tx(bars + 8u * c, PX2_ROWS * PX2_ROW_BYTES);
+                tma_load_3d(ring + (uint32_t)c * PX2_STAGE_BYTES, tmap, tx, ty + PX2_ROWS * c, (int)f, bars + 8u * c);
+            }
+        }
+    }
+
+    auto row = [&](uint32_t srow, int jn) {
+        // ---------------- phase 1: row jn ---------------------------------------------------------------------
+        uint32_t m4 = 0, c4 = 0, e4 = 0, hm = 0, hc = 0;
+        if (jn >= 0 && jn < h) {  // uniform
+            const uint4 cur = lds_v4(srow + (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u);
+            const bool owned = jn >= r0 && jn < r1;
+            const int jq = jn - bqh;
+            if (QUAD && (uint32_t)jq < (uint32_t)bqh) {  // uniform: a row of the OCR quadrant
+                if (col_brq) {
+                    PxOut o;
+                    vec_quadrant<GRAY>(cur, owned, lut, alpha, o);
+                    c4 = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
+                    e4 = o.e4 & em4;
+                    m4 = o.m4;
+                    if (owned && active) {
+                        stg_v4(ui_p, o.ui);
+                        stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), o.ocrw);
+                        if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), o.scw);
+                    }
+                } else if (owned) {
+                    PxOut o;
+                    vec_plain<GRAY>(cur, lut, alpha, o);
+                    m4 = o.m4;
+                    if (active) stg_v4(ui_p, o.ui);
+                } else m4 = vec_marker_only(cur, lut);
+                if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
+                    const uint4 hv = lds_v4(srow + h_off);
+                    PxOut o;
+                    vec_quadrant<GRAY>(hv, false, lut, alpha, o);
+                    hm = o.m4 & hvm4;
+                    hc = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & hcm4 : 0u;
+                }
+            } else {
+                if (owned) {
+                    PxOut o;
+                    vec_plain<GRAY>(cur, lut, alpha, o);
+                    m4 = o.m4;
+                    if (active) stg_v4(ui_p, o.ui);
+                } else m4 = vec_marker_only(cur, lut);  // halo row: flags only
+                if (edge && hvm4) hm = vec_marker_only(lds_v4(srow + h_off), lut) & hvm4;
+            }
+            m4 &= vm4;
+        }
+        mwin = (mwin << 4) | m4;
+        hmwin = (hmwin << 4) | hm;
+        if (QUAD) { cwin = (cwin << 4) | c4; ewin = (ewin << 4) | e4; hcwin = (hcwin << 4) | hc; }
+        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
+
+        // ---------------- phase 2: row jc = jn - LAG ----------------------------------------------------------
+        const int jc = jn - LAG;
+        if (jc < r0 || jc >= r1) return;  // uniform
+        // rows jc-1, jc, jc+1 sit at nibbles LAG+1, LAG, LAG-1 of the windows
+        constexpr uint32_t ROWS3 = 0xFFFu << (4 * (LAG - 1));
+        uint32_t d4 = 0;
+        if (__any_sync(FULL, ((mwin | hmwin) & ROWS3) != 0u)) {  // (almost every row of a map has no marker pixel nearby)
+            const uint32_t mc = (mwin >> (4 * LAG)) & 0xFu;
+            uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
+            const uint32_t hmc = (hmwin >> (4 * LAG)) & 0xFu;
+            if (lane == 0) l = hmc;
+            if (lane == 31) rr = hmc;
+            d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> (4 * (LAG + 1))) | (mwin >> (4 * (LAG - 1)))) & vm4;
+            // the four words of the bitmap: 8 lanes' nibbles each
+            uint32_t v = d4 << (4 * (lane & 7));
+            v |= __shfl_xor_sync(FULL, v, 1);
+            v |= __shfl_xor_sync(FULL, v, 2);
+            v |= __shfl_xor_sync(FULL, v, 4);
+            if (bits_lane) bits_p[jc & 31] = v;
+        } else if (bits_lane) bits_p[jc & 31] = 0u;
+        if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));  // lsd_p already points one row ahead of jn
+
+        if (!QUAD) return;
+        const int jqc = jc - bqh;
+        if ((uint32_t)jqc >= (uint32_t)bqh) return;  // uniform
+        const uint32_t eb = active ? (ewin >> (4 * LAG)) & 0xFu : 0u;
+        if (__any_sync(FULL, eb != 0u)) {
+            // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
+            // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit
+            uint32_t lwin = __shfl_up_sync(FULL, cwin, 1), rwin = __shfl_down_sync(FULL, cwin, 1);
+            if (lane == 0) lwin = hcwin;
+            if (lane == 31) rwin = hcwin;
+            uint32_t found = 0;  // bit e: pixel e has a core neighbour
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                // core bits of columns -4 .. +7 around the lane's first pixel, row jn - k
+                const uint32_t cm = ((lwin >> (4 * k)) & 0xFu) | (((cwin >> (4 * k)) & 0xFu) << 4) | (((rwin >> (4 * k)) & 0xFu) << 8);
+#pragma unroll
+                for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
+            }
+            const uint32_t todo = eb & found;
+#pragma unroll 1
+            for (int e = 0; e < 4; e++) {
+                if ((todo >> e) & 1u) {
+                    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                        frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)(i_lo + e)) * 4u));
+                    ocr_f[(uint32_t)jqc * a.q_pitch + qpos + e] = (uint8_t)(255u - luma8_bgra(word));
+                }
+            }
+        }
+    };
+
+    // The common row: outside the OCR quadrant, rows jn and jn - 1 both owned.  Straight-line code: no row tests, the
+    // halo is ONE pixel (the 3x3 cross only looks one column out) read by every lane at a lane-dependent offset and
+    // kept by lanes 0 / 31 alone, the (L, L, L, 255) word is one IMAD of the biased luma word:
+    // 0x4B0000LL * 0x010101 + 0xB4000000 = 0xFFLLLLLL (mod 2^32).
+    const uint32_t hp_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : (uint32_t)(PX2_HALO - 1) * 4u;  // (lanes 1..30 read lane 0's word: a broadcast)
+    const uint32_t hp_bit = lane == 0 ? (hvm4 & 8u) : (lane == 31 ? (hvm4 & 1u) : 0u);  // where the halo pixel's flag goes in the nibble
+    auto row_fast = [&](uint32_t srow, int jn) {
+        const uint4 cur = lds_v4(srow + (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u);
+        uint32_t hp;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(srow + hp_off));
+        uint4 ui;
+        if (GRAY) {
+            ui.x = luma_biased_i2f(cur.x) * 0x010101u + 0xB4000000u; ui.y = luma_biased_i2f(cur.y) * 0x010101u + 0xB4000000u;
+            ui.z = luma_biased_i2f(cur.z) * 0x010101u + 0xB4000000u; ui.w = luma_biased_i2f(cur.w) * 0x010101u + 0xB4000000u;
+        } else {
+            ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
+            ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
+        }
+        if (active) stg_v4(ui_p, ui);
+        uint32_t m4 = 0, hm = 0;
+        if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut) & vm4;  // rare
+        if (bright_bytes(hp) && hp_bit) hm = (marker_nibble(make_uint4(hp, 0u, 0u, 0u), lut) & 1u) ? hp_bit : 0u;  // rarer
+        mwin = (mwin << 4) | m4;
+        hmwin = (hmwin << 4) | hm;
+        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
+        // phase 2: row jc = jn - 1 (rows jc - 1, jc, jc + 1 at nibbles 2, 1, 0)
+        uint32_t d4 = 0;
+        if (__any_sync(FULL, ((mwin | hmwin) & 0xFFFu) != 0u)) {
+            const uint32_t mc = (mwin >> 4) & 0xFu;
+            uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
+            const uint32_t hmc = (hmwin >> 4) & 0xFu;
+            if (lane == 0) l = hmc;
+            if (lane == 31) rr = hmc;
+            d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> 8) | mwin) & vm4;
+            uint32_t v = d4 << (4 * (lane & 7));
+            v |= __shfl_xor_sync(FULL, v, 1);
+            v |= __shfl_xor_sync(FULL, v, 2);
+            v |= __shfl_xor_sync(FULL, v, 4);
+            if (bits_lane) bits_p[(jn - 1) & 31] = v;
+        } else if (bits_lane) bits_p[(jn - 1) & 31] = 0u;
+        if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));
+    };
+
+    // ---- main loop over the chunks of two rows ------------------------------------------------------------------
+    uint32_t stage = 0, phase = 0;
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; c++) {
+        mbar_wait(bars + 8u * stage, phase);
+        const uint32_t sbase = ring + stage * PX2_STAGE_BYTES;
+        const int jn = j_first + PX2_ROWS * c;
+        if (!QUAD && jn > r0 && jn + 1 < r1) {  // uniform: both rows owned, both with an owned row above
+#pragma unroll 1
+            for (int rr = 0; rr < PX2_ROWS; rr++) row_fast(sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+        } else {
+#pragma unroll 1
+            for (int rr = 0; rr < PX2_ROWS; rr++)
+                if (jn + rr < j_end) row(sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+        }
+        __syncwarp();  // every lane has read the stage: it may be refilled
+        if (lane == 0 && c + PX2_STAGES < n_chunks) {
+            mbar_expect_tx(bars + 8u * stage, PX2_ROWS * PX2_ROW_BYTES);
+            tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * (c + PX2_STAGES), (int)f, bars + 8u * stage);
+        }
+        if (++stage == PX2_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    // the rows of the window still to be dilated (phase 1 of rows >= j_end is idle): rows r1 - LAG .. r1 - 1 were
+    // handled by the loop itself because it runs to j_end = r1 + LAG
+}
+
+// Two launches per batch: the items that own pixels of the OCR quadrant (QUAD: three rows of halo, OCR classes, the
+// 7x7 search) and all the others plus the button tests.  One population of warps per launch keeps each launch's
+// instruction footprint small — as one kernel the two paths evicted each other from the instruction caches (37 % of
+// the stall samples were instruction fetches).
+template <bool GRAY, bool QUAD>
+__global__ void __launch_bounds__(PX2_THREADS, 8) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
+    extern __shared__ __align__(128) uint8_t px2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x * PX2_WARPS + warp;
+    const uint32_t nqb = a.qb1 - a.qb0, nqs = a.qs1 - a.qs0;
+    uint32_t f, band, strip;
+    if (QUAD) {
+        const uint32_t per_frame = nqb * nqs;
+        f = item / per_frame;
+        if (f >= a.n_frames) return;
+        const uint32_t sub = item - f * per_frame, bq = sub / nqs;
+        band = a.qb0 + bq; strip = a.qs0 + (sub - bq * nqs);
+    } else {
+        const uint32_t n_plain = a.nbands * a.nstrips - nqb * nqs, per_frame = n_plain + 1u;
+        f = item / per_frame;
+        if (f >= a.n_frames) return;
+        uint32_t sub = item - f * per_frame;
+        if (sub == n_plain) {
+            // ---- close-deployment button test (vision-cpu/src/lib.rs:115-135) -----------------
+            const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
+            uint32_t cnt = 0;
+            const uint32_t npx = a.btn_w * a.btn_h;
+            for (uint32_t idx = lane; idx < npx; idx += 32) {
+                const uint32_t y = idx / a.btn_w, x = idx - y * a.btn_w;
+                const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                    frame + (uint64_t)(a.btn_y + y) * a.pitch + (uint64_t)(a.btn_x + x) * 4u));
+                cnt += smh_button_red((word >> 16) & 0xFFu, (word >> 8) & 0xFFu, word & 0xFFu) ? 1u : 0u;
+            }
+            cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (lane == 0) {
+                a.red[f] = cnt;
+                // `red_pixels as f32 / (w*h) as f32 < 0.65` -> map closed
+                a.open[f] = __fdiv_rn((float)cnt, (float)npx) < SMH_BTN_RED_RATIO_THRESHOLD ? 0 : 1;
+            }
+            return;
+        }
+        // bands above the quadrant's, then its bands without its strips, then the bands below
+        const uint32_t above = a.qb0 * a.nstrips, beside = nqb * (a.nstrips - nqs);
+        if (sub < above) { band = sub / a.nstrips; strip = sub - band * a.nstrips; }
+        else if (sub < above + beside) {
+            sub -= above;
+            const uint32_t per = a.nstrips - nqs, bq = sub / per, k = sub - bq * per;
+            band = a.qb0 + bq; strip = k < a.qs0 ? k : k + nqs;
+        } else {
+            sub -= above + beside;
+            const uint32_t bq = sub / a.nstrips;
+            band = a.qb1 + bq; strip = sub - bq * a.nstrips;
+        }
+    }
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(px2_smem) + (uint32_t)warp * PX2_WARP_BYTES;
+    const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    px2_item<GRAY, QUAD>(&tmap, a, f, band, strip, ring, bars);
+}
+
+}  // namespace smh

@@ -22,6 +22,8 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "kernels_lsd.cuh"
+#include "kernels_px.cuh"
 #include "kernels_next.cuh"
 #include "kernels_icons.cuh"
 
@@ -34,6 +36,10 @@ thread_local std::string g_create_error;
 // chunks in flight in smh_b200_process_host_batch: upload of chunk c+2, kernels of c+1, download of c
 #ifndef SMH_PIPE_DEPTH
 #define SMH_PIPE_DEPTH 3
+#endif
+// warps per frame of the line search (kernels_lsd.cuh)
+#ifndef SMH_LSD2_WARPS
+#define SMH_LSD2_WARPS 4
 #endif
 // smh_b200_process_batch splits a large batch into chunks that run on up to this many internal streams
 #define SMH_BATCH_LANES_MAX 8
@@ -238,6 +244,12 @@ int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint
     return SMH_OK;
 }
 
+// SMH_B200_OLD_PIXELS=1: the round-1 pixel pass (per-lane cp.async, 30-column strips, separate k_pack_bits) for A/B runs
+bool old_pixels() {
+    static const bool on = [] { const char* e = getenv("SMH_B200_OLD_PIXELS"); return e && e[0] == '1'; }();
+    return on;
+}
+
 int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool stats) {
     if (P->n == n && P->W == g.W && P->H == g.H) {
         if (stats && !P->stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
@@ -245,8 +257,11 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     }
     P->release();
     P->geo = g;
+    // every plane carries the capture's 16-byte phase as a left pad (a TMA box / 128-bit vector must start on a 16-byte
+    // boundary of the capture); k_pixels2's quadrant planes are padded further so that a 128-column strip's bytes start
+    // on a 128-byte boundary
     P->pad = g.map[0] & 3u;
-    P->qpad = (P->pad + g.brq[2]) & 3u;
+    P->qpad = old_pixels() ? ((P->pad + g.brq[2]) & 3u) : ((P->pad + g.brq[2]) & 127u);
     P->nvec = (P->pad + g.map[2] + 3u) / 4u;
     int rc;
     if ((rc = alloc_plane(h, &P->ui, n, g.map[2], g.map[3], 4, P->pad))) return rc;
@@ -301,9 +316,9 @@ bool fold_pack_enabled() {
 
 // Launch the fused pixel pass over n frames.  `frames` origin may be a cropped view of the
 // capture: (ox, oy) is the frame coordinate of its first byte.
-int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch,
-                  uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
-                  int grayscale, uint32_t rows_per_band, cudaStream_t st) {
+int launch_pixels_old(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch,
+                      uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
+                      int grayscale, uint32_t rows_per_band, cudaStream_t st) {
     const Geometry& g = P.geo;
     smh::PixelArgs a{};
     a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
@@ -335,6 +350,79 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     kern<<<(unsigned)blocks, smh::PX_THREADS, smh::PX_SMEM_BYTES, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
+    return SMH_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// The fused pixel pass over n frames (k_pixels2, kernels_px.cuh).  `frames` may be a cropped view of the capture:
+// (ox, oy) is the frame coordinate of its first byte, rows_avail the rows it holds.
+int launch_pixels2(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
+                   uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform, int grayscale, cudaStream_t st) {
+    const Geometry& g = P.geo;
+    if ((pitch & 15u) || (frame_stride & 15u) || ((uintptr_t)frames & 15u))
+        return fail(h, SMH_E_ALIGN, "captured frames must be 16-byte aligned (base %p, pitch %u, stride %llu)",
+                    (const void*)frames, pitch, (unsigned long long)frame_stride);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(h, SMH_E_NOGPU, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tmap;
+    {
+        const uint64_t fs = frame_stride ? frame_stride : (uint64_t)pitch * rows_avail;
+        const cuuint64_t dims[3] = {pitch / 4u, rows_avail, n};
+        const cuuint64_t strides[2] = {pitch, fs};
+        const cuuint32_t box[3] = {smh::PX2_BOX_W, smh::PX2_ROWS, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, SMH_E_ARG, "cuTensorMapEncodeTiled failed with %d (pitch %u, rows %u, frames %u)", (int)r, pitch, rows_avail, n);
+    }
+    smh::Pixel2Args a{};
+    a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
+    a.map_x = g.map[0] - ox; a.map_y = g.map[1] - oy; a.w = g.map[2]; a.h = g.map[3];
+    a.bqw = g.brq[2]; a.bqh = g.brq[3]; a.pad = P.pad;
+    if ((a.map_x - a.pad) & 3u) return fail(h, SMH_E_ALIGN, "the capture view must start on a multiple of 4 pixels (x0 %u)", ox);
+    a.btn_x = g.btn[0] - ox; a.btn_y = g.btn[1] - oy; a.btn_w = g.btn[2]; a.btn_h = g.btn[3];
+    a.ui = P.ui.ptr; a.ui_stride = P.ui.frame_stride; a.ui_pitch = P.ui.pitch;
+    a.lsd = P.lsd.ptr; a.lsd_stride = P.lsd.frame_stride; a.lsd_pitch = P.lsd.pitch;
+    a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch; a.q_pad = P.qpad;
+    a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
+    a.red = P.red; a.open = P.open;
+    a.nbands = (a.h + 31u) / 32u; a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
+    a.lut = h->d_lut;
+    a.bits = P.bits; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
+    // the items that own pixels of the OCR quadrant: strips [qs0, qs1) x bands [qb0, qb1)
+    a.qs0 = (a.bqw + a.pad) / 128u; a.qs1 = (2u * a.bqw + a.pad + 127u) / 128u;
+    if (a.qs1 > a.nstrips) a.qs1 = a.nstrips;
+    a.qb0 = a.bqh / 32u; a.qb1 = (2u * a.bqh + 31u) / 32u;
+    if (a.qb1 > a.nbands) a.qb1 = a.nbands;
+    if (a.qs0 >= a.qs1 || a.qb0 >= a.qb1) { a.qs0 = a.qs1 = 0; a.qb0 = a.qb1 = 0; }
+    // one warp per (frame, band, strip) item, plus one per frame for the button test; two launches (see k_pixels2)
+    const uint64_t n_quad = (uint64_t)(a.qb1 - a.qb0) * (a.qs1 - a.qs0);
+    const uint64_t items_p = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips - n_quad + 1u), items_q = (uint64_t)n * n_quad;
+    const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
+    if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
+    if (grayscale) smh::k_pixels2<true, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+    else smh::k_pixels2<false, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    if (blocks_q) {
+        if (grayscale) smh::k_pixels2<true, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        else smh::k_pixels2<false, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
     return SMH_OK;
 }
 
@@ -371,9 +459,16 @@ Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
     return V;
 }
 
+int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
+                  uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
+                  int grayscale, uint32_t rows_per_band, cudaStream_t st) {
+    if (old_pixels()) return launch_pixels_old(h, P, frames, frame_stride, pitch, ox, oy, n, per_frame_start_y, start_y_uniform, grayscale, rows_per_band, st);
+    return launch_pixels2(h, P, frames, frame_stride, pitch, rows_avail, ox, oy, n, per_frame_start_y, start_y_uniform, grayscale, st);
+}
+
 // 1-bit tile-major copy of the dilated masks (what the line search and the icon match read)
 int launch_pack(smh_b200* h, const Planes& P, uint32_t n, cudaStream_t st) {
-    if (fold_pack_enabled()) return SMH_OK;  // the pixel pass wrote the bitmap
+    if (fold_pack_enabled() || !old_pixels()) return SMH_OK;  // the pixel pass wrote the bitmap
     const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
     if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
     smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
@@ -452,34 +547,53 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
     a.lines = P.lines; a.n_lines = P.n_lines;
     a.stats = stats ? P.stats : nullptr;
     CU(h, cudaMemsetAsync(P.counter, 0, sizeof(uint32_t), st));
-    // persistent grid: as many CTAs as stay resident (or one per frame when there are fewer)
+    if (stats) CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
+    // the limit on dynamic shared memory is a property of the kernel on this device, shared by every handle: only ever raise it
+    auto raise_smem = [&](const void* fn, size_t dyn, size_t* cur) -> int {
+        if (dyn > 32768 && dyn > *cur) {
+            CU(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            *cur = dyn;
+        }
+        return SMH_OK;
+    };
+    static std::mutex mu;
+    static size_t raised[64][4] = {{0}};
+    if (prune && a.gap_limit >= 1 && a.gap_limit <= 32) {
+        // k_lsd2: a small CTA per frame in flight, warp 0 its master (kernels_lsd.cuh); persistent CTAs
+        constexpr int NW = SMH_LSD2_WARPS;
+        const size_t dyn = (sizeof(smh::Lsd2Shared<NW>) + 15) / 16 * 16 + (size_t)P.bg.tx * 33u * sizeof(uint32_t);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int rc;
+            if ((rc = raise_smem((const void*)smh::k_lsd2<NW, false>, dyn, &raised[h->device & 63][0]))) return rc;
+            if ((rc = raise_smem((const void*)smh::k_lsd2<NW, true>, dyn, &raised[h->device & 63][1]))) return rc;
+        }
+        int nb = 0;
+        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd2<NW, false>, NW * 32, dyn));
+        const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
+        const uint32_t grid = n < resident ? n : resident;
+        if (stats) smh::k_lsd2<NW, true><<<grid, NW * 32, dyn, st>>>(a);
+        else smh::k_lsd2<NW, false><<<grid, NW * 32, dyn, st>>>(a);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return SMH_OK;
+    }
+    // the literal search (every ray of every seed; any max_gap): one CTA per frame in flight
     // one tile-row of the bitmap + its fringe map + the window around the current seed
     const size_t dyn = ((size_t)P.bg.tx * 32u * 2u + (size_t)smh::LSD_WIN_ROWS * 8u) * sizeof(uint32_t);
     {
-        // the limit is a property of the kernel on this device, shared by every handle: only ever raise it
-        static std::mutex mu;
-        static size_t raised[64] = {0};
         std::lock_guard<std::mutex> g(mu);
-        size_t& cur = raised[h->device & 63];
-        if (dyn > 32768 && dyn > cur) {
-            CU(h, cudaFuncSetAttribute(smh::k_lsd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            CU(h, cudaFuncSetAttribute(smh::k_lsd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            cur = dyn;
-        }
+        int rc;
+        if ((rc = raise_smem((const void*)smh::k_lsd<false>, dyn, &raised[h->device & 63][2]))) return rc;
+        if ((rc = raise_smem((const void*)smh::k_lsd<true>, dyn, &raised[h->device & 63][3]))) return rc;
     }
+    a.prune = 0;
     int nb = 0;
     CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, dyn));
-    // tuning knob: cap the persistent CTAs per SM (leaves registers for a pixel pass running beside the search)
-    static const int cap = [] { const char* e = getenv("SMH_B200_LSD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    if (cap >= 1 && nb > cap) nb = cap;
     const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
     const uint32_t grid = n < resident ? n : resident;
-    if (stats) {
-        CU(h, cudaMemsetAsync(P.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
-        smh::k_lsd<true><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
-    } else {
-        smh::k_lsd<false><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
-    }
+    if (stats) smh::k_lsd<true><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
+    else smh::k_lsd<false><<<grid, smh::LSD_THREADS, dyn, st>>>(a);
     h->launches++;
     CU(h, cudaGetLastError());
     return SMH_OK;
@@ -744,7 +858,7 @@ int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, 
     const Geometry& g = h->geo;
     // the fresh thresholded scales image goes to a scratch plane; find_scales_preprocess merges
     // rows >= start_y into the persistent host image, so pass start_y = 0 here
-    int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, 0, grayscale,
+    int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->uy1 - h->uy0, h->ux0, h->uy0, 1, false, 0, grayscale,
                            pick_rows_per_band(h, 1, g.map[3]), h->s_main);
     if (rc) return rc;
     CU(h, cudaEventRecord(h->ev_pixels, h->s_main));
@@ -1141,7 +1255,7 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
     const bool whole = (flags & (SMH_BATCH_SKIP_PIXELS | SMH_BATCH_SKIP_LSD | SMH_BATCH_SERIAL)) || n < 2u * chunk || lanes < 2;
     if (whole) {
         if (!(flags & SMH_BATCH_SKIP_PIXELS)) {
-            if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, start_y != nullptr, 0,
+            if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, H, 0, 0, n, start_y != nullptr, 0,
                                     flags & SMH_BATCH_GRAYSCALE, rows_per_band, st)))
                 return rc;
             if (flags & SMH_BATCH_MINIMAP)
@@ -1174,7 +1288,7 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
             cudaStream_t ls = h->lane_streams[lane];
             const Planes V = planes_view(h->batch, f0, cn, lane);
             const uint8_t* fr = d_frames + (uint64_t)f0 * frame_stride;
-            if ((rc = launch_pixels(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, start_y != nullptr, 0,
+            if ((rc = launch_pixels(h, V, fr, frame_stride, pitch_bytes, H, 0, 0, cn, start_y != nullptr, 0,
                                     flags & SMH_BATCH_GRAYSCALE, rows_per_band, ls)))
                 return rc;
             if (flags & SMH_BATCH_MINIMAP)
@@ -1377,7 +1491,7 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         CU(h, cudaStreamWaitEvent(st, ev_up, 0));
         if (reused) CU(h, cudaStreamWaitEvent(st, ev_down, 0));
         if (start_y) CU(h, cudaMemcpyAsync(P.start_y, start_y + done, (size_t)c * 4, cudaMemcpyHostToDevice, st));
-        if ((rc = launch_pixels(h, P, stage, ustride, upitch, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
+        if ((rc = launch_pixels(h, P, stage, ustride, upitch, rows, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
                                 pick_rows_per_band(h, c, g.map[3]), st)))
             return rc;
         if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found)

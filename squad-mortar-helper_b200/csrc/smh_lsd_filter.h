@@ -76,6 +76,26 @@ SMH_LF_HD void smh_lsd_filter_span(float cx, float cy, float d2, int* lo, int* h
     *hi = (int)ceilf(c + half) + 1;                      /* angle-table rounding are << 0.1 degree */
 }
 
+
+/* The same for a QUARTER: the white pixels of one pixel row between columns a and b (centres at (cxa, cy) ..
+ * (cxb, cy) from the seed, cxa <= cxb, at most 8 pixels apart).  Along a row the direction of a pixel centre is
+ * monotonic in x (cy != 0) and the half-angle asin(0.7082 / D) is largest at the row's NEAREST point, so
+ * [min(dir_a, dir_b) - half(dmin), max(dir_a, dir_b) + half(dmin)] covers every pixel between them.  A quarter
+ * that comes closer than one pixel to the seed (this includes cy == 0 with the seed between a and b, where the
+ * direction jumps by 180 degrees) marks every ray.  dmin2 / dmax2: squared distance range of the quarter. */
+SMH_LF_HD void smh_lsd_filter_quarter(float cy, float cxa, float cxb, float* dmin2, float* dmax2, int* lo, int* hi) {
+    const float cy2 = cy * cy, da = cxa * cxa + cy2, db = cxb * cxb + cy2;
+    *dmax2 = da > db ? da : db;
+    *dmin2 = (cxa < 0.0f && cxb > 0.0f) ? cy2 : (da < db ? da : db);
+    if (*dmin2 < 1.0f) { *lo = 0; *hi = SMH_LSD_RAYS - 1; return; }
+    const float per_rad = 572.9577951f;
+    const float aa = atan2f(cy, cxa) * per_rad, ab = atan2f(cy, cxb) * per_rad;
+    const float x = 0.7082f / sqrtf(*dmin2);
+    const float half = x * (1.0f + 0.25f * x * x) * per_rad + 0.01f;
+    *lo = (int)floorf((aa < ab ? aa : ab) - half) - 1;
+    *hi = (int)ceilf((aa > ab ? aa : ab) + half) + 1;
+}
+
 /* OR the ray interval [lo, hi] (mod 3600) into a 113-word bitmap; ATOMIC_OR(word_ptr, mask) */
 #define SMH_LSD_FILTER_SET_BITS(bits, lo_, hi_, ATOMIC_OR)                                        \
     do {                                                                                          \

@@ -17,14 +17,25 @@ def hostcheck():
     L = ctypes.CDLL(str(build.build_hostcheck()))
     L.smh_hostcheck_lsd_filter.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    L.smh_hostcheck_lsd_filter_quarters.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float,
+                                                    ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
     return L
 
 
 def marked_rays(L, img, x, y, gap):
+    """Rays kept by the per-pixel form AND by the quarter form k_lsd2 runs (every bitmap phase 0..7 of the
+    8-pixel quarters): both must be supersets of the rays that matter, the quarter form of the per-pixel one."""
     img = np.ascontiguousarray(img, np.uint8)
     out = np.zeros(3600, np.uint8)
     nw = L.smh_hostcheck_lsd_filter(img.ctypes.data, img.shape[1], img.shape[0], x, y, gap, out.ctypes.data)
-    return nw, out.astype(bool)
+    keep = out.astype(bool)
+    for pad in (0, 3, 5):
+        q = np.zeros(3600, np.uint8)
+        L.smh_hostcheck_lsd_filter_quarters(img.ctypes.data, img.shape[1], img.shape[0], pad, x, y, gap, q.ctypes.data)
+        q = q.astype(bool)
+        assert not (keep & ~q).any(), f"quarter marking (pad {pad}) drops rays the per-pixel marking keeps at seed {(x, y)} gap {gap}"
+        keep_q = q
+    return nw, keep & keep_q
 
 
 def check_seeds(L, img, seeds, gap):
@@ -84,7 +95,7 @@ def test_filter_border_and_hand_made_shapes(hostcheck):
         img[280:283, x:x + 4] = 255
     rng = np.random.default_rng(3)
     seeds = pick_seeds(img, rng, 250) + [(0, 4), (3, 0), (199, 4), (3, 249), (1, 1), (398, 151)]
-    for gap in (15, 22, 3):
+    for gap in (15, 22, 3, 4, 32, 1, 2):
         check_seeds(hostcheck, img, seeds, gap)
 
 

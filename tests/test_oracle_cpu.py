@@ -257,3 +257,32 @@ def test_gpuflavour_dilate_is_the_2x2_box_model():
     box = np.zeros_like(raw)
     box[1:h - 1, 1:w - 1] = np.maximum.reduce([raw[0:h - 2, 0:w - 2], raw[0:h - 2, 1:w - 1], raw[1:h - 1, 0:w - 2], raw[1:h - 1, 1:w - 1]])
     assert np.array_equal(O.gpuflavour_dilate(raw), box)
+
+
+def test_marker_predicate_against_the_reference_kernels_own_table():
+    """tests/golden/k8_marker_table.npz is an OUTPUT OF THE REFERENCE: its K8 (mask_marker_lines, vision-gpu/cuda/cuda.cu:616-635)
+    compiled unmodified and run over all 2^24 colours on a B200 (tools/k8_table.py).  The oracle's restatement of
+    vision-gpu's predicate must reproduce it exactly; vision-cpu's predicate (what the product is checked against)
+    differs from it on exactly the colours where the two HSV formulas round apart (D1) — each of them one step of
+    h, s or v away from flipping."""
+    k8 = np.unpackbits(np.load(GOLDEN / "k8_marker_table.npz")["bits"]).astype(bool)
+    assert np.array_equal(O.gpuflavour_table_marker() == 1, k8)
+    cpu = O.table_marker() == 1
+    diff = np.nonzero(cpu != k8)[0]
+    assert len(diff) == 136
+    th, ts, tv = O.table_hsv()
+    hh, ss, vv = th[diff].astype(np.int32), ts[diff].astype(np.int32), tv[diff].astype(np.int32)
+
+    def pred(h, s, v):
+        ok = np.zeros(h.shape, bool)
+        for mh, ms, mv in ((105, 100, 100), (285, 46, 85), (158, 60, 91)):
+            ok |= (np.abs(h - mh) <= 15) & ((np.abs(s - ms) <= 15) | (np.abs(s - (ms - 50)) <= 15)) & (np.abs(v - mv) <= 15)
+        return ok & (s >= 35)
+    base = pred(hh, ss, vv)
+    assert np.array_equal(base, cpu[diff])
+    flips = np.zeros(len(diff), bool)
+    for dh in (-1, 0, 1):
+        for ds in (-1, 0, 1):
+            for dv in (-1, 0, 1):
+                flips |= pred((hh + dh) % 360, ss + ds, vv + dv) != base
+    assert flips.all()
