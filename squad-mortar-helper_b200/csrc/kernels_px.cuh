@@ -5,7 +5,7 @@
 // reference kernels K1-K9 (vision-gpu/cuda/cuda.cu:312-546,616-635 + NPP dilate) and restates the vision-cpu
 // arithmetic (vision-cpu/src/lib.rs:110-280,357-375) bit for bit (vec_plain / vec_quadrant in kernels.cuh).
 //
-// Warp-autonomous, no block barrier.  A work item is (frame, band of 32 map rows = one tile-row of the bitmap,
+// Warp-autonomous, no block barrier.  A work item is (frame, band of 64 map rows = two tile-rows of the bitmap,
 // strip of 128 columns = 4 bitmap tiles) or a frame's button test.  Columns are PADDED coordinates X = x + pad,
 // pad = map_x & 3: the map ROI starts at an arbitrary pixel column of the capture (1219 at 1440p) and a TMA box
 // must start on a 16-byte boundary (measured: tools/tma_probe.cu — an odd pixel start raises an illegal
@@ -52,6 +52,10 @@ constexpr int PX2_THREADS = 128;
 constexpr int PX2_WARPS = PX2_THREADS / 32;
 constexpr int PX2_STAGES = 3;
 constexpr int PX2_ROWS = 2;                      // rows per TMA box
+#ifndef PX2_BAND_ROWS
+#define PX2_BAND_ROWS 64
+#endif
+constexpr int PX2_BAND = PX2_BAND_ROWS;          // map rows per work item (a multiple of 32: whole tile-rows of the bitmap)
 constexpr int PX2_HALO = 4;                      // halo pixels either side of the strip
 constexpr int PX2_BOX_W = 128 + 2 * PX2_HALO;    // pixels per box row
 constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     // 544
@@ -84,6 +88,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // nibble -> 4 bytes of 0/255
 __device__ __forceinline__ uint32_t nibble_bytes(uint32_t d4) { return ((d4 * 0x00204081u) & 0x01010101u) * 255u; }
 
+template <bool B> struct PxTag { static constexpr bool value = B; };
+
 template <bool GRAY, bool QUAD>
 __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Args& a, uint32_t f, uint32_t band, uint32_t strip,
                                          uint32_t ring, uint32_t bars) {
@@ -91,7 +97,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     const int lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const int w = (int)a.w, h = (int)a.h, bqw = (int)a.bqw, bqh = (int)a.bqh;
-    const int r0 = (int)band * 32, r1 = min(r0 + 32, h);
+    const int r0 = (int)band * PX2_BAND, r1 = min(r0 + PX2_BAND, h);
     const int x_base = (int)strip * 128 - (int)a.pad;  // map column of the strip's first pixel (X = 128 strip)
     const int i_lo = x_base + 4 * lane;              // map column of the lane's first pixel
     const bool active = i_lo < w;                     // the lane's vector starts left of the map's right edge: it stores
@@ -112,7 +118,9 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         // an OCR core pixel is visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
         cm4 |= (inq && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
     }
-    // the halo vector next to lanes 0 / 31: columns x_base - 4 .. x_base - 1 / x_base + 128 .. x_base + 131
+    // the halo next to lanes 0 / 31: columns x_base - 4 .. x_base - 1 / x_base + 128 .. x_base + 131.  Outside the OCR
+    // quadrant only the adjacent pixel matters (the 3x3 cross looks one column out): ONE pixel, read by every lane at
+    // a lane-dependent offset (lanes 1..30 read lane 0's word, a broadcast) and kept by lanes 0 / 31 alone.
     const bool edge = lane == 0 || lane == 31;
     const int h_lo = lane == 0 ? x_base - PX2_HALO : x_base + 128;
     uint32_t hvm4 = 0, hcm4 = 0;
@@ -123,7 +131,10 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         hvm4 |= valid ? (1u << e) : 0u;
         hcm4 |= (QUAD && valid && i >= bqw && i < 2 * bqw && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
     }
-    const uint32_t h_off = lane == 0 ? 0u : (uint32_t)(PX2_HALO + 128) * 4u;  // byte offset of the halo vector in a box row
+    const uint32_t own_off = (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u;  // the lane's vector in a box row
+    const uint32_t h_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : 0u;   // the halo vector (QUAD)
+    const uint32_t hp_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : (uint32_t)(PX2_HALO - 1) * 4u;  // the halo pixel
+    const uint32_t hp_bit = lane == 0 ? (hvm4 & 8u) : (lane == 31 ? (hvm4 & 1u) : 0u);  // where its flag goes in the halo nibble
     const bool col_brq = em4 != 0u;
     const uint32_t qpos = (uint32_t)(i_lo - bqw + (int)a.q_pad);  // byte position in a quadrant row (used when col_brq)
 
@@ -133,17 +144,18 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     const int tx = (int)a.map_x + x_base - PX2_HALO, ty = (int)a.map_y + j_first;
 
     const uint32_t X_lo = strip * 128u + 4u * (uint32_t)lane;  // plane column of the lane's first pixel
-    uint8_t* ui_p = a.ui + (uint64_t)f * a.ui_stride + (int64_t)j_first * (int64_t)a.ui_pitch + X_lo * 4u;
-    uint8_t* lsd_p = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)(j_first - LAG) * (int64_t)a.lsd_pitch + X_lo;
+    uint8_t* ui_p = a.ui + (uint64_t)f * a.ui_stride + (int64_t)j_first * (int64_t)a.ui_pitch + X_lo * 4u;       // row jn
+    uint8_t* lsd_p = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)(j_first - LAG) * (int64_t)a.lsd_pitch + X_lo;  // row jn - LAG
     uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
     uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
-    // bitmap: word of tile (band, 4 strip + lane / 8), row jc & 31
+    // bitmap: word of tile (jc >> 5, 4 strip + lane / 8), row jc & 31 — one running pointer per lane
     const uint32_t btile = 4u * strip + (uint32_t)(lane >> 3);
-    uint32_t* bits_p = a.bits + (uint64_t)f * a.bits_stride + (((uint64_t)band * a.bits_tx + btile) << 5);
     const bool bits_lane = (lane & 7) == 0 && btile < a.bits_tx;
+    uint32_t* bits_p = a.bits + (uint64_t)f * a.bits_stride + (((uint64_t)(r0 >> 5) * a.bits_tx + btile) << 5);  // row r0
+    const uint32_t bits_jump = a.bits_tx * 32u - 32u;  // from the last row of a tile to the first of the tile below
 
     uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
-    uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo vector
+    uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo
 
     // ---- prologue: the first PX2_STAGES chunks are requested ------------------------------------------------
     if (lane == 0) {
@@ -156,46 +168,85 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         }
     }
 
-    auto row = [&](uint32_t srow, int jn) {
+    // FAST rows (the bulk): row jn and row jn - LAG are both owned (so inside the map), and in a QUAD item both are rows
+    // of the quadrant; the generic form tests all of that per row.
+    auto row = [&](auto tag, uint32_t srow, int jn) {
+        constexpr bool FAST = decltype(tag)::value;
         // ---------------- phase 1: row jn ---------------------------------------------------------------------
         uint32_t m4 = 0, c4 = 0, e4 = 0, hm = 0, hc = 0;
-        if (jn >= 0 && jn < h) {  // uniform
-            const uint4 cur = lds_v4(srow + (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u);
-            const bool owned = jn >= r0 && jn < r1;
+        if (FAST || (jn >= 0 && jn < h)) {  // uniform
+            const uint4 cur = lds_v4(srow + own_off);
+            const bool owned = FAST || (jn >= r0 && jn < r1);
             const int jq = jn - bqh;
-            if (QUAD && (uint32_t)jq < (uint32_t)bqh) {  // uniform: a row of the OCR quadrant
-                if (col_brq) {
-                    PxOut o;
-                    vec_quadrant<GRAY>(cur, owned, lut, alpha, o);
-                    c4 = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
-                    e4 = o.e4 & em4;
-                    m4 = o.m4;
-                    if (owned && active) {
-                        stg_v4(ui_p, o.ui);
-                        stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), o.ocrw);
-                        if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), o.scw);
+            if (QUAD && (FAST || (uint32_t)jq < (uint32_t)bqh)) {  // uniform: a row of the OCR quadrant
+                // Two levels.  Almost every row of a map has neither a bright near-grey pixel (OCR classes), nor a pixel of
+                // luma 0 (scales), nor a marker-bright one in the strip or its halo: then the row is luma + constant stores.
+                // The halo vector is read by every lane (lanes 1..30 read lane 0's: a broadcast) and kept by lanes 0 / 31.
+                const uint4 hv = lds_v4(srow + h_off);
+                const uint32_t any = or4(cur), hany = (edge && hvm4) ? or4(hv) : 0u;
+                uint32_t lb0 = 0, lb1 = 0, lb2 = 0, lb3 = 0;
+                bool rare = !owned || bright_bytes(any | hany) != 0u || (hany & 0x00808080u) == 0x00808080u;
+                if (owned) {
+                    lb0 = luma_biased_i2f(cur.x); lb1 = luma_biased_i2f(cur.y); lb2 = luma_biased_i2f(cur.z); lb3 = luma_biased_i2f(cur.w);
+                    if (col_brq) rare = rare || (any & 0x00808080u) == 0x00808080u || min(min(lb0, lb1), min(lb2, lb3)) == BIAS;
+                }
+                if (!__any_sync(FULL, rare)) {
+                    if (active) {
+                        uint4 ui;
+                        if (GRAY) {
+                            ui.x = lb0 * 0x010101u + 0xB4000000u; ui.y = lb1 * 0x010101u + 0xB4000000u;
+                            ui.z = lb2 * 0x010101u + 0xB4000000u; ui.w = lb3 * 0x010101u + 0xB4000000u;
+                        } else {
+                            ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
+                            ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
+                        }
+                        stg_v4(ui_p, ui);
+                        if (col_brq) {
+                            stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), 0xFFFFFFFFu);
+                            if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), 0xFFFFFFFFu);
+                        }
                     }
-                } else if (owned) {
-                    PxOut o;
-                    vec_plain<GRAY>(cur, lut, alpha, o);
-                    m4 = o.m4;
-                    if (active) stg_v4(ui_p, o.ui);
-                } else m4 = vec_marker_only(cur, lut);
-                if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
-                    const uint4 hv = lds_v4(srow + h_off);
-                    PxOut o;
-                    vec_quadrant<GRAY>(hv, false, lut, alpha, o);
-                    hm = o.m4 & hvm4;
-                    hc = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & hcm4 : 0u;
+                } else {
+                    if (col_brq) {
+                        PxOut o;
+                        vec_quadrant<GRAY>(cur, owned, lut, alpha, o);
+                        c4 = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
+                        e4 = o.e4 & em4;
+                        m4 = o.m4;
+                        if (owned && active) {
+                            stg_v4(ui_p, o.ui);
+                            stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), o.ocrw);
+                            if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), o.scw);
+                        }
+                    } else if (owned) {
+                        PxOut o;
+                        vec_plain<GRAY>(cur, lut, alpha, o);
+                        m4 = o.m4;
+                        if (active) stg_v4(ui_p, o.ui);
+                    } else m4 = vec_marker_only(cur, lut);
+                    if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
+                        PxOut o;
+                        vec_quadrant<GRAY>(hv, false, lut, alpha, o);
+                        hm = o.m4 & hvm4;
+                        hc = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & hcm4 : 0u;
+                    }
                 }
             } else {
+                uint32_t hp;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(srow + hp_off));
                 if (owned) {
-                    PxOut o;
-                    vec_plain<GRAY>(cur, lut, alpha, o);
-                    m4 = o.m4;
-                    if (active) stg_v4(ui_p, o.ui);
-                } else m4 = vec_marker_only(cur, lut);  // halo row: flags only
-                if (edge && hvm4) hm = vec_marker_only(lds_v4(srow + h_off), lut) & hvm4;
+                    uint4 ui;
+                    if (GRAY) {  // (L, L, L, 255) = 0x4B0000LL * 0x010101 + 0xB4000000 (mod 2^32): one IMAD per pixel
+                        ui.x = luma_biased_i2f(cur.x) * 0x010101u + 0xB4000000u; ui.y = luma_biased_i2f(cur.y) * 0x010101u + 0xB4000000u;
+                        ui.z = luma_biased_i2f(cur.z) * 0x010101u + 0xB4000000u; ui.w = luma_biased_i2f(cur.w) * 0x010101u + 0xB4000000u;
+                    } else {
+                        ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
+                        ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
+                    }
+                    if (active) stg_v4(ui_p, ui);
+                }
+                if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut);  // rare
+                if (bright_bytes(hp) && hp_bit) hm = (marker_nibble(make_uint4(hp, 0u, 0u, 0u), lut) & 1u) ? hp_bit : 0u;  // rarer
             }
             m4 &= vm4;
         }
@@ -206,29 +257,32 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
 
         // ---------------- phase 2: row jc = jn - LAG ----------------------------------------------------------
         const int jc = jn - LAG;
-        if (jc < r0 || jc >= r1) return;  // uniform
+        if (!FAST && (jc < r0 || jc >= r1)) return;  // uniform
         // rows jc-1, jc, jc+1 sit at nibbles LAG+1, LAG, LAG-1 of the windows
         constexpr uint32_t ROWS3 = 0xFFFu << (4 * (LAG - 1));
-        uint32_t d4 = 0;
         if (__any_sync(FULL, ((mwin | hmwin) & ROWS3) != 0u)) {  // (almost every row of a map has no marker pixel nearby)
             const uint32_t mc = (mwin >> (4 * LAG)) & 0xFu;
             uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
             const uint32_t hmc = (hmwin >> (4 * LAG)) & 0xFu;
             if (lane == 0) l = hmc;
             if (lane == 31) rr = hmc;
-            d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> (4 * (LAG + 1))) | (mwin >> (4 * (LAG - 1)))) & vm4;
+            const uint32_t d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> (4 * (LAG + 1))) | (mwin >> (4 * (LAG - 1)))) & vm4;
             // the four words of the bitmap: 8 lanes' nibbles each
             uint32_t v = d4 << (4 * (lane & 7));
             v |= __shfl_xor_sync(FULL, v, 1);
             v |= __shfl_xor_sync(FULL, v, 2);
             v |= __shfl_xor_sync(FULL, v, 4);
-            if (bits_lane) bits_p[jc & 31] = v;
-        } else if (bits_lane) bits_p[jc & 31] = 0u;
-        if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));  // lsd_p already points one row ahead of jn
+            if (bits_lane) *bits_p = v;
+            if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));  // lsd_p already points one row ahead
+        } else {
+            if (bits_lane) *bits_p = 0u;
+            if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, 0u);
+        }
+        bits_p += (jc & 31) == 31 ? 1u + bits_jump : 1u;
 
         if (!QUAD) return;
         const int jqc = jc - bqh;
-        if ((uint32_t)jqc >= (uint32_t)bqh) return;  // uniform
+        if (!FAST && (uint32_t)jqc >= (uint32_t)bqh) return;  // uniform
         const uint32_t eb = active ? (ewin >> (4 * LAG)) & 0xFu : 0u;
         if (__any_sync(FULL, eb != 0u)) {
             // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
@@ -256,49 +310,6 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         }
     };
 
-    // The common row: outside the OCR quadrant, rows jn and jn - 1 both owned.  Straight-line code: no row tests, the
-    // halo is ONE pixel (the 3x3 cross only looks one column out) read by every lane at a lane-dependent offset and
-    // kept by lanes 0 / 31 alone, the (L, L, L, 255) word is one IMAD of the biased luma word:
-    // 0x4B0000LL * 0x010101 + 0xB4000000 = 0xFFLLLLLL (mod 2^32).
-    const uint32_t hp_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : (uint32_t)(PX2_HALO - 1) * 4u;  // (lanes 1..30 read lane 0's word: a broadcast)
-    const uint32_t hp_bit = lane == 0 ? (hvm4 & 8u) : (lane == 31 ? (hvm4 & 1u) : 0u);  // where the halo pixel's flag goes in the nibble
-    auto row_fast = [&](uint32_t srow, int jn) {
-        const uint4 cur = lds_v4(srow + (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u);
-        uint32_t hp;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(srow + hp_off));
-        uint4 ui;
-        if (GRAY) {
-            ui.x = luma_biased_i2f(cur.x) * 0x010101u + 0xB4000000u; ui.y = luma_biased_i2f(cur.y) * 0x010101u + 0xB4000000u;
-            ui.z = luma_biased_i2f(cur.z) * 0x010101u + 0xB4000000u; ui.w = luma_biased_i2f(cur.w) * 0x010101u + 0xB4000000u;
-        } else {
-            ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
-            ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
-        }
-        if (active) stg_v4(ui_p, ui);
-        uint32_t m4 = 0, hm = 0;
-        if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut) & vm4;  // rare
-        if (bright_bytes(hp) && hp_bit) hm = (marker_nibble(make_uint4(hp, 0u, 0u, 0u), lut) & 1u) ? hp_bit : 0u;  // rarer
-        mwin = (mwin << 4) | m4;
-        hmwin = (hmwin << 4) | hm;
-        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
-        // phase 2: row jc = jn - 1 (rows jc - 1, jc, jc + 1 at nibbles 2, 1, 0)
-        uint32_t d4 = 0;
-        if (__any_sync(FULL, ((mwin | hmwin) & 0xFFFu) != 0u)) {
-            const uint32_t mc = (mwin >> 4) & 0xFu;
-            uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
-            const uint32_t hmc = (hmwin >> 4) & 0xFu;
-            if (lane == 0) l = hmc;
-            if (lane == 31) rr = hmc;
-            d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> 8) | mwin) & vm4;
-            uint32_t v = d4 << (4 * (lane & 7));
-            v |= __shfl_xor_sync(FULL, v, 1);
-            v |= __shfl_xor_sync(FULL, v, 2);
-            v |= __shfl_xor_sync(FULL, v, 4);
-            if (bits_lane) bits_p[(jn - 1) & 31] = v;
-        } else if (bits_lane) bits_p[(jn - 1) & 31] = 0u;
-        if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));
-    };
-
     // ---- main loop over the chunks of two rows ------------------------------------------------------------------
     uint32_t stage = 0, phase = 0;
 #pragma unroll 1
@@ -306,13 +317,15 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         mbar_wait(bars + 8u * stage, phase);
         const uint32_t sbase = ring + stage * PX2_STAGE_BYTES;
         const int jn = j_first + PX2_ROWS * c;
-        if (!QUAD && jn > r0 && jn + 1 < r1) {  // uniform: both rows owned, both with an owned row above
+        // both rows of the chunk and the rows LAG above them owned; in a QUAD item all of them rows of the quadrant
+        const bool fast = jn - LAG >= r0 && jn + 1 < r1 && (!QUAD || (jn - LAG >= bqh && jn + 1 < 2 * bqh));
+        if (fast) {
 #pragma unroll 1
-            for (int rr = 0; rr < PX2_ROWS; rr++) row_fast(sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+            for (int rr = 0; rr < PX2_ROWS; rr++) row(PxTag<true>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
         } else {
 #pragma unroll 1
             for (int rr = 0; rr < PX2_ROWS; rr++)
-                if (jn + rr < j_end) row(sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+                if (jn + rr < j_end) row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
         }
         __syncwarp();  // every lane has read the stage: it may be refilled
         if (lane == 0 && c + PX2_STAGES < n_chunks) {
@@ -321,8 +334,6 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         }
         if (++stage == PX2_STAGES) { stage = 0; phase ^= 1u; }
     }
-    // the rows of the window still to be dilated (phase 1 of rows >= j_end is idle): rows r1 - LAG .. r1 - 1 were
-    // handled by the loop itself because it runs to j_end = r1 + LAG
 }
 
 // Two launches per batch: the items that own pixels of the OCR quadrant (QUAD: three rows of halo, OCR classes, the

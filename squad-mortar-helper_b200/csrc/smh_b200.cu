@@ -399,13 +399,13 @@ int launch_pixels2(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t
     a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch; a.q_pad = P.qpad;
     a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
     a.red = P.red; a.open = P.open;
-    a.nbands = (a.h + 31u) / 32u; a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
+    a.nbands = (a.h + smh::PX2_BAND - 1u) / smh::PX2_BAND; a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
     a.lut = h->d_lut;
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
     // the items that own pixels of the OCR quadrant: strips [qs0, qs1) x bands [qb0, qb1)
     a.qs0 = (a.bqw + a.pad) / 128u; a.qs1 = (2u * a.bqw + a.pad + 127u) / 128u;
     if (a.qs1 > a.nstrips) a.qs1 = a.nstrips;
-    a.qb0 = a.bqh / 32u; a.qb1 = (2u * a.bqh + 31u) / 32u;
+    a.qb0 = a.bqh / smh::PX2_BAND; a.qb1 = (2u * a.bqh + smh::PX2_BAND - 1u) / smh::PX2_BAND;
     if (a.qb1 > a.nbands) a.qb1 = a.nbands;
     if (a.qs0 >= a.qs1 || a.qb0 >= a.qb1) { a.qs0 = a.qs1 = 0; a.qb0 = a.qb1 = 0; }
     // one warp per (frame, band, strip) item, plus one per frame for the button test; two launches (see k_pixels2)
