@@ -176,13 +176,14 @@ int32_t smh_b200_process(smh_b200 *h, const uint8_t *bgra, uint32_t W, uint32_t 
 
 /* A device image plane: pixel (i,j) of frame f lives at
  *   ptr + f*frame_stride + j*pitch + (i + pad)*bytes_per_pixel.
- * Rows are 16-byte aligned and `pad` (0..3 px) keeps the plane's 16-byte vector grid in phase
- * with the captured frame's, so the kernels move every plane with aligned 128-bit accesses. */
+ * Rows are 128-byte aligned and `pad` keeps the plane's 16-byte vector grid in phase with the captured frame's
+ * (a TMA box and a 128-bit vector must start on a 16-byte boundary of the capture); the quadrant planes are padded
+ * further so that a 128-column strip of the pixel pass starts on a 128-byte boundary in them too. */
 typedef struct {
     uint8_t *ptr;
     uint64_t frame_stride;
     uint32_t pitch;
-    uint32_t pad;
+    uint32_t pad;             /* left pad in pixels: 0..3 for the map planes, up to 127 for the quadrant planes */
     uint32_t width, height, bytes_per_pixel;
     uint32_t reserved;
 } smh_b200_plane;
@@ -193,7 +194,7 @@ typedef struct {
     smh_b200_plane ui_map;     /* RGBA8 w*h */
     smh_b200_plane lsd_image;  /* L8 w*h, dilated marker mask 0/255 */
     smh_b200_plane ocr_out;    /* L8 bqw*bqh */
-    smh_b200_plane scales;     /* L8 bqw*bqh (rows < start_y[f] untouched) */
+    smh_b200_plane scales;     /* L8 bqw*bqh; rows < start_y[f] are zero: every frame of a batch starts from a fresh buffer (D9) */
     float *lines;              /* device, [n][32][4] */
     uint32_t *n_lines;         /* device, [n] */
     uint32_t *red_pixels;      /* device, [n] */
@@ -253,6 +254,30 @@ int32_t smh_b200_process_host_batch(smh_b200 *h, const uint8_t *frames, uint32_t
                                     uint32_t max_gap, uint32_t flags, uint32_t chunk,
                                     const smh_b200_host_results *res);
 
+/* ---- several GPUs of one box -------------------------------------------------------------
+ * The reference is single-device (vision-gpu/src/cuda.rs:34, `Device::get_device(0)`); frames are independent, so a
+ * batch is split into contiguous frame ranges — GPU g of G takes frames [g*n/G, (g+1)*n/G) — each run by its own host
+ * thread on its own handle (context + streams) through smh_b200_process_host_batch.  No inter-GPU traffic, no
+ * collective; results land in `res` in the caller's frame order. */
+typedef struct smh_b200_multi smh_b200_multi;
+/* devices: n_dev CUDA device ordinals (a device may appear once). */
+int32_t smh_b200_multi_create(const int32_t *devices, uint32_t n_dev, smh_b200_multi **out);
+void smh_b200_multi_destroy(smh_b200_multi *m);
+const char *smh_b200_multi_last_error(smh_b200_multi *m);
+uint32_t smh_b200_multi_device_count(smh_b200_multi *m);
+/* the frame range GPU g of n_dev takes of a batch of n frames: [*first, *first + *count) */
+void smh_b200_shard_range(uint32_t n, uint32_t n_dev, uint32_t g, uint32_t *first, uint32_t *count);
+/* Same arguments and results as smh_b200_process_host_batch.  load_map_markers_rgba/n_markers/size: templates for
+ * SMH_BATCH_FILTER_ICONS (may be NULL / 0).  Returns the first non-zero code of any shard. */
+int32_t smh_b200_multi_process_host_batch(smh_b200_multi *m, const uint8_t *frames, uint32_t n, uint32_t W, uint32_t H,
+                                          uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
+                                          uint32_t max_gap, uint32_t flags, uint32_t chunk,
+                                          const smh_b200_host_results *res);
+/* smh_b200_load_map_markers on every device of the set */
+int32_t smh_b200_multi_load_map_markers(smh_b200_multi *m, const uint8_t *rgba, uint32_t n_markers, uint32_t size);
+/* per-device wall-clock seconds of the last smh_b200_multi_process_host_batch (host threads run concurrently) */
+int32_t smh_b200_multi_last_times(smh_b200_multi *m, double *seconds, uint32_t n);
+
 /* calc_meters_to_px_ratio for every frame of the last smh_b200_process_batch on this handle, reading its
  * device-resident `scales` planes.  scales: HOST [n][3], n_scales: HOST [n] (0..3 each); results land in
  * the HOST arrays ratio[n], found[n] after the call (it synchronises `stream`). */
@@ -268,6 +293,19 @@ int32_t smh_b200_stream_synchronize(smh_b200 *h, void *stream);
 
 /* number of kernel launches this handle has issued (bench.py's gpu_launches claim) */
 uint64_t smh_b200_launch_count(smh_b200 *h);
+
+/* Per-stage timing of the last frame through the trait calls — the reference's `Timeshares`
+ * (vision-common/src/debug.rs:3-29, filled by debug_waterfall! around every call, src/vision/mod.rs:54-64).
+ * Same eleven stages, same order.  host_ms[i]: wall-clock time of the stage's last call (what the reference records);
+ * device_ms[i]: CUDA-event time of the device work that call enqueued (kernels + copies; 0 where the stage has none —
+ * the fused pixel pass runs inside crop_to_map, so isolate_map_markers / mask_marker_lines cost nothing here).
+ * SMH_STAGE_OCR is the callback of smh_b200_process (Tesseract's place).  Either array may be NULL. */
+enum { SMH_STAGE_LOAD_FRAME = 0, SMH_STAGE_CROP_TO_MAP, SMH_STAGE_FIND_MINIMAP, SMH_STAGE_OCR_PREPROCESS, SMH_STAGE_OCR,
+       SMH_STAGE_FIND_SCALES_PREPROCESS, SMH_STAGE_CALC_METERS_TO_PX_RATIO, SMH_STAGE_ISOLATE_MAP_MARKERS,
+       SMH_STAGE_FILTER_MAP_MARKER_ICONS, SMH_STAGE_MASK_MARKER_LINES, SMH_STAGE_FIND_MARKER_LINES, SMH_STAGE_COUNT };
+int32_t smh_b200_timeshares(smh_b200 *h, float host_ms[SMH_STAGE_COUNT], float device_ms[SMH_STAGE_COUNT]);
+/* the stage's name as the reference spells it ("load_frame", ...); NULL when out of range */
+const char *smh_b200_stage_name(uint32_t stage);
 
 /* ---- synthetic captures; replaces src/capture.rs in the benchmarks ------- */
 typedef struct {

@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.smh_oracle_find_minimap_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     L.smh_oracle_find_minimap.argtypes = [vp, u32p]
     L.smh_oracle_gpuflavour_table_marker.argtypes = [vp]
+    L.smh_oracle_synth_frames.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.smh_oracle_gpuflavour_rays_in.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.smh_oracle_rays_in_dirs.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, vp, vp]
     L.smh_oracle_gpuflavour_dilate.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -367,4 +368,17 @@ def gpuflavour_table_marker() -> np.ndarray:
     """K8's marker predicate (vision-gpu's HSV formulas) over all 2^24 colours."""
     out = np.empty(1 << 24, np.uint8)
     lib().smh_oracle_gpuflavour_table_marker(out.ctypes.data)
+    return out
+
+
+def synth_frames(W: int, H: int, first: int, n: int, seed: int = 0x534D4800_00000000, n_segments: int = 8, n_blips: int = 12,
+                 n_labels: int = 2, map_open: bool = True, blip_band_pct: int = 100) -> np.ndarray:
+    """The benchmarks' synthetic captures (same generator as the product's rasterisers, byte-identical) without
+    loading the product library -> [n, H, W, 4] uint8 BGRA."""
+    class P(C.Structure):
+        _fields_ = [("seed", C.c_uint64)] + [(k, C.c_uint32) for k in ("W", "H", "n_segments", "n_blips", "n_labels", "map_open", "blip_band_pct", "reserved")]
+    p = P(seed, W, H, n_segments, n_blips, n_labels, 1 if map_open else 0, blip_band_pct, 0)
+    out = np.empty((n, H, W, 4), np.uint8)
+    if lib().smh_oracle_synth_frames(C.byref(p), first, n, out.ctypes.data) != 0:
+        raise ValueError("synth_frames: bad parameters")
     return out

@@ -16,6 +16,7 @@
 #endif
 
 #include "../include/smh_consts.h"
+#include "../squad-mortar-helper_b200/csrc/smh_synth.h"
 
 /* ---------------------------------------------------------------- Rust cast semantics */
 
@@ -987,4 +988,23 @@ int smh_oracle_gpuflavour_is_marker(uint8_t r8, uint8_t g8, uint8_t b8) {
 void smh_oracle_gpuflavour_table_marker(uint8_t *out) {
 #pragma omp parallel for schedule(static)
     for (uint32_t c = 0; c < (1u << 24); c++) out[c] = (uint8_t)smh_oracle_gpuflavour_is_marker((uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c);
+}
+
+/* ---------------------------------------------------------------- synthetic captures (bench workload) */
+int smh_oracle_synth_frames(const void *params, uint32_t first, uint32_t n, uint8_t *out) {
+    const smh_synth_params *p = (const smh_synth_params *)params;
+    uint32_t roi[12];
+    if (!p || !out || p->n_labels > SMH_SYNTH_MAX_LABELS || smh_oracle_roi(p->W, p->H, roi)) return -1;
+    smh_synth_segment *segs = (smh_synth_segment *)malloc(sizeof(smh_synth_segment) * (p->n_segments + 1));
+    smh_synth_blip *blips = (smh_synth_blip *)malloc(sizeof(smh_synth_blip) * (p->n_blips + 1));
+    for (uint32_t f = 0; f < n; f++) {
+        smh_synth_frame_desc d;
+        smh_synth_scene_frame(p, roi, first + f, &d, segs, blips);
+        uint32_t *dst = (uint32_t *)(out + (size_t)f * p->W * p->H * 4);
+#pragma omp parallel for schedule(static)
+        for (uint32_t y = 0; y < p->H; y++)
+            for (uint32_t x = 0; x < p->W; x++) dst[(size_t)y * p->W + x] = smh_synth_pixel(&d, segs, blips, (int32_t)x, (int32_t)y);
+    }
+    free(segs); free(blips);
+    return 0;
 }

@@ -137,6 +137,11 @@ int smh_oracle_process_frame(smh_oracle *o, const uint8_t *bgra, uint32_t W, uin
                              float lines[32][4], uint32_t *n_lines);
 
 
+/* Synthetic captures of the benchmarks (the generator of SURVEY.md 8(d), squad-mortar-helper_b200/csrc/smh_synth.h, shared
+ * with the product's rasterisers and byte-identical to them): frames [first, first + n) -> host BGRA, tightly packed.
+ * params = {seed(u64), W, H, n_segments, n_blips, n_labels, map_open, blip_band_pct, reserved} (u32 each). */
+int smh_oracle_synth_frames(const void *params, uint32_t first, uint32_t n, uint8_t *out);
+
 /* ---- `vision-gpu` flavour: the reference's CUDA kernels restated on the CPU ------------------------
  * vision-cpu and vision-gpu are two implementations of one specification by one author that differ in
  * documented details.  vision-cpu cannot be built here (no Rust toolchain) but vision-gpu's

@@ -25,7 +25,12 @@ SYMBOLS = [
     "smh_b200_synth_frames_host", "smh_b200_synth_frames_device", "smh_b200_colour_table",
     "smh_b200_find_minimap", "smh_b200_calc_meters_to_px_ratio", "smh_b200_process", "smh_b200_batch_meters_to_px_ratio",
     "smh_b200_load_map_markers", "smh_b200_filter_map_marker_icons",
+    "smh_b200_timeshares", "smh_b200_stage_name", "smh_b200_shard_range",
+    "smh_b200_multi_create", "smh_b200_multi_destroy", "smh_b200_multi_last_error", "smh_b200_multi_device_count",
+    "smh_b200_multi_process_host_batch", "smh_b200_multi_load_map_markers", "smh_b200_multi_last_times",
 ]
+STAGES = ["load_frame", "crop_to_map", "find_minimap", "ocr_preprocess", "ocr", "find_scales_preprocess", "calc_meters_to_px_ratio",
+          "isolate_map_markers", "filter_map_marker_icons", "mask_marker_lines", "find_marker_lines"]
 
 
 class Plane(C.Structure):
@@ -120,6 +125,16 @@ def lib() -> C.CDLL:
         "smh_b200_batch_meters_to_px_ratio": (i32, [vp, vp, vp, u32, vp, vp, vp]),
         "smh_b200_load_map_markers": (i32, [vp, vp, u32, u32]),
         "smh_b200_filter_map_marker_icons": (i32, [vp, P(i32), P(u32), P(u32)]),
+        "smh_b200_timeshares": (i32, [vp, P(f32), P(f32)]),
+        "smh_b200_stage_name": (C.c_char_p, [u32]),
+        "smh_b200_shard_range": (None, [u32, u32, u32, P(u32), P(u32)]),
+        "smh_b200_multi_create": (i32, [P(i32), u32, P(vp)]),
+        "smh_b200_multi_destroy": (None, [vp]),
+        "smh_b200_multi_last_error": (C.c_char_p, [vp]),
+        "smh_b200_multi_device_count": (u32, [vp]),
+        "smh_b200_multi_process_host_batch": (i32, [vp, vp, u32, u32, u32, u32, u64, vp, u32, u32, u32, P(HostResults)]),
+        "smh_b200_multi_load_map_markers": (i32, [vp, vp, u32, u32]),
+        "smh_b200_multi_last_times": (i32, [vp, P(C.c_double), u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

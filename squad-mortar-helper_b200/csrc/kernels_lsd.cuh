@@ -29,6 +29,13 @@ constexpr int L2_GRP_CAP = 1024;   // white quarters of a seed's window over all
 constexpr int L2_WIN_T = 6;        // window tiles per axis: ceil((2 * (70 + 3) + 1 + 31) / 32)
 constexpr int L2_WIN_PITCH = 7;    // words per window row (odd: lane = row stores are conflict-free)
 constexpr int L2_DEAD = 16;
+// Rays of a 32-ray group that keep it marching one ray per lane beyond the window, on the global bitmap.  Measured on
+// B200 (1024 dense 1440p frames, profiles/r3w_sweep2.txt): 10 -> 3.96 ms, 16 -> 3.83, 24 -> 3.73, never (33) -> 3.47: the
+// scattered bitmap loads of 32 diverging rays cost more than the ray-per-warp blocks they save, so it is off.
+#ifndef L2_LANES_MIN_N
+#define L2_LANES_MIN_N 33
+#endif
+constexpr int L2_LANES_MIN = L2_LANES_MIN_N;
 
 enum { L2_JOB_SEED = 0, L2_JOB_ROW_DONE = 1 };
 
@@ -38,7 +45,7 @@ struct Lsd2Shared {
     float4 dead[L2_DEAD];  // (x, y, rho^2, raw^2)
     uint32_t ring[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
     uint32_t grp[NW][L2_GRP_CAP / NW];  // m8 | (x offset of the quarter's first column + 160) << 8 | (row offset + 128) << 17
-    uint32_t surv[L2_SURV_CAP];         // k | gap << 16
+    uint32_t surv[L2_SURV_CAP];         // l2_pack(ray, gap, next block)
     uint32_t win[L2_WIN_T * 32 * L2_WIN_PITCH];
     unsigned long long bkey[NW];
     float2 bend[NW];
@@ -106,17 +113,17 @@ __device__ __forceinline__ void l2_mark(uint32_t* bits, int lo, int hi) {
     }
 }
 
-// First `limit` samples (a multiple of 8) of one ray per LANE, read from the seed's window (all of them lie inside
-// it).  Returns 0: still marching (gap = current run of non-white samples), 1: stopped on a gap that began at
-// (gx, gy), 2: (gx, gy) is the first sample outside the image.  Same arithmetic as march_fast (kernels.cuh);
-// a batch of 8 white samples — the body of a marker line — skips the automaton.
-template <bool STATS>
-__device__ __forceinline__ int l2_march_window(const Win2& wv, int limit, float px, float py, int gap_limit, float dx, float dy,
-                                               float& gx, float& gy, int& gap, uint32_t& steps) {
-    float x = px, y = py, xo = 0.0f, yo = 0.0f;
-    gx = px; gy = py; gap = 0;
+// `nsteps` more samples (a multiple of 8) of one ray per LANE, continuing from the accumulated offsets (xo, yo) and the
+// gap state (gap, gx, gy); read from the seed's window (IMG = Win2: all of them lie inside it) or from the bitmap
+// (IMG = Bits).  Returns 0: still marching (gap = current run of non-white samples), 1: stopped on a gap that began
+// at (gx, gy), 2: (gx, gy) is the first sample outside the image.  Same arithmetic as march_fast (kernels.cuh); a
+// batch of 8 white samples — the body of a marker line — skips the automaton.
+template <bool STATS, typename IMG>
+__device__ __forceinline__ int l2_march_lanes(const IMG& wv, int nsteps, float px, float py, int gap_limit, float dx, float dy,
+                                              float& xo, float& yo, float& gx, float& gy, int& gap, uint32_t& steps) {
+    float x = __fadd_rn(xo, px), y = __fadd_rn(yo, py);
     int state = 0;
-    for (int n0 = 0; n0 < limit && state == 0; n0 += 8) {
+    for (int n0 = 0; n0 < nsteps && state == 0; n0 += 8) {
         float xs[8], ys[8];
         uint32_t wh = 0, inb = 0;  // bit u: sample u is white / inside the image
 #pragma unroll
@@ -153,14 +160,17 @@ __device__ __forceinline__ int l2_march_window(const Win2& wv, int limit, float 
 
 struct L2Best { unsigned long long key; float ex, ey; };
 
-// One ray per WARP from block c0 on (samples 32 c0 ..) on the global bitmap; folds the result into `best`
+// A ray handed over from the lane-per-ray march: ray index | current gap << 12 | next block (32 samples) << 18
+__device__ __forceinline__ uint32_t l2_pack(int k, int gap, int c) { return (uint32_t)k | ((uint32_t)gap << 12) | ((uint32_t)c << 18); }
+
+// One ray per WARP from its block on (samples 32 c ..) on the global bitmap; folds the result into `best`
 // (the same value in every lane).
 template <bool STATS>
-__device__ __forceinline__ void l2_march_long(const Bits& im, const LsdArgs& a, int c0, uint32_t e, float px, float py, L2Best& best,
+__device__ __forceinline__ void l2_march_long(const Bits& im, const LsdArgs& a, uint32_t e, float px, float py, L2Best& best,
                                               uint32_t& steps_u) {
     const int lane = threadIdx.x & 31, sub = lane & (LSD_CKPT - 1);
-    const int k2 = (int)(e & 0xFFFFu);
-    uint32_t gap_in = e >> 16;
+    const int k2 = (int)(e & 0xFFFu), c0 = (int)(e >> 18);
+    uint32_t gap_in = (e >> 12) & 0x3Fu;
     const float2 d = __ldg(&a.rays[k2]);
     const float2* cp = a.ckpt + (uint64_t)k2 * a.n_ckpt + (lane / LSD_CKPT) + c0 * (32 / LSD_CKPT);
     float2 c1 = __ldg(cp);
@@ -439,38 +449,50 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                     const uint32_t v = __shfl_sync(FULL, vmine, wl);
                     if (v == 0u) continue;
                     any_ray = true;
-                    bool alive = false;
-                    int k = w * 32 + lane, gap = 0;
-                    if ((v >> lane) & 1u) {
-                        const float2 d = __ldg(&a.rays[k]);
-                        float gx, gy;
-                        const int state = win_steps > 0 ? l2_march_window<STATS>(wv, win_steps, px, py, a.gap_limit, d.x, d.y, gx, gy, gap, steps) : 0;
-                        if (state == 0) alive = true;
-                        else {
-                            float ex, ey, len;
-                            if (state == 1) {  // the gap's first sample is inside the image and not white: lib.rs:426-429 holds
-                                ex = __fsub_rn(gx, d.x); ey = __fsub_rn(gy, d.y);
-                                const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
-                                len = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-                            } else len = ray_finish(im, gx, gy, px, py, d.x, d.y, ex, ey);
-                            const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k;
-                            if (key >= best.key) { best.key = key; best.ex = ex; best.ey = ey; }
-                        }
+                    // lane = ray: the window's samples first, then 32 samples at a time on the bitmap while enough rays of the
+                    // group live (a lane-per-ray step costs ~18 instructions per group, a ray-per-warp step ~2 per ray)
+                    const int k = w * 32 + lane;
+                    bool alive = ((v >> lane) & 1u) != 0u;
+                    int gap = 0, c = c0;
+                    float xo = 0.0f, yo = 0.0f, gx = px, gy = py;
+                    float2 d = make_float2(0.0f, 0.0f);
+                    if (alive) d = __ldg(&a.rays[k]);
+                    auto finish = [&](int state) {  // the ray ended: its end point and length into the lane's best
+                        float ex, ey, len;
+                        if (state == 1) {  // the gap's first sample is inside the image and not white: lib.rs:426-429 holds
+                            ex = __fsub_rn(gx, d.x); ey = __fsub_rn(gy, d.y);
+                            const float ddx = __fsub_rn(px, ex), ddy = __fsub_rn(py, ey);
+                            len = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                        } else len = ray_finish(im, gx, gy, px, py, d.x, d.y, ex, ey);
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(len) << 32) | (uint32_t)k;
+                        if (key >= best.key) { best.key = key; best.ex = ex; best.ey = ey; }
+                    };
+                    if (alive && win_steps > 0) {
+                        const int state = l2_march_lanes<STATS>(wv, win_steps, px, py, a.gap_limit, d.x, d.y, xo, yo, gx, gy, gap, steps);
+                        if (state) { finish(state); alive = false; }
                     }
-                    const uint32_t am = __ballot_sync(FULL, alive);
+                    uint32_t am = __ballot_sync(FULL, alive);
+                    while (win_steps > 0 && __popc(am) >= L2_LANES_MIN) {
+                        if (alive) {
+                            const int state = l2_march_lanes<STATS>(im, 32, px, py, a.gap_limit, d.x, d.y, xo, yo, gx, gy, gap, steps);
+                            if (state) { finish(state); alive = false; }
+                        }
+                        c++;
+                        am = __ballot_sync(FULL, alive);
+                    }
                     if (am) {  // survivors continue one ray per warp: through the shared list, so that all warps share them
                         uint32_t slot = 0;
                         if (lane == 0) slot = atomicAdd(&sh.n_surv, (uint32_t)__popc(am));
                         slot = __shfl_sync(FULL, slot, 0);
                         const uint32_t mine = slot + (uint32_t)__popc(am & LT);
                         const bool fits = slot + (uint32_t)__popc(am) <= (uint32_t)L2_SURV_CAP;  // uniform
-                        if (fits) { if (alive) sh.surv[mine] = (uint32_t)k | ((uint32_t)gap << 16); }
+                        if (fits) { if (alive) sh.surv[mine] = l2_pack(k, gap, c); }
                         else {
                             if (lane == 0 && slot <= (uint32_t)L2_SURV_CAP) sh.surv_end = slot;  // the list is whole up to here
                             for (uint32_t todo = am; todo; todo &= todo - 1u) {  // list full: march them here and now
                                 const int sl = __ffs(todo) - 1;
-                                const uint32_t e = __shfl_sync(FULL, (uint32_t)k | ((uint32_t)gap << 16), sl);
-                                l2_march_long<STATS>(im, a, c0, e, px, py, best, steps_u);
+                                const uint32_t e = __shfl_sync(FULL, l2_pack(k, gap, c), sl);
+                                l2_march_long<STATS>(im, a, e, px, py, best, steps_u);
                             }
                         }
                     }
@@ -505,7 +527,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                 // ---- survivors: one ray per warp, shared over the warps -----------------------------------
                 {
                     const uint32_t ns = min(sh.n_surv, sh.surv_end);
-                    for (uint32_t j = warp; j < ns; j += NW) l2_march_long<STATS>(im, a, c0, sh.surv[j], px, py, best, steps_u);
+                    for (uint32_t j = warp; j < ns; j += NW) l2_march_long<STATS>(im, a, sh.surv[j], px, py, best, steps_u);
                 }
                 // warp argmax of (len, k): the LAST index among the longest rays (D6)
                 {

@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                  :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0u;
+}
+
 // nibble -> 4 bytes of 0/255
 __device__ __forceinline__ uint32_t nibble_bytes(uint32_t d4) { return ((d4 * 0x00204081u) & 0x01010101u) * 255u; }
 
@@ -157,8 +164,8 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
     uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo
 
-    // ---- prologue: the first PX2_STAGES chunks are requested ------------------------------------------------
-    if (lane == 0) {
+    // ---- prologue: the first PX2_STAGES chunks are requested (every operand of the copy is warp-uniform) --------
+    if (elect_one()) {
 #pragma unroll
         for (int c = 0; c < PX2_STAGES; c++) {
             if (c < n_chunks) {
@@ -179,56 +186,64 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
             const bool owned = FAST || (jn >= r0 && jn < r1);
             const int jq = jn - bqh;
             if (QUAD && (FAST || (uint32_t)jq < (uint32_t)bqh)) {  // uniform: a row of the OCR quadrant
-                // Two levels.  Almost every row of a map has neither a bright near-grey pixel (OCR classes), nor a pixel of
-                // luma 0 (scales), nor a marker-bright one in the strip or its halo: then the row is luma + constant stores.
+                // Every lane tests its own vector's OR against the cheap necessary conditions (a marker colour has a channel
+                // >= 178; both OCR classes need every channel >= 130, i.e. bit 7 of all three bytes; scales needs a pixel of
+                // luma 0) and classifies pixel by pixel only then: almost every vector of a map passes straight through.
                 // The halo vector is read by every lane (lanes 1..30 read lane 0's: a broadcast) and kept by lanes 0 / 31.
                 const uint4 hv = lds_v4(srow + h_off);
-                const uint32_t any = or4(cur), hany = (edge && hvm4) ? or4(hv) : 0u;
-                uint32_t lb0 = 0, lb1 = 0, lb2 = 0, lb3 = 0;
-                bool rare = !owned || bright_bytes(any | hany) != 0u || (hany & 0x00808080u) == 0x00808080u;
-                if (owned) {
-                    lb0 = luma_biased_i2f(cur.x); lb1 = luma_biased_i2f(cur.y); lb2 = luma_biased_i2f(cur.z); lb3 = luma_biased_i2f(cur.w);
-                    if (col_brq) rare = rare || (any & 0x00808080u) == 0x00808080u || min(min(lb0, lb1), min(lb2, lb3)) == BIAS;
-                }
-                if (!__any_sync(FULL, rare)) {
-                    if (active) {
-                        uint4 ui;
-                        if (GRAY) {
-                            ui.x = lb0 * 0x010101u + 0xB4000000u; ui.y = lb1 * 0x010101u + 0xB4000000u;
-                            ui.z = lb2 * 0x010101u + 0xB4000000u; ui.w = lb3 * 0x010101u + 0xB4000000u;
-                        } else {
-                            ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
-                            ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
+                const uint32_t any = or4(cur);
+                uint32_t lb[4] = {BIAS + 1u, BIAS + 1u, BIAS + 1u, BIAS + 1u};  // biased luma words 0x4B0000LL (owned rows)
+                if (owned) { lb[0] = luma_biased_i2f(cur.x); lb[1] = luma_biased_i2f(cur.y); lb[2] = luma_biased_i2f(cur.z); lb[3] = luma_biased_i2f(cur.w); }
+                uint32_t ocrw = 0xFFFFFFFFu, scw = 0xFFFFFFFFu;
+                if (bright_bytes(any)) m4 = marker_nibble(cur, lut);  // rare
+                if (col_brq) {
+                    const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
+                    if ((any & 0x00808080u) == 0x00808080u) {  // rare: possibly a bright near-grey pixel (vision-cpu/src/lib.rs:39-53,188-193)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
+                            const uint32_t mx = max(cr, max(cg, cb)), mn = min(cr, min(cg, cb));
+                            if (mx == mn && mn >= SMH_OCR_BRIGHT) {
+                                c4 |= 1u << e;
+                                ocrw ^= (lb[e] & 0xFFu) << (8 * e);  // 255 - luma
+                            } else if (4u * (mx - mn) <= SMH_OCR_MONO_EDGE && mn >= SMH_OCR_BRIGHT_EDGE) e4 |= 1u << e;
                         }
-                        stg_v4(ui_p, ui);
-                        if (col_brq) {
-                            stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), 0xFFFFFFFFu);
-                            if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), 0xFFFFFFFFu);
-                        }
+                        c4 = jq <= bqh - SMH_OCR_RADIUS ? c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
+                        e4 &= em4;
                     }
-                } else {
+                    if (min(min(lb[0], lb[1]), min(lb[2], lb[3])) == BIAS) {  // rare: a pixel with luma 0
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            if (lb[e] == BIAS) scw &= ~(0xFFu << (8 * e));
+                    }
+                }
+                if (owned && active) {
+                    uint4 ui;
+                    if (GRAY) {
+                        ui.x = lb[0] * 0x010101u + 0xB4000000u; ui.y = lb[1] * 0x010101u + 0xB4000000u;
+                        ui.z = lb[2] * 0x010101u + 0xB4000000u; ui.w = lb[3] * 0x010101u + 0xB4000000u;
+                    } else {
+                        ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
+                        ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
+                    }
+                    stg_v4(ui_p, ui);
                     if (col_brq) {
-                        PxOut o;
-                        vec_quadrant<GRAY>(cur, owned, lut, alpha, o);
-                        c4 = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & cm4 : 0u;  // rows above the vertical clip only (D10)
-                        e4 = o.e4 & em4;
-                        m4 = o.m4;
-                        if (owned && active) {
-                            stg_v4(ui_p, o.ui);
-                            stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), o.ocrw);
-                            if ((uint32_t)jq >= start_y) stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), o.scw);
+                        stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), ocrw);
+                        stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), (uint32_t)jq >= start_y ? scw : 0u);  // rows above start_y: zero (D9, a fresh buffer)
+                    }
+                }
+                if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
+                    const uint32_t hany = or4(hv);
+                    if (bright_bytes(hany)) hm = marker_nibble(hv, lut) & hvm4;
+                    if ((hany & 0x00808080u) == 0x00808080u && jq <= bqh - SMH_OCR_RADIUS) {
+                        const uint32_t wd[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
+                            const uint32_t mx = max(cr, max(cg, cb)), mn = min(cr, min(cg, cb));
+                            if (mx == mn && mn >= SMH_OCR_BRIGHT) hc |= 1u << e;
                         }
-                    } else if (owned) {
-                        PxOut o;
-                        vec_plain<GRAY>(cur, lut, alpha, o);
-                        m4 = o.m4;
-                        if (active) stg_v4(ui_p, o.ui);
-                    } else m4 = vec_marker_only(cur, lut);
-                    if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
-                        PxOut o;
-                        vec_quadrant<GRAY>(hv, false, lut, alpha, o);
-                        hm = o.m4 & hvm4;
-                        hc = jq <= bqh - SMH_OCR_RADIUS ? o.c4 & hcm4 : 0u;
+                        hc &= hcm4;
                     }
                 }
             } else {
@@ -328,7 +343,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 if (jn + rr < j_end) row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
         }
         __syncwarp();  // every lane has read the stage: it may be refilled
-        if (lane == 0 && c + PX2_STAGES < n_chunks) {
+        if (c + PX2_STAGES < n_chunks && elect_one()) {
             mbar_expect_tx(bars + 8u * stage, PX2_ROWS * PX2_ROW_BYTES);
             tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * (c + PX2_STAGES), (int)f, bars + 8u * stage);
         }

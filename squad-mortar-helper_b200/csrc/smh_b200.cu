@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -172,6 +173,10 @@ struct smh_b200 {
     std::mutex err_mu;
     std::string err;
     std::atomic<uint64_t> launches{0};
+    // Timeshares (vision-common/src/debug.rs:3-29): per stage the wall-clock of its last call and the device time of what it enqueued
+    float stage_host_ms[SMH_STAGE_COUNT] = {0};
+    float stage_dev_ms[SMH_STAGE_COUNT] = {0};
+    cudaEvent_t stage_ev[SMH_STAGE_COUNT][2] = {};
     float2* d_rays = nullptr;  // 3600 (cos, sin)
     float2* d_ckpt = nullptr;  // accumulated ray offsets every LSD_CKPT steps, [3600][n_ckpt]
     uint32_t n_ckpt = 0;
@@ -234,6 +239,25 @@ int fail(smh_b200* h, int code, const char* fmt, ...) {
         if (e__ != cudaSuccess)                                                             \
             return fail(h, (int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
+
+// One trait call = one stage of the reference's Timeshares: wall-clock over the scope, CUDA events around the
+// device work (begin() / end() on the stream it is enqueued on; every trait call synchronises that stream itself).
+struct StageTimer {
+    smh_b200* h; int stage; std::chrono::steady_clock::time_point t0; cudaStream_t st = nullptr; bool open = false;
+    StageTimer(smh_b200* h_, int stage_) : h(h_), stage(stage_), t0(std::chrono::steady_clock::now()) { if (h) h->stage_dev_ms[stage] = 0.0f; }
+    void begin(cudaStream_t s) { if (h && h->stage_ev[stage][0]) { st = s; open = cudaEventRecord(h->stage_ev[stage][0], s) == cudaSuccess; } }
+    void end() {  // after the caller synchronised `st`
+        if (open && cudaEventRecord(h->stage_ev[stage][1], st) == cudaSuccess && cudaEventSynchronize(h->stage_ev[stage][1]) == cudaSuccess) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, h->stage_ev[stage][0], h->stage_ev[stage][1]) == cudaSuccess) h->stage_dev_ms[stage] = ms;
+        }
+        open = false;
+    }
+    ~StageTimer() {
+        if (open) end();
+        if (h) h->stage_host_ms[stage] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint32_t height, uint32_t bpp, uint32_t pad) {
     p->width = width; p->height = height; p->bytes_per_pixel = bpp; p->pad = pad;
@@ -570,6 +594,9 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
         }
         int nb = 0;
         CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd2<NW, false>, NW * 32, dyn));
+        // tuning knob: cap the persistent CTAs per SM (fewer CTAs than frames = the faster CTAs take more frames)
+        static const int cap = [] { const char* e = getenv("SMH_B200_LSD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+        if (cap >= 1 && nb > cap) nb = cap;
         const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
         const uint32_t grid = n < resident ? n : resident;
         if (stats) smh::k_lsd2<NW, true><<<grid, NW * 32, dyn, st>>>(a);
@@ -694,8 +721,25 @@ extern "C" {
 
 const char* smh_b200_last_error(smh_b200* h) {
     if (!h) return g_create_error.c_str();
+    // a copy per calling thread: the two branches of a frame may fail concurrently on one handle
+    thread_local std::string copy;
     std::lock_guard<std::mutex> g(h->err_mu);
-    return h->err.c_str();
+    copy = h->err;
+    return copy.c_str();
+}
+
+const char* smh_b200_stage_name(uint32_t stage) {
+    static const char* const names[SMH_STAGE_COUNT] = {"load_frame", "crop_to_map", "find_minimap", "ocr_preprocess", "ocr",
+        "find_scales_preprocess", "calc_meters_to_px_ratio", "isolate_map_markers", "filter_map_marker_icons", "mask_marker_lines",
+        "find_marker_lines"};
+    return stage < SMH_STAGE_COUNT ? names[stage] : nullptr;
+}
+
+int32_t smh_b200_timeshares(smh_b200* h, float host_ms[SMH_STAGE_COUNT], float device_ms[SMH_STAGE_COUNT]) {
+    if (!h) return SMH_E_ARG;
+    if (host_ms) memcpy(host_ms, h->stage_host_ms, sizeof h->stage_host_ms);
+    if (device_ms) memcpy(device_ms, h->stage_dev_ms, sizeof h->stage_dev_ms);
+    return SMH_OK;
 }
 
 int32_t smh_b200_roi(uint32_t W, uint32_t H, uint32_t roi[12]) {
@@ -731,7 +775,7 @@ int32_t smh_b200_create(int32_t device, smh_b200** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) {
+    if (prop.major != 10 || prop.minor != 0) {
         fail(nullptr, SMH_E_NOGPU, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
         delete h;
         return SMH_E_NOGPU;
@@ -740,6 +784,8 @@ int32_t smh_b200_create(int32_t device, smh_b200** out) {
     CUC(cudaStreamCreateWithFlags(&h->s_markers, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&h->s_scales, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&h->ev_pixels, cudaEventDisableTiming));
+    for (int s = 0; s < SMH_STAGE_COUNT; s++)
+        for (int k = 0; k < 2; k++) CUC(cudaEventCreate(&h->stage_ev[s][k]));
     // ray directions: theta_k = (k as f32 / 10.0).to_radians(); (cos, sin) from the host libm so
     // that they are the bits vision-cpu computes (vision-cpu/src/lib.rs:398-399,437; D11)
     std::vector<float2> rays(SMH_LSD_RAYS);
@@ -787,6 +833,7 @@ void smh_b200_destroy(smh_b200* h) {
     if (h->s_markers) cudaStreamDestroy(h->s_markers);
     if (h->s_scales) cudaStreamDestroy(h->s_scales);
     if (h->ev_pixels) cudaEventDestroy(h->ev_pixels);
+    for (auto& pair : h->stage_ev) for (auto e : pair) if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -814,6 +861,7 @@ int32_t smh_b200_debug_lsd_profile(smh_b200* h, uint64_t out[16], int32_t reset)
 
 int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t H, uint32_t pitch_bytes) {
     if (!h || !bgra || pitch_bytes < W * 4u) return fail(h, SMH_E_ARG, "load_frame: bad argument");
+    StageTimer tm(h, SMH_STAGE_LOAD_FRAME);
     CU(h, cudaSetDevice(h->device));
     if (!h->have_frame || h->geo.W != W || h->geo.H != H) {
         // resolution change: rebuild every per-resolution buffer (vision-cpu/src/lib.rs:70-88,
@@ -843,9 +891,11 @@ int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32
         CU(h, cudaMemset(h->d_scales_keep, 0, nq));
     }
     const Geometry& g = h->geo;
+    tm.begin(h->s_main);
     CU(h, cudaMemcpy2DAsync(h->d_frame, h->upitch, bgra + (size_t)h->uy0 * pitch_bytes + (size_t)h->ux0 * 4u, pitch_bytes,
                             (size_t)(g.W - h->ux0) * 4u, h->uy1 - h->uy0, cudaMemcpyHostToDevice, h->s_main));
     CU(h, cudaStreamSynchronize(h->s_main));  // the caller may drop the frame now
+    tm.end();
     h->have_frame = true; h->cropped = false; h->map_open = false;
     h->ocr_fetched = h->lsd_fetched = false;
     return SMH_OK;
@@ -854,8 +904,10 @@ int32_t smh_b200_load_frame(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32
 int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, uint32_t xywh[4], const uint8_t** ui_map_rgba) {
     if (!h || !map_open) return fail(h, SMH_E_ARG, "crop_to_map: bad argument");
     if (!h->have_frame) return fail(h, SMH_E_STATE, "crop_to_map before load_frame");
+    StageTimer tm(h, SMH_STAGE_CROP_TO_MAP);
     CU(h, cudaSetDevice(h->device));
     const Geometry& g = h->geo;
+    tm.begin(h->s_main);
     // the fresh thresholded scales image goes to a scratch plane; find_scales_preprocess merges
     // rows >= start_y into the persistent host image, so pass start_y = 0 here
     int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->uy1 - h->uy0, h->ux0, h->uy0, 1, false, 0, grayscale,
@@ -867,6 +919,7 @@ int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, 
     CU(h, cudaMemcpyAsync(h_red + 1, h->one.open, 1, cudaMemcpyDeviceToHost, h->s_main));
     if ((rc = download_plane(h, &h->one.ui, 0, 1, h->h_ui, h->s_main))) return rc;
     CU(h, cudaStreamSynchronize(h->s_main));
+    tm.end();
     h->red_pixels = h_red[0];
     h->map_open = (reinterpret_cast<uint8_t*>(h_red + 1))[0] != 0;
     h->grayscale = grayscale;
@@ -895,11 +948,14 @@ int32_t smh_b200_ocr_preprocess(smh_b200* h, const uint8_t** out, size_t* len) {
     int rc = need_open_map(h, "ocr_preprocess");
     if (rc) return rc;
     std::lock_guard<std::mutex> g(h->scales_mu);
+    StageTimer tm(h, SMH_STAGE_OCR_PREPROCESS);
     CU(h, cudaSetDevice(h->device));
     if (!h->ocr_fetched) {
         CU(h, cudaStreamWaitEvent(h->s_scales, h->ev_pixels, 0));
+        tm.begin(h->s_scales);
         if ((rc = download_plane(h, &h->one.ocr, 0, 1, h->h_ocr, h->s_scales))) return rc;
         CU(h, cudaStreamSynchronize(h->s_scales));
+        tm.end();
         h->ocr_fetched = true;
     }
     if (out) *out = h->h_ocr;
@@ -913,16 +969,19 @@ int32_t smh_b200_find_scales_preprocess(smh_b200* h, uint32_t start_y, const uin
     const uint32_t qw = h->geo.brq[2], qh = h->geo.brq[3];
     if (start_y > qh) return fail(h, SMH_E_RANGE, "find_scales_preprocess: scales_start_y %u > height %u", start_y, qh);
     std::lock_guard<std::mutex> g(h->scales_mu);
+    StageTimer tm(h, SMH_STAGE_FIND_SCALES_PREPROCESS);
     CU(h, cudaSetDevice(h->device));
     if (start_y < qh) {
         // rows >= start_y come from this frame; rows above keep the previous content (D9)
         const smh_b200_plane& p = h->one.scales;
         CU(h, cudaStreamWaitEvent(h->s_scales, h->ev_pixels, 0));
+        tm.begin(h->s_scales);
         CU(h, cudaMemcpy2DAsync(h->h_scales + (size_t)start_y * qw, qw, p.ptr + (size_t)start_y * p.pitch + p.pad, p.pitch,
                                 qw, qh - start_y, cudaMemcpyDeviceToHost, h->s_scales));
         CU(h, cudaMemcpy2DAsync(h->d_scales_keep + (size_t)start_y * qw, qw, p.ptr + (size_t)start_y * p.pitch + p.pad, p.pitch,
                                 qw, qh - start_y, cudaMemcpyDeviceToDevice, h->s_scales));
         CU(h, cudaStreamSynchronize(h->s_scales));
+        tm.end();
     }
     if (out) *out = h->h_scales;
     if (wh) { wh[0] = qw; wh[1] = qh; }
@@ -932,6 +991,7 @@ int32_t smh_b200_find_scales_preprocess(smh_b200* h, uint32_t start_y, const uin
 int32_t smh_b200_isolate_map_markers(smh_b200* h) {
     int rc = need_open_map(h, "isolate_map_markers");
     if (rc) return rc;
+    StageTimer tm(h, SMH_STAGE_ISOLATE_MAP_MARKERS);
     // the marker predicate was evaluated inside the fused pixel pass; nothing left to launch
     return SMH_OK;
 }
@@ -978,8 +1038,10 @@ int32_t smh_b200_filter_map_marker_icons(smh_b200* h, int32_t* found, uint32_t x
     std::lock_guard<std::mutex> g(h->markers_mu);
     if (!h->d_icons) return fail(h, SMH_E_STATE, "filter_map_marker_icons before load_map_markers");
     if (h->icons_applied) return fail(h, SMH_E_STATE, "filter_map_marker_icons: already applied to this frame");
+    StageTimer tm(h, SMH_STAGE_FILTER_MAP_MARKER_ICONS);
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    tm.begin(h->s_markers);
     if ((rc = launch_pack(h, h->one, 1, h->s_markers))) return rc;
     if ((rc = launch_icons(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, h->s_markers))) return rc;
     uint32_t* hs = reinterpret_cast<uint32_t*>(h->h_small + 248);  // (the scales branch owns 216..243)
@@ -987,6 +1049,7 @@ int32_t smh_b200_filter_map_marker_icons(smh_b200* h, int32_t* found, uint32_t x
     CU(h, cudaMemcpyAsync(hs + 2, h->one.icon_sad, 4, cudaMemcpyDeviceToHost, h->s_markers));
     CU(h, cudaMemcpyAsync(hs + 3, h->one.icon_found, 1, cudaMemcpyDeviceToHost, h->s_markers));
     CU(h, cudaStreamSynchronize(h->s_markers));
+    tm.end();
     h->icons_applied = true; h->lsd_fetched = false;
     h->icon_found = reinterpret_cast<uint8_t*>(hs + 3)[0] ? 1 : 0;
     h->icon_xy[0] = hs[0]; h->icon_xy[1] = hs[1];
@@ -1000,6 +1063,7 @@ int32_t smh_b200_mask_marker_lines(smh_b200* h) {
     int rc = need_open_map(h, "mask_marker_lines");
     if (rc) return rc;
     std::lock_guard<std::mutex> g(h->markers_mu);
+    StageTimer tm(h, SMH_STAGE_MASK_MARKER_LINES);
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));  // the dilated mask is ready after this
     return SMH_OK;
@@ -1046,13 +1110,20 @@ int32_t smh_b200_find_longest_line(smh_b200* h, float x, float y, float max_gap,
 static int marker_lines_enqueue(smh_b200* h, uint32_t max_gap) {
     int rc;
     CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
+    CU(h, cudaEventRecord(h->stage_ev[SMH_STAGE_FIND_MARKER_LINES][0], h->s_markers));
     if ((rc = launch_lsd(h, h->one, 1, (float)max_gap, false, false, true, h->s_markers))) return rc;
     CU(h, cudaMemcpyAsync(h->h_small, h->one.lines, 128 * sizeof(float), cudaMemcpyDeviceToHost, h->s_markers));
     CU(h, cudaMemcpyAsync(h->h_small + 128, h->one.n_lines, 4, cudaMemcpyDeviceToHost, h->s_markers));
+    CU(h, cudaEventRecord(h->stage_ev[SMH_STAGE_FIND_MARKER_LINES][1], h->s_markers));
     return SMH_OK;
 }
 static int marker_lines_collect(smh_b200* h, float lines[32][4], uint32_t* n) {
     CU(h, cudaStreamSynchronize(h->s_markers));
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, h->stage_ev[SMH_STAGE_FIND_MARKER_LINES][0], h->stage_ev[SMH_STAGE_FIND_MARKER_LINES][1]) == cudaSuccess)
+            h->stage_dev_ms[SMH_STAGE_FIND_MARKER_LINES] = ms;
+    }
     const uint32_t cnt = *reinterpret_cast<uint32_t*>(h->h_small + 128);
     *n = cnt;
     memcpy(lines, h->h_small, (size_t)cnt * 16);
@@ -1064,21 +1135,27 @@ int32_t smh_b200_find_marker_lines(smh_b200* h, uint32_t max_gap, float lines[32
     if (rc) return rc;
     if (!lines || !n) return fail(h, SMH_E_ARG, "find_marker_lines: null output");
     std::lock_guard<std::mutex> g(h->markers_mu);
+    const auto t0 = std::chrono::steady_clock::now();
     CU(h, cudaSetDevice(h->device));
     if ((rc = marker_lines_enqueue(h, max_gap))) return rc;
-    return marker_lines_collect(h, lines, n);
+    rc = marker_lines_collect(h, lines, n);
+    h->stage_host_ms[SMH_STAGE_FIND_MARKER_LINES] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
 }
 
 int32_t smh_b200_find_minimap(smh_b200* h, int32_t* found, uint32_t rect[4]) {
     if (!h || !found || !rect) return fail(h, SMH_E_ARG, "find_minimap: bad argument");
     if (!h->have_frame) return fail(h, SMH_E_STATE, "find_minimap before load_frame");
+    StageTimer tm(h, SMH_STAGE_FIND_MINIMAP);
     CU(h, cudaSetDevice(h->device));
+    tm.begin(h->s_main);
     int rc;
     if ((rc = launch_minimap(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, h->s_main))) return rc;
     uint32_t* hs = reinterpret_cast<uint32_t*>(h->h_small + 208);
     CU(h, cudaMemcpyAsync(hs, h->one.minimap, 16, cudaMemcpyDeviceToHost, h->s_main));
     CU(h, cudaMemcpyAsync(hs + 4, h->one.minimap_found, 1, cudaMemcpyDeviceToHost, h->s_main));
     CU(h, cudaStreamSynchronize(h->s_main));
+    tm.end();
     *found = reinterpret_cast<uint8_t*>(hs + 4)[0] ? 1 : 0;
     memcpy(rect, hs, 16);
     return SMH_OK;
@@ -1090,10 +1167,12 @@ int32_t smh_b200_calc_meters_to_px_ratio(smh_b200* h, const smh_b200_scale* scal
     if (rc) return rc;
     if (!found || !ratio || (n_scales && !scales) || n_scales > 3) return fail(h, SMH_E_ARG, "calc_meters_to_px_ratio: bad argument");
     std::lock_guard<std::mutex> g(h->scales_mu);
+    StageTimer tm(h, SMH_STAGE_CALC_METERS_TO_PX_RATIO);
     CU(h, cudaSetDevice(h->device));
     *found = 0;
     if (n_debug) *n_debug = 0;
     if (n_scales == 0) return SMH_OK;  // `if scales.is_empty() { return None }`
+    tm.begin(h->s_scales);
     // pinned scratch: [216..225) scales in, then the results
     uint32_t* in = reinterpret_cast<uint32_t*>(h->h_small + 216);
     for (uint32_t k = 0; k < n_scales; k++) { in[3 * k] = scales[k].meters; in[3 * k + 1] = scales[k].x; in[3 * k + 2] = scales[k].y; }
@@ -1111,6 +1190,7 @@ int32_t smh_b200_calc_meters_to_px_ratio(smh_b200* h, const smh_b200_scale* scal
     CU(h, cudaMemcpyAsync(hf, h->one.mpx_found, 1, cudaMemcpyDeviceToHost, h->s_scales));
     CU(h, cudaMemcpyAsync(hf + 1, h->one.mpx_ndebug, 1, cudaMemcpyDeviceToHost, h->s_scales));
     CU(h, cudaStreamSynchronize(h->s_scales));
+    tm.end();
     *found = hf[0] ? 1 : 0;
     *ratio = hr[0];
     if (debug_lines) memcpy(debug_lines, hd, (size_t)hf[1] * 16);
@@ -1142,7 +1222,8 @@ int32_t smh_b200_process(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t 
         if (!scales_rc) {
             smh_b200_scale sc[3]; uint32_t ns = 0, start_y = 0xFFFFFFFFu;
             memset(sc, 0, sizeof sc);
-            const int32_t orc = ocr(user, ocr_img, h->geo.brq[2], h->geo.brq[3], sc, &ns, &start_y);
+            int32_t orc;
+            { StageTimer tmo(h, SMH_STAGE_OCR); orc = ocr(user, ocr_img, h->geo.brq[2], h->geo.brq[3], sc, &ns, &start_y); }
             if (orc) scales_rc = fail(h, orc, "process: the ocr callback failed with %d", orc);
             else if (ns > 0 && start_y != 0xFFFFFFFFu) {
                 if (ns > 3) ns = 3;
@@ -1597,58 +1678,18 @@ struct Scene {
     std::vector<smh_synth_segment> segs;
     std::vector<smh_synth_blip> blips;
 };
-struct Rng {
-    uint64_t s;
-    uint64_t next() { s = smh_splitmix64(s); return s; }
-    uint32_t below(uint32_t n) { return n ? (uint32_t)(next() % n) : 0u; }
-};
 int build_scene(const smh_b200_synth_params* p, uint32_t first, uint32_t n, Scene* sc) {
     Geometry g;
     int rc = compute_geometry(p->W, p->H, &g);
     if (rc) return rc;
     if (p->n_labels > SMH_SYNTH_MAX_LABELS) return SMH_E_ARG;
+    static_assert(sizeof(smh_synth_params) == sizeof(smh_b200_synth_params), "the generator's parameters are the ABI's");
     sc->desc.resize(n); sc->segs.resize((size_t)n * p->n_segments); sc->blips.resize((size_t)n * p->n_blips);
-    const int32_t mx = (int32_t)g.map[0], my = (int32_t)g.map[1], mw = (int32_t)g.map[2], mh = (int32_t)g.map[3];
-    for (uint32_t f = 0; f < n; f++) {
-        smh_synth_frame_desc& d = sc->desc[f];
-        memset(&d, 0, sizeof d);
-        d.seed = p->seed + first + f;
-        d.W = p->W; d.H = p->H;
-        memcpy(d.btn, g.btn, 16); memcpy(d.map, g.map, 16);
-        d.map_open = p->map_open; d.n_segments = p->n_segments; d.n_blips = p->n_blips; d.n_labels = p->n_labels;
-        Rng rng{smh_splitmix64(d.seed ^ 0x534D4800ull)};
-        for (uint32_t k = 0; k < p->n_segments; k++) {
-            smh_synth_segment& s = sc->segs[(size_t)f * p->n_segments + k];
-            for (;;) {  // random end points inside the map, 60..600 px apart
-                s.x0 = mx + 10 + (int32_t)rng.below((uint32_t)mw - 20); s.y0 = my + 10 + (int32_t)rng.below((uint32_t)mh - 20);
-                s.x1 = mx + 10 + (int32_t)rng.below((uint32_t)mw - 20); s.y1 = my + 10 + (int32_t)rng.below((uint32_t)mh - 20);
-                const int64_t dx = s.x1 - s.x0, dy = s.y1 - s.y0, l2 = dx * dx + dy * dy;
-                if (l2 >= 60 * 60 && l2 <= 600 * 600) break;
-            }
-            s.team = rng.below(3);
-        }
-        const uint32_t band = p->blip_band_pct == 0 || p->blip_band_pct > 100 ? 100 : p->blip_band_pct;
-        const uint32_t bh = (uint32_t)((uint64_t)mh * band / 100u);
-        for (uint32_t k = 0; k < p->n_blips; k++) {
-            smh_synth_blip& q = sc->blips[(size_t)f * p->n_blips + k];
-            q.size = 2 + rng.below(3);
-            q.x = mx + 6 + (int32_t)rng.below((uint32_t)mw - 12);
-            q.y = my + 6 + (int32_t)rng.below((bh > 12 ? bh : 13) - 12);
-            q.team = rng.below(3);
-        }
-        // labels inside the bottom-right quadrant; the last one hugs the right/bottom edge (D10 clip)
-        const int32_t qx = (int32_t)g.brq[0], qy = (int32_t)g.brq[1], qw = (int32_t)g.brq[2], qh = (int32_t)g.brq[3];
-        for (uint32_t k = 0; k < p->n_labels; k++) {
-            const int32_t spanx = qw - SMH_SYNTH_BAR_W, spany = qh - (SMH_SYNTH_LABEL_H + 8);
-            if (k + 1 == p->n_labels && k > 0) {
-                d.labels[k].x = qx + qw - SMH_SYNTH_LABEL_W + 2;           // crosses the right edge of the map
-                d.labels[k].y = qy + qh - SMH_SYNTH_LABEL_H + 3;           // crosses the bottom edge
-            } else {
-                d.labels[k].x = qx + (spanx > 1 ? (int32_t)rng.below((uint32_t)spanx) : 0);
-                d.labels[k].y = qy + (spany > 1 ? (int32_t)rng.below((uint32_t)spany) : 0);
-            }
-        }
-    }
+    uint32_t roi[12];
+    memcpy(roi, g.btn, 16); memcpy(roi + 4, g.map, 16); memcpy(roi + 8, g.brq, 16);
+    for (uint32_t f = 0; f < n; f++)
+        smh_synth_scene_frame(reinterpret_cast<const smh_synth_params*>(p), roi, first + f, &sc->desc[f],
+                              sc->segs.data() + (size_t)f * p->n_segments, sc->blips.data() + (size_t)f * p->n_blips);
     return SMH_OK;
 }
 }  // namespace
@@ -1715,6 +1756,120 @@ int32_t smh_b200_colour_table(smh_b200* h, uint32_t which, uint8_t* host_out) {
     CU(h, cudaMemcpyAsync(host_out, d, 1u << 24, cudaMemcpyDeviceToHost, h->s_main));
     CU(h, cudaStreamSynchronize(h->s_main));
     cudaFree(d);
+    return SMH_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// several GPUs of one box: contiguous frame ranges, one host thread + handle per GPU, no collective
+// ------------------------------------------------------------------------------------------
+struct smh_b200_multi {
+    std::vector<smh_b200*> h;
+    std::vector<double> seconds;
+    std::mutex err_mu;
+    std::string err;
+};
+
+extern "C" {
+
+void smh_b200_shard_range(uint32_t n, uint32_t n_dev, uint32_t g, uint32_t* first, uint32_t* count) {
+    if (n_dev == 0 || g >= n_dev) { if (first) *first = 0; if (count) *count = 0; return; }
+    const uint32_t a = (uint32_t)((uint64_t)g * n / n_dev), b = (uint32_t)((uint64_t)(g + 1) * n / n_dev);
+    if (first) *first = a;
+    if (count) *count = b - a;
+}
+
+int32_t smh_b200_multi_create(const int32_t* devices, uint32_t n_dev, smh_b200_multi** out) {
+    if (!devices || !out || n_dev == 0 || n_dev > 64) return SMH_E_ARG;
+    *out = nullptr;
+    for (uint32_t i = 0; i < n_dev; i++)
+        for (uint32_t j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(nullptr, SMH_E_ARG, "multi_create: device %d listed twice", devices[i]);
+    smh_b200_multi* m = new smh_b200_multi();
+    for (uint32_t i = 0; i < n_dev; i++) {
+        smh_b200* hd = nullptr;
+        const int rc = smh_b200_create(devices[i], &hd);
+        if (rc) { smh_b200_multi_destroy(m); return rc; }  // (the text is in smh_b200_last_error(NULL))
+        m->h.push_back(hd);
+    }
+    m->seconds.assign(n_dev, 0.0);
+    *out = m;
+    return SMH_OK;
+}
+
+void smh_b200_multi_destroy(smh_b200_multi* m) {
+    if (!m) return;
+    for (smh_b200* hd : m->h) smh_b200_destroy(hd);
+    delete m;
+}
+
+const char* smh_b200_multi_last_error(smh_b200_multi* m) {
+    if (!m) return "";
+    std::lock_guard<std::mutex> g(m->err_mu);
+    thread_local std::string copy;
+    copy = m->err;
+    return copy.c_str();
+}
+
+uint32_t smh_b200_multi_device_count(smh_b200_multi* m) { return m ? (uint32_t)m->h.size() : 0u; }
+
+int32_t smh_b200_multi_load_map_markers(smh_b200_multi* m, const uint8_t* rgba, uint32_t n_markers, uint32_t size) {
+    if (!m) return SMH_E_ARG;
+    for (smh_b200* hd : m->h) {
+        const int rc = smh_b200_load_map_markers(hd, rgba, n_markers, size);
+        if (rc) { std::lock_guard<std::mutex> g(m->err_mu); m->err = smh_b200_last_error(hd); return rc; }
+    }
+    return SMH_OK;
+}
+
+int32_t smh_b200_multi_last_times(smh_b200_multi* m, double* seconds, uint32_t n) {
+    if (!m || !seconds || n < m->h.size()) return SMH_E_ARG;
+    for (size_t i = 0; i < m->h.size(); i++) seconds[i] = m->seconds[i];
+    return SMH_OK;
+}
+
+int32_t smh_b200_multi_process_host_batch(smh_b200_multi* m, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H,
+                                          uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y, uint32_t max_gap,
+                                          uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
+    if (!m || !frames || !res || n == 0) return SMH_E_ARG;
+    Geometry g;
+    int rc = compute_geometry(W, H, &g);
+    if (rc) { std::lock_guard<std::mutex> lk(m->err_mu); m->err = "multi_process_host_batch: a frame size the reference panics on"; return rc; }
+    const size_t npx = (size_t)g.map[2] * g.map[3], nq = (size_t)g.brq[2] * g.brq[3];
+    const uint32_t G = (uint32_t)m->h.size();
+    std::vector<int> codes(G, 0);
+    std::vector<std::thread> th;
+    for (uint32_t d = 0; d < G; d++) {
+        th.emplace_back([&, d] {
+            uint32_t first = 0, cnt = 0;
+            smh_b200_shard_range(n, G, d, &first, &cnt);
+            const auto t0 = std::chrono::steady_clock::now();
+            if (cnt) {
+                smh_b200_host_results r = *res;  // the shard's slice of every result array
+                if (r.ui_map) r.ui_map += (size_t)first * npx * 4;
+                if (r.ocr_out) r.ocr_out += (size_t)first * nq;
+                if (r.scales) r.scales += (size_t)first * nq;
+                if (r.lsd_image) r.lsd_image += (size_t)first * npx;
+                r.lines += (size_t)first * 128; r.n_lines += first; r.red_pixels += first; r.map_open += first;
+                if (r.minimap) r.minimap += (size_t)first * 4;
+                if (r.minimap_found) r.minimap_found += first;
+                if (r.icon_found) r.icon_found += first;
+                if (r.icon_xy) r.icon_xy += (size_t)first * 2;
+                if (r.icon_sad) r.icon_sad += first;
+                codes[d] = smh_b200_process_host_batch(m->h[d], frames + (uint64_t)first * frame_stride, cnt, W, H, pitch_bytes, frame_stride,
+                                                       start_y ? start_y + first : nullptr, max_gap, flags, chunk, &r);
+            }
+            m->seconds[d] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    }
+    for (auto& t2 : th) t2.join();
+    for (uint32_t d = 0; d < G; d++)
+        if (codes[d]) {
+            std::lock_guard<std::mutex> lk(m->err_mu);
+            m->err = std::string("device shard ") + std::to_string(d) + ": " + smh_b200_last_error(m->h[d]);
+            return codes[d];
+        }
     return SMH_OK;
 }
 

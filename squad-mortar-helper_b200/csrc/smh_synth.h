@@ -6,6 +6,10 @@
 // OS screen grabs (src/capture.rs), which the benchmarks replace with these frames.
 #pragma once
 #include <stdint.h>
+#include <string.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
 
 #if defined(__CUDACC__)
 #define SYN_HD __host__ __device__ __forceinline__
@@ -129,4 +133,62 @@ SYN_HD uint32_t smh_synth_pixel(const smh_synth_frame_desc* d, const smh_synth_s
         if (hit_team >= 0) smh_synth_team_rgb((uint32_t)hit_team, jit, &r, &g, &b);
     }
     return b | (g << 8) | (r << 16) | 0xFF000000u;
+}
+
+
+// ---- scene of one frame (host side; shared by the library's rasterisers and the oracle's, so that the
+//      reference arm of bench.py can make the workload's frames without loading the product library) ----------
+typedef struct {
+    uint64_t seed;        // frame k uses seed + k
+    uint32_t W, H;
+    uint32_t n_segments, n_blips, n_labels, map_open, blip_band_pct, reserved;
+} smh_synth_params;       // = smh_b200_synth_params (include/smh_b200.h)
+
+static inline uint32_t smh_synth_below(uint64_t* s, uint32_t n) {
+    *s = smh_splitmix64(*s);
+    return n ? (uint32_t)(*s % n) : 0u;
+}
+
+// roi = {button xywh, map xywh, brq xywh} of the frame size (smh_b200_roi / smh_oracle_roi).  segs: n_segments entries,
+// blips: n_blips entries.
+static inline void smh_synth_scene_frame(const smh_synth_params* p, const uint32_t roi[12], uint32_t frame_index,
+                                         smh_synth_frame_desc* d, smh_synth_segment* segs, smh_synth_blip* blips) {
+    memset(d, 0, sizeof *d);
+    d->seed = p->seed + frame_index;
+    d->W = p->W; d->H = p->H;
+    memcpy(d->btn, roi, 16); memcpy(d->map, roi + 4, 16);
+    d->map_open = p->map_open; d->n_segments = p->n_segments; d->n_blips = p->n_blips; d->n_labels = p->n_labels;
+    const int32_t mx = (int32_t)roi[4], my = (int32_t)roi[5], mw = (int32_t)roi[6], mh = (int32_t)roi[7];
+    uint64_t rng = smh_splitmix64(d->seed ^ 0x534D4800ull);
+    for (uint32_t k = 0; k < p->n_segments; k++) {
+        smh_synth_segment* s = &segs[k];
+        for (;;) {  // random end points inside the map, 60..600 px apart
+            s->x0 = mx + 10 + (int32_t)smh_synth_below(&rng, (uint32_t)mw - 20); s->y0 = my + 10 + (int32_t)smh_synth_below(&rng, (uint32_t)mh - 20);
+            s->x1 = mx + 10 + (int32_t)smh_synth_below(&rng, (uint32_t)mw - 20); s->y1 = my + 10 + (int32_t)smh_synth_below(&rng, (uint32_t)mh - 20);
+            const int64_t dx = s->x1 - s->x0, dy = s->y1 - s->y0, l2 = dx * dx + dy * dy;
+            if (l2 >= 60 * 60 && l2 <= 600 * 600) break;
+        }
+        s->team = smh_synth_below(&rng, 3);
+    }
+    const uint32_t band = p->blip_band_pct == 0 || p->blip_band_pct > 100 ? 100 : p->blip_band_pct;
+    const uint32_t bh = (uint32_t)((uint64_t)mh * band / 100u);
+    for (uint32_t k = 0; k < p->n_blips; k++) {
+        smh_synth_blip* q = &blips[k];
+        q->size = 2 + smh_synth_below(&rng, 3);
+        q->x = mx + 6 + (int32_t)smh_synth_below(&rng, (uint32_t)mw - 12);
+        q->y = my + 6 + (int32_t)smh_synth_below(&rng, (bh > 12 ? bh : 13) - 12);
+        q->team = smh_synth_below(&rng, 3);
+    }
+    // labels inside the bottom-right quadrant; the last one hugs the right/bottom edge (D10 clip)
+    const int32_t qx = (int32_t)roi[8], qy = (int32_t)roi[9], qw = (int32_t)roi[10], qh = (int32_t)roi[11];
+    for (uint32_t k = 0; k < p->n_labels; k++) {
+        const int32_t spanx = qw - SMH_SYNTH_BAR_W, spany = qh - (SMH_SYNTH_LABEL_H + 8);
+        if (k + 1 == p->n_labels && k > 0) {
+            d->labels[k].x = qx + qw - SMH_SYNTH_LABEL_W + 2;           // crosses the right edge of the map
+            d->labels[k].y = qy + qh - SMH_SYNTH_LABEL_H + 3;           // crosses the bottom edge
+        } else {
+            d->labels[k].x = qx + (spanx > 1 ? (int32_t)smh_synth_below(&rng, (uint32_t)spanx) : 0);
+            d->labels[k].y = qy + (spany > 1 ? (int32_t)smh_synth_below(&rng, (uint32_t)spany) : 0);
+        }
+    }
 }
