@@ -215,6 +215,9 @@ typedef struct {
 #define SMH_BATCH_FILTER_ICONS 128u /* run the (reference-disabled) icon template match between the mask and the
                                        line search; needs smh_b200_load_map_markers */
 #define SMH_BATCH_MINIMAP 32u   /* also run find_minimap on every open frame (src/vision/find_minimap.rs) */
+#define SMH_BATCH_UI_L8 256u     /* smh_b200_process_host_batch with GRAYSCALE: res->ui_map receives the L plane (n * w*h bytes) —
+                                   every pixel of a grayscale ui_map is (L, L, L, 255), so a caller that can show an L8 image
+                                   saves the widening pass and three quarters of the host writes */
 #define SMH_BATCH_LSD_EXHAUSTIVE 16u /* march all 3600 rays of every seed (no isolated-blob pruning): makes
                                         the ray-step counter comparable with the CPU oracle's */
 
@@ -229,7 +232,7 @@ int32_t smh_b200_process_batch(smh_b200 *h, const uint8_t *d_frames, uint32_t n,
 
 /* Host-resident results of a batch, tightly packed (what the trait hands back per frame). */
 typedef struct {
-    uint8_t *ui_map;      /* n * w*h*4   (may be NULL to skip) */
+    uint8_t *ui_map;      /* n * w*h*4   (may be NULL to skip); n * w*h with SMH_BATCH_UI_L8 */
     uint8_t *ocr_out;     /* n * bqw*bqh (may be NULL) */
     uint8_t *scales;      /* n * bqw*bqh (may be NULL) */
     uint8_t *lsd_image;   /* n * w*h     (may be NULL) */
@@ -248,11 +251,21 @@ typedef struct {
  * runs the path and copies the results back, pipelined over chunks of `chunk` frames on
  * internal streams; returns after everything has landed in `res`.  With SMH_BATCH_GRAYSCALE the
  * ui_map crosses the bus as its L plane and is widened to (L, L, L, 255) in `res->ui_map` by host
- * threads of the library.  Flags honoured: GRAYSCALE, SKIP_LSD, MINIMAP, FILTER_ICONS. */
+ * threads of the library (or handed over as it is: SMH_BATCH_UI_L8).  Flags honoured: GRAYSCALE, UI_L8, SKIP_LSD,
+ * MINIMAP, FILTER_ICONS. */
 int32_t smh_b200_process_host_batch(smh_b200 *h, const uint8_t *frames, uint32_t n, uint32_t W, uint32_t H,
                                     uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
                                     uint32_t max_gap, uint32_t flags, uint32_t chunk,
                                     const smh_b200_host_results *res);
+
+/* The same pipeline over a bounded RING of host buffers — how a capture loop with a fixed pool of frame buffers feeds
+ * it: `frames` holds ring_n frames, frame f of the n processed is frames[f % ring_n] and its results land at index
+ * f % ring_n of every array of `res` (sized for ring_n frames; start_y still has n entries).  The caller owns the
+ * reuse discipline: a slot's results are overwritten ring_n frames later.  ring_n >= 4 * chunk. */
+int32_t smh_b200_process_host_stream(smh_b200 *h, const uint8_t *frames, uint32_t ring_n, uint32_t n, uint32_t W, uint32_t H,
+                                     uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t *start_y,
+                                     uint32_t max_gap, uint32_t flags, uint32_t chunk,
+                                     const smh_b200_host_results *res);
 
 /* ---- several GPUs of one box -------------------------------------------------------------
  * The reference is single-device (vision-gpu/src/cuda.rs:34, `Device::get_device(0)`); frames are independent, so a

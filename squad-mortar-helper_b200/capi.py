@@ -13,7 +13,7 @@ import os
 LIB_PATH = Path(os.environ.get("SMH_B200_LIB", PKG / "libsmh_b200.so"))
 
 SMH_OK, SMH_E_ARG, SMH_E_GEOMETRY, SMH_E_STATE, SMH_E_ALIGN, SMH_E_NOGPU, SMH_E_RANGE = 0, -1, -2, -3, -4, -5, -6
-BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP, BATCH_SERIAL, BATCH_FILTER_ICONS = 1, 2, 4, 8, 16, 32, 64, 128
+BATCH_GRAYSCALE, BATCH_LSD_STATS, BATCH_SKIP_LSD, BATCH_SKIP_PIXELS, BATCH_LSD_EXHAUSTIVE, BATCH_MINIMAP, BATCH_SERIAL, BATCH_FILTER_ICONS, BATCH_UI_L8 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 # every symbol include/smh_b200.h declares (tests assert the library exports all of them)
 SYMBOLS = [
@@ -25,7 +25,7 @@ SYMBOLS = [
     "smh_b200_synth_frames_host", "smh_b200_synth_frames_device", "smh_b200_colour_table",
     "smh_b200_find_minimap", "smh_b200_calc_meters_to_px_ratio", "smh_b200_process", "smh_b200_batch_meters_to_px_ratio",
     "smh_b200_load_map_markers", "smh_b200_filter_map_marker_icons",
-    "smh_b200_timeshares", "smh_b200_stage_name", "smh_b200_shard_range",
+    "smh_b200_timeshares", "smh_b200_stage_name", "smh_b200_shard_range", "smh_b200_process_host_stream",
     "smh_b200_multi_create", "smh_b200_multi_destroy", "smh_b200_multi_last_error", "smh_b200_multi_device_count",
     "smh_b200_multi_process_host_batch", "smh_b200_multi_load_map_markers", "smh_b200_multi_last_times",
 ]
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
         "smh_b200_load_map_markers": (i32, [vp, vp, u32, u32]),
         "smh_b200_filter_map_marker_icons": (i32, [vp, P(i32), P(u32), P(u32)]),
         "smh_b200_timeshares": (i32, [vp, P(f32), P(f32)]),
+        "smh_b200_process_host_stream": (i32, [vp, vp, u32, u32, u32, u32, u32, u64, vp, u32, u32, u32, P(HostResults)]),
         "smh_b200_stage_name": (C.c_char_p, [u32]),
         "smh_b200_shard_range": (None, [u32, u32, u32, P(u32), P(u32)]),
         "smh_b200_multi_create": (i32, [P(i32), u32, P(vp)]),

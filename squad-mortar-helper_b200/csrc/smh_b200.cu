@@ -581,29 +581,35 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
         return SMH_OK;
     };
     static std::mutex mu;
-    static size_t raised[64][4] = {{0}};
+    static size_t raised[64][6] = {{0}};
     if (prune && a.gap_limit >= 1 && a.gap_limit <= 32) {
-        // k_lsd2: a small CTA per frame in flight, warp 0 its master (kernels_lsd.cuh); persistent CTAs
-        constexpr int NW = SMH_LSD2_WARPS;
-        const size_t dyn = (sizeof(smh::Lsd2Shared<NW>) + 15) / 16 * 16 + (size_t)P.bg.tx * 33u * sizeof(uint32_t);
-        {
-            std::lock_guard<std::mutex> g(mu);
-            int rc;
-            if ((rc = raise_smem((const void*)smh::k_lsd2<NW, false>, dyn, &raised[h->device & 63][0]))) return rc;
-            if ((rc = raise_smem((const void*)smh::k_lsd2<NW, true>, dyn, &raised[h->device & 63][1]))) return rc;
-        }
-        int nb = 0;
-        CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd2<NW, false>, NW * 32, dyn));
-        // tuning knob: cap the persistent CTAs per SM (fewer CTAs than frames = the faster CTAs take more frames)
-        static const int cap = [] { const char* e = getenv("SMH_B200_LSD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-        if (cap >= 1 && nb > cap) nb = cap;
-        const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
-        const uint32_t grid = n < resident ? n : resident;
-        if (stats) smh::k_lsd2<NW, true><<<grid, NW * 32, dyn, st>>>(a);
-        else smh::k_lsd2<NW, false><<<grid, NW * 32, dyn, st>>>(a);
-        h->launches++;
-        CU(h, cudaGetLastError());
-        return SMH_OK;
+        // k_lsd2: a small CTA per frame in flight, warp 0 its master (kernels_lsd.cuh); persistent CTAs.  A batch that cannot
+        // fill the SMs anyway (the trait's single frame) takes wider CTAs: the bulk phases of a seed finish sooner
+        auto launch = [&](auto nw_tag, int slot) -> int {
+            constexpr int NW = decltype(nw_tag)::value;
+            const size_t dyn = (sizeof(smh::Lsd2Shared<NW>) + 15) / 16 * 16 + (size_t)P.bg.tx * 33u * sizeof(uint32_t);
+            {
+                std::lock_guard<std::mutex> g(mu);
+                int rc;
+                if ((rc = raise_smem((const void*)smh::k_lsd2<NW, false>, dyn, &raised[h->device & 63][slot]))) return rc;
+                if ((rc = raise_smem((const void*)smh::k_lsd2<NW, true>, dyn, &raised[h->device & 63][slot + 1]))) return rc;
+            }
+            int nb = 0;
+            CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd2<NW, false>, NW * 32, dyn));
+            // tuning knob: cap the persistent CTAs per SM (fewer CTAs than frames = the faster CTAs take more frames)
+            static const int cap = [] { const char* e = getenv("SMH_B200_LSD_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+            if (cap >= 1 && nb > cap) nb = cap;
+            const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
+            const uint32_t grid = n < resident ? n : resident;
+            if (stats) smh::k_lsd2<NW, true><<<grid, NW * 32, dyn, st>>>(a);
+            else smh::k_lsd2<NW, false><<<grid, NW * 32, dyn, st>>>(a);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            return SMH_OK;
+        };
+        static const int lat_nw = [] { const char* e = getenv("SMH_B200_LSD_LATENCY_WARPS"); return e ? atoi(e) : 8; }();
+        if (n * 2u <= (uint32_t)h->sm_count && lat_nw == 8) return launch(std::integral_constant<int, 8>(), 4);
+        return launch(std::integral_constant<int, SMH_LSD2_WARPS>(), 0);
     }
     // the literal search (every ray of every seed; any max_gap): one CTA per frame in flight
     // one tile-row of the bitmap + its fringe map + the window around the current seed
@@ -1213,7 +1219,9 @@ int32_t smh_b200_process(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t 
         if ((rc = smh_b200_isolate_map_markers(h))) return rc;
         if ((rc = smh_b200_mask_marker_lines(h))) return rc;
         std::lock_guard<std::mutex> g(h->markers_mu);
+        const auto t0 = std::chrono::steady_clock::now();
         if ((rc = marker_lines_enqueue(h, max_gap))) return rc;
+        h->stage_host_ms[SMH_STAGE_FIND_MARKER_LINES] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     int scales_rc = SMH_OK;
     if (ocr) {                                                                                     // mod.rs:124-216
@@ -1237,7 +1245,10 @@ int32_t smh_b200_process(smh_b200* h, const uint8_t* bgra, uint32_t W, uint32_t 
     }
     if (detect_markers) {
         std::lock_guard<std::mutex> g(h->markers_mu);
+        const auto t0 = std::chrono::steady_clock::now();
         if ((rc = marker_lines_collect(h, out->markers, &out->n_markers))) return rc;
+        // (enqueue + collect: the search itself ran under the scales branch)
+        h->stage_host_ms[SMH_STAGE_FIND_MARKER_LINES] += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return scales_rc;
 }
@@ -1419,9 +1430,11 @@ int32_t smh_b200_stream_synchronize(smh_b200* h, void* stream) {
     return SMH_OK;
 }
 
-int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H,
-                                    uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
-                                    uint32_t max_gap, uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
+// ring_n = 0: frame f of the batch is frames[f] and its results land at index f.  ring_n > 0 (streaming with bounded
+// buffers): frame f is frames[f % ring_n] and its results land at index f % ring_n of every result array.
+static int32_t host_batch_impl(smh_b200* h, const uint8_t* frames, uint32_t n, uint32_t ring_n, uint32_t W, uint32_t H,
+                               uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
+                               uint32_t max_gap, uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
     if (!h || !frames || !res || n == 0 || !res->lines || !res->n_lines || !res->red_pixels || !res->map_open)
         return fail(h, SMH_E_ARG, "process_host_batch: bad argument");
     CU(h, cudaSetDevice(h->device));
@@ -1430,6 +1443,9 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
     if (rc) return fail(h, rc, "process_host_batch: %ux%u is a frame size the reference panics on", W, H);
     if (chunk == 0) chunk = 32;
     if (chunk > n) chunk = n;
+    if (ring_n && ring_n < (SMH_PIPE_DEPTH + 1u) * chunk)
+        return fail(h, SMH_E_ARG, "process_host_stream: the ring must hold at least %u frames (%u chunks of %u in flight + one being refilled)",
+                    (SMH_PIPE_DEPTH + 1u) * chunk, (unsigned)SMH_PIPE_DEPTH, chunk);
     const bool icons = flags & SMH_BATCH_FILTER_ICONS;
     if (icons && !h->d_icons) return fail(h, SMH_E_STATE, "process_host_batch: FILTER_ICONS before load_map_markers");
     constexpr int DEPTH = SMH_PIPE_DEPTH;
@@ -1473,8 +1489,10 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
     // device and each plane of a chunk then crosses the bus as ONE contiguous copy.
     // grayscale ui_map: every pixel is (L, L, L, 255) — only L crosses the bus, host threads widen it (HostPool)
     static const bool l8_ok = [] { const char* e = getenv("SMH_B200_UI_L8"); return !(e && e[0] == '0'); }();
-    const bool ui_l8 = res->ui_map && (flags & SMH_BATCH_GRAYSCALE) && l8_ok;
-    if (ui_l8) {
+    if ((flags & SMH_BATCH_UI_L8) && !(flags & SMH_BATCH_GRAYSCALE)) return fail(h, SMH_E_ARG, "process_host_batch: UI_L8 needs GRAYSCALE");
+    const bool l8_out = res->ui_map && (flags & SMH_BATCH_UI_L8);           // the caller takes the L plane as it is
+    const bool ui_l8 = res->ui_map && (flags & SMH_BATCH_GRAYSCALE) && (l8_ok || l8_out);  // the L plane crosses the bus
+    if (ui_l8 && !l8_out) {
         if (h->pool.th.empty()) {
             // measured on a 16-core B200 host, 1024 x 1440p frames: 2 threads 6.5 k frames/s, 4 -> 7.8 k, 8 -> 7.5 k, 12 -> 7.4 k
             // (the RGBA rows over the bus instead: 7.25 k)
@@ -1529,6 +1547,8 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         if (left < 2u * chunk) { const uint32_t half = (left + 1u) / 2u; c = half > quarter ? half : quarter; }
         if (c > chunk) c = chunk;
         if (c > left) c = left;
+        const uint32_t slot = ring_n ? done % ring_n : done;  // where the chunk's frames and results live on the host
+        if (ring_n && c > ring_n - slot) c = ring_n - slot;   // a chunk never straddles the end of the ring
         kth++;
         Planes& P = h->pipe[b];
         uint8_t* stage = h->d_stage + (size_t)b * ustride * chunk;
@@ -1538,7 +1558,7 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         cudaStream_t st = s_up;
         if (reused) CU(h, cudaStreamWaitEvent(st, ev_run, 0));
         stamp(st);
-        const uint8_t* src0 = frames + (uint64_t)done * frame_stride;
+        const uint8_t* src0 = frames + (uint64_t)slot * frame_stride;
         if (h2d_mode == 1 && frame_stride == (uint64_t)pitch_bytes * H) {
             // one 3-D copy per rectangle for the whole chunk (depth = frames)
             cudaMemcpy3DParms mp{};
@@ -1585,10 +1605,10 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
             if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st, !icons))) return rc;
         uint8_t* const pack0 = h->d_pack + (size_t)b * pack_frame * chunk;
         struct Want { const smh_b200_plane* pl; uint8_t* host; };
-        const Want wants[4] = {{res->ui_map ? &P.ui : nullptr, res->ui_map ? res->ui_map + (size_t)done * npx * 4 : nullptr},
-                               {res->ocr_out ? &P.ocr : nullptr, res->ocr_out ? res->ocr_out + (size_t)done * nq : nullptr},
-                               {res->scales ? &P.scales : nullptr, res->scales ? res->scales + (size_t)done * nq : nullptr},
-                               {res->lsd_image ? &P.lsd : nullptr, res->lsd_image ? res->lsd_image + (size_t)done * npx : nullptr}};
+        const Want wants[4] = {{res->ui_map ? &P.ui : nullptr, res->ui_map ? res->ui_map + (size_t)slot * npx * 4 : nullptr},
+                               {res->ocr_out ? &P.ocr : nullptr, res->ocr_out ? res->ocr_out + (size_t)slot * nq : nullptr},
+                               {res->scales ? &P.scales : nullptr, res->scales ? res->scales + (size_t)slot * nq : nullptr},
+                               {res->lsd_image ? &P.lsd : nullptr, res->lsd_image ? res->lsd_image + (size_t)slot * npx : nullptr}};
         uint8_t* cursor = pack0;
         for (const Want& wnt : wants) {  // rows without their pitch padding, plane after plane
             if (!wnt.pl) continue;
@@ -1613,6 +1633,11 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         cursor = pack0;
         for (const Want& wnt : wants) {
             if (!wnt.pl) continue;
+            if (l8_out && wnt.pl == &P.ui) {  // straight into the caller's L8 buffer
+                CU(h, cudaMemcpyAsync(res->ui_map + (size_t)slot * npx, cursor, npx * c, cudaMemcpyDeviceToHost, st));
+                cursor += npx * c;
+                continue;
+            }
             if (ui_l8 && wnt.pl == &P.ui) {
                 // the slot's landing area is free once the workers widened its previous occupant
                 h->pool.wait_zero(h->gray_pending[b]);
@@ -1633,18 +1658,18 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
             CU(h, cudaMemcpyAsync(wnt.host, cursor, bytes, cudaMemcpyDeviceToHost, st));
             cursor += bytes;
         }
-        CU(h, cudaMemcpyAsync(res->lines + (size_t)done * 128, P.lines, (size_t)c * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(h, cudaMemcpyAsync(res->n_lines + done, P.n_lines, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
-        CU(h, cudaMemcpyAsync(res->red_pixels + done, P.red, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
-        CU(h, cudaMemcpyAsync(res->map_open + done, P.open, (size_t)c, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->lines + (size_t)slot * 128, P.lines, (size_t)c * 128 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->n_lines + slot, P.n_lines, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->red_pixels + slot, P.red, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(res->map_open + slot, P.open, (size_t)c, cudaMemcpyDeviceToHost, st));
         if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found) {
-            CU(h, cudaMemcpyAsync(res->minimap + (size_t)done * 4, P.minimap, (size_t)c * 16, cudaMemcpyDeviceToHost, st));
-            CU(h, cudaMemcpyAsync(res->minimap_found + done, P.minimap_found, (size_t)c, cudaMemcpyDeviceToHost, st));
+            CU(h, cudaMemcpyAsync(res->minimap + (size_t)slot * 4, P.minimap, (size_t)c * 16, cudaMemcpyDeviceToHost, st));
+            CU(h, cudaMemcpyAsync(res->minimap_found + slot, P.minimap_found, (size_t)c, cudaMemcpyDeviceToHost, st));
         }
         if (icons) {
-            if (res->icon_found) CU(h, cudaMemcpyAsync(res->icon_found + done, P.icon_found, (size_t)c, cudaMemcpyDeviceToHost, st));
-            if (res->icon_xy) CU(h, cudaMemcpyAsync(res->icon_xy + (size_t)done * 2, P.icon_xy, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
-            if (res->icon_sad) CU(h, cudaMemcpyAsync(res->icon_sad + done, P.icon_sad, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
+            if (res->icon_found) CU(h, cudaMemcpyAsync(res->icon_found + slot, P.icon_found, (size_t)c, cudaMemcpyDeviceToHost, st));
+            if (res->icon_xy) CU(h, cudaMemcpyAsync(res->icon_xy + (size_t)slot * 2, P.icon_xy, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
+            if (res->icon_sad) CU(h, cudaMemcpyAsync(res->icon_sad + slot, P.icon_sad, (size_t)c * 4, cudaMemcpyDeviceToHost, st));
         }
         stamp(st);
         CU(h, cudaEventRecord(ev_down, st));
@@ -1661,11 +1686,24 @@ int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t
         for (auto e : tev) cudaEventDestroy(e);
     }
     for (auto s : h->pipe_streams) CU(h, cudaStreamSynchronize(s));
-    if (ui_l8) {
+    if (ui_l8 && !l8_out) {
         for (int i = 0; i < DEPTH; i++) h->pool.wait_zero(h->gray_pending[i]);
         if (h->pool.failed.exchange(0)) return fail(h, SMH_E_STATE, "process_host_batch: a host worker failed to wait for its download");
     }
     return SMH_OK;
+}
+
+int32_t smh_b200_process_host_batch(smh_b200* h, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H,
+                                    uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
+                                    uint32_t max_gap, uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
+    return host_batch_impl(h, frames, n, 0, W, H, pitch_bytes, frame_stride, start_y, max_gap, flags, chunk, res);
+}
+
+int32_t smh_b200_process_host_stream(smh_b200* h, const uint8_t* frames, uint32_t ring_n, uint32_t n, uint32_t W, uint32_t H,
+                                     uint32_t pitch_bytes, uint64_t frame_stride, const uint32_t* start_y,
+                                     uint32_t max_gap, uint32_t flags, uint32_t chunk, const smh_b200_host_results* res) {
+    if (ring_n == 0) return fail(h, SMH_E_ARG, "process_host_stream: empty ring");
+    return host_batch_impl(h, frames, n, ring_n, W, H, pitch_bytes, frame_stride, start_y, max_gap, flags, chunk, res);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,9 +1,10 @@
 """Frame-wise sharding across the GPUs of one box.
 
 Frames are independent (the only cross-frame state in the reference is buffer reuse), so a batch is
-split into static contiguous ranges, one per rank, with NO data-path collective; ranks only meet at
-a barrier and to combine their timings (max) and frame counts (sum).  `torch.distributed` is the
-plumbing: NCCL on the GPU box, gloo in the CPU tests.
+split into static contiguous ranges, one per GPU, with NO data-path collective.  Inside one process the
+C ABI does the split itself (smh_b200_multi_process_host_batch, one host thread + handle per GPU); under
+torchrun (bench.py) every rank takes its range with the same arithmetic — this module is that arithmetic,
+checked against smh_b200_shard_range in tests/test_sharding_cpu.py.
 """
 from __future__ import annotations
 
@@ -18,20 +19,3 @@ def shard_range(rank: int, world: int, total: int) -> tuple[int, int]:
 def weak_shard(rank: int, per_rank: int) -> tuple[int, int]:
     """Weak scaling (bench.py): every rank owns `per_rank` frames; global index = rank*per_rank + i."""
     return rank * per_rank, (rank + 1) * per_rank
-
-
-def combine(frames_done: int, elapsed_ms: float, dist=None, device=None) -> tuple[int, float]:
-    """(sum of frames over ranks, max of elapsed time over ranks).  `dist` is an initialised
-    torch.distributed module or None for a single process."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return frames_done, elapsed_ms
-    import torch
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-    f = torch.tensor([frames_done], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dist.all_reduce(f, op=dist.ReduceOp.SUM)
-    return int(f.cpu()[0]), float(t.cpu()[0])
-
-
-def frames_per_second(frames_done: int, elapsed_ms: float) -> float:
-    return frames_done / (elapsed_ms * 1e-3)

@@ -311,8 +311,10 @@ class B200Vision:
 
     def process_host_batch(self, frames: np.ndarray, *, start_y=None, max_gap: int = 15, grayscale: bool = True,
                            chunk: int = 32, want=("ui_map", "ocr_out", "scales"), out: dict | None = None,
-                           frames_ptr: int | None = None, shape=None) -> dict:
-        """End-to-end batch from host frames [n,H,W,4]; returns tightly packed host arrays."""
+                           frames_ptr: int | None = None, shape=None, ui_l8: bool = False, _multi=None,
+                           ring: int = 0, n_total: int | None = None) -> dict:
+        """End-to-end batch from host frames [n,H,W,4]; returns tightly packed host arrays.  ui_l8 (with grayscale):
+        ui_map comes back as its L plane [n,h,w] instead of RGBA."""
         if frames is not None:
             n, H, W = frames.shape[:3]
             assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
@@ -325,7 +327,7 @@ class B200Vision:
         if out is None:
             out = {}
         res = capi.HostResults()
-        shapes = {"ui_map": (n, h, w, 4), "ocr_out": (n, qh, qw), "scales": (n, qh, qw), "lsd_image": (n, h, w)}
+        shapes = {"ui_map": (n, h, w) if ui_l8 else (n, h, w, 4), "ocr_out": (n, qh, qw), "scales": (n, qh, qw), "lsd_image": (n, h, w)}
         for k in ("ui_map", "ocr_out", "scales", "lsd_image"):
             if k in want:
                 if k not in out:
@@ -349,11 +351,30 @@ class B200Vision:
         if start_y is not None:
             sy = np.ascontiguousarray(start_y, np.uint32)
         flags = (capi.BATCH_GRAYSCALE if grayscale else 0) | (capi.BATCH_MINIMAP if "minimap" in want else 0) | \
-                (capi.BATCH_FILTER_ICONS if "icons" in want else 0)
+                (capi.BATCH_FILTER_ICONS if "icons" in want else 0) | (capi.BATCH_UI_L8 if ui_l8 else 0)
+        if _multi is not None:  # the same call spread over several GPUs (B200VisionMulti)
+            rc = self._L.smh_b200_multi_process_host_batch(_multi, frames_ptr, n, W, H, W * 4, W * H * 4,
+                                                           sy.ctypes.data if sy is not None else None, max_gap, flags, chunk, C.byref(res))
+            if rc != 0:
+                raise capi.VisionError(rc, (self._L.smh_b200_multi_last_error(_multi) or b"").decode())
+            return out
+        if ring:  # streaming over a ring of `n` host buffers: n_total frames, results at index f % n
+            check(self._h, self._L.smh_b200_process_host_stream(self._h, frames_ptr, n, n_total or n, W, H, W * 4, W * H * 4,
+                                                                sy.ctypes.data if sy is not None else None, max_gap, flags,
+                                                                chunk, C.byref(res)))
+            return out
         check(self._h, self._L.smh_b200_process_host_batch(self._h, frames_ptr, n, W, H, W * 4, W * H * 4,
                                                            sy.ctypes.data if sy is not None else None, max_gap, flags,
                                                            chunk, C.byref(res)))
         return out
+
+    def timeshares(self) -> dict:
+        """The reference's Timeshares (vision-common/src/debug.rs:3-29) of the last frame through the trait calls:
+        stage -> (host_ms, device_ms)."""
+        hm = (C.c_float * len(capi.STAGES))()
+        dm = (C.c_float * len(capi.STAGES))()
+        check(self._h, self._L.smh_b200_timeshares(self._h, hm, dm))
+        return {name: (float(hm[i]), float(dm[i])) for i, name in enumerate(capi.STAGES)}
 
     def download_plane(self, plane: capi.Plane, first: int, count: int, stream: int = 0) -> np.ndarray:
         """Copy frames [first, first+count) of a device plane into a packed host array (synchronises)."""
@@ -374,3 +395,55 @@ class B200Vision:
         out = np.empty(1 << 24, np.uint8)
         check(self._h, self._L.smh_b200_colour_table(self._h, which, out.ctypes.data))
         return out
+
+
+class B200VisionMulti:
+    """Several GPUs of one box behind one call (smh_b200_multi_*): a batch of host frames is split into contiguous
+    frame ranges, one host thread + handle per GPU, no collective."""
+
+    def __init__(self, devices):
+        self._L = capi.lib()
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._L.smh_b200_multi_create(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise capi.VisionError(rc, (self._L.smh_b200_last_error(None) or b"").decode())
+        self._m = h
+        self.devices = list(devices)
+
+    def close(self):
+        if self._m:
+            self._L.smh_b200_multi_destroy(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def shard_range(self, n: int, g: int):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._L.smh_b200_shard_range(n, len(self.devices), g, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def load_map_markers(self, templates: np.ndarray) -> None:
+        t = np.ascontiguousarray(templates, np.uint8)
+        rc = self._L.smh_b200_multi_load_map_markers(self._m, t.ctypes.data, t.shape[0], t.shape[1])
+        if rc != 0:
+            raise capi.VisionError(rc, (self._L.smh_b200_multi_last_error(self._m) or b"").decode())
+
+    def process_host_batch(self, frames, **kw) -> dict:
+        # argument handling is B200Vision.process_host_batch's; only the final call differs
+        return B200Vision.process_host_batch(_MultiShim(self._L), frames, _multi=self._m, **kw)
+
+    def last_times(self):
+        out = (C.c_double * len(self.devices))()
+        self._L.smh_b200_multi_last_times(self._m, out, len(self.devices))
+        return list(out)
+
+
+class _MultiShim:
+    def __init__(self, L):
+        self._L = L
+        self._h = None
