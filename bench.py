@@ -156,40 +156,45 @@ def gather(world, dist, torch, values):
     return [[float(x) for x in o.cpu()] for o in out]
 
 
-def bus_ceiling(torch, barrier, seconds=0.4):
-    """Pinned-copy bandwidth of this rank with both directions busy — every rank at once, as in the e2e leg."""
-    nbytes = 256 << 20
+def bus_ceiling(torch, barrier, seconds=0.25):
+    """Pinned-copy bandwidth of this rank, every rank at once (as in the e2e leg): uploads alone, downloads alone, and
+    both directions together.  -> GB/s (h2d_alone, d2h_alone, h2d_with_d2h, d2h_with_h2d)"""
+    nbytes = 128 << 20
     hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     din = torch.empty(nbytes, dtype=torch.uint8, device="cuda"); dout = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    for _ in range(2):
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         with torch.cuda.stream(s1):
-            din.copy_(hin, non_blocking=True)
+            e[0].record()
         with torch.cuda.stream(s2):
-            hout.copy_(dout, non_blocking=True)
-    torch.cuda.synchronize()
-    barrier()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    reps = 0
-    t0 = time.perf_counter()
-    with torch.cuda.stream(s1):
-        e[0].record()
-    with torch.cuda.stream(s2):
-        e[2].record()
-    while time.perf_counter() - t0 < seconds:
+            e[2].record()
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            if up:
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+            reps += 1
+            if reps % 8 == 0:
+                torch.cuda.synchronize()
         with torch.cuda.stream(s1):
-            din.copy_(hin, non_blocking=True)
+            e[1].record()
         with torch.cuda.stream(s2):
-            hout.copy_(dout, non_blocking=True)
-        reps += 1
-        if reps % 4 == 0:
-            torch.cuda.synchronize()
-    with torch.cuda.stream(s1):
-        e[1].record()
-    with torch.cuda.stream(s2):
-        e[3].record()
-    torch.cuda.synchronize()
-    return reps * nbytes / (e[0].elapsed_time(e[1]) * 1e-3) / 1e9, reps * nbytes / (e[2].elapsed_time(e[3]) * 1e-3) / 1e9
+            e[3].record()
+        torch.cuda.synchronize()
+        return (reps * nbytes / (e[0].elapsed_time(e[1]) * 1e-3) / 1e9 if up else 0.0,
+                reps * nbytes / (e[2].elapsed_time(e[3]) * 1e-3) / 1e9 if down else 0.0)
+    run(True, True)
+    up_alone = run(True, False)[0]
+    down_alone = run(False, True)[1]
+    up_both, down_both = run(True, True)
+    return up_alone, down_alone, up_both, down_both
 
 
 def run_e2e(args, vision, frames, roi, n, world, barrier, torch, dist, oracle_lines):
@@ -241,18 +246,20 @@ def run_e2e(args, vision, frames, roi, n, world, barrier, torch, dist, oracle_li
         res[name] = {"value": world * n * e_steps / max(per_rank), "per_rank_frames_per_s": [n * e_steps / t for t in per_rank],
                      "d2h_bytes_per_step": d2h, "lines_match_oracle": ok}
         del outs
-    h2d_gbs, d2h_gbs = bus_ceiling(torch, barrier)
-    bw = gather(world, dist, torch, [h2d_gbs, d2h_gbs])
-    d2h_pf = res["rgba"]["d2h_bytes_per_step"] / n
-    ceiling = sum(min(b[0] * 1e9 / (h2d / n), b[1] * 1e9 / d2h_pf) for b in bw)
+    bw = gather(world, dist, torch, list(bus_ceiling(torch, barrier)))
+    h2d_pf, d2h_pf = h2d / n, res["rgba"]["d2h_bytes_per_step"] / n
+    # a frame needs its upload, its download, and their sum through whatever the two directions share (host memory, root complex)
+    ceiling = sum(1.0 / max(h2d_pf / (b[0] * 1e9), d2h_pf / (b[1] * 1e9), (h2d_pf + d2h_pf) / ((b[2] + b[3]) * 1e9)) for b in bw)
     return {"value": res["rgba"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res["rgba"]["d2h_bytes_per_step"],
             "frames_per_step": n, "steps": e_steps, "ring_frames": ring,
             "per_rank_frames_per_s": res["rgba"]["per_rank_frames_per_s"], "lines_match_oracle": res["rgba"]["lines_match_oracle"],
             "ui_l8": {"value": res["l8"]["value"], "per_rank_frames_per_s": res["l8"]["per_rank_frames_per_s"],
                       "note": "SMH_BATCH_UI_L8: the caller takes ui_map as its L plane (no widening pass on the host)"},
-            "bus": {"per_rank_pinned_copy_GBs_h2d_d2h_concurrent": bw, "ceiling_frames_per_s": ceiling,
-                    "frac_of_ceiling": res["rgba"]["value"] / ceiling if ceiling else None,
-                    "note": "every rank copying 256 MiB pinned blocks both ways at once; ceiling = sum over ranks of min(h2d / upload bytes, d2h / download bytes) per frame"},
+            "bus": {"per_rank_pinned_copy_GBs": {"h2d_alone": [b[0] for b in bw], "d2h_alone": [b[1] for b in bw],
+                                                 "h2d_with_d2h": [b[2] for b in bw], "d2h_with_h2d": [b[3] for b in bw]},
+                    "ceiling_frames_per_s": ceiling, "frac_of_ceiling": res["rgba"]["value"] / ceiling if ceiling else None,
+                    "note": "every rank copying 128 MiB pinned blocks at once; per rank a frame takes at least max(upload bytes / h2d alone, "
+                            "download bytes / d2h alone, (upload + download bytes) / (h2d + d2h with both directions busy)); ceiling = sum over ranks"},
             "note": "smh_b200_process_host_stream: a ring of pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines "
                     "back into a ring of pinned result buffers, 3 chunks of 32 frames in flight; the grayscale ui_map crosses the bus as its L plane "
                     "and is widened to RGBA in the caller's buffer by the library's host threads inside the timed region"}

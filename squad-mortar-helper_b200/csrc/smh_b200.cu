@@ -180,7 +180,6 @@ struct smh_b200 {
     float2* d_rays = nullptr;  // 3600 (cos, sin)
     float2* d_ckpt = nullptr;  // accumulated ray offsets every LSD_CKPT steps, [3600][n_ckpt]
     uint32_t n_ckpt = 0;
-    uint32_t* d_span = nullptr;  // ray span per pixel offset (line-search filter)
     uint32_t* d_lut = nullptr; // marker predicate bit table, 2^24 bits
     // marker icon templates (smh_b200_load_map_markers): one allocation, see smh::IconTable
     uint32_t* d_icons = nullptr;
@@ -268,12 +267,6 @@ int alloc_plane(smh_b200* h, smh_b200_plane* p, uint32_t n, uint32_t width, uint
     return SMH_OK;
 }
 
-// SMH_B200_OLD_PIXELS=1: the round-1 pixel pass (per-lane cp.async, 30-column strips, separate k_pack_bits) for A/B runs
-bool old_pixels() {
-    static const bool on = [] { const char* e = getenv("SMH_B200_OLD_PIXELS"); return e && e[0] == '1'; }();
-    return on;
-}
-
 int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool stats) {
     if (P->n == n && P->W == g.W && P->H == g.H) {
         if (stats && !P->stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
@@ -285,7 +278,7 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     // boundary of the capture); k_pixels2's quadrant planes are padded further so that a 128-column strip's bytes start
     // on a 128-byte boundary
     P->pad = g.map[0] & 3u;
-    P->qpad = old_pixels() ? ((P->pad + g.brq[2]) & 3u) : ((P->pad + g.brq[2]) & 127u);
+    P->qpad = (P->pad + g.brq[2]) & 127u;
     P->nvec = (P->pad + g.map[2] + 3u) / 4u;
     int rc;
     if ((rc = alloc_plane(h, &P->ui, n, g.map[2], g.map[3], 4, P->pad))) return rc;
@@ -328,55 +321,6 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     return SMH_OK;
 }
 
-// SMH_B200_FOLD_PACK=1: the pixel pass also writes the line search's bitmap (no k_pack_bits launch).  Measured on
-// B200, 1024 dense 1440p frames, two batches in flight: step 6.50 -> 6.21 ms (+4.7 % frames/s), but the pixel pass
-// itself slows from 2.88 to 3.22 ms (its 15 byte stores per warp row land as 4-byte pieces in 4-5 tiles) and
-// drops from 76 % to 68 % of the measured copy bandwidth.  Off by default: the separate 0.39 ms kernel keeps
-// the HBM-bound pass at its best store pattern.
-bool fold_pack_enabled() {
-    static const bool on = [] { const char* e = getenv("SMH_B200_FOLD_PACK"); return e && e[0] == '1'; }();
-    return on;
-}
-
-// Launch the fused pixel pass over n frames.  `frames` origin may be a cropped view of the
-// capture: (ox, oy) is the frame coordinate of its first byte.
-int launch_pixels_old(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch,
-                      uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
-                      int grayscale, uint32_t rows_per_band, cudaStream_t st) {
-    const Geometry& g = P.geo;
-    smh::PixelArgs a{};
-    a.frames = frames; a.frame_stride = frame_stride; a.pitch = pitch;
-    a.map_x = g.map[0] - ox; a.map_y = g.map[1] - oy; a.w = g.map[2]; a.h = g.map[3];
-    a.bqw = g.brq[2]; a.bqh = g.brq[3];
-    a.btn_x = g.btn[0] - ox; a.btn_y = g.btn[1] - oy; a.btn_w = g.btn[2]; a.btn_h = g.btn[3];
-    a.pad = P.pad; a.gx0 = a.map_x - a.pad; a.nvec = P.nvec; a.qpad = P.qpad;
-    if ((a.gx0 & 3u) || (pitch & 15u) || (frame_stride & 15u) || ((uintptr_t)frames & 15u))
-        return fail(h, SMH_E_ALIGN, "captured frames must be 16-byte aligned (base %p, pitch %u, stride %llu, x0 %u)",
-                    (const void*)frames, pitch, (unsigned long long)frame_stride, a.gx0);
-    a.ui = P.ui.ptr; a.ui_stride = P.ui.frame_stride; a.ui_pitch = P.ui.pitch;
-    a.lsd = P.lsd.ptr; a.lsd_stride = P.lsd.frame_stride; a.lsd_pitch = P.lsd.pitch;
-    a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch;
-    a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
-    a.red = P.red; a.open = P.open;
-    a.rows_per_band = rows_per_band; a.nbands = (a.h + rows_per_band - 1) / rows_per_band;
-    a.grayscale = grayscale ? 1u : 0u;
-    a.lut = h->d_lut;
-    // the bitmap of the dilated mask is written by the same pass (SMH_B200_FOLD_PACK=0: by k_pack_bits afterwards)
-    a.bits = fold_pack_enabled() ? P.bits : nullptr; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
-    a.n_frames = n;
-    a.nstrips = (a.nvec + smh::PX_STRIP - 1) / smh::PX_STRIP;
-    auto kern = a.bits ? (grayscale ? smh::k_pixels<true, true> : smh::k_pixels<false, true>)
-                       : (grayscale ? smh::k_pixels<true, false> : smh::k_pixels<false, false>);
-    // one warp per (frame, band, strip) item plus one per frame for the button test
-    const uint64_t items = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips + 1u);
-    const uint64_t blocks = (items + smh::PX_WARPS - 1) / smh::PX_WARPS;
-    if (blocks > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
-    kern<<<(unsigned)blocks, smh::PX_THREADS, smh::PX_SMEM_BYTES, st>>>(a);
-    h->launches++;
-    CU(h, cudaGetLastError());
-    return SMH_OK;
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -393,7 +337,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 // The fused pixel pass over n frames (k_pixels2, kernels_px.cuh).  `frames` may be a cropped view of the capture:
 // (ox, oy) is the frame coordinate of its first byte, rows_avail the rows it holds.
-int launch_pixels2(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
+int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
                    uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform, int grayscale, cudaStream_t st) {
     const Geometry& g = P.geo;
     if ((pitch & 15u) || (frame_stride & 15u) || ((uintptr_t)frames & 15u))
@@ -483,25 +427,7 @@ Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
     return V;
 }
 
-int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
-                  uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform,
-                  int grayscale, uint32_t rows_per_band, cudaStream_t st) {
-    if (old_pixels()) return launch_pixels_old(h, P, frames, frame_stride, pitch, ox, oy, n, per_frame_start_y, start_y_uniform, grayscale, rows_per_band, st);
-    return launch_pixels2(h, P, frames, frame_stride, pitch, rows_avail, ox, oy, n, per_frame_start_y, start_y_uniform, grayscale, st);
-}
-
-// 1-bit tile-major copy of the dilated masks (what the line search and the icon match read)
-int launch_pack(smh_b200* h, const Planes& P, uint32_t n, cudaStream_t st) {
-    if (fold_pack_enabled() || !old_pixels()) return SMH_OK;  // the pixel pass wrote the bitmap
-    const dim3 grid((P.bg.tx + 7u) / 8u, P.bg.ty, n);
-    if (n > 65535u) return fail(h, SMH_E_ARG, "batch too large for one launch");
-    smh::k_pack_bits<<<grid, 256, 0, st>>>(P.lsd.ptr, P.lsd.frame_stride, P.lsd.pitch, P.bg, P.bits, P.bits_stride);
-    h->launches++;
-    CU(h, cudaGetLastError());
-    return SMH_OK;
-}
-
-// Marker icon template match over n frames (after launch_pack): scores, then edits mask + bitmap.
+// Marker icon template match over n frames (after the pixel pass): scores, then edits mask + bitmap.
 int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t ox, uint32_t oy,
                  uint32_t n, bool use_open, cudaStream_t st) {
     if (!h->d_icons) return fail(h, SMH_E_STATE, "filter_map_marker_icons before load_map_markers");
@@ -556,16 +482,13 @@ int launch_icons(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t f
     return SMH_OK;
 }
 
-int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st,
-               bool pack = true) {
-    if (pack) { int rc = launch_pack(h, P, n, st); if (rc) return rc; }
+int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use_open, bool stats, bool prune, cudaStream_t st) {
     { int rc = ensure_ray_ckpt(h, P, st); if (rc) return rc; }
     smh::LsdArgs a{};
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.g = P.bg;
-    a.rays = h->d_rays; a.ckpt = h->d_ckpt; a.n_ckpt = h->n_ckpt; a.span_tab = h->d_span; a.max_gap = max_gap;
+    a.rays = h->d_rays; a.ckpt = h->d_ckpt; a.n_ckpt = h->n_ckpt; a.max_gap = max_gap;
     // `gap.0 >= max_gap` on an integer-valued counter <=> counter >= ceil(max_gap)
     a.gap_limit = (max_gap != max_gap || max_gap >= 2147483648.0f) ? 2147483647 : (max_gap <= -2147483648.0f ? -2147483647 : (int)ceilf(max_gap));
-    a.prune = prune ? 1 : 0;
     a.n_frames = n; a.counter = P.counter;
     a.open = use_open ? P.open : nullptr;
     a.lines = P.lines; a.n_lines = P.n_lines;
@@ -612,15 +535,14 @@ int launch_lsd(smh_b200* h, const Planes& P, uint32_t n, float max_gap, bool use
         return launch(std::integral_constant<int, SMH_LSD2_WARPS>(), 0);
     }
     // the literal search (every ray of every seed; any max_gap): one CTA per frame in flight
-    // one tile-row of the bitmap + its fringe map + the window around the current seed
-    const size_t dyn = ((size_t)P.bg.tx * 32u * 2u + (size_t)smh::LSD_WIN_ROWS * 8u) * sizeof(uint32_t);
+    // one tile-row of the bitmap + its fringe map
+    const size_t dyn = (size_t)P.bg.tx * 32u * 2u * sizeof(uint32_t);
     {
         std::lock_guard<std::mutex> g(mu);
         int rc;
         if ((rc = raise_smem((const void*)smh::k_lsd<false>, dyn, &raised[h->device & 63][2]))) return rc;
         if ((rc = raise_smem((const void*)smh::k_lsd<true>, dyn, &raised[h->device & 63][3]))) return rc;
     }
-    a.prune = 0;
     int nb = 0;
     CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smh::k_lsd<false>, smh::LSD_THREADS, dyn));
     const uint32_t resident = (uint32_t)(h->sm_count * (nb > 0 ? nb : 1));
@@ -674,22 +596,6 @@ void batch_tuning(const smh_b200* h, uint32_t* chunk, uint32_t* lanes) {
     if (l <= 0) l = 1;
     if (l > SMH_BATCH_LANES_MAX) l = SMH_BATCH_LANES_MAX;
     *chunk = (uint32_t)c; *lanes = (uint32_t)l;
-}
-
-uint32_t pick_rows_per_band(const smh_b200* h, uint32_t n, uint32_t map_h) {
-    // batches: 32-row bands.  The pass is bound by how DRAM takes its stores, not by instructions or
-    // by the halo re-reads: with short bands all bands of a frame are in flight together and each
-    // output row is completed within a short window (measured on B200, 1024 frames 1440p: 8 rows
-    // 3.57 ms, 16 -> 3.05, 32 -> 2.91, 64 -> 2.98, 128 -> 3.19, 274 -> 3.63, whole map -> 4.27;
-    // profiles/r1g_variants.txt).  A lone frame: enough bands to cover the SMs
-    static const int forced = [] { const char* e = getenv("SMH_B200_ROWS_PER_BAND"); return e ? atoi(e) : 0; }();  // tuning knob
-    if (forced >= 8) return (uint32_t)forced;
-    if (n >= 16) return 32;
-    uint32_t want = (uint32_t)h->sm_count * 2u / (n ? n : 1u);
-    uint32_t rows = want ? (map_h + want - 1) / want : map_h;
-    if (rows < 8) rows = 8;
-    if (rows > 32) rows = 32;
-    return rows;
 }
 
 void fill_batch_out(const Planes& P, bool stats, bool minimap, bool icons, smh_b200_batch* out) {
@@ -802,13 +708,6 @@ int32_t smh_b200_create(int32_t device, smh_b200** out) {
     }
     CUC(cudaMalloc(&h->d_rays, sizeof(float2) * SMH_LSD_RAYS));
     CUC(cudaMemcpy(h->d_rays, rays.data(), sizeof(float2) * SMH_LSD_RAYS, cudaMemcpyHostToDevice));
-    {   // ray spans by pixel offset for the line-search filter
-        const int n_span = 4 * smh::LSD_SPAN_N * smh::LSD_SPAN_N;
-        CUC(cudaMalloc(&h->d_span, (size_t)n_span * sizeof(uint32_t)));
-        smh::k_build_span_table<<<(n_span + 255) / 256, 256, 0, h->s_main>>>(h->d_span);
-        h->launches++;
-        CUC(cudaGetLastError());
-    }
     // exact marker predicate memoised over all 2^24 colours (2 MB, stays in L2)
     CUC(cudaMalloc(&h->d_lut, (1u << 24) / 8));
     smh::k_build_marker_lut<<<(1u << 19) / 256, 256, 0, h->s_main>>>(h->d_lut);
@@ -828,7 +727,7 @@ void smh_b200_destroy(smh_b200* h) {
     cudaDeviceSynchronize();
     free_single(h);
     h->batch.release(); for (auto& P : h->pipe) P.release();
-    cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_span); cudaFree(h->d_lut); cudaFree(h->d_icons); cudaFree(h->d_longest); cudaFree(h->d_view);
+    cudaFree(h->d_stage); cudaFree(h->d_pack); cudaFree(h->d_rays); cudaFree(h->d_ckpt); cudaFree(h->d_lut); cudaFree(h->d_icons); cudaFree(h->d_longest); cudaFree(h->d_view);
     cudaFreeHost(h->h_small); cudaFreeHost(h->h_view); cudaFreeHost(h->h_gray);
     for (auto e : h->ev_gray) if (e) cudaEventDestroy(e);
     for (auto s : h->pipe_streams) cudaStreamDestroy(s);
@@ -850,16 +749,6 @@ int32_t smh_b200_bind_thread(smh_b200* h) {
 }
 
 uint64_t smh_b200_launch_count(smh_b200* h) { return h ? h->launches.load() : 0; }
-
-// tuning aid (not in the header): per-phase cycle counters of k_lsd, zero unless built with -DLSD_PROFILE
-int32_t smh_b200_debug_lsd_profile(smh_b200* h, uint64_t out[16], int32_t reset) {
-    if (!h || !out) return SMH_E_ARG;
-    CU(h, cudaSetDevice(h->device));
-    CU(h, cudaDeviceSynchronize());
-    CU(h, cudaMemcpyFromSymbol(out, smh::g_lsd_prof, 16 * sizeof(uint64_t)));
-    if (reset) { uint64_t z[16] = {0}; CU(h, cudaMemcpyToSymbol(smh::g_lsd_prof, z, sizeof z)); }
-    return SMH_OK;
-}
 
 // ------------------------------------------------------------------------------------------
 // per-frame trait methods
@@ -916,8 +805,7 @@ int32_t smh_b200_crop_to_map(smh_b200* h, int32_t grayscale, int32_t* map_open, 
     tm.begin(h->s_main);
     // the fresh thresholded scales image goes to a scratch plane; find_scales_preprocess merges
     // rows >= start_y into the persistent host image, so pass start_y = 0 here
-    int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->uy1 - h->uy0, h->ux0, h->uy0, 1, false, 0, grayscale,
-                           pick_rows_per_band(h, 1, g.map[3]), h->s_main);
+    int rc = launch_pixels(h, h->one, h->d_frame, 0, h->upitch, h->uy1 - h->uy0, h->ux0, h->uy0, 1, false, 0, grayscale, h->s_main);
     if (rc) return rc;
     CU(h, cudaEventRecord(h->ev_pixels, h->s_main));
     uint32_t* h_red = reinterpret_cast<uint32_t*>(h->h_small + 200);
@@ -1048,7 +936,6 @@ int32_t smh_b200_filter_map_marker_icons(smh_b200* h, int32_t* found, uint32_t x
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamWaitEvent(h->s_markers, h->ev_pixels, 0));
     tm.begin(h->s_markers);
-    if ((rc = launch_pack(h, h->one, 1, h->s_markers))) return rc;
     if ((rc = launch_icons(h, h->one, h->d_frame, 0, h->upitch, h->ux0, h->uy0, 1, false, h->s_markers))) return rc;
     uint32_t* hs = reinterpret_cast<uint32_t*>(h->h_small + 248);  // (the scales branch owns 216..243)
     CU(h, cudaMemcpyAsync(hs, h->one.icon_xy, 8, cudaMemcpyDeviceToHost, h->s_markers));
@@ -1336,7 +1223,6 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
             if (start_y[i] > g.brq[3]) return fail(h, SMH_E_RANGE, "process_batch: start_y[%u]=%u > %u", i, start_y[i], g.brq[3]);
         CU(h, cudaMemcpyAsync(h->batch.start_y, start_y, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     }
-    const uint32_t rows_per_band = pick_rows_per_band(h, n, g.map[3]);
     // Large batches: frames are independent, so the batch runs as chunks taken in turn by a few internal
     // streams (pixel pass -> bitmap -> line search per chunk).  The line search is latency-bound and its
     // persistent CTAs leave issue slots and, in the tail of every wave, whole SMs idle; the HBM-bound
@@ -1348,17 +1234,16 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
     if (whole) {
         if (!(flags & SMH_BATCH_SKIP_PIXELS)) {
             if ((rc = launch_pixels(h, h->batch, d_frames, frame_stride, pitch_bytes, H, 0, 0, n, start_y != nullptr, 0,
-                                    flags & SMH_BATCH_GRAYSCALE, rows_per_band, st)))
+                                    flags & SMH_BATCH_GRAYSCALE, st)))
                 return rc;
             if (flags & SMH_BATCH_MINIMAP)
                 if ((rc = launch_minimap(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
         }
         if (icons) {
-            if ((rc = launch_pack(h, h->batch, n, st))) return rc;
             if ((rc = launch_icons(h, h->batch, d_frames, frame_stride, pitch_bytes, 0, 0, n, true, st))) return rc;
         }
         if (!(flags & SMH_BATCH_SKIP_LSD))
-            if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st, !icons))) return rc;
+            if ((rc = launch_lsd(h, h->batch, n, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), st))) return rc;
     } else {
         if ((rc = ensure_ray_ckpt(h, h->batch, st))) return rc;
         if (stats) CU(h, cudaMemsetAsync(h->batch.stats, 0, (size_t)n * 3 * sizeof(unsigned long long), st));
@@ -1381,15 +1266,14 @@ int32_t smh_b200_process_batch(smh_b200* h, const uint8_t* d_frames, uint32_t n,
             const Planes V = planes_view(h->batch, f0, cn, lane);
             const uint8_t* fr = d_frames + (uint64_t)f0 * frame_stride;
             if ((rc = launch_pixels(h, V, fr, frame_stride, pitch_bytes, H, 0, 0, cn, start_y != nullptr, 0,
-                                    flags & SMH_BATCH_GRAYSCALE, rows_per_band, ls)))
+                                    flags & SMH_BATCH_GRAYSCALE, ls)))
                 return rc;
             if (flags & SMH_BATCH_MINIMAP)
                 if ((rc = launch_minimap(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, true, ls))) return rc;
             if (icons) {
-                if ((rc = launch_pack(h, V, cn, ls))) return rc;
                 if ((rc = launch_icons(h, V, fr, frame_stride, pitch_bytes, 0, 0, cn, true, ls))) return rc;
             }
-            if ((rc = launch_lsd(h, V, cn, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), ls, !icons))) return rc;
+            if ((rc = launch_lsd(h, V, cn, (float)max_gap, true, stats, !(flags & SMH_BATCH_LSD_EXHAUSTIVE), ls))) return rc;
         }
         for (uint32_t l = 0; l < lanes; l++) {
             CU(h, cudaEventRecord(h->lane_events[1 + l], h->lane_streams[l]));
@@ -1592,17 +1476,15 @@ static int32_t host_batch_impl(smh_b200* h, const uint8_t* frames, uint32_t n, u
         CU(h, cudaStreamWaitEvent(st, ev_up, 0));
         if (reused) CU(h, cudaStreamWaitEvent(st, ev_down, 0));
         if (start_y) CU(h, cudaMemcpyAsync(P.start_y, start_y + done, (size_t)c * 4, cudaMemcpyHostToDevice, st));
-        if ((rc = launch_pixels(h, P, stage, ustride, upitch, rows, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE,
-                                pick_rows_per_band(h, c, g.map[3]), st)))
+        if ((rc = launch_pixels(h, P, stage, ustride, upitch, rows, ux0, uy0, c, start_y != nullptr, 0, flags & SMH_BATCH_GRAYSCALE, st)))
             return rc;
         if ((flags & SMH_BATCH_MINIMAP) && res->minimap && res->minimap_found)
             if ((rc = launch_minimap(h, P, stage, ustride, upitch, ux0, uy0, c, true, st))) return rc;
         if (icons) {
-            if ((rc = launch_pack(h, P, c, st))) return rc;
             if ((rc = launch_icons(h, P, stage, ustride, upitch, ux0, uy0, c, true, st))) return rc;
         }
         if (!(flags & SMH_BATCH_SKIP_LSD))
-            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st, !icons))) return rc;
+            if ((rc = launch_lsd(h, P, c, (float)max_gap, true, false, true, st))) return rc;
         uint8_t* const pack0 = h->d_pack + (size_t)b * pack_frame * chunk;
         struct Want { const smh_b200_plane* pl; uint8_t* host; };
         const Want wants[4] = {{res->ui_map ? &P.ui : nullptr, res->ui_map ? res->ui_map + (size_t)slot * npx * 4 : nullptr},

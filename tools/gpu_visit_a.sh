@@ -4,11 +4,9 @@
 tag=${1:-r3a}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-SMH_B200_LIB=$PWD/build/variants/lib_prof.so timeout 300 python tools/lsd_profile.py 1024 > gpurun_out/${tag}_lsd_profile.txt 2>&1
-cat gpurun_out/${tag}_lsd_profile.txt
 timeout 300 python bench.py --no-e2e --no-cpu-baseline --steps 5 > gpurun_out/${tag}_bench_quick.json 2> gpurun_out/${tag}_bench_quick.err
 tail -c 600 gpurun_out/${tag}_bench_quick.json
-for k in k_lsd k_pixels; do
+for k in k_lsd2 k_pixels2; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$k" -c 1 -s 3 -f -o gpurun_out/${tag}_${k} \
      python bench.py --frames 1024 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --serial > gpurun_out/${tag}_ncu_${k}.log 2>&1
   ncu -i gpurun_out/${tag}_${k}.ncu-rep --page details > gpurun_out/${tag}_${k}_details.txt 2>&1
