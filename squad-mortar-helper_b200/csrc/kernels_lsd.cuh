@@ -44,7 +44,7 @@ struct Lsd2Shared {
     float4 lines[SMH_LSD_MAX_LINES];
     float4 dead[L2_DEAD];  // (x, y, rho^2, raw^2)
     uint32_t ring[SMH_LSD_FILTER_MAX_WINDOWS][SMH_LSD_BITMAP_WORDS + 3];
-    uint32_t grp[NW][L2_GRP_CAP / NW];  // m8 | (x offset of the quarter's first column + 160) << 8 | (row offset + 128) << 17
+    uint32_t grp[L2_GRP_CAP];  // white quarters of the window: m8 | (x offset of its first column + 160) << 8 | (row offset + 128) << 17
     uint32_t surv[L2_SURV_CAP];         // l2_pack(ray, gap, next block)
     uint32_t win[L2_WIN_T * 32 * L2_WIN_PITCH];
     unsigned long long bkey[NW];
@@ -52,7 +52,7 @@ struct Lsd2Shared {
     unsigned long long steps;
     struct Job { int job, isx, isy, skip; float px, py; } jobs[2];  // double-buffered: the master writes the next one while the last is read
     int n;
-    uint32_t n_dead, n_surv, surv_end, grp_over, near2, far2, frame;
+    uint32_t n_dead, n_surv, surv_end, n_grp, near2, far2, frame;
 };
 
 // The window of a seed, row-major: rows [y0, ..) x words [tx0, tx0 + ntx) of the bitmap.
@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
     const bool dead_ok = F.nw >= 1 && F.border[0] == 0;  // "ring 1 empty => no line" holds for every seed
     const int win_steps = F.radius >= 65 ? 64 : (F.radius >= 33 ? 32 : 0);  // samples that stay inside the window
     const int WR = F.radius + LSD_WIN_EXTRA;  // window radius around the raw seed pixel
-    constexpr int SEG = L2_GRP_CAP / NW;
 
     for (int i = threadIdx.x; i < SMH_LSD_FILTER_MAX_WINDOWS * (SMH_LSD_BITMAP_WORDS + 3); i += NW * 32) (&sh.ring[0][0])[i] = 0u;
 
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             sh.frame = atomicAdd(a.counter, 1u);
-            sh.n = 0; sh.n_dead = 0u; sh.n_surv = 0u; sh.surv_end = (uint32_t)L2_SURV_CAP; sh.grp_over = 0u;
+            sh.n = 0; sh.n_dead = 0u; sh.n_surv = 0u; sh.surv_end = (uint32_t)L2_SURV_CAP; sh.n_grp = 0u;
             sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.steps = 0ull;
         }
         __syncthreads();
@@ -363,12 +362,11 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                     }
                 }
                 __syncthreads();
-                // ---- exact ray filter: every warp lists the white quarters of its tiles of the (2R+1)^2 window
-                //      around the centre and marks the rays each can serve (lane = quarter) ---------------------
+                // ---- exact ray filter: the warps list the white quarters of the (2R+1)^2 window around the centre, tile
+                //      by tile, into one shared list (slots by warp-aggregated atomics: the order does not matter) ... -----
                 const int fx = (int)px, fy = (int)py, R = F.radius;  // px, py >= 0
                 const float hx = px - (float)fx, hy = py - (float)fy;  // 0 or 0.5
                 {
-                    uint32_t n_grp = 0;
                     const int x0 = max(fx - R, 0), x1 = min(fx + R, W - 1), y0 = max(fy - R, 0), y1 = min(fy + R, H - 1);
                     const int X0 = x0 + (int)PAD, X1 = x1 + (int)PAD;
                     const int ta = (y0 - wv.y0) >> 5, tb = (y1 - wv.y0) >> 5, ua = (X0 >> 5) - wv.tx0, ub = (X1 >> 5) - wv.tx0;
@@ -382,51 +380,57 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                         const int Xw = (wv.tx0 + txx) << 5;
                         if (Xw < X0) w &= 0xFFFFFFFFu << (X0 - Xw);
                         if (Xw + 31 > X1) w &= 0xFFFFFFFFu >> (Xw + 31 - X1);
-                        if (!__any_sync(FULL, w != 0u)) continue;
+                        // the tile's quarters, by byte position: 4 ballots, one atomic for the tile
+                        uint32_t have[4], cnt = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { have[q] = __ballot_sync(FULL, ((w >> (8 * q)) & 0xFFu) != 0u); cnt += (uint32_t)__popc(have[q]); }
+                        if (cnt == 0u) continue;
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&sh.n_grp, cnt);
+                        base = __shfl_sync(FULL, base, 0);
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t m8 = (w >> (8 * q)) & 0xFFu;
-                            const uint32_t have = __ballot_sync(FULL, m8 != 0u);
-                            if (have == 0u) continue;
-                            const uint32_t slot = n_grp + (uint32_t)__popc(have & LT);
-                            if (m8 && slot < (uint32_t)SEG)
-                                sh.grp[warp][slot] = m8 | ((uint32_t)(Xw + 8 * q - (int)PAD - fx + 160) << 8) | ((uint32_t)(y - fy + 128) << 17);
-                            n_grp += (uint32_t)__popc(have);
-                        }
-                    }
-                    __syncwarp();
-                    if (n_grp > (uint32_t)SEG) { if (lane == 0) sh.grp_over = 1u; }  // too many white pixels around
-                    else {
-                        float near2 = 0.0f, far2 = 3.0e38f;
-                        const float a2 = F.r2_lo[0];
-                        for (uint32_t i = lane; i < n_grp; i += 32) {
-                            const uint32_t e = sh.grp[warp][i], m8 = e & 0xFFu;
-                            const int ox = (int)((e >> 8) & 0x1FFu) - 160, oy = (int)(e >> 17) - 128;
-                            const float cy = (float)oy + 0.5f - hy;
-                            const float cxa = (float)(ox + __ffs(m8) - 1) + 0.5f - hx, cxb = (float)(ox + 31 - __clz((int)m8)) + 0.5f - hx;
-                            float dmin2, dmax2;
-                            int lo, hi;
-                            smh_lsd_filter_quarter(cy, cxa, cxb, &dmin2, &dmax2, &lo, &hi);
-                            if (dmax2 < a2) near2 = fmaxf(near2, dmax2);
-                            else {
-                                if (dmin2 < a2) near2 = fmaxf(near2, a2);  // straddles the inner disc's rim: no dead cluster from this seed
-                                far2 = fminf(far2, fmaxf(dmin2, a2));
-#pragma unroll
-                                for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
-                                    if (j < F.nw && dmax2 >= F.r2_lo[j] && dmin2 <= F.r2_hi[j]) l2_mark(sh.ring[j], lo, hi);
-                            }
-                        }
-                        const uint32_t n2 = __reduce_max_sync(FULL, __float_as_uint(near2));  // positive floats order like their bits
-                        const uint32_t f2 = __reduce_min_sync(FULL, __float_as_uint(far2));
-                        if (lane == 0) {
-                            if (n2) atomicMax(&sh.near2, n2);
-                            if (f2 != __float_as_uint(3.0e38f)) atomicMin(&sh.far2, f2);
+                            const uint32_t slot = base + (uint32_t)__popc(have[q] & LT);
+                            if (m8 && slot < (uint32_t)L2_GRP_CAP)
+                                sh.grp[slot] = m8 | ((uint32_t)(Xw + 8 * q - (int)PAD - fx + 160) << 8) | ((uint32_t)(y - fy + 128) << 17);
+                            base += (uint32_t)__popc(have[q]);
                         }
                     }
                 }
                 __syncthreads();
+                // ---- ... and mark the rays every quarter can serve, ring by ring: one quarter per lane, all warps ----------
+                const uint32_t n_grp = sh.n_grp;
+                const bool everything = n_grp > (uint32_t)L2_GRP_CAP;  // too many white pixels around: every ray is marched
+                if (!everything) {
+                    float near2 = 0.0f, far2 = 3.0e38f;
+                    const float a2 = F.r2_lo[0];
+                    for (uint32_t i = threadIdx.x; i < n_grp; i += NW * 32) {
+                        const uint32_t e = sh.grp[i], m8 = e & 0xFFu;
+                        const int ox = (int)((e >> 8) & 0x1FFu) - 160, oy = (int)(e >> 17) - 128;
+                        const float cy = (float)oy + 0.5f - hy;
+                        const float cxa = (float)(ox + __ffs(m8) - 1) + 0.5f - hx, cxb = (float)(ox + 31 - __clz((int)m8)) + 0.5f - hx;
+                        float dmin2, dmax2;
+                        int lo, hi;
+                        smh_lsd_filter_quarter(cy, cxa, cxb, &dmin2, &dmax2, &lo, &hi);
+                        if (dmax2 < a2) near2 = fmaxf(near2, dmax2);
+                        else {
+                            if (dmin2 < a2) near2 = fmaxf(near2, a2);  // straddles the inner disc's rim: no dead cluster from this seed
+                            far2 = fminf(far2, fmaxf(dmin2, a2));
+#pragma unroll
+                            for (int j = 0; j < SMH_LSD_FILTER_MAX_WINDOWS; j++)
+                                if (j < F.nw && dmax2 >= F.r2_lo[j] && dmin2 <= F.r2_hi[j]) l2_mark(sh.ring[j], lo, hi);
+                        }
+                    }
+                    const uint32_t n2 = __reduce_max_sync(FULL, __float_as_uint(near2));  // positive floats order like their bits
+                    const uint32_t f2 = __reduce_min_sync(FULL, __float_as_uint(far2));
+                    if (lane == 0) {
+                        if (n2) atomicMax(&sh.near2, n2);
+                        if (f2 != __float_as_uint(3.0e38f)) atomicMin(&sh.far2, f2);
+                    }
+                }
+                __syncthreads();
                 // ---- AND of the usable rings, word by word = 32 consecutive rays = one lane-per-ray group -------
-                const bool everything = sh.grp_over != 0u;
                 L2Best best{0ull, px, py};
                 bool any_ray = false;
                 const int c0 = win_steps / 32;
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                                 rowmask &= __ballot_sync(FULL, nzr != 0u);
                             }
                         }
-                        if (lane == 0) { sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.n_dead = n_dead; sh.grp_over = 0u; }
+                        if (lane == 0) { sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.n_dead = n_dead; sh.n_grp = 0u; }
                     }
                     continue;  // the master's writes are published by the next barrier
                 }
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                             rowmask &= __ballot_sync(FULL, nzr != 0u);
                         }
                     }
-                    if (lane == 0) { sh.n_surv = 0u; sh.surv_end = (uint32_t)L2_SURV_CAP; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.grp_over = 0u; }
+                    if (lane == 0) { sh.n_surv = 0u; sh.surv_end = (uint32_t)L2_SURV_CAP; sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.n_grp = 0u; }
                 }
                 // no barrier here: the next thing the workers read (sh.job) is published by the barrier at the loop's head
             }

@@ -9,7 +9,7 @@ python - <<PY
 import json
 try:
     d=json.loads(open("gpurun_out/${tag}_bench_quick.json").readline()); k=d["kernels"]
-    print("fps %.0f  step %.3f ms  px %.3f ms  lsd %.3f ms  frac %.3f  seeds/frame %.1f steps/frame %.0f" % (d["value"], d["ms_per_step"], k["k_pixels"]["ms"], k["k_lsd"]["ms"], d["roofline"]["frac"], k["k_lsd"]["seeds_per_frame"], k["k_lsd"]["ray_steps_per_frame"]))
+    print("fps %.0f  step %.3f ms  px %.3f ms  lsd %.3f ms  frac %.3f  seeds/frame %.1f steps/frame %.0f" % (d["value"], d["ms_per_step"], k["k_pixels2"]["ms"], k["k_lsd2"]["ms"], d["roofline"]["frac"], k["k_lsd2"]["seeds_per_frame"], k["k_lsd2"]["ray_steps_per_frame"]))
 except Exception as e:
     print("bench failed", e); print(open("gpurun_out/${tag}_bench_quick.err").read()[-2000:])
 PY
