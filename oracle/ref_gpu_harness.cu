@@ -56,7 +56,27 @@ struct refgpu {
     uint8_t* lsd_kernel_dilate = nullptr;
     Line* longest_lines = nullptr;
     uint64_t seeds = 0, launches = 0;
+    // per-kernel device time (CUDA events around every launch) when `timing` is on: K1..K10 of SURVEY.md 2.2 + the upload
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kernel_us[12] = {0};
+    uint64_t kernel_launches[12] = {0};
 };
+
+enum { RK_UPLOAD = 0, RK_K1 = 1, RK_K2 = 2, RK_K3 = 3, RK_K4 = 4, RK_K5 = 5, RK_K6 = 6, RK_K7 = 7, RK_K8 = 8, RK_K9 = 9, RK_K10 = 10 };
+// bracket one launch with events on its stream and add the elapsed time to the kernel's account
+#define TIMED(r, k, stream, launch)                                                              \
+    do {                                                                                         \
+        if ((r)->timing) cudaEventRecord((r)->ev0, stream);                                      \
+        launch;                                                                                  \
+        if ((r)->timing) {                                                                       \
+            cudaEventRecord((r)->ev1, stream);                                                   \
+            cudaEventSynchronize((r)->ev1);                                                      \
+            float ms__ = 0.0f;                                                                   \
+            cudaEventElapsedTime(&ms__, (r)->ev0, (r)->ev1);                                     \
+            (r)->kernel_us[k] += 1e3 * ms__; (r)->kernel_launches[k]++;                          \
+        }                                                                                        \
+    } while (0)
 
 static void release(refgpu* r) {
     cudaFree(r->frame); cudaFree(r->red_pixels); cudaFree(r->ui_map); cudaFree(r->cropped_map); cudaFree(r->cropped_brq);
@@ -97,7 +117,7 @@ static inline dim3 grid2d(uint32_t w, uint32_t h, uint32_t bx, uint32_t by) { re
 // back, stream sync, host fold keeping the FIRST strictly greater length
 static int ref_longest(refgpu* r, const uint8_t* d_img, uint32_t w, uint32_t h, float x, float y, float max_gap,
                        float line[4], float* len_sq) {
-    find_longest_line<<<8, (360 * 10) / 8, 0, r->markers_stream>>>(d_img, w, h, Point{x, y}, max_gap, r->longest_lines);
+    TIMED(r, RK_K10, r->markers_stream, (find_longest_line<<<8, (360 * 10) / 8, 0, r->markers_stream>>>(d_img, w, h, Point{x, y}, max_gap, r->longest_lines)));
     r->launches++;
     Line block[8];
     RCHECK(cudaMemcpyAsync(block, r->longest_lines, sizeof block, cudaMemcpyDeviceToHost, r->markers_stream));
@@ -135,6 +155,7 @@ int refgpu_create(refgpu** out) {
     RCHECK(cudaStreamCreateWithFlags(&r->stream_b, cudaStreamNonBlocking));
     RCHECK(cudaStreamCreateWithFlags(&r->markers_stream, cudaStreamNonBlocking));
     RCHECK(cudaStreamCreateWithFlags(&r->scales_stream, cudaStreamNonBlocking));
+    RCHECK(cudaEventCreate(&r->ev0)); RCHECK(cudaEventCreate(&r->ev1));
     *out = r;
     return 0;
 }
@@ -144,6 +165,7 @@ void refgpu_destroy(refgpu* r) {
     cudaDeviceSynchronize();
     release(r);
     cudaStreamDestroy(r->stream_a); cudaStreamDestroy(r->stream_b); cudaStreamDestroy(r->markers_stream); cudaStreamDestroy(r->scales_stream);
+    cudaEventDestroy(r->ev0); cudaEventDestroy(r->ev1);
     delete r;
 }
 
@@ -166,7 +188,7 @@ int refgpu_process_frame(refgpu* r, const uint8_t* bgra, uint32_t W, uint32_t H,
     // red_pixels <- 0, stream sync
     cudaFree(r->frame); r->frame = nullptr;
     RCHECK(cudaMalloc(&r->frame, (size_t)W * H * 4));
-    RCHECK(cudaMemcpyAsync(r->frame, bgra, (size_t)W * H * 4, cudaMemcpyHostToDevice, r->stream_a));
+    TIMED(r, RK_UPLOAD, r->stream_a, RCHECK(cudaMemcpyAsync(r->frame, bgra, (size_t)W * H * 4, cudaMemcpyHostToDevice, r->stream_a)));
     const uint32_t zero = 0;
     RCHECK(cudaMemcpyAsync(r->red_pixels, &zero, 4, cudaMemcpyHostToDevice, r->stream_a));
     RCHECK(cudaStreamSynchronize(r->stream_a));
@@ -174,8 +196,8 @@ int refgpu_process_frame(refgpu* r, const uint8_t* bgra, uint32_t W, uint32_t H,
     // ---- crop_to_map — :206-297
     {
         const uint32_t bx = roi[0], by = roi[1], bw = roi[2], bh = roi[3];
-        count_close_deployment_button_red_pixels<<<grid2d(bw, bh, 16, 16), dim3(16, 16), 4, r->stream_a>>>(
-            r->frame, W, bx, by, bw, bh, r->red_pixels);
+        TIMED(r, RK_K1, r->stream_a, (count_close_deployment_button_red_pixels<<<grid2d(bw, bh, 16, 16), dim3(16, 16), 4, r->stream_a>>>(
+            r->frame, W, bx, by, bw, bh, r->red_pixels)));
         r->launches++;
         uint32_t red = 0;
         RCHECK(cudaMemcpyAsync(&red, r->red_pixels, 4, cudaMemcpyDeviceToHost, r->stream_a));
@@ -187,9 +209,9 @@ int refgpu_process_frame(refgpu* r, const uint8_t* bgra, uint32_t W, uint32_t H,
     }
     {
         const uint32_t x = roi[4], y = roi[5];
-        if (grayscale) crop_to_map_grayscale<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->stream_a>>>(r->frame, W, x, y, w, h, r->cropped_map, r->ui_map);
-        else crop_to_map<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->stream_a>>>(r->frame, W, x, y, w, h, r->cropped_map, r->ui_map);
-        crop_to_map_brq<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->stream_b>>>(r->frame, W, x + qw, y + qh, qw, qh, r->cropped_brq);
+        if (grayscale) TIMED(r, RK_K3, r->stream_a, (crop_to_map_grayscale<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->stream_a>>>(r->frame, W, x, y, w, h, r->cropped_map, r->ui_map)));
+        else TIMED(r, RK_K2, r->stream_a, (crop_to_map<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->stream_a>>>(r->frame, W, x, y, w, h, r->cropped_map, r->ui_map)));
+        TIMED(r, RK_K4, r->stream_b, (crop_to_map_brq<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->stream_b>>>(r->frame, W, x + qw, y + qh, qw, qh, r->cropped_brq)));
         r->launches += 2;
         std::vector<uint8_t> ui_host((size_t)w * h * 4);  // `vec![0u8; ..]` per frame, pageable (:289-290)
         RCHECK(cudaMemcpyAsync(ui_host.data(), r->ui_map, ui_host.size(), cudaMemcpyDeviceToHost, r->stream_a));
@@ -200,16 +222,17 @@ int refgpu_process_frame(refgpu* r, const uint8_t* bgra, uint32_t W, uint32_t H,
     if (cropped_brq) RCHECK(cudaMemcpy(cropped_brq, r->cropped_brq, (size_t)qw * qh * 3, cudaMemcpyDeviceToHost));
 
     // ---- markers branch: isolate_map_markers (:348-371), mask_marker_lines (:432-475), find_marker_lines (:477-487)
-    isolate_map_markers<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(r->cropped_map, w, h);
+    TIMED(r, RK_K7, r->markers_stream, (isolate_map_markers<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(r->cropped_map, w, h)));
     r->launches++;
     RCHECK(cudaStreamSynchronize(r->markers_stream));
     if (cropped_map_isolated) RCHECK(cudaMemcpy(cropped_map_isolated, r->cropped_map, (size_t)w * h * 3, cudaMemcpyDeviceToHost));
-    mask_marker_lines<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(r->cropped_map, w, h, r->lsd_image_dilate);
+    TIMED(r, RK_K8, r->markers_stream, (mask_marker_lines<<<grid2d(w, h, 8, 8), dim3(8, 8), 0, r->markers_stream>>>(r->cropped_map, w, h, r->lsd_image_dilate)));
     r->launches++;
     RCHECK(cudaStreamSynchronize(r->markers_stream));
     if (raw_mask) RCHECK(cudaMemcpy(raw_mask, r->lsd_image_dilate, (size_t)w * h, cudaMemcpyDeviceToHost));
     {
-        const int res = gpu_dilate(r->lsd_image_dilate, r->lsd_image, w, h, r->lsd_kernel_dilate, 2, 2);  // NPP, default stream
+        int res = 0;
+        TIMED(r, RK_K9, (cudaStream_t)0, (res = gpu_dilate(r->lsd_image_dilate, r->lsd_image, w, h, r->lsd_kernel_dilate, 2, 2)));  // NPP, default stream
         r->launches++;
         if (res != 0) { snprintf(g_err, sizeof g_err, "nppiDilate_8u_C1R error %d", res); return res; }
         RCHECK(cudaMemcpy(r->lsd_image_host, r->lsd_image, (size_t)w * h, cudaMemcpyDeviceToHost));  // copy_from_gpu (blocking)
@@ -226,12 +249,12 @@ int refgpu_process_frame(refgpu* r, const uint8_t* bgra, uint32_t W, uint32_t H,
     }
 
     // ---- scales branch: ocr_preprocess (:300-321), [Tesseract], find_scales_preprocess (:323-346)
-    ocr_preprocess<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->scales_stream>>>(r->cropped_brq, qw, qh, r->ocr_out);
+    TIMED(r, RK_K5, r->scales_stream, (ocr_preprocess<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->scales_stream>>>(r->cropped_brq, qw, qh, r->ocr_out)));
     r->launches++;
     RCHECK(cudaMemcpyAsync(r->ocr_out_host, r->ocr_out, (size_t)qw * qh, cudaMemcpyDeviceToHost, r->scales_stream));
     RCHECK(cudaStreamSynchronize(r->scales_stream));
     if (ocr_out) memcpy(ocr_out, r->ocr_out_host, (size_t)qw * qh);
-    find_scales_preprocess<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->scales_stream>>>(r->cropped_brq, qw, qh, start_y, r->scales);
+    TIMED(r, RK_K6, r->scales_stream, (find_scales_preprocess<<<grid2d(qw, qh, 8, 8), dim3(8, 8), 0, r->scales_stream>>>(r->cropped_brq, qw, qh, start_y, r->scales)));
     r->launches++;
     RCHECK(cudaMemcpyAsync(r->scales_host.data(), r->scales, (size_t)qw * qh, cudaMemcpyDeviceToHost, r->scales_stream));
     RCHECK(cudaStreamSynchronize(r->scales_stream));
@@ -250,18 +273,22 @@ int refgpu_find_longest_line_in(refgpu* r, const uint8_t* img, uint32_t w, uint3
     return rc;
 }
 
-/* Wall-clock frames/s of refgpu_process_frame over `n` host frames (tightly stacked), `reps` passes. */
+/* Wall-clock frames/s of refgpu_process_frame over `n` host frames (tightly stacked): `warm` untimed frames, then
+ * `passes` timed passes over all n frames; frames_per_s[passes] (take the median). */
 int refgpu_time_frames(refgpu* r, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, int grayscale, uint32_t max_gap,
-                       uint32_t reps, double* frames_per_s, uint64_t* seeds_total, uint64_t* launches_total) {
+                       uint32_t warm, uint32_t passes, double* frames_per_s, uint64_t* seeds_total, uint64_t* launches_total) {
     uint64_t seeds = 0;
-    int open = 0;
-    int rc = refgpu_process_frame(r, frames, W, H, grayscale, 0, max_gap, &open, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                  nullptr, nullptr, nullptr, nullptr, nullptr);  // warm-up (allocations, module load)
-    if (rc) return rc;
+    int open = 0, rc = 0;
+    r->timing = false;
+    for (uint32_t i = 0; i < warm; i++) {  // allocations, module load, clocks
+        rc = refgpu_process_frame(r, frames + (size_t)(i % n) * W * H * 4, W, H, grayscale, 0, max_gap, &open, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
     RCHECK(cudaDeviceSynchronize());
     const uint64_t l0 = r->launches;
-    const auto t0 = std::chrono::steady_clock::now();
-    for (uint32_t k = 0; k < reps; k++)
+    for (uint32_t k = 0; k < passes; k++) {
+        const auto t0 = std::chrono::steady_clock::now();
         for (uint32_t i = 0; i < n; i++) {
             uint64_t s = 0;
             rc = refgpu_process_frame(r, frames + (size_t)i * W * H * 4, W, H, grayscale, 0, max_gap, &open, nullptr, nullptr, nullptr,
@@ -269,12 +296,34 @@ int refgpu_time_frames(refgpu* r, const uint8_t* frames, uint32_t n, uint32_t W,
             if (rc) return rc;
             seeds += s;
         }
-    RCHECK(cudaDeviceSynchronize());
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (frames_per_s) *frames_per_s = (double)n * reps / dt;
+        RCHECK(cudaDeviceSynchronize());
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (frames_per_s) frames_per_s[k] = (double)n / dt;
+    }
     if (seeds_total) *seeds_total = seeds;
     if (launches_total) *launches_total = r->launches - l0;
     return 0;
+}
+
+/* Device time of every reference kernel (CUDA events around each launch, reference launch shapes) summed over `n`
+ * frames: us[11] = {upload, K1, K2, K3, K4, K5, K6, K7, K8, K9 (NPP), K10 (all seeds)}, launches[11] likewise. */
+int refgpu_kernel_times(refgpu* r, const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, int grayscale, uint32_t max_gap,
+                        double* us, uint64_t* launches) {
+    int open = 0, rc = 0;
+    r->timing = false;
+    for (uint32_t i = 0; i < 4; i++) {
+        rc = refgpu_process_frame(r, frames + (size_t)(i % n) * W * H * 4, W, H, grayscale, 0, max_gap, &open, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 12; k++) { r->kernel_us[k] = 0.0; r->kernel_launches[k] = 0; }
+    r->timing = true;
+    for (uint32_t i = 0; i < n && !rc; i++)
+        rc = refgpu_process_frame(r, frames + (size_t)i * W * H * 4, W, H, grayscale, 0, max_gap, &open, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    r->timing = false;
+    for (int k = 0; k < 11; k++) { us[k] = r->kernel_us[k]; launches[k] = r->kernel_launches[k]; }
+    return rc;
 }
 
 }  // extern "C"

@@ -37,8 +37,9 @@ def lib() -> C.CDLL:
                                           [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
         L.refgpu_find_longest_line_in.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float,
                                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]
-        L.refgpu_time_frames.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+        L.refgpu_time_frames.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                          C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.refgpu_kernel_times.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.refgpu_ray_dirs.argtypes = [vp, vp]
         L.refgpu_rays_per_seed.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_float, vp]
         L.refgpu_block_winners.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_float, vp]
@@ -103,17 +104,34 @@ class RefGpu:
             raise RuntimeError(f"refgpu_find_longest_line_in rc={rc}: {self.L.refgpu_last_error().decode()}")
         return np.array(list(line), np.float32), np.float32(ln.value)
 
-    def time_frames(self, frames: np.ndarray, grayscale=True, max_gap=15, reps=1) -> dict:
-        """frames: [n, H, W, 4] host BGRA.  Wall-clock frames/s of the reference's per-frame sequence."""
+    def time_frames(self, frames: np.ndarray, grayscale=True, max_gap=15, warm=8, passes=5) -> dict:
+        """frames: [n, H, W, 4] host BGRA.  Wall-clock frames/s of the reference's per-frame sequence: `warm` untimed
+        frames, then `passes` timed passes over all frames (median reported, all listed)."""
         frames = np.ascontiguousarray(frames)
         n, H, W = frames.shape[:3]
-        fps, seeds, launches = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
-        rc = self.L.refgpu_time_frames(self.h, frames.ctypes.data, n, W, H, int(grayscale), max_gap, reps, C.byref(fps),
+        fps = (C.c_double * passes)()
+        seeds, launches = C.c_uint64(0), C.c_uint64(0)
+        rc = self.L.refgpu_time_frames(self.h, frames.ctypes.data, n, W, H, int(grayscale), max_gap, warm, passes, fps,
                                        C.byref(seeds), C.byref(launches))
         if rc:
             raise RuntimeError(f"refgpu_time_frames rc={rc}: {self.L.refgpu_last_error().decode()}")
-        return {"frames_per_s": fps.value, "seeds_per_frame": seeds.value / (n * reps),
-                "launches_per_frame": launches.value / (n * reps)}
+        vals = sorted(fps)
+        return {"frames_per_s": vals[len(vals) // 2], "frames_per_s_passes": list(fps), "seeds_per_frame": seeds.value / (n * passes),
+                "launches_per_frame": launches.value / (n * passes)}
+
+    def kernel_times(self, frames: np.ndarray, grayscale=True, max_gap=15) -> dict:
+        """Device time of every reference kernel (CUDA events around each launch) per frame, in microseconds."""
+        frames = np.ascontiguousarray(frames)
+        n, H, W = frames.shape[:3]
+        us = (C.c_double * 11)()
+        cnt = (C.c_uint64 * 11)()
+        rc = self.L.refgpu_kernel_times(self.h, frames.ctypes.data, n, W, H, int(grayscale), max_gap, us, cnt)
+        if rc:
+            raise RuntimeError(f"refgpu_kernel_times rc={rc}: {self.L.refgpu_last_error().decode()}")
+        names = ["upload (pageable H2D, 14.7 MB)", "K1 count_close_deployment_button_red_pixels", "K2 crop_to_map", "K3 crop_to_map_grayscale",
+                 "K4 crop_to_map_brq", "K5 ocr_preprocess", "K6 find_scales_preprocess", "K7 isolate_map_markers", "K8 mask_marker_lines",
+                 "K9 nppiDilate_8u_C1R", "K10 find_longest_line (all seeds of the frame)"]
+        return {nm: {"us_per_frame": us[i] / n, "launches_per_frame": cnt[i] / n} for i, nm in enumerate(names) if cnt[i]}
 
     def _ck(self, rc, what):
         if rc:

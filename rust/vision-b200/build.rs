@@ -10,8 +10,8 @@ fn main() {
     let src = PathBuf::from(env::var("SMH_B200_SRC").unwrap_or_else(|_| "../..".into()));
     let csrc = src.join("squad-mortar-helper_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
-    for f in ["smh_b200.cu", "kernels.cuh", "kernels_next.cuh", "kernels_icons.cuh", "smh_host_widen.cpp", "smh_pixel.h", "smh_synth.h",
-              "smh_lsd_filter.h"] {
+    for f in ["smh_b200.cu", "kernels.cuh", "kernels_px.cuh", "kernels_lsd.cuh", "kernels_next.cuh", "kernels_icons.cuh", "smh_host_widen.cpp",
+              "smh_pixel.h", "smh_synth.h", "smh_lsd_filter.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", src.join("include/smh_b200.h").display());

@@ -6,8 +6,10 @@
 //! fallback: `init()` returns `Err` on a machine without a Blackwell GPU and the app's existing
 //! `hardware::gpu()` error path (src/vision/hardware.rs:66-82) takes over.
 //!
-//! UNCOMPILED in this repository (no Rust toolchain in the build image); the same
-//! C ABI is exercised by the ctypes mirror squad-mortar-helper_b200/vision.py and its tests.
+//! A SKETCH, NOT A TESTED CRATE: it has never been compiled (no Rust toolchain in the build image), so the
+//! crate / macro names taken from the reference (`smh_vision_common`, `export_dylib_wrapper!`) and the trait conformance
+//! are unverified; compile it against the reference workspace before relying on it.  What IS tested is the C ABI
+//! underneath, through the ctypes mirror squad-mortar-helper_b200/vision.py (same calls, same order).
 mod ffi;
 
 use std::{ffi::CStr, ptr, sync::Arc};
@@ -61,6 +63,41 @@ impl B200Vision {
         let (mut found, mut xy, mut sad) = (0i32, [0u32; 2], 0u32);
         self.check(unsafe { ffi::smh_b200_filter_map_marker_icons(self.h, &mut found, xy.as_mut_ptr(), &mut sad) })?;
         Ok(if found != 0 { Some((xy[0], xy[1], sad)) } else { None })
+    }
+}
+
+impl B200Vision {
+    /// `find_minimap` on the device copy of the loaded frame — src/vision/find_minimap.rs:51-146 (called at mod.rs:85).
+    #[allow(dead_code)]
+    pub fn find_minimap(&self) -> Result<Option<[u32; 4]>, AnyError> {
+        let (mut found, mut rect) = (0i32, [0u32; 4]);
+        self.check(unsafe { ffi::smh_b200_find_minimap(self.h, &mut found, rect.as_mut_ptr()) })?;
+        Ok(if found != 0 { Some(rect) } else { None }) // left, right, top, bottom
+    }
+
+    /// `calc_meters_to_px_ratio` on the image `find_scales_preprocess` last returned — src/vision/mpx_ratio.rs:3-133.
+    #[allow(dead_code)]
+    pub fn calc_meters_to_px_ratio(&self, scales: &[(u32, (u32, u32))]) -> Result<Option<f64>, AnyError> {
+        let sc: Vec<ffi::smh_b200_scale> = scales.iter().take(3).map(|&(meters, (x, y))| ffi::smh_b200_scale { meters, x, y }).collect();
+        let (mut found, mut ratio, mut n_debug) = (0i32, 0f64, 0u32);
+        let mut debug = [[0u32; 4]; 3];
+        self.check(unsafe {
+            ffi::smh_b200_calc_meters_to_px_ratio(self.h, sc.as_ptr(), sc.len() as u32, &mut found, &mut ratio, debug.as_mut_ptr(), &mut n_debug)
+        })?;
+        Ok(if found != 0 { Some(ratio) } else { None })
+    }
+
+    /// The reference's `Timeshares` (vision-common/src/debug.rs:3-29) of the last frame: per stage (wall-clock ms of
+    /// the call, CUDA-event ms of the device work it enqueued), in the reference's stage order.
+    #[allow(dead_code)]
+    pub fn timeshares(&self) -> Result<[(f32, f32); ffi::SMH_STAGE_COUNT], AnyError> {
+        let (mut host, mut dev) = ([0f32; ffi::SMH_STAGE_COUNT], [0f32; ffi::SMH_STAGE_COUNT]);
+        self.check(unsafe { ffi::smh_b200_timeshares(self.h, host.as_mut_ptr(), dev.as_mut_ptr()) })?;
+        let mut out = [(0f32, 0f32); ffi::SMH_STAGE_COUNT];
+        for i in 0..ffi::SMH_STAGE_COUNT {
+            out[i] = (host[i], dev[i]);
+        }
+        Ok(out)
     }
 }
 
@@ -144,16 +181,9 @@ impl Vision for B200Vision {
         self.check(unsafe { ffi::smh_b200_mask_marker_lines(self.h) })
     }
 
-    // The two trait methods the reference carries commented out (vision-common/src/lib.rs:46,53).  They are
-    // written as they would read with the trait lines restored; until then they are inherent methods below.
-    /*
-    fn load_map_markers(&mut self, map_marker_size: u32) -> Result<(), Self::Error> {
-        B200Vision::load_map_markers(self, map_marker_size)
-    }
-    fn filter_map_marker_icons(&self) -> Result<(), Self::Error> {
-        B200Vision::filter_map_marker_icons(self).map(|_| ())
-    }
-    */
+    // The two trait methods the reference carries commented out (vision-common/src/lib.rs:46,53) exist as the inherent
+    // methods `load_map_markers_rgba` / `filter_map_marker_icons` above; with the trait lines restored they would forward
+    // to those (the TGA decode / resize of `load_markers` stays host-side `image` work, markers/mod.rs:96-119).
 
     fn find_longest_line(&self, _image: &Self::LSDImage, pt: Point<f32>, max_gap: f32) -> Result<(Line<f32>, f32), Self::Error> {
         let (mut line, mut len) = ([0f32; 4], 0f32);
