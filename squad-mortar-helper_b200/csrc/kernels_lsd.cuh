@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                                 rowmask &= __ballot_sync(FULL, nzr != 0u);
                             }
                         }
+                        __syncwarp();  // every lane has read near2 / far2
                         if (lane == 0) { sh.near2 = 0u; sh.far2 = __float_as_uint(3.0e38f); sh.n_dead = n_dead; sh.n_grp = 0u; }
                     }
                     continue;  // the master's writes are published by the next barrier
