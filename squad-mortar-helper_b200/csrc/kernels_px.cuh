@@ -42,24 +42,46 @@ struct Pixel2Args {
     const uint32_t* start_y;  // device [n] or nullptr
     uint32_t start_y_uniform;
     uint32_t* red; uint8_t* open;
-    uint32_t nbands, nstrips, n_frames;
-    uint32_t qb0, qb1, qs0, qs1;  // bands x strips that own pixels of the OCR quadrant (the QUAD launch's items)
+    uint32_t nstrips, n_frames;
+    // The QUAD launch's items own the strips [qs0, qs1) of the rows [qr0, qr1) (multiples of 32 around the OCR quadrant,
+    // qr1 clipped to h) in bands of PX2_BAND_Q rows; the plain launch owns the rest in bands of PX2_BAND_P rows:
+    // every strip above (na bands per strip) and below (nc), the other strips beside (nb).  nq = bands of a QUAD strip.
+    uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq;
     const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
     uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
 };
 
-constexpr int PX2_THREADS = 128;
-constexpr int PX2_WARPS = PX2_THREADS / 32;
-constexpr int PX2_STAGES = 3;
-constexpr int PX2_ROWS = 2;                      // rows per TMA box
-#ifndef PX2_BAND_ROWS
-#define PX2_BAND_ROWS 64
+#ifndef PX2_WARPS_N
+#define PX2_WARPS_N 4
 #endif
-constexpr int PX2_BAND = PX2_BAND_ROWS;          // map rows per work item (a multiple of 32: whole tile-rows of the bitmap)
+constexpr int PX2_WARPS = PX2_WARPS_N;           // warps (= items) per CTA; 32 resident warps per SM either way
+constexpr int PX2_THREADS = PX2_WARPS * 32;
+#ifndef PX2_STAGES_N
+#define PX2_STAGES_N 3
+#endif
+#ifndef PX2_ROWS_N
+#define PX2_ROWS_N 2
+#endif
+#ifndef PX2_BAND_P_ROWS
+#define PX2_BAND_P_ROWS 64
+#endif
+#ifndef PX2_BAND_Q_ROWS
+#define PX2_BAND_Q_ROWS 64
+#endif
+constexpr int PX2_STAGES = PX2_STAGES_N;
+constexpr int PX2_ROWS = PX2_ROWS_N;             // rows per TMA box
+constexpr int PX2_BAND_P = PX2_BAND_P_ROWS;      // map rows per work item of the plain launch / the QUAD launch
+constexpr int PX2_BAND_Q = PX2_BAND_Q_ROWS;      //   (multiples of 32: whole tile-rows of the bitmap)
 constexpr int PX2_HALO = 4;                      // halo pixels either side of the strip
-constexpr int PX2_BOX_W = 128 + 2 * PX2_HALO;    // pixels per box row
-constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     // 544
-constexpr int PX2_STAGE_BYTES = 1152;            // 2 x 544 rounded up to a multiple of 128
+#ifndef PX2_PROBE   // tuning probes only (tools/): 1 = no luma arithmetic, 2 = also no ui_map stores.  Results are wrong.
+#define PX2_PROBE 0
+#endif
+constexpr int PX2_BOX_W = 128;                   // pixels per row of a strip box (512 bytes, whole 128-byte lines when the
+constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     //   capture's map starts on one); the halo arrives in two boxes of its own
+constexpr int PX2_HALO_OFF = PX2_ROWS * PX2_ROW_BYTES;  // stage layout: strip rows | left halo rows (16 B each) | right halo rows
+constexpr int PX2_HALO_SLOT = PX2_ROWS * PX2_HALO * 4;
+constexpr int PX2_STAGE_BYTES = (PX2_HALO_OFF + 2 * PX2_HALO_SLOT + 127) / 128 * 128;
+constexpr int PX2_STAGE_TX = PX2_ROWS * PX2_ROW_BYTES;  // bytes the bulk copy of a stage delivers
 constexpr int PX2_WARP_BYTES = PX2_STAGES * PX2_STAGE_BYTES + 128;  // ring + mbarriers
 constexpr int PX2_SMEM_BYTES = PX2_WARPS * PX2_WARP_BYTES;
 
@@ -85,6 +107,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                  :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
+// 16 bytes global -> shared by the calling lane; the lane's next cp_async_arrive tracks it
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+// the calling lane arrives on the mbarrier once its earlier cp.async copies have landed (the arrival is part of the
+// barrier's initial count)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+}
+
 // one lane of the (converged) warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t p;
@@ -95,16 +127,20 @@ __device__ __forceinline__ bool elect_one() {
 // nibble -> 4 bytes of 0/255
 __device__ __forceinline__ uint32_t nibble_bytes(uint32_t d4) { return ((d4 * 0x00204081u) & 0x01010101u) * 255u; }
 
+#if PX2_PROBE == 1 || PX2_PROBE == 2
+#define PX_LUMA(w) ((w) | BIAS | 1u)
+#else
+#define PX_LUMA(w) luma_biased_i2f(w)
+#endif
 template <bool B> struct PxTag { static constexpr bool value = B; };
 
 template <bool GRAY, bool QUAD>
-__device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Args& a, uint32_t f, uint32_t band, uint32_t strip,
+__device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Args& a, uint32_t f, int r0, int r1, uint32_t strip,
                                          uint32_t ring, uint32_t bars) {
     constexpr int LAG = QUAD ? SMH_OCR_RADIUS : 1;   // rows phase 2 runs behind phase 1 (= rows of halo above / below)
     const int lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const int w = (int)a.w, h = (int)a.h, bqw = (int)a.bqw, bqh = (int)a.bqh;
-    const int r0 = (int)band * PX2_BAND, r1 = min(r0 + PX2_BAND, h);
     const int x_base = (int)strip * 128 - (int)a.pad;  // map column of the strip's first pixel (X = 128 strip)
     const int i_lo = x_base + 4 * lane;              // map column of the lane's first pixel
     const bool active = i_lo < w;                     // the lane's vector starts left of the map's right edge: it stores
@@ -138,9 +174,9 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         hvm4 |= valid ? (1u << e) : 0u;
         hcm4 |= (QUAD && valid && i >= bqw && i < 2 * bqw && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
     }
-    const uint32_t own_off = (uint32_t)(PX2_HALO * 4) + (uint32_t)lane * 16u;  // the lane's vector in a box row
-    const uint32_t h_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : 0u;   // the halo vector (QUAD)
-    const uint32_t hp_off = lane == 31 ? (uint32_t)(PX2_HALO + 128) * 4u : (uint32_t)(PX2_HALO - 1) * 4u;  // the halo pixel
+    const uint32_t own_off = (uint32_t)lane * 16u;  // the lane's vector in a strip row
+    const uint32_t h_off = lane == 31 ? (uint32_t)PX2_HALO_SLOT : 0u;   // the halo vector of a row (QUAD), from the stage's halo rows
+    const uint32_t hp_off = lane == 31 ? (uint32_t)PX2_HALO_SLOT : (uint32_t)(PX2_HALO - 1) * 4u;  // the halo pixel
     const uint32_t hp_bit = lane == 0 ? (hvm4 & 8u) : (lane == 31 ? (hvm4 & 1u) : 0u);  // where its flag goes in the halo nibble
     const bool col_brq = em4 != 0u;
     const uint32_t qpos = (uint32_t)(i_lo - bqw + (int)a.q_pad);  // byte position in a quadrant row (used when col_brq)
@@ -148,13 +184,16 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     // ---- rows: read [j_first, j_end), owned (stored) [r0, r1) -----------------------------------------------
     const int j_first = r0 - LAG, j_end = r1 + LAG;
     const int n_chunks = (j_end - j_first + PX2_ROWS - 1) / PX2_ROWS;
-    const int tx = (int)a.map_x + x_base - PX2_HALO, ty = (int)a.map_y + j_first;
+    const int tx = (int)a.map_x + x_base, ty = (int)a.map_y + j_first;
 
     const uint32_t X_lo = strip * 128u + 4u * (uint32_t)lane;  // plane column of the lane's first pixel
     uint8_t* ui_p = a.ui + (uint64_t)f * a.ui_stride + (int64_t)j_first * (int64_t)a.ui_pitch + X_lo * 4u;       // row jn
     uint8_t* lsd_p = a.lsd + (uint64_t)f * a.lsd_stride + (int64_t)(j_first - LAG) * (int64_t)a.lsd_pitch + X_lo;  // row jn - LAG
     uint8_t* ocr_f = a.ocr + (uint64_t)f * a.q_stride;
-    uint8_t* sc_f = a.scales + (uint64_t)f * a.q_stride;
+    // the lane's word of quadrant row jn - bqh in ocr_out (the same offset from a.scales is its word in scales); outside
+    // the quadrant's rows / columns the pointer is never dereferenced
+    uint8_t* ocr_p = ocr_f + ((int64_t)(j_first - bqh) * (int64_t)a.q_pitch + (int64_t)(int32_t)qpos);
+    const int64_t sc_delta = a.scales - a.ocr;
     // bitmap: word of tile (jc >> 5, 4 strip + lane / 8), row jc & 31 — one running pointer per lane
     const uint32_t btile = 4u * strip + (uint32_t)(lane >> 3);
     const bool bits_lane = (lane & 7) == 0 && btile < a.bits_tx;
@@ -165,19 +204,34 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo
 
     // ---- prologue: the first PX2_STAGES chunks are requested (every operand of the copy is warp-uniform) --------
-    if (elect_one()) {
+    // A stage = the strip's rows, one bulk tensor copy of whole 128-byte lines issued by an elected lane, + the 4 pixels
+    // left / right of them, 16-byte cp.async copies by lanes 0 / 31 (a second and third box, or a box of 136 pixels,
+    // cost the copy engine as much again as the strip itself: measured).  The stage's mbarrier counts three arrivals.
+    // A halo vector with a column of the map lies inside the capture's row (16-byte aligned, pitch a multiple of 16).
+    const uint8_t* halo_src = frame + (int64_t)ty * (int64_t)a.pitch + (int64_t)((int)a.map_x + h_lo + (PX2_PROBE == 4 ? (lane == 0 ? 4 : -4) : 0)) * 4;  // row j_first
+    const uint32_t halo_dst = lane == 31 ? (uint32_t)(PX2_HALO_OFF + PX2_HALO_SLOT) : (uint32_t)PX2_HALO_OFF;
+    auto request = [&](uint32_t sbase, uint32_t bar, int c) {
+        if (edge) {
+            if (hvm4 && PX2_PROBE != 3) {
 #pragma unroll
-        for (int c = 0; c < PX2_STAGES; c++) {
-            if (c < n_chunks) {
-                mbar_expect_tx(bars + 8u * c, PX2_ROWS * PX2_ROW_BYTES);
-                tma_load_3d(ring + (uint32_t)c * PX2_STAGE_BYTES, tmap, tx, ty + PX2_ROWS * c, (int)f, bars + 8u * c);
+                for (int rr = 0; rr < PX2_ROWS; rr++)
+                    if ((uint32_t)(j_first + PX2_ROWS * c + rr) < (uint32_t)h)
+                        cp_async_16(sbase + halo_dst + (uint32_t)rr * (PX2_HALO * 4), halo_src + (int64_t)(PX2_ROWS * c + rr) * (int64_t)a.pitch);
             }
+            cp_async_arrive(bar);
         }
-    }
+        if (elect_one()) {
+            mbar_expect_tx(bar, PX2_STAGE_TX);
+            tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * c, (int)f, bar);
+        }
+    };
+#pragma unroll
+    for (int c = 0; c < PX2_STAGES; c++)
+        if (c < n_chunks) request(ring + (uint32_t)c * PX2_STAGE_BYTES, bars + 8u * c, c);
 
     // FAST rows (the bulk): row jn and row jn - LAG are both owned (so inside the map), and in a QUAD item both are rows
     // of the quadrant; the generic form tests all of that per row.
-    auto row = [&](auto tag, uint32_t srow, int jn) {
+    auto row = [&](auto tag, uint32_t srow, uint32_t hrow, int jn) {
         constexpr bool FAST = decltype(tag)::value;
         // ---------------- phase 1: row jn ---------------------------------------------------------------------
         uint32_t m4 = 0, c4 = 0, e4 = 0, hm = 0, hc = 0;
@@ -190,15 +244,17 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 // >= 178; both OCR classes need every channel >= 130, i.e. bit 7 of all three bytes; scales needs a pixel of
                 // luma 0) and classifies pixel by pixel only then: almost every vector of a map passes straight through.
                 // The halo vector is read by every lane (lanes 1..30 read lane 0's: a broadcast) and kept by lanes 0 / 31.
-                const uint4 hv = lds_v4(srow + h_off);
+                const uint4 hv = lds_v4(hrow + h_off);
                 const uint32_t any = or4(cur);
                 uint32_t lb[4] = {BIAS + 1u, BIAS + 1u, BIAS + 1u, BIAS + 1u};  // biased luma words 0x4B0000LL (owned rows)
-                if (owned) { lb[0] = luma_biased_i2f(cur.x); lb[1] = luma_biased_i2f(cur.y); lb[2] = luma_biased_i2f(cur.z); lb[3] = luma_biased_i2f(cur.w); }
+                if (owned) { lb[0] = PX_LUMA(cur.x); lb[1] = PX_LUMA(cur.y); lb[2] = PX_LUMA(cur.z); lb[3] = PX_LUMA(cur.w); }
                 uint32_t ocrw = 0xFFFFFFFFu, scw = 0xFFFFFFFFu;
                 if (bright_bytes(any)) m4 = marker_nibble(cur, lut);  // rare
                 if (col_brq) {
-                    const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
                     if ((any & 0x00808080u) == 0x00808080u) {  // rare: possibly a bright near-grey pixel (vision-cpu/src/lib.rs:39-53,188-193)
+                        // (the vector is read again: a volatile load keeps the byte extraction below inside this branch)
+                        const uint4 again = lds_v4(srow + own_off);
+                        const uint32_t wd[4] = {again.x, again.y, again.z, again.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
@@ -226,10 +282,10 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                         ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
                         ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
                     }
-                    stg_v4(ui_p, ui);
+                    if (PX2_PROBE < 2) stg_v4(ui_p, ui);
                     if (col_brq) {
-                        stg_u32(ocr_f + ((uint32_t)jq * a.q_pitch + qpos), ocrw);
-                        stg_u32(sc_f + ((uint32_t)jq * a.q_pitch + qpos), (uint32_t)jq >= start_y ? scw : 0u);  // rows above start_y: zero (D9, a fresh buffer)
+                        stg_u32(ocr_p, ocrw);
+                        stg_u32(ocr_p + sc_delta, (uint32_t)jq >= start_y ? scw : 0u);  // rows above start_y: zero (D9, a fresh buffer)
                     }
                 }
                 if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
@@ -248,17 +304,17 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 }
             } else {
                 uint32_t hp;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(srow + hp_off));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(hrow + hp_off));
                 if (owned) {
                     uint4 ui;
                     if (GRAY) {  // (L, L, L, 255) = 0x4B0000LL * 0x010101 + 0xB4000000 (mod 2^32): one IMAD per pixel
-                        ui.x = luma_biased_i2f(cur.x) * 0x010101u + 0xB4000000u; ui.y = luma_biased_i2f(cur.y) * 0x010101u + 0xB4000000u;
-                        ui.z = luma_biased_i2f(cur.z) * 0x010101u + 0xB4000000u; ui.w = luma_biased_i2f(cur.w) * 0x010101u + 0xB4000000u;
+                        ui.x = PX_LUMA(cur.x) * 0x010101u + 0xB4000000u; ui.y = PX_LUMA(cur.y) * 0x010101u + 0xB4000000u;
+                        ui.z = PX_LUMA(cur.z) * 0x010101u + 0xB4000000u; ui.w = PX_LUMA(cur.w) * 0x010101u + 0xB4000000u;
                     } else {
                         ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
                         ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
                     }
-                    if (active) stg_v4(ui_p, ui);
+                    if (active && PX2_PROBE < 2) stg_v4(ui_p, ui);
                 }
                 if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut);  // rare
                 if (bright_bytes(hp) && hp_bit) hm = (marker_nibble(make_uint4(hp, 0u, 0u, 0u), lut) & 1u) ? hp_bit : 0u;  // rarer
@@ -268,10 +324,13 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         mwin = (mwin << 4) | m4;
         hmwin = (hmwin << 4) | hm;
         if (QUAD) { cwin = (cwin << 4) | c4; ewin = (ewin << 4) | e4; hcwin = (hcwin << 4) | hc; }
-        ui_p += a.ui_pitch; lsd_p += a.lsd_pitch;
+        ui_p += a.ui_pitch;
+        if (QUAD) ocr_p += a.q_pitch;
 
         // ---------------- phase 2: row jc = jn - LAG ----------------------------------------------------------
         const int jc = jn - LAG;
+        uint8_t* const lsd_row = lsd_p;  // row jc
+        lsd_p += a.lsd_pitch;
         if (!FAST && (jc < r0 || jc >= r1)) return;  // uniform
         // rows jc-1, jc, jc+1 sit at nibbles LAG+1, LAG, LAG-1 of the windows
         constexpr uint32_t ROWS3 = 0xFFFu << (4 * (LAG - 1));
@@ -288,10 +347,10 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
             v |= __shfl_xor_sync(FULL, v, 2);
             v |= __shfl_xor_sync(FULL, v, 4);
             if (bits_lane) *bits_p = v;
-            if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, nibble_bytes(d4));  // lsd_p already points one row ahead
+            if (active) stg_u32(lsd_row, nibble_bytes(d4));
         } else {
             if (bits_lane) *bits_p = 0u;
-            if (active) stg_u32(lsd_p - (int64_t)a.lsd_pitch, 0u);
+            if (active) stg_u32(lsd_row, 0u);
         }
         bits_p += (jc & 31) == 31 ? 1u + bits_jump : 1u;
 
@@ -325,28 +384,27 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         }
     };
 
-    // ---- main loop over the chunks of two rows ------------------------------------------------------------------
+    // ---- main loop over the chunks of PX2_ROWS rows -------------------------------------------------------------
     uint32_t stage = 0, phase = 0;
 #pragma unroll 1
     for (int c = 0; c < n_chunks; c++) {
         mbar_wait(bars + 8u * stage, phase);
         const uint32_t sbase = ring + stage * PX2_STAGE_BYTES;
         const int jn = j_first + PX2_ROWS * c;
-        // both rows of the chunk and the rows LAG above them owned; in a QUAD item all of them rows of the quadrant
-        const bool fast = jn - LAG >= r0 && jn + 1 < r1 && (!QUAD || (jn - LAG >= bqh && jn + 1 < 2 * bqh));
+        // every row of the chunk and the rows LAG above them owned; in a QUAD item all of them rows of the quadrant
+        const bool fast = jn - LAG >= r0 && jn + PX2_ROWS - 1 < r1 && (!QUAD || (jn - LAG >= bqh && jn + PX2_ROWS - 1 < 2 * bqh));
         if (fast) {
 #pragma unroll 1
-            for (int rr = 0; rr < PX2_ROWS; rr++) row(PxTag<true>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+            for (int rr = 0; rr < PX2_ROWS; rr++)
+                row(PxTag<true>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, sbase + PX2_HALO_OFF + (uint32_t)rr * (PX2_HALO * 4), jn + rr);
         } else {
 #pragma unroll 1
             for (int rr = 0; rr < PX2_ROWS; rr++)
-                if (jn + rr < j_end) row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
+                if (jn + rr < j_end)
+                    row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, sbase + PX2_HALO_OFF + (uint32_t)rr * (PX2_HALO * 4), jn + rr);
         }
         __syncwarp();  // every lane has read the stage: it may be refilled
-        if (c + PX2_STAGES < n_chunks && elect_one()) {
-            mbar_expect_tx(bars + 8u * stage, PX2_ROWS * PX2_ROW_BYTES);
-            tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * (c + PX2_STAGES), (int)f, bars + 8u * stage);
-        }
+        if (c + PX2_STAGES < n_chunks) request(sbase, bars + 8u * stage, c + PX2_STAGES);
         if (++stage == PX2_STAGES) { stage = 0; phase ^= 1u; }
     }
 }
@@ -356,20 +414,23 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
 // instruction footprint small — as one kernel the two paths evicted each other from the instruction caches (37 % of
 // the stall samples were instruction fetches).
 template <bool GRAY, bool QUAD>
-__global__ void __launch_bounds__(PX2_THREADS, 8) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
+__global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
     extern __shared__ __align__(128) uint8_t px2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t item = blockIdx.x * PX2_WARPS + warp;
-    const uint32_t nqb = a.qb1 - a.qb0, nqs = a.qs1 - a.qs0;
-    uint32_t f, band, strip;
+    const uint32_t nqs = a.qs1 - a.qs0;
+    uint32_t f, strip;
+    int r0, r1;
     if (QUAD) {
-        const uint32_t per_frame = nqb * nqs;
+        const uint32_t per_frame = a.nq * nqs;
         f = item / per_frame;
         if (f >= a.n_frames) return;
         const uint32_t sub = item - f * per_frame, bq = sub / nqs;
-        band = a.qb0 + bq; strip = a.qs0 + (sub - bq * nqs);
+        strip = a.qs0 + (sub - bq * nqs);
+        r0 = (int)(a.qr0 + bq * PX2_BAND_Q); r1 = min(r0 + PX2_BAND_Q, (int)a.qr1);
     } else {
-        const uint32_t n_plain = a.nbands * a.nstrips - nqb * nqs, per_frame = n_plain + 1u;
+        const uint32_t above = a.na * a.nstrips, beside = a.nb * (a.nstrips - nqs), n_plain = above + beside + a.nc * a.nstrips;
+        const uint32_t per_frame = n_plain + 1u;
         f = item / per_frame;
         if (f >= a.n_frames) return;
         uint32_t sub = item - f * per_frame;
@@ -392,28 +453,28 @@ __global__ void __launch_bounds__(PX2_THREADS, 8) k_pixels2(const __grid_constan
             }
             return;
         }
-        // bands above the quadrant's, then its bands without its strips, then the bands below
-        const uint32_t above = a.qb0 * a.nstrips, beside = nqb * (a.nstrips - nqs);
-        if (sub < above) { band = sub / a.nstrips; strip = sub - band * a.nstrips; }
+        // the rows above the QUAD launch's, then the strips beside its own, then the rows below
+        uint32_t lo, hi, bq;
+        if (sub < above) { bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = 0u; hi = a.qr0; }
         else if (sub < above + beside) {
             sub -= above;
-            const uint32_t per = a.nstrips - nqs, bq = sub / per, k = sub - bq * per;
-            band = a.qb0 + bq; strip = k < a.qs0 ? k : k + nqs;
+            const uint32_t per = a.nstrips - nqs, k = sub % per;
+            bq = sub / per; strip = k < a.qs0 ? k : k + nqs; lo = a.qr0; hi = a.qr1;
         } else {
             sub -= above + beside;
-            const uint32_t bq = sub / a.nstrips;
-            band = a.qb1 + bq; strip = sub - bq * a.nstrips;
+            bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = a.qr1; hi = a.h;
         }
+        r0 = (int)(lo + bq * PX2_BAND_P); r1 = min(r0 + PX2_BAND_P, (int)hi);
     }
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(px2_smem) + (uint32_t)warp * PX2_WARP_BYTES;
     const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 1u);
+        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 3u);  // the elected lane + lanes 0 and 31
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    px2_item<GRAY, QUAD>(&tmap, a, f, band, strip, ring, bars);
+    px2_item<GRAY, QUAD>(&tmap, a, f, r0, r1, strip, ring, bars);
 }
 
 }  // namespace smh

@@ -337,6 +337,17 @@ EncodeTiledFn encode_tiled_fn() {
 
 // The fused pixel pass over n frames (k_pixels2, kernels_px.cuh).  `frames` may be a cropped view of the capture:
 // (ox, oy) is the frame coordinate of its first byte, rows_avail the rows it holds.
+// tuning: SMH_B200_TMA_PROMO = 0 (none), 64, 128 (default), 256
+static CUtensorMapL2promotion tmap_promotion() {
+    static const CUtensorMapL2promotion v = [] {
+        const char* e = getenv("SMH_B200_TMA_PROMO");
+        const int k = e ? atoi(e) : 128;
+        return k == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : k == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+             : k == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
+    return v;
+}
+
 int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
                    uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform, int grayscale, cudaStream_t st) {
     const Geometry& g = P.geo;
@@ -345,7 +356,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
                     (const void*)frames, pitch, (unsigned long long)frame_stride);
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(h, SMH_E_NOGPU, "cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tmap;
+    CUtensorMap tmap;  // the strips' boxes: 128 pixels x PX2_ROWS rows
     {
         const uint64_t fs = frame_stride ? frame_stride : (uint64_t)pitch * rows_avail;
         const cuuint64_t dims[3] = {pitch / 4u, rows_avail, n};
@@ -353,7 +364,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
         const cuuint32_t box[3] = {smh::PX2_BOX_W, smh::PX2_ROWS, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_SWIZZLE_NONE, tmap_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(h, SMH_E_ARG, "cuTensorMapEncodeTiled failed with %d (pitch %u, rows %u, frames %u)", (int)r, pitch, rows_avail, n);
     }
     smh::Pixel2Args a{};
@@ -367,18 +378,22 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch; a.q_pad = P.qpad;
     a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
     a.red = P.red; a.open = P.open;
-    a.nbands = (a.h + smh::PX2_BAND - 1u) / smh::PX2_BAND; a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
+    a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
     a.lut = h->d_lut;
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
-    // the items that own pixels of the OCR quadrant: strips [qs0, qs1) x bands [qb0, qb1)
+    // the QUAD launch's items: strips [qs0, qs1) x rows [qr0, qr1) around the OCR quadrant (see Pixel2Args)
     a.qs0 = (a.bqw + a.pad) / 128u; a.qs1 = (2u * a.bqw + a.pad + 127u) / 128u;
     if (a.qs1 > a.nstrips) a.qs1 = a.nstrips;
-    a.qb0 = a.bqh / smh::PX2_BAND; a.qb1 = (2u * a.bqh + smh::PX2_BAND - 1u) / smh::PX2_BAND;
-    if (a.qb1 > a.nbands) a.qb1 = a.nbands;
-    if (a.qs0 >= a.qs1 || a.qb0 >= a.qb1) { a.qs0 = a.qs1 = 0; a.qb0 = a.qb1 = 0; }
+    a.qr0 = a.bqh & ~31u; a.qr1 = (2u * a.bqh + 31u) & ~31u;
+    if (a.qr1 > a.h) a.qr1 = a.h;
+    if (a.qs0 >= a.qs1 || a.qr0 >= a.qr1) { a.qs0 = a.qs1 = 0; a.qr0 = a.qr1 = 0; }
+    const uint32_t BP = smh::PX2_BAND_P, BQ = smh::PX2_BAND_Q;
+    a.na = (a.qr0 + BP - 1u) / BP; a.nb = (a.qr1 - a.qr0 + BP - 1u) / BP; a.nc = (a.h - a.qr1 + BP - 1u) / BP;
+    a.nq = (a.qr1 - a.qr0 + BQ - 1u) / BQ;
     // one warp per (frame, band, strip) item, plus one per frame for the button test; two launches (see k_pixels2)
-    const uint64_t n_quad = (uint64_t)(a.qb1 - a.qb0) * (a.qs1 - a.qs0);
-    const uint64_t items_p = (uint64_t)n * ((uint64_t)a.nbands * a.nstrips - n_quad + 1u), items_q = (uint64_t)n * n_quad;
+    const uint32_t nqs = a.qs1 - a.qs0;
+    const uint64_t items_p = (uint64_t)n * ((uint64_t)(a.na + a.nc) * a.nstrips + (uint64_t)a.nb * (a.nstrips - nqs) + 1u);
+    const uint64_t items_q = (uint64_t)n * a.nq * nqs;
     const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
     if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
     if (grayscale) smh::k_pixels2<true, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
