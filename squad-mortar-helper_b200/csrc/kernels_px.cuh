@@ -49,6 +49,12 @@ struct Pixel2Args {
     uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq;
     const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
     uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
+    // What a strip's outermost columns tell the strip next door, [frame][strip][side 0 = first columns, 1 = last][edge_hp
+    // rows] bytes, cleared before the pass and stored only where a warp found something; k_px_seams reads them:
+    //   bit 0      the first / last pixel of the row is a marker pixel
+    //   bits 1-3   OCR core flags of the first / last three pixels (in column order)
+    //   bits 4-6   OCR edge pixels among them whose 7x7 window found no core pixel inside the strip
+    uint8_t* edge; uint64_t edge_stride; uint32_t edge_hp;
 };
 
 #ifndef PX2_WARPS_N
@@ -76,12 +82,10 @@ constexpr int PX2_HALO = 4;                      // halo pixels either side of t
 #ifndef PX2_PROBE   // tuning probes only (tools/): 1 = no luma arithmetic, 2 = also no ui_map stores.  Results are wrong.
 #define PX2_PROBE 0
 #endif
-constexpr int PX2_BOX_W = 128;                   // pixels per row of a strip box (512 bytes, whole 128-byte lines when the
-constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     //   capture's map starts on one); the halo arrives in two boxes of its own
-constexpr int PX2_HALO_OFF = PX2_ROWS * PX2_ROW_BYTES;  // stage layout: strip rows | left halo rows (16 B each) | right halo rows
-constexpr int PX2_HALO_SLOT = PX2_ROWS * PX2_HALO * 4;
-constexpr int PX2_STAGE_BYTES = (PX2_HALO_OFF + 2 * PX2_HALO_SLOT + 127) / 128 * 128;
-constexpr int PX2_STAGE_TX = PX2_ROWS * PX2_ROW_BYTES;  // bytes the bulk copy of a stage delivers
+constexpr int PX2_BOX_W = 128;                   // pixels per row of a strip box: 512 bytes, whole 128-byte lines when the
+constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     //   capture's map starts on one
+constexpr int PX2_STAGE_BYTES = PX2_ROWS * PX2_ROW_BYTES;
+constexpr int PX2_STAGE_TX = PX2_STAGE_BYTES;    // bytes the bulk copy of a stage delivers
 constexpr int PX2_WARP_BYTES = PX2_STAGES * PX2_STAGE_BYTES + 128;  // ring + mbarriers
 constexpr int PX2_SMEM_BYTES = PX2_WARPS * PX2_WARP_BYTES;
 
@@ -105,16 +109,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
-}
-
-// 16 bytes global -> shared by the calling lane; the lane's next cp_async_arrive tracks it
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
-}
-// the calling lane arrives on the mbarrier once its earlier cp.async copies have landed (the arrival is part of the
-// barrier's initial count)
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
 }
 
 // one lane of the (converged) warp
@@ -161,23 +155,11 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         // an OCR core pixel is visible to a neighbour's search only below the clip min(x+3, w-3) (D10)
         cm4 |= (inq && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
     }
-    // the halo next to lanes 0 / 31: columns x_base - 4 .. x_base - 1 / x_base + 128 .. x_base + 131.  Outside the OCR
-    // quadrant only the adjacent pixel matters (the 3x3 cross looks one column out): ONE pixel, read by every lane at
-    // a lane-dependent offset (lanes 1..30 read lane 0's word, a broadcast) and kept by lanes 0 / 31 alone.
+    // Nobody reads a pixel of another strip: the first / last columns' flags go to the neighbour through Pixel2Args::edge
+    // (rare stores) and k_px_seams finishes the pixels either side of a seam.  A halo read of the neighbour's line —
+    // as a wider box, a second box, cp.async or a plain load — cost the pass a quarter of its time (measured).
     const bool edge = lane == 0 || lane == 31;
-    const int h_lo = lane == 0 ? x_base - PX2_HALO : x_base + 128;
-    uint32_t hvm4 = 0, hcm4 = 0;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const int i = h_lo + e;
-        const bool valid = edge && i >= 0 && i < w;
-        hvm4 |= valid ? (1u << e) : 0u;
-        hcm4 |= (QUAD && valid && i >= bqw && i < 2 * bqw && i - bqw <= bqw - SMH_OCR_RADIUS) ? (1u << e) : 0u;
-    }
     const uint32_t own_off = (uint32_t)lane * 16u;  // the lane's vector in a strip row
-    const uint32_t h_off = lane == 31 ? (uint32_t)PX2_HALO_SLOT : 0u;   // the halo vector of a row (QUAD), from the stage's halo rows
-    const uint32_t hp_off = lane == 31 ? (uint32_t)PX2_HALO_SLOT : (uint32_t)(PX2_HALO - 1) * 4u;  // the halo pixel
-    const uint32_t hp_bit = lane == 0 ? (hvm4 & 8u) : (lane == 31 ? (hvm4 & 1u) : 0u);  // where its flag goes in the halo nibble
     const bool col_brq = em4 != 0u;
     const uint32_t qpos = (uint32_t)(i_lo - bqw + (int)a.q_pad);  // byte position in a quadrant row (used when col_brq)
 
@@ -201,40 +183,29 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     const uint32_t bits_jump = a.bits_tx * 32u - 32u;  // from the last row of a tile to the first of the tile below
 
     uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
-    uint32_t hmwin = 0, hcwin = 0;          // edge lanes: the same for the halo
+    // lanes 0 / 31: this strip's flag bytes for its neighbour (side 0 / 1), row 0
+    uint8_t* const edge_base = a.edge + (uint64_t)f * a.edge_stride + (uint64_t)(2u * strip + (lane == 31 ? 1u : 0u)) * a.edge_hp;
+    // the window bits of row jc that the neighbour needs: lane 0's first three pixels, lane 31's last three
+    constexpr uint32_t NIB = 4 * (QUAD ? SMH_OCR_RADIUS : 1);
+    const uint32_t seam_mask = lane == 0 ? (0x7u << NIB) : (lane == 31 ? (0xEu << NIB) : 0u);
 
     // ---- prologue: the first PX2_STAGES chunks are requested (every operand of the copy is warp-uniform) --------
-    // A stage = the strip's rows, one bulk tensor copy of whole 128-byte lines issued by an elected lane, + the 4 pixels
-    // left / right of them, 16-byte cp.async copies by lanes 0 / 31 (a second and third box, or a box of 136 pixels,
-    // cost the copy engine as much again as the strip itself: measured).  The stage's mbarrier counts three arrivals.
-    // A halo vector with a column of the map lies inside the capture's row (16-byte aligned, pitch a multiple of 16).
-    const uint8_t* halo_src = frame + (int64_t)ty * (int64_t)a.pitch + (int64_t)((int)a.map_x + h_lo + (PX2_PROBE == 4 ? (lane == 0 ? 4 : -4) : 0)) * 4;  // row j_first
-    const uint32_t halo_dst = lane == 31 ? (uint32_t)(PX2_HALO_OFF + PX2_HALO_SLOT) : (uint32_t)PX2_HALO_OFF;
-    auto request = [&](uint32_t sbase, uint32_t bar, int c) {
-        if (edge) {
-            if (hvm4 && PX2_PROBE != 3) {
+    if (elect_one()) {
 #pragma unroll
-                for (int rr = 0; rr < PX2_ROWS; rr++)
-                    if ((uint32_t)(j_first + PX2_ROWS * c + rr) < (uint32_t)h)
-                        cp_async_16(sbase + halo_dst + (uint32_t)rr * (PX2_HALO * 4), halo_src + (int64_t)(PX2_ROWS * c + rr) * (int64_t)a.pitch);
+        for (int c = 0; c < PX2_STAGES; c++) {
+            if (c < n_chunks) {
+                mbar_expect_tx(bars + 8u * c, PX2_STAGE_TX);
+                tma_load_3d(ring + (uint32_t)c * PX2_STAGE_BYTES, tmap, tx, ty + PX2_ROWS * c, (int)f, bars + 8u * c);
             }
-            cp_async_arrive(bar);
         }
-        if (elect_one()) {
-            mbar_expect_tx(bar, PX2_STAGE_TX);
-            tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * c, (int)f, bar);
-        }
-    };
-#pragma unroll
-    for (int c = 0; c < PX2_STAGES; c++)
-        if (c < n_chunks) request(ring + (uint32_t)c * PX2_STAGE_BYTES, bars + 8u * c, c);
+    }
 
     // FAST rows (the bulk): row jn and row jn - LAG are both owned (so inside the map), and in a QUAD item both are rows
     // of the quadrant; the generic form tests all of that per row.
-    auto row = [&](auto tag, uint32_t srow, uint32_t hrow, int jn) {
+    auto row = [&](auto tag, uint32_t srow, int jn) {
         constexpr bool FAST = decltype(tag)::value;
         // ---------------- phase 1: row jn ---------------------------------------------------------------------
-        uint32_t m4 = 0, c4 = 0, e4 = 0, hm = 0, hc = 0;
+        uint32_t m4 = 0, c4 = 0, e4 = 0;
         if (FAST || (jn >= 0 && jn < h)) {  // uniform
             const uint4 cur = lds_v4(srow + own_off);
             const bool owned = FAST || (jn >= r0 && jn < r1);
@@ -243,8 +214,6 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 // Every lane tests its own vector's OR against the cheap necessary conditions (a marker colour has a channel
                 // >= 178; both OCR classes need every channel >= 130, i.e. bit 7 of all three bytes; scales needs a pixel of
                 // luma 0) and classifies pixel by pixel only then: almost every vector of a map passes straight through.
-                // The halo vector is read by every lane (lanes 1..30 read lane 0's: a broadcast) and kept by lanes 0 / 31.
-                const uint4 hv = lds_v4(hrow + h_off);
                 const uint32_t any = or4(cur);
                 uint32_t lb[4] = {BIAS + 1u, BIAS + 1u, BIAS + 1u, BIAS + 1u};  // biased luma words 0x4B0000LL (owned rows)
                 if (owned) { lb[0] = PX_LUMA(cur.x); lb[1] = PX_LUMA(cur.y); lb[2] = PX_LUMA(cur.z); lb[3] = PX_LUMA(cur.w); }
@@ -288,23 +257,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                         stg_u32(ocr_p + sc_delta, (uint32_t)jq >= start_y ? scw : 0u);  // rows above start_y: zero (D9, a fresh buffer)
                     }
                 }
-                if (edge && hvm4) {  // the halo vector: marker bits + the core bits a neighbour's search may see
-                    const uint32_t hany = or4(hv);
-                    if (bright_bytes(hany)) hm = marker_nibble(hv, lut) & hvm4;
-                    if ((hany & 0x00808080u) == 0x00808080u && jq <= bqh - SMH_OCR_RADIUS) {
-                        const uint32_t wd[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const uint32_t cb = wd[e] & 0xFFu, cg = (wd[e] >> 8) & 0xFFu, cr = (wd[e] >> 16) & 0xFFu;
-                            const uint32_t mx = max(cr, max(cg, cb)), mn = min(cr, min(cg, cb));
-                            if (mx == mn && mn >= SMH_OCR_BRIGHT) hc |= 1u << e;
-                        }
-                        hc &= hcm4;
-                    }
-                }
             } else {
-                uint32_t hp;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hp) : "r"(hrow + hp_off));
                 if (owned) {
                     uint4 ui;
                     if (GRAY) {  // (L, L, L, 255) = 0x4B0000LL * 0x010101 + 0xB4000000 (mod 2^32): one IMAD per pixel
@@ -317,13 +270,11 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                     if (active && PX2_PROBE < 2) stg_v4(ui_p, ui);
                 }
                 if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut);  // rare
-                if (bright_bytes(hp) && hp_bit) hm = (marker_nibble(make_uint4(hp, 0u, 0u, 0u), lut) & 1u) ? hp_bit : 0u;  // rarer
             }
             m4 &= vm4;
         }
         mwin = (mwin << 4) | m4;
-        hmwin = (hmwin << 4) | hm;
-        if (QUAD) { cwin = (cwin << 4) | c4; ewin = (ewin << 4) | e4; hcwin = (hcwin << 4) | hc; }
+        if (QUAD) { cwin = (cwin << 4) | c4; ewin = (ewin << 4) | e4; }
         ui_p += a.ui_pitch;
         if (QUAD) ocr_p += a.q_pitch;
 
@@ -334,12 +285,12 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         if (!FAST && (jc < r0 || jc >= r1)) return;  // uniform
         // rows jc-1, jc, jc+1 sit at nibbles LAG+1, LAG, LAG-1 of the windows
         constexpr uint32_t ROWS3 = 0xFFFu << (4 * (LAG - 1));
-        if (__any_sync(FULL, ((mwin | hmwin) & ROWS3) != 0u)) {  // (almost every row of a map has no marker pixel nearby)
+        uint32_t fl = 0;  // lanes 0 / 31: what the neighbouring strip must know about this row (Pixel2Args::edge)
+        if (__any_sync(FULL, (mwin & ROWS3) != 0u)) {  // (almost every row of a map has no marker pixel nearby)
             const uint32_t mc = (mwin >> (4 * LAG)) & 0xFu;
             uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
-            const uint32_t hmc = (hmwin >> (4 * LAG)) & 0xFu;
-            if (lane == 0) l = hmc;
-            if (lane == 31) rr = hmc;
+            if (lane == 0) l = 0u;    // the pixel across the seam: k_px_seams
+            if (lane == 31) rr = 0u;
             const uint32_t d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> (4 * (LAG + 1))) | (mwin >> (4 * (LAG - 1)))) & vm4;
             // the four words of the bitmap: 8 lanes' nibbles each
             uint32_t v = d4 << (4 * (lane & 7));
@@ -348,40 +299,49 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
             v |= __shfl_xor_sync(FULL, v, 4);
             if (bits_lane) *bits_p = v;
             if (active) stg_u32(lsd_row, nibble_bytes(d4));
+            if (edge) fl = lane == 0 ? (mc & 1u) : (mc >> 3);
         } else {
             if (bits_lane) *bits_p = 0u;
             if (active) stg_u32(lsd_row, 0u);
         }
         bits_p += (jc & 31) == 31 ? 1u + bits_jump : 1u;
 
-        if (!QUAD) return;
         const int jqc = jc - bqh;
-        if (!FAST && (uint32_t)jqc >= (uint32_t)bqh) return;  // uniform
-        const uint32_t eb = active ? (ewin >> (4 * LAG)) & 0xFu : 0u;
-        if (__any_sync(FULL, eb != 0u)) {
-            // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
-            // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit
-            uint32_t lwin = __shfl_up_sync(FULL, cwin, 1), rwin = __shfl_down_sync(FULL, cwin, 1);
-            if (lane == 0) lwin = hcwin;
-            if (lane == 31) rwin = hcwin;
-            uint32_t found = 0;  // bit e: pixel e has a core neighbour
+        if (QUAD && (FAST || (uint32_t)jqc < (uint32_t)bqh)) {  // uniform: a row of the OCR quadrant
+            constexpr uint32_t ROW1 = 0xFu << (4 * LAG);
+            if (__any_sync(FULL, ((ewin & ROW1) | (cwin & seam_mask)) != 0u)) {
+                // rare: an OCR edge pixel keeps its value iff a core pixel lies in its 7x7 window
+                // (vision-cpu/src/lib.rs:196-216); rows/columns outside the quadrant carry no core bit.  The part of a
+                // window that lies in the neighbouring strip is k_px_seams' business: it gets this strip's outermost
+                // core bits and the edge pixels still looking for one.
+                const uint32_t eb = (ewin >> (4 * LAG)) & 0xFu;
+                uint32_t lwin = __shfl_up_sync(FULL, cwin, 1), rwin = __shfl_down_sync(FULL, cwin, 1);
+                if (lane == 0) lwin = 0u;
+                if (lane == 31) rwin = 0u;
+                uint32_t found = 0;  // bit e: pixel e has a core neighbour
 #pragma unroll
-            for (int k = 0; k < 7; k++) {
-                // core bits of columns -4 .. +7 around the lane's first pixel, row jn - k
-                const uint32_t cm = ((lwin >> (4 * k)) & 0xFu) | (((cwin >> (4 * k)) & 0xFu) << 4) | (((rwin >> (4 * k)) & 0xFu) << 8);
+                for (int k = 0; k < 7; k++) {
+                    // core bits of columns -4 .. +7 around the lane's first pixel, row jn - k
+                    const uint32_t cm = ((lwin >> (4 * k)) & 0xFu) | (((cwin >> (4 * k)) & 0xFu) << 4) | (((rwin >> (4 * k)) & 0xFu) << 8);
 #pragma unroll
-                for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
-            }
-            const uint32_t todo = eb & found;
+                    for (int e = 0; e < 4; e++) found |= (cm & (0x7Fu << (e + 1))) ? (1u << e) : 0u;
+                }
+                const uint32_t todo = eb & found;
 #pragma unroll 1
-            for (int e = 0; e < 4; e++) {
-                if ((todo >> e) & 1u) {
-                    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
-                        frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)(i_lo + e)) * 4u));
-                    ocr_f[(uint32_t)jqc * a.q_pitch + qpos + e] = (uint8_t)(255u - luma8_bgra(word));
+                for (int e = 0; e < 4; e++) {
+                    if ((todo >> e) & 1u) {
+                        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                            frame + (uint64_t)(a.map_y + (uint32_t)jc) * a.pitch + (uint64_t)(a.map_x + (uint32_t)(i_lo + e)) * 4u));
+                        ocr_f[(uint32_t)jqc * a.q_pitch + qpos + e] = (uint8_t)(255u - luma8_bgra(word));
+                    }
+                }
+                if (edge) {
+                    const uint32_t cc = (cwin >> (4 * LAG)) & 0xFu, pend = eb & ~found;
+                    fl |= lane == 0 ? ((cc & 7u) << 1) | ((pend & 7u) << 4) : ((cc >> 1) << 1) | ((pend >> 1) << 4);
                 }
             }
         }
+        if (fl && PX2_PROBE != 3) edge_base[jc] = (uint8_t)fl;
     };
 
     // ---- main loop over the chunks of PX2_ROWS rows -------------------------------------------------------------
@@ -396,15 +356,18 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         if (fast) {
 #pragma unroll 1
             for (int rr = 0; rr < PX2_ROWS; rr++)
-                row(PxTag<true>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, sbase + PX2_HALO_OFF + (uint32_t)rr * (PX2_HALO * 4), jn + rr);
+                row(PxTag<true>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
         } else {
 #pragma unroll 1
             for (int rr = 0; rr < PX2_ROWS; rr++)
                 if (jn + rr < j_end)
-                    row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, sbase + PX2_HALO_OFF + (uint32_t)rr * (PX2_HALO * 4), jn + rr);
+                    row(PxTag<false>(), sbase + (uint32_t)rr * PX2_ROW_BYTES, jn + rr);
         }
         __syncwarp();  // every lane has read the stage: it may be refilled
-        if (c + PX2_STAGES < n_chunks) request(sbase, bars + 8u * stage, c + PX2_STAGES);
+        if (c + PX2_STAGES < n_chunks && elect_one()) {
+            mbar_expect_tx(bars + 8u * stage, PX2_STAGE_TX);
+            tma_load_3d(sbase, tmap, tx, ty + PX2_ROWS * (c + PX2_STAGES), (int)f, bars + 8u * stage);
+        }
         if (++stage == PX2_STAGES) { stage = 0; phase ^= 1u; }
     }
 }
@@ -470,11 +433,67 @@ __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const _
     const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 3u);  // the elected lane + lanes 0 and 31
+        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     px2_item<GRAY, QUAD>(&tmap, a, f, r0, r1, strip, ring, bars);
+}
+
+// The pixels either side of a seam between two strips, from the flags the strips left in Pixel2Args::edge: the 3x3
+// cross of a marker pixel reaches one column across (dilated mask + its bitmap), the 7x7 window of an OCR edge pixel
+// three (vision-cpu/src/lib.rs:196-216).  One thread per (frame, seam, four rows); almost all of them read two zero
+// words and leave.
+__global__ void __launch_bounds__(256) k_px_seams(const Pixel2Args a) {
+    const uint32_t nrq = a.edge_hp >> 2, nseams = a.nstrips - 1u;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t rq = (uint32_t)(idx % nrq);
+    const uint64_t t = idx / nrq;
+    const uint32_t b = 1u + (uint32_t)(t % nseams), f = (uint32_t)(t / nseams);  // the seam left of strip b
+    if (f >= a.n_frames) return;
+    const uint8_t* ef = a.edge + (uint64_t)f * a.edge_stride;
+    const uint8_t* L = ef + (uint64_t)(2u * b - 1u) * a.edge_hp;  // strip b - 1, its last columns
+    const uint8_t* R = ef + (uint64_t)(2u * b) * a.edge_hp;       // strip b, its first columns
+    const uint32_t lw = *reinterpret_cast<const uint32_t*>(L + 4u * rq), rw = *reinterpret_cast<const uint32_t*>(R + 4u * rq);
+    if (!(lw | rw)) return;
+    const uint32_t X0 = 128u * b;  // plane column of strip b's first pixel
+    const int bqw = (int)a.bqw, bqh = (int)a.bqh, h = (int)a.h, w = (int)a.w;
+    for (int k = 0; k < 4; k++) {
+        const int j = (int)(4u * rq) + k;
+        if (j >= h) break;
+        const uint32_t lb = (lw >> (8 * k)) & 0xFFu, rb = (rw >> (8 * k)) & 0xFFu;
+        // ---- dilation across the seam: a marker pixel in one strip's outermost column sets its neighbour's
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            if (!((side ? rb : lb) & 1u)) continue;
+            const uint32_t X = side ? X0 - 1u : X0;
+            const int i = (int)X - (int)a.pad;
+            if (i < 0 || i >= w) continue;
+            a.lsd[(uint64_t)f * a.lsd_stride + (uint64_t)j * a.lsd_pitch + X] = 255;
+            atomicOr(a.bits + (uint64_t)f * a.bits_stride + ((((uint64_t)(j >> 5) * a.bits_tx + (X >> 5)) << 5) + (uint32_t)(j & 31)), 1u << (X & 31u));
+        }
+        // ---- OCR edge pixels that found no core pixel inside their own strip: the other strip's part of the window
+        const uint32_t pl = (lb >> 4) & 7u, pr = (rb >> 4) & 7u;  // pixels X0 - 3 .. X0 - 1 / X0 .. X0 + 2
+        if (!(pl | pr)) continue;
+        uint32_t cl = 0, cr = 0;  // core flags of those six columns over the window's rows (quadrant rows only carry any)
+        for (int jj = max(j - SMH_OCR_RADIUS, bqh); jj <= min(j + SMH_OCR_RADIUS, min(2 * bqh, h) - 1); jj++) {
+            cl |= ((uint32_t)L[jj] >> 1) & 7u;
+            cr |= ((uint32_t)R[jj] >> 1) & 7u;
+        }
+        uint32_t fix = 0;  // bit c: pixel X0 - 3 + c keeps its value
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (((pl >> c) & 1u) && (cr & ((2u << c) - 1u))) fix |= 1u << c;               // sees strip b's columns 0 .. c
+            if (((pr >> c) & 1u) && (cl & (7u & ~((1u << c) - 1u)))) fix |= 8u << c;      // sees strip b - 1's last 3 - c
+        }
+        for (int c = 0; c < 6; c++) {
+            if (!((fix >> c) & 1u)) continue;
+            const int i = (int)X0 - 3 + c - (int)a.pad;  // map column (inside the quadrant: the pixel was classified there)
+            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(
+                a.frames + (uint64_t)f * a.frame_stride + (uint64_t)(a.map_y + (uint32_t)j) * a.pitch + (uint64_t)(a.map_x + (uint32_t)i) * 4u));
+            a.ocr[(uint64_t)f * a.q_stride + (uint64_t)(j - bqh) * a.q_pitch + (uint32_t)(i - bqw + (int)a.q_pad)] = (uint8_t)(255u - luma8_bgra(word));
+        }
+    }
 }
 
 }  // namespace smh

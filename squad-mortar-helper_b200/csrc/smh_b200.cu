@@ -102,8 +102,10 @@ struct Planes {
     uint32_t* bits = nullptr;     // tile-major 1-bit copies of the dilated masks (line-search input)
     uint64_t bits_stride = 0;     // words per frame
     smh::BitsGeom bg{};
+    uint8_t* edge = nullptr;      // what the strips of the pixel pass tell their neighbours (Pixel2Args::edge)
+    uint64_t edge_stride = 0; uint32_t edge_hp = 0;
     void release() {
-        cudaFree(bits); cudaFree(minimap); cudaFree(minimap_found);
+        cudaFree(bits); cudaFree(edge); cudaFree(minimap); cudaFree(minimap_found);
         cudaFree(icon_best); cudaFree(icon_found); cudaFree(icon_xy); cudaFree(icon_sad);
         cudaFree(mpx_in); cudaFree(mpx_n); cudaFree(mpx_ratio); cudaFree(mpx_found); cudaFree(mpx_debug); cudaFree(mpx_ndebug);
         cudaFree(ui.ptr); cudaFree(lsd.ptr); cudaFree(ocr.ptr); cudaFree(scales.ptr);
@@ -316,6 +318,9 @@ int ensure_planes(smh_b200* h, Planes* P, uint32_t n, const Geometry& g, bool st
     P->bits_stride = (uint64_t)P->bg.tx * P->bg.ty * 32u;
     CU(h, cudaMalloc(&P->bits, P->bits_stride * n * sizeof(uint32_t)));
     CU(h, cudaMemset(P->bits, 0, P->bits_stride * n * sizeof(uint32_t)));  // the pixel pass never writes rows >= h / columns >= nvec
+    P->edge_hp = round_up(g.map[3], 4u);
+    P->edge_stride = (uint64_t)((P->pad + g.map[2] + 127u) / 128u) * 2u * P->edge_hp;
+    CU(h, cudaMalloc(&P->edge, P->edge_stride * n));
     if (stats) CU(h, cudaMalloc(&P->stats, (size_t)n * 3 * sizeof(unsigned long long)));
     P->n = n; P->W = g.W; P->H = g.H;
     return SMH_OK;
@@ -381,6 +386,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
     a.lut = h->d_lut;
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
+    a.edge = P.edge; a.edge_stride = P.edge_stride; a.edge_hp = P.edge_hp;
     // the QUAD launch's items: strips [qs0, qs1) x rows [qr0, qr1) around the OCR quadrant (see Pixel2Args)
     a.qs0 = (a.bqw + a.pad) / 128u; a.qs1 = (2u * a.bqw + a.pad + 127u) / 128u;
     if (a.qs1 > a.nstrips) a.qs1 = a.nstrips;
@@ -396,6 +402,8 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     const uint64_t items_q = (uint64_t)n * a.nq * nqs;
     const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
     if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
+    static const bool no_seams = getenv("SMH_B200_PX_NOSEAMS") != nullptr;  // tuning probe
+    if (!no_seams) CU(h, cudaMemsetAsync(P.edge, 0, P.edge_stride * n, st));  // the strips' notes to their neighbours: stored only where nonzero
     if (grayscale) smh::k_pixels2<true, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
     else smh::k_pixels2<false, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
     h->launches++;
@@ -403,6 +411,12 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     if (blocks_q) {
         if (grayscale) smh::k_pixels2<true, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
         else smh::k_pixels2<false, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
+    if (a.nstrips > 1u && !no_seams) {  // the pixels either side of the seams between strips
+        const uint64_t threads = (uint64_t)n * (a.nstrips - 1u) * (a.edge_hp >> 2);
+        smh::k_px_seams<<<(unsigned)((threads + 255u) / 256u), 256, 0, st>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
     }
@@ -439,6 +453,7 @@ Planes planes_view(const Planes& P, uint32_t f0, uint32_t cn, uint32_t lane) {
     V.minimap += (size_t)f0 * 4; V.minimap_found += f0;
     V.icon_best += f0; V.icon_found += f0; V.icon_xy += (size_t)f0 * 2; V.icon_sad += f0;
     V.bits += (uint64_t)f0 * P.bits_stride;
+    V.edge += (uint64_t)f0 * P.edge_stride;
     return V;
 }
 
