@@ -11,16 +11,22 @@
 // must start on a 16-byte boundary (measured: tools/tma_probe.cu — an odd pixel start raises an illegal
 // instruction), so every plane carries the capture's 16-byte phase as a left pad of 0..3 pixels and strip,
 // vector and bitmap-word boundaries coincide in all of them.  Lane l owns the 4 pixels X = 128 s + 4 l .. of
-// every row: 512 contiguous, 128-byte aligned bytes of ui_map and 128 of lsd_image per warp row.  Lane 0 issues
-// one cp.async.bulk.tensor per chunk of two rows (box = 136 pixels x 2 rows: the strip plus a 4-pixel halo
-// either side, out-of-frame pixels arrive as zeros) into a three-stage ring of the warp's own shared memory and
-// the lanes wait on the stage's mbarrier; nobody computes an address or commits / waits for a copy of its own.
+// every row: 512 contiguous, 128-byte aligned bytes of ui_map and 128 of lsd_image per warp row.  An elected lane
+// issues one cp.async.bulk.tensor per chunk of two rows (box = 128 pixels x 2 rows: whole 128-byte lines when the
+// map starts on one, pixels outside the map's columns / rows are not fetched and arrive as zeros) into a
+// three-stage ring of the warp's own shared memory and the lanes wait on the stage's mbarrier; nobody computes
+// an address or commits / waits for a copy of its own.
 //   phase 1 (row jn)      classify the lane's 4 pixels, store ui_map / provisional ocr_out / scales, shift the
-//                         row's flag nibbles (marker, OCR core, OCR edge) into window registers; lanes 0 and 31
-//                         also classify the halo vector next to them.
+//                         row's flag nibbles (marker, OCR core, OCR edge) into window registers.
 //   phase 2 (row jn - lag) 3x3-cross dilation (up/down from the window, left/right by shuffle) -> lsd_image bytes
 //                         and, gathered by a 3-step butterfly, the four 32-pixel words of the bitmap; the 7x7
 //                         neighbour search of the rare OCR edge pixels.  lag = 1 outside the OCR quadrant, 3 in it.
+// No warp reads a pixel of another strip.  What the 3x3 cross and the 7x7 window need from across a seam between two
+// strips travels as one flag byte per (strip, side, row), stored only where nonzero (Pixel2Args::edge), and
+// k_px_seams — one thread per seam and four rows, almost all of which read two zero words — finishes the pixels
+// either side.  Round 2 measured the alternatives on the 1024-frame batch (profiles/README.md): a box of 136 pixels
+// (128 + a 4-pixel halo either side, 3.02 ms), second and third 4-pixel boxes (3.04 ms), cp.async halos (3.15 ms),
+// halos out of the neighbouring warp's ring with the warps of a CTA in lockstep (3.3 - 3.6 ms); this form 2.88 ms.
 #pragma once
 #include <cuda.h>
 
@@ -78,10 +84,6 @@ constexpr int PX2_STAGES = PX2_STAGES_N;
 constexpr int PX2_ROWS = PX2_ROWS_N;             // rows per TMA box
 constexpr int PX2_BAND_P = PX2_BAND_P_ROWS;      // map rows per work item of the plain launch / the QUAD launch
 constexpr int PX2_BAND_Q = PX2_BAND_Q_ROWS;      //   (multiples of 32: whole tile-rows of the bitmap)
-constexpr int PX2_HALO = 4;                      // halo pixels either side of the strip
-#ifndef PX2_PROBE   // tuning probes only (tools/): 1 = no luma arithmetic, 2 = also no ui_map stores.  Results are wrong.
-#define PX2_PROBE 0
-#endif
 constexpr int PX2_BOX_W = 128;                   // pixels per row of a strip box: 512 bytes, whole 128-byte lines when the
 constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     //   capture's map starts on one
 constexpr int PX2_STAGE_BYTES = PX2_ROWS * PX2_ROW_BYTES;
@@ -121,11 +123,6 @@ __device__ __forceinline__ bool elect_one() {
 // nibble -> 4 bytes of 0/255
 __device__ __forceinline__ uint32_t nibble_bytes(uint32_t d4) { return ((d4 * 0x00204081u) & 0x01010101u) * 255u; }
 
-#if PX2_PROBE == 1 || PX2_PROBE == 2
-#define PX_LUMA(w) ((w) | BIAS | 1u)
-#else
-#define PX_LUMA(w) luma_biased_i2f(w)
-#endif
 template <bool B> struct PxTag { static constexpr bool value = B; };
 
 template <bool GRAY, bool QUAD>
@@ -216,7 +213,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 // luma 0) and classifies pixel by pixel only then: almost every vector of a map passes straight through.
                 const uint32_t any = or4(cur);
                 uint32_t lb[4] = {BIAS + 1u, BIAS + 1u, BIAS + 1u, BIAS + 1u};  // biased luma words 0x4B0000LL (owned rows)
-                if (owned) { lb[0] = PX_LUMA(cur.x); lb[1] = PX_LUMA(cur.y); lb[2] = PX_LUMA(cur.z); lb[3] = PX_LUMA(cur.w); }
+                if (owned) { lb[0] = luma_biased_i2f(cur.x); lb[1] = luma_biased_i2f(cur.y); lb[2] = luma_biased_i2f(cur.z); lb[3] = luma_biased_i2f(cur.w); }
                 uint32_t ocrw = 0xFFFFFFFFu, scw = 0xFFFFFFFFu;
                 if (bright_bytes(any)) m4 = marker_nibble(cur, lut);  // rare
                 if (col_brq) {
@@ -251,7 +248,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                         ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
                         ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
                     }
-                    if (PX2_PROBE < 2) stg_v4(ui_p, ui);
+                    stg_v4(ui_p, ui);
                     if (col_brq) {
                         stg_u32(ocr_p, ocrw);
                         stg_u32(ocr_p + sc_delta, (uint32_t)jq >= start_y ? scw : 0u);  // rows above start_y: zero (D9, a fresh buffer)
@@ -261,13 +258,13 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 if (owned) {
                     uint4 ui;
                     if (GRAY) {  // (L, L, L, 255) = 0x4B0000LL * 0x010101 + 0xB4000000 (mod 2^32): one IMAD per pixel
-                        ui.x = PX_LUMA(cur.x) * 0x010101u + 0xB4000000u; ui.y = PX_LUMA(cur.y) * 0x010101u + 0xB4000000u;
-                        ui.z = PX_LUMA(cur.z) * 0x010101u + 0xB4000000u; ui.w = PX_LUMA(cur.w) * 0x010101u + 0xB4000000u;
+                        ui.x = luma_biased_i2f(cur.x) * 0x010101u + 0xB4000000u; ui.y = luma_biased_i2f(cur.y) * 0x010101u + 0xB4000000u;
+                        ui.z = luma_biased_i2f(cur.z) * 0x010101u + 0xB4000000u; ui.w = luma_biased_i2f(cur.w) * 0x010101u + 0xB4000000u;
                     } else {
                         ui.x = __byte_perm(cur.x, alpha, 0x7012); ui.y = __byte_perm(cur.y, alpha, 0x7012);
                         ui.z = __byte_perm(cur.z, alpha, 0x7012); ui.w = __byte_perm(cur.w, alpha, 0x7012);
                     }
-                    if (active && PX2_PROBE < 2) stg_v4(ui_p, ui);
+                    if (active) stg_v4(ui_p, ui);
                 }
                 if (bright_bytes(or4(cur))) m4 = marker_nibble(cur, lut);  // rare
             }
@@ -341,7 +338,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
                 }
             }
         }
-        if (fl && PX2_PROBE != 3) edge_base[jc] = (uint8_t)fl;
+        if (fl) edge_base[jc] = (uint8_t)fl;
     };
 
     // ---- main loop over the chunks of PX2_ROWS rows -------------------------------------------------------------

@@ -342,17 +342,6 @@ EncodeTiledFn encode_tiled_fn() {
 
 // The fused pixel pass over n frames (k_pixels2, kernels_px.cuh).  `frames` may be a cropped view of the capture:
 // (ox, oy) is the frame coordinate of its first byte, rows_avail the rows it holds.
-// tuning: SMH_B200_TMA_PROMO = 0 (none), 64, 128 (default), 256
-static CUtensorMapL2promotion tmap_promotion() {
-    static const CUtensorMapL2promotion v = [] {
-        const char* e = getenv("SMH_B200_TMA_PROMO");
-        const int k = e ? atoi(e) : 128;
-        return k == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : k == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-             : k == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    }();
-    return v;
-}
-
 int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t frame_stride, uint32_t pitch, uint32_t rows_avail,
                    uint32_t ox, uint32_t oy, uint32_t n, bool per_frame_start_y, uint32_t start_y_uniform, int grayscale, cudaStream_t st) {
     const Geometry& g = P.geo;
@@ -364,12 +353,15 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     CUtensorMap tmap;  // the strips' boxes: 128 pixels x PX2_ROWS rows
     {
         const uint64_t fs = frame_stride ? frame_stride : (uint64_t)pitch * rows_avail;
-        const cuuint64_t dims[3] = {pitch / 4u, rows_avail, n};
+        // the tensor ends with the map (columns rounded up to a 32-byte sector): what a box holds beyond it — the right
+        // part of the last strip, the rows a band looks at below the map — is zero-filled without being fetched
+        const uint32_t vx = g.map[0] - ox + g.map[2], vy = g.map[1] - oy + g.map[3];
+        const cuuint64_t dims[3] = {std::min<uint32_t>(pitch / 4u, round_up(vx, 8u)), std::min<uint32_t>(rows_avail, vy), n};
         const cuuint64_t strides[2] = {pitch, fs};
         const cuuint32_t box[3] = {smh::PX2_BOX_W, smh::PX2_ROWS, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, tmap_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(h, SMH_E_ARG, "cuTensorMapEncodeTiled failed with %d (pitch %u, rows %u, frames %u)", (int)r, pitch, rows_avail, n);
     }
     smh::Pixel2Args a{};
@@ -402,8 +394,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     const uint64_t items_q = (uint64_t)n * a.nq * nqs;
     const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
     if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
-    static const bool no_seams = getenv("SMH_B200_PX_NOSEAMS") != nullptr;  // tuning probe
-    if (!no_seams) CU(h, cudaMemsetAsync(P.edge, 0, P.edge_stride * n, st));  // the strips' notes to their neighbours: stored only where nonzero
+    CU(h, cudaMemsetAsync(P.edge, 0, P.edge_stride * n, st));  // the strips' notes to their neighbours: stored only where nonzero
     if (grayscale) smh::k_pixels2<true, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
     else smh::k_pixels2<false, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
     h->launches++;
@@ -414,7 +405,7 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
         h->launches++;
         CU(h, cudaGetLastError());
     }
-    if (a.nstrips > 1u && !no_seams) {  // the pixels either side of the seams between strips
+    if (a.nstrips > 1u) {  // the pixels either side of the seams between strips
         const uint64_t threads = (uint64_t)n * (a.nstrips - 1u) * (a.edge_hp >> 2);
         smh::k_px_seams<<<(unsigned)((threads + 255u) / 256u), 256, 0, st>>>(a);
         h->launches++;

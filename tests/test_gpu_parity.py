@@ -131,6 +131,41 @@ def test_random_noise_frames(vision):
         assert_same(gpu_run(vision, f, False, 2, 4), oracle_run(f, False, 2, 4), f"noise rgb {W}x{H}", scales_from=2)
 
 
+@pytest.mark.parametrize("W,H", [(2560, 1440), (1920, 1080), (1281, 721)])
+def test_strip_seams(vision, W, H):
+    """The pixel pass works in strips of 128 (padded) columns and reads nothing of the neighbouring strip: the
+    3x3 cross and the OCR 7x7 window reach across a seam through k_px_seams.  Content ONLY in the six columns around
+    every seam (marker colours everywhere, bright grey / near-grey in the OCR quadrant), sparse enough that a
+    pixel's only partners are across the seam."""
+    rng = np.random.default_rng(W * 7 + H)
+    base = synth.frames_host(synth.SynthParams(W, H, **synth.PLAIN), 0, 1)[0]
+    r = O.roi(W, H)
+    x, y, w, h = r["map"]
+    qx, qy, qw, qh = r["brq"]
+    pad = x & 3
+    for density in (0.02, 0.3):
+        f = base.copy()
+        roi = f[y:y + h, x:x + w, :3]
+        roi[:] = (40, 60, 50)  # nothing: dark, not grey
+        noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        grey = rng.integers(125, 256, (h, w, 1), dtype=np.uint8)
+        jitter = rng.integers(0, 14, (h, w, 3), dtype=np.uint8) * (rng.random((h, w, 1)) < 0.5)
+        greyish = np.clip(grey.astype(np.int32) + jitter, 0, 255).astype(np.uint8)
+        near = np.zeros(w, dtype=bool)
+        for s in range(1, (pad + w + 127) // 128):
+            c = 128 * s - pad  # map column of the strip's first pixel
+            near[max(c - 3, 0):min(c + 3, w)] = True
+        pick = near[None, :] & (rng.random((h, w)) < density)
+        inq = np.zeros((h, w), dtype=bool)
+        inq[qy - y:qy - y + qh, qx - x:qx - x + qw] = True
+        roi[pick & ~inq] = noise[pick & ~inq]
+        roi[pick & inq] = greyish[pick & inq]
+        half = pick & inq & (rng.random((h, w)) < 0.3)
+        roi[half] = noise[half]  # marker colours inside the quadrant as well
+        assert_same(gpu_run(vision, f, True, 0, 15), oracle_run(f, True, 0, 15), f"seams {W}x{H} {density}")
+        assert_same(gpu_run(vision, f, False, 1, 2), oracle_run(f, False, 1, 2), f"seams rgb {W}x{H} {density}", scales_from=1)
+
+
 def test_map_closed_and_threshold_boundary(vision):
     p = synth.SynthParams(1280, 720, map_open=False)
     frame = synth.frames_host(p, 0, 1)[0]
