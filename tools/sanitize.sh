@@ -5,7 +5,7 @@
 # host batch.  usage: tools/sanitize.sh <tag>   (run on the GPU box; summaries land in gpurun_out/<tag>_sanitize_*.txt)
 tag=${1:-san}
 mkdir -p gpurun_out
-sel='test_golden_synthetic_cases or test_two_branches_concurrently or test_map_closed_and_threshold_boundary or test_debug_views or test_batch_with_closed_maps_and_rgb or test_host_batch or test_stream_over_a_ring or test_ui_map_as_its_l_plane'
+sel='test_golden_synthetic_cases or test_two_branches_concurrently or test_map_closed_and_threshold_boundary or test_debug_views or test_strip_seams or test_random_noise_frames or test_batch_with_closed_maps_and_rgb or test_host_batch or test_stream_over_a_ring or test_ui_map_as_its_l_plane'
 status=0
 for tool in memcheck racecheck synccheck initcheck; do
   log=gpurun_out/${tag}_sanitize_${tool}.txt
