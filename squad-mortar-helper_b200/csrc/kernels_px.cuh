@@ -173,11 +173,12 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     // the quadrant's rows / columns the pointer is never dereferenced
     uint8_t* ocr_p = ocr_f + ((int64_t)(j_first - bqh) * (int64_t)a.q_pitch + (int64_t)(int32_t)qpos);
     const int64_t sc_delta = a.scales - a.ocr;
-    // bitmap: word of tile (jc >> 5, 4 strip + lane / 8), row jc & 31 — one running pointer per lane
+    // bitmap: word of tile (jc >> 5, 4 strip + lane / 8), row jc & 31.  The eight lanes of a group all hold the group's
+    // word of a row; lane 8 g + k keeps row (jc & ~7) + k's and every eighth row the warp stores four whole 32-byte
+    // sectors (a 4-byte store per row and tile cost the memory system far more than its bytes: tools/tile_probe2.cu)
     const uint32_t btile = 4u * strip + (uint32_t)(lane >> 3);
-    const bool bits_lane = (lane & 7) == 0 && btile < a.bits_tx;
-    uint32_t* bits_p = a.bits + (uint64_t)f * a.bits_stride + (((uint64_t)(r0 >> 5) * a.bits_tx + btile) << 5);  // row r0
-    const uint32_t bits_jump = a.bits_tx * 32u - 32u;  // from the last row of a tile to the first of the tile below
+    uint32_t* const bits_f = a.bits + (uint64_t)f * a.bits_stride;
+    uint32_t bits_keep = 0;
 
     uint32_t mwin = 0, cwin = 0, ewin = 0;  // flag nibbles of rows jn, jn-1, ... (newest in bits 0-3)
     // lanes 0 / 31: this strip's flag bytes for its neighbour (side 0 / 1), row 0
@@ -283,25 +284,27 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
         // rows jc-1, jc, jc+1 sit at nibbles LAG+1, LAG, LAG-1 of the windows
         constexpr uint32_t ROWS3 = 0xFFFu << (4 * (LAG - 1));
         uint32_t fl = 0;  // lanes 0 / 31: what the neighbouring strip must know about this row (Pixel2Args::edge)
+        uint32_t v = 0;   // the bitmap word of the lane's group of eight
         if (__any_sync(FULL, (mwin & ROWS3) != 0u)) {  // (almost every row of a map has no marker pixel nearby)
             const uint32_t mc = (mwin >> (4 * LAG)) & 0xFu;
             uint32_t l = __shfl_up_sync(FULL, mc, 1), rr = __shfl_down_sync(FULL, mc, 1);
             if (lane == 0) l = 0u;    // the pixel across the seam: k_px_seams
             if (lane == 31) rr = 0u;
             const uint32_t d4 = (mc | (mc << 1) | (mc >> 1) | (l >> 3) | (rr << 3) | (mwin >> (4 * (LAG + 1))) | (mwin >> (4 * (LAG - 1)))) & vm4;
-            // the four words of the bitmap: 8 lanes' nibbles each
-            uint32_t v = d4 << (4 * (lane & 7));
+            v = d4 << (4 * (lane & 7));
             v |= __shfl_xor_sync(FULL, v, 1);
             v |= __shfl_xor_sync(FULL, v, 2);
             v |= __shfl_xor_sync(FULL, v, 4);
-            if (bits_lane) *bits_p = v;
             if (active) stg_u32(lsd_row, nibble_bytes(d4));
             if (edge) fl = lane == 0 ? (mc & 1u) : (mc >> 3);
         } else {
-            if (bits_lane) *bits_p = 0u;
             if (active) stg_u32(lsd_row, 0u);
         }
-        bits_p += (jc & 31) == 31 ? 1u + bits_jump : 1u;
+        if ((lane & 7) == (jc & 7)) bits_keep = v;
+        if ((jc & 7) == 7 || jc == r1 - 1) {  // uniform: the rows (jc & ~7) .. jc of the four tiles
+            const int j = (jc & ~7) + (lane & 7);
+            if (j <= jc && btile < a.bits_tx) bits_f[((((uint32_t)j >> 5) * a.bits_tx + btile) << 5) + ((uint32_t)j & 31u)] = bits_keep;
+        }
 
         const int jqc = jc - bqh;
         if (QUAD && (FAST || (uint32_t)jqc < (uint32_t)bqh)) {  // uniform: a row of the OCR quadrant

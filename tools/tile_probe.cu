@@ -37,14 +37,14 @@ __global__ void k(const uint32_t* __restrict__ in, uint32_t* __restrict__ ui, ui
             }
     }
 }
-template <int SW, int MODE> float run(const uint32_t* in, uint32_t* ui, uint8_t* lsd, int n, int smem = 0) {
+template <int SW, int MODE> float run(const uint32_t* in, uint32_t* ui, uint8_t* lsd, int n, int smem = 0, int threads = 128) {
     constexpr int NS = (RW + SW - 1) / SW, NB = RH / BAND;
     const long items = (long)n * NS * NB;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     float best = 1e9;
     for (int it = 0; it < 5; it++) {
         cudaEventRecord(a);
-        k<SW, MODE><<<(unsigned)((items + 3) / 4), 128, smem>>>(in, ui, lsd, n);
+        k<SW, MODE><<<(unsigned)((items + threads / 32 - 1) / (threads / 32)), threads, smem>>>(in, ui, lsd, n);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b); if (it && ms < best) best = ms;
     }
@@ -80,6 +80,12 @@ int main() {
     cudaFuncSetAttribute(k<128, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, -1);
     for (int kb : {1, 4, 8, 12, 20, 27, 36}) {  // dynamic shared memory caps the CTAs per SM: 227 KB / (kb + 1) -> 10, 8, 6, 4 CTAs of 4 warps
         t = run<128, 0>(in, ui, lsd, n, kb * 1024); printf("strip 128 r+w4+w1, %2d KB smem per CTA  %.3f ms  %.0f GB/s\n", kb, t, roi * 9 / t / 1e6);
+    }
+    // resident warps per SM capped by unused dynamic shared memory while the carve-out stays below its maximum (70 % = 164 KB)
+    cudaFuncSetAttribute(k<128, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 70);
+    for (int kb : {9, 12, 15, 19, 25, 39}) {
+        int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k<128, 0>, 128, kb * 1024);
+        t = run<128, 0>(in, ui, lsd, n, kb * 1024); printf("strip 128 r+w4+w1, carve-out 70 %%, %2d KB per CTA (%2d CTAs = %2d warps per SM)  %.3f ms  %.0f GB/s\n", kb, nb, nb * 4, t, roi * 9 / t / 1e6);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
