@@ -9,7 +9,7 @@ torch.distributed (NCCL) is only used for the barrier and for gathering per-rank
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline       HBM roofline of the bandwidth-bound kernel (k_pixels2: two launches), CUDA-event timed in the step
+  roofline       HBM roofline of the bandwidth-bound kernel (k_pixels2 + k_px_seams), CUDA-event timed in the step
   roofline_step  the same for the whole step (algorithmic bytes of a step / ms_per_step / peak)
   kernels        per-kernel time inside the timed region (pixel pass, line search) + LSD work figures
   per_rank       ms_per_step / pixel pass / line search of every rank (names the cause of any N-GPU shortfall)
@@ -415,7 +415,7 @@ def main() -> None:
                 torch.cuda.current_stream().wait_stream(s_)
 
     def step_split(ev):
-        # per-kernel durations: the pixel pass (two launches) and the line search over the whole batch, each timed alone
+        # per-kernel durations: the pixel pass (k_pixels2 + k_px_seams) and the line search over the whole batch, each timed alone
         vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, skip_lsd=True, stream=stream)
         ev[1].record()
         vision.process_batch(fp, n, W, H, max_gap=MAX_GAP, grayscale=True, skip_pixels=True, stream=stream)
@@ -546,7 +546,7 @@ def main() -> None:
                        "l2": f"inputs {n * W * H * 4 / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
                        "parallelism": f"frame-sharded x{world}, no collectives",
                        "batches_in_flight": n_fly},
-            "roofline": {"kernel": "k_pixels2 (two launches: plain items + OCR-quadrant items)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "k_pixels2 (one launch: plain and OCR-quadrant CTAs interleaved) + k_px_seams", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bpf * n, "kernel_ms": px_ms,
                          "note": "of measured copy bandwidth; HBM-bound pixel pass over the whole batch timed alone "

@@ -53,6 +53,7 @@ struct Pixel2Args {
     // qr1 clipped to h) in bands of PX2_BAND_Q rows; the plain launch owns the rest in bands of PX2_BAND_P rows:
     // every strip above (na bands per strip) and below (nc), the other strips beside (nb).  nq = bands of a QUAD strip.
     uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq;
+    uint32_t blocks_q;      // CTAs of QUAD items in a merged launch
     const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
     uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
     // What a strip's outermost columns tell the strip next door, [frame][strip][side 0 = first columns, 1 = last][edge_hp
@@ -372,25 +373,41 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
     }
 }
 
-// Two launches per batch: the items that own pixels of the OCR quadrant (QUAD: three rows of halo, OCR classes, the
-// 7x7 search) and all the others plus the button tests.  One population of warps per launch keeps each launch's
-// instruction footprint small — as one kernel the two paths evicted each other from the instruction caches (37 % of
-// the stall samples were instruction fetches).
-template <bool GRAY, bool QUAD>
+// One launch: the items that own pixels of the OCR quadrant (QUAD: three rows of halo, OCR classes, the 7x7 search —
+// bound by instruction issue) are spread evenly among the plain ones (bound by HBM) and the button tests, CTA by CTA,
+// so that every SM holds both kinds all the time (MODE 2; 2.72 ms against 2.82 ms as two launches and 2.77 ms as one
+// launch with the QUAD CTAs first).  MODE 0 / 1: one kind per launch (SMH_B200_PX_MERGED=0).
+template <bool GRAY, int MODE>
 __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
     extern __shared__ __align__(128) uint8_t px2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t item = blockIdx.x * PX2_WARPS + warp;
+    bool quad = MODE == 1;
+    uint32_t blk = blockIdx.x;
+    if (MODE == 2) {  // block b is the q-th QUAD CTA if the count of QUAD CTAs below b + 1 exceeds the count below b
+        const uint32_t q0 = (uint32_t)((uint64_t)blockIdx.x * a.blocks_q / gridDim.x), q1 = (uint32_t)(((uint64_t)blockIdx.x + 1u) * a.blocks_q / gridDim.x);
+        quad = q1 > q0;
+        blk = quad ? q0 : blockIdx.x - q0;
+    }
+    const uint32_t item = blk * PX2_WARPS + warp;
     const uint32_t nqs = a.qs1 - a.qs0;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(px2_smem) + (uint32_t)warp * PX2_WARP_BYTES;
+    const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     uint32_t f, strip;
     int r0, r1;
-    if (QUAD) {
+    if (quad) {
         const uint32_t per_frame = a.nq * nqs;
         f = item / per_frame;
         if (f >= a.n_frames) return;
         const uint32_t sub = item - f * per_frame, bq = sub / nqs;
         strip = a.qs0 + (sub - bq * nqs);
         r0 = (int)(a.qr0 + bq * PX2_BAND_Q); r1 = min(r0 + PX2_BAND_Q, (int)a.qr1);
+        if (MODE != 0) px2_item<GRAY, true>(&tmap, a, f, r0, r1, strip, ring, bars);
     } else {
         const uint32_t above = a.na * a.nstrips, beside = a.nb * (a.nstrips - nqs), n_plain = above + beside + a.nc * a.nstrips;
         const uint32_t per_frame = n_plain + 1u;
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const _
             }
             return;
         }
-        // the rows above the QUAD launch's, then the strips beside its own, then the rows below
+        // the rows above the QUAD items', then the strips beside their own, then the rows below
         uint32_t lo, hi, bq;
         if (sub < above) { bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = 0u; hi = a.qr0; }
         else if (sub < above + beside) {
@@ -428,16 +445,8 @@ __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const _
             bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = a.qr1; hi = a.h;
         }
         r0 = (int)(lo + bq * PX2_BAND_P); r1 = min(r0 + PX2_BAND_P, (int)hi);
+        if (MODE != 1) px2_item<GRAY, false>(&tmap, a, f, r0, r1, strip, ring, bars);
     }
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(px2_smem) + (uint32_t)warp * PX2_WARP_BYTES;
-    const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < PX2_STAGES; s++) mbar_init(bars + 8u * s, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    px2_item<GRAY, QUAD>(&tmap, a, f, r0, r1, strip, ring, bars);
 }
 
 // The pixels either side of a seam between two strips, from the flags the strips left in Pixel2Args::edge: the 3x3

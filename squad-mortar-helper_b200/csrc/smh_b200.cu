@@ -388,22 +388,32 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     const uint32_t BP = smh::PX2_BAND_P, BQ = smh::PX2_BAND_Q;
     a.na = (a.qr0 + BP - 1u) / BP; a.nb = (a.qr1 - a.qr0 + BP - 1u) / BP; a.nc = (a.h - a.qr1 + BP - 1u) / BP;
     a.nq = (a.qr1 - a.qr0 + BQ - 1u) / BQ;
-    // one warp per (frame, band, strip) item, plus one per frame for the button test; two launches (see k_pixels2)
+    // one warp per (frame, band, strip) item, plus one per frame for the button test (see k_pixels2)
     const uint32_t nqs = a.qs1 - a.qs0;
     const uint64_t items_p = (uint64_t)n * ((uint64_t)(a.na + a.nc) * a.nstrips + (uint64_t)a.nb * (a.nstrips - nqs) + 1u);
     const uint64_t items_q = (uint64_t)n * a.nq * nqs;
     const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
     if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
     CU(h, cudaMemsetAsync(P.edge, 0, P.edge_stride * n, st));  // the strips' notes to their neighbours: stored only where nonzero
-    if (grayscale) smh::k_pixels2<true, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
-    else smh::k_pixels2<false, false><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
-    h->launches++;
-    CU(h, cudaGetLastError());
-    if (blocks_q) {
-        if (grayscale) smh::k_pixels2<true, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
-        else smh::k_pixels2<false, true><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+    static const bool merged = [] { const char* e = getenv("SMH_B200_PX_MERGED"); return e ? atoi(e) != 0 : true; }();
+    if (merged) {  // one launch, the two kinds of CTAs interleaved (k_pixels2)
+        a.blocks_q = (uint32_t)blocks_q;
+        if (blocks_p + blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
+        if (grayscale) smh::k_pixels2<true, 2><<<(unsigned)(blocks_p + blocks_q), smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        else smh::k_pixels2<false, 2><<<(unsigned)(blocks_p + blocks_q), smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
         h->launches++;
         CU(h, cudaGetLastError());
+    } else {
+        if (grayscale) smh::k_pixels2<true, 0><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        else smh::k_pixels2<false, 0><<<(unsigned)blocks_p, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        if (blocks_q) {
+            if (grayscale) smh::k_pixels2<true, 1><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+            else smh::k_pixels2<false, 1><<<(unsigned)blocks_q, smh::PX2_THREADS, smh::PX2_SMEM_BYTES, st>>>(tmap, a);
+            h->launches++;
+            CU(h, cudaGetLastError());
+        }
     }
     if (a.nstrips > 1u) {  // the pixels either side of the seams between strips
         const uint64_t threads = (uint64_t)n * (a.nstrips - 1u) * (a.edge_hp >> 2);

@@ -176,7 +176,7 @@ def test_chunked_streams_equal_one_launch(vision, monkeypatch, chunk, lanes):
     monkeypatch.setenv("SMH_B200_BATCH_LANES", str(lanes))
     l0 = vision.launch_count()
     b = vision.process_batch(dev.data_ptr(), n, W, H, start_y=start_y, max_gap=15, lsd_stats=True, minimap=True, stream=st)
-    per_chunk = 5  # pixel pass (plain + OCR-quadrant launches + the seams between strips), minimap, line search
+    per_chunk = 4  # pixel pass (k_pixels2 + the seams between strips), minimap, line search
     assert vision.launch_count() - l0 == per_chunk * ((n + chunk - 1) // chunk), "expected one launch of each kernel per chunk"
     rb = _results(vision, b, n)
     mm_b = _device_array(b.minimap, n * 16).cpu().numpy(), _device_array(b.minimap_found, n).cpu().numpy()
