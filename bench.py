@@ -266,27 +266,34 @@ def run_e2e(args, vision, frames, roi, n, world, barrier, torch, dist, oracle_li
 
 
 def run_latency(vision, synth, torch):
-    """One frame through the trait calls in the orchestrator's order (src/vision/mod.rs:66-223)."""
+    """One frame through the trait calls in the orchestrator's order (src/vision/mod.rs:66-223): from a pageable host frame
+    (what the reference's capture hands over) and from a pinned one (a capture loop that allocates its frame pool pinned)."""
     out = {}
     for name, (w, h) in (("1920x1080", (1920, 1080)), ("2560x1440", (W, H))):
-        frame = synth.frames_host(synth.SynthParams(w, h), 0, 1)[0]
-        wall, dev, shares = [], [], None
-        for it in range(12):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            vision.load_frame(frame)
-            got = vision.crop_to_map(True)
-            assert got is not None
-            vision.isolate_map_markers(); vision.mask_marker_lines()
-            vision.find_marker_lines(MAX_GAP)
-            vision.ocr_preprocess(); vision.find_scales_preprocess(0)
-            dt = (time.perf_counter() - t0) * 1e3
-            ts = vision.timeshares()
-            if it >= 2:
-                wall.append(dt); dev.append(sum(v[1] for v in ts.values())); shares = ts
-        out[name] = {"wall_ms": statistics.median(wall), "device_ms": statistics.median(dev),
-                     "device_ms_without_upload": statistics.median(dev) - shares["load_frame"][1],
-                     "stages_host_ms_device_ms": {k: [round(v[0], 4), round(v[1], 4)] for k, v in shares.items() if v[0] or v[1]}}
+        pageable = synth.frames_host(synth.SynthParams(w, h), 0, 1)[0]
+        pinned = torch.from_numpy(pageable).pin_memory().numpy()
+        for kind, frame in (("", pageable), ("pinned_frame", pinned)):
+            wall, dev, shares = [], [], None
+            for it in range(12):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                vision.load_frame(frame)
+                got = vision.crop_to_map(True)
+                assert got is not None
+                vision.isolate_map_markers(); vision.mask_marker_lines()
+                vision.find_marker_lines(MAX_GAP)
+                vision.ocr_preprocess(); vision.find_scales_preprocess(0)
+                dt = (time.perf_counter() - t0) * 1e3
+                ts = vision.timeshares()
+                if it >= 2:
+                    wall.append(dt); dev.append(sum(v[1] for v in ts.values())); shares = ts
+            rec = {"wall_ms": statistics.median(wall), "device_ms": statistics.median(dev),
+                   "device_ms_without_upload": statistics.median(dev) - shares["load_frame"][1],
+                   "stages_host_ms_device_ms": {k: [round(v[0], 4), round(v[1], 4)] for k, v in shares.items() if v[0] or v[1]}}
+            if kind:
+                out[name][kind] = rec
+            else:
+                out[name] = rec
     return out
 
 

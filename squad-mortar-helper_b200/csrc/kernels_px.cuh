@@ -50,9 +50,9 @@ struct Pixel2Args {
     uint32_t* red; uint8_t* open;
     uint32_t nstrips, n_frames;
     // The QUAD launch's items own the strips [qs0, qs1) of the rows [qr0, qr1) (multiples of 32 around the OCR quadrant,
-    // qr1 clipped to h) in bands of PX2_BAND_Q rows; the plain launch owns the rest in bands of PX2_BAND_P rows:
+    // qr1 clipped to h) in bands of `band` rows (a multiple of 8; 64 for a batch that fills the SMs); the plain items own the rest:
     // every strip above (na bands per strip) and below (nc), the other strips beside (nb).  nq = bands of a QUAD strip.
-    uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq;
+    uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq, band;
     uint32_t blocks_q;      // CTAs of QUAD items in a merged launch
     const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
     uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
@@ -75,16 +75,8 @@ constexpr int PX2_THREADS = PX2_WARPS * 32;
 #ifndef PX2_ROWS_N
 #define PX2_ROWS_N 2
 #endif
-#ifndef PX2_BAND_P_ROWS
-#define PX2_BAND_P_ROWS 64
-#endif
-#ifndef PX2_BAND_Q_ROWS
-#define PX2_BAND_Q_ROWS 64
-#endif
 constexpr int PX2_STAGES = PX2_STAGES_N;
 constexpr int PX2_ROWS = PX2_ROWS_N;             // rows per TMA box
-constexpr int PX2_BAND_P = PX2_BAND_P_ROWS;      // map rows per work item of the plain launch / the QUAD launch
-constexpr int PX2_BAND_Q = PX2_BAND_Q_ROWS;      //   (multiples of 32: whole tile-rows of the bitmap)
 constexpr int PX2_BOX_W = 128;                   // pixels per row of a strip box: 512 bytes, whole 128-byte lines when the
 constexpr int PX2_ROW_BYTES = PX2_BOX_W * 4;     //   capture's map starts on one
 constexpr int PX2_STAGE_BYTES = PX2_ROWS * PX2_ROW_BYTES;
@@ -406,7 +398,7 @@ __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const _
         if (f >= a.n_frames) return;
         const uint32_t sub = item - f * per_frame, bq = sub / nqs;
         strip = a.qs0 + (sub - bq * nqs);
-        r0 = (int)(a.qr0 + bq * PX2_BAND_Q); r1 = min(r0 + PX2_BAND_Q, (int)a.qr1);
+        r0 = (int)(a.qr0 + bq * a.band); r1 = min(r0 + (int)a.band, (int)a.qr1);
         if (MODE != 0) px2_item<GRAY, true>(&tmap, a, f, r0, r1, strip, ring, bars);
     } else {
         const uint32_t above = a.na * a.nstrips, beside = a.nb * (a.nstrips - nqs), n_plain = above + beside + a.nc * a.nstrips;
@@ -444,7 +436,7 @@ __global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const _
             sub -= above + beside;
             bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = a.qr1; hi = a.h;
         }
-        r0 = (int)(lo + bq * PX2_BAND_P); r1 = min(r0 + PX2_BAND_P, (int)hi);
+        r0 = (int)(lo + bq * a.band); r1 = min(r0 + (int)a.band, (int)hi);
         if (MODE != 1) px2_item<GRAY, false>(&tmap, a, f, r0, r1, strip, ring, bars);
     }
 }

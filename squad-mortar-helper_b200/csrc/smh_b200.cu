@@ -385,7 +385,10 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.qr0 = a.bqh & ~31u; a.qr1 = (2u * a.bqh + 31u) & ~31u;
     if (a.qr1 > a.h) a.qr1 = a.h;
     if (a.qs0 >= a.qs1 || a.qr0 >= a.qr1) { a.qs0 = a.qs1 = 0; a.qr0 = a.qr1 = 0; }
-    const uint32_t BP = smh::PX2_BAND_P, BQ = smh::PX2_BAND_Q;
+    // rows per item: 64; a batch too small to fill the SMs with those (the trait's single frame) takes 16-row bands
+    // (four times the warps, a quarter of the rows each: the pass of one frame is bound by a warp's chain of rows)
+    a.band = (uint64_t)n * a.nstrips * ((a.h + 63u) / 64u) >= 8ull * (uint64_t)h->sm_count ? 64u : 16u;
+    const uint32_t BP = a.band, BQ = a.band;
     a.na = (a.qr0 + BP - 1u) / BP; a.nb = (a.qr1 - a.qr0 + BP - 1u) / BP; a.nc = (a.h - a.qr1 + BP - 1u) / BP;
     a.nq = (a.qr1 - a.qr0 + BQ - 1u) / BQ;
     // one warp per (frame, band, strip) item, plus one per frame for the button test (see k_pixels2)
