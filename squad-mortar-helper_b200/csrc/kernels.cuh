@@ -138,6 +138,10 @@ struct Bits {
         const uint32_t X = x + pad;
         return (word(X >> 5, y) >> (X & 31u)) & 1u;
     }
+    // any (x, y): the coordinates are clamped into the image, the caller masks the result of a sample outside it
+    __device__ __forceinline__ uint32_t white_anywhere(uint32_t x, uint32_t y) const {
+        return white(min(x, w - 1u), min(y, h - 1u)) ? 1u : 0u;
+    }
 };
 
 struct LsdArgs {

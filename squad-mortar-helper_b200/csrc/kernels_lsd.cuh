@@ -64,6 +64,13 @@ struct Win2 {
         const uint32_t X = x + pad;
         return (p[((int)y - y0) * L2_WIN_PITCH + (int)(X >> 5) - tx0] >> (X & 31u)) & 1u;
     }
+    // the same for ANY (x, y): a word of the window's array is read whatever the coordinates (the caller masks the
+    // result of a sample outside the image), so that the load needs no branch around it
+    __device__ __forceinline__ uint32_t white_anywhere(uint32_t x, uint32_t y) const {
+        const uint32_t X = x + pad;
+        const int ry = min(max((int)y - y0, 0), L2_WIN_T * 32 - 1), rt = min(max((int)(X >> 5) - tx0, 0), L2_WIN_T - 1);
+        return (p[ry * L2_WIN_PITCH + rt] >> (X & 31u)) & 1u;
+    }
 };
 
 // Clear columns [xlo, xhi] of row r of the tile-row in shared memory (pitch 33).
@@ -131,10 +138,10 @@ __device__ __forceinline__ int l2_march_lanes(const IMG& wv, int nsteps, float p
             xs[u] = x; ys[u] = y;
             const uint32_t ix = (uint32_t)(__float_as_int(__fadd_rd(x, 12582912.0f)) - 0x4B400000);
             const uint32_t iy = (uint32_t)(__float_as_int(__fadd_rd(y, 12582912.0f)) - 0x4B400000);
-            if (ix < wv.w && iy < wv.h) {
-                inb |= 1u << u;
-                wh |= (wv.white(ix, iy) ? 1u : 0u) << u;
-            }
+            // (no branch around the load: eight dependent branch-and-load rounds per batch were most of a window march)
+            const uint32_t in = (ix < wv.w && iy < wv.h) ? 1u : 0u;
+            inb |= in << u;
+            wh |= (wv.white_anywhere(ix, iy) & in) << u;
             xo = __fadd_rn(xo, dx); yo = __fadd_rn(yo, dy);
             x = __fadd_rn(xo, px); y = __fadd_rn(yo, py);
         }
@@ -434,10 +441,15 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                 L2Best best{0ull, px, py};
                 bool any_ray = false;
                 const int c0 = win_steps / 32;
-                // (lane l of a warp takes word warp + NW * l: one pass over the rings, then only the non-empty words are visited)
+                // (every lane takes one word: one pass over the rings, then only the non-empty words are visited.  A marker line
+                // through the seed leaves rays in two opposite directions, 56 words apart: the words of the second half go to
+                // the warps half a CTA further on, so that the four words of such a seed fall to four different warps)
                 uint32_t vmine = 0u;
+                constexpr int L2_HALF = SMH_LSD_BITMAP_WORDS / 2;  // 56
+                static_assert(NW * 16 >= SMH_LSD_BITMAP_WORDS - L2_HALF, "sixteen lanes of every warp cover half the words");
+                const int wmine = lane < 16 ? (warp + NW * lane < L2_HALF ? warp + NW * lane : SMH_LSD_BITMAP_WORDS)
+                                            : L2_HALF + (warp + NW - NW / 2) % NW + NW * (lane - 16);
                 {
-                    const int wmine = warp + NW * lane;
                     if (wmine < SMH_LSD_BITMAP_WORDS) {
                         vmine = 0xFFFFFFFFu;
 #pragma unroll
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                     }
                 }
                 for (uint32_t nzw = __ballot_sync(FULL, vmine != 0u); nzw; nzw &= nzw - 1u) {
-                    const int wl = __ffs(nzw) - 1, w = warp + NW * wl;
+                    const int wl = __ffs(nzw) - 1, w = __shfl_sync(FULL, wmine, wl);
                     const uint32_t v = __shfl_sync(FULL, vmine, wl);
                     if (v == 0u) continue;
                     any_ray = true;

@@ -69,6 +69,9 @@ struct Pixel2Args {
 #endif
 constexpr int PX2_WARPS = PX2_WARPS_N;           // warps (= items) per CTA; 32 resident warps per SM either way
 constexpr int PX2_THREADS = PX2_WARPS * 32;
+#ifndef PX2_MIN_CTAS
+#define PX2_MIN_CTAS (32 / PX2_WARPS)   // resident CTAs per SM the register allocation aims at
+#endif
 #ifndef PX2_STAGES_N
 #define PX2_STAGES_N 3
 #endif
@@ -370,7 +373,7 @@ __device__ __forceinline__ void px2_item(const CUtensorMap* tmap, const Pixel2Ar
 // so that every SM holds both kinds all the time (MODE 2; 2.72 ms against 2.82 ms as two launches and 2.77 ms as one
 // launch with the QUAD CTAs first).  MODE 0 / 1: one kind per launch (SMH_B200_PX_MERGED=0).
 template <bool GRAY, int MODE>
-__global__ void __launch_bounds__(PX2_THREADS, 32 / PX2_WARPS) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
+__global__ void __launch_bounds__(PX2_THREADS, PX2_MIN_CTAS) k_pixels2(const __grid_constant__ CUtensorMap tmap, const Pixel2Args a) {
     extern __shared__ __align__(128) uint8_t px2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool quad = MODE == 1;
