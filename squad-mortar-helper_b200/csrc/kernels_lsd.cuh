@@ -171,8 +171,9 @@ struct L2Best { unsigned long long key; float ex, ey; };
 __device__ __forceinline__ uint32_t l2_pack(int k, int gap, int c) { return (uint32_t)k | ((uint32_t)gap << 12) | ((uint32_t)c << 18); }
 
 // One ray per WARP from its block on (samples 32 c ..) on the global bitmap; folds the result into `best`
-// (the same value in every lane).
-template <bool STATS>
+// (the same value in every lane).  DEEP: the wide CTAs that serve one frame's latency (more loads in flight per ray:
+// 0.90 -> 0.87 ms for a 1080p frame); a full batch is bound by throughput, and there the speculative loads cost 10 %.
+template <bool STATS, bool DEEP>
 __device__ __forceinline__ void l2_march_long(const Bits& im, const LsdArgs& a, uint32_t e, float px, float py, L2Best& best,
                                               uint32_t& steps_u) {
     const int lane = threadIdx.x & 31, sub = lane & (LSD_CKPT - 1);
@@ -190,17 +191,45 @@ __device__ __forceinline__ void l2_march_long(const Bits& im, const LsdArgs& a, 
             if (sub >= q) { xo = __fadd_rn(xo, d.x); yo = __fadd_rn(yo, d.y); }
         xprev = __fadd_rn(xo, px); yprev = __fadd_rn(yo, py);
     }
-    // two blocks in flight: block c+1 is fetched (table value loaded one iteration earlier) before block c is decided
     float gx, gy;
-    cp += 32 / LSD_CKPT;
-    float2 c2 = __ldg(cp);
-    RayBlock b = ray_block_fetch(im, c1, sub, d.x, d.y, px, py);
-    while (true) {
+    if (DEEP) {
+        // Four blocks at a time: their table values, then their bitmap words, are four independent loads each — a block at a
+        // time the ray paid two dependent global-memory latencies per 32 samples.  (A ray rarely ends in the first block of
+        // a group: it came this far because the line it follows is long.)  The table holds n_ckpt values per ray, two
+        // blocks more than any ray inside the mask can need; a group that reaches beyond them repeats the last ones.
+        const float2* const cend = a.ckpt + (uint64_t)(k2 + 1) * a.n_ckpt - 1;
+        while (true) {
+            float2 ck[4];
+#pragma unroll
+            for (int i = 1; i < 4; i++) { const float2* q = cp + i * (32 / LSD_CKPT); ck[i] = __ldg(q <= cend ? q : cend); }
+            ck[0] = c1;
+            RayBlock B[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) B[i] = ray_block_fetch(im, ck[i], sub, d.x, d.y, px, py);
+            bool done = false;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (!done) {
+                    done = ray_block_decide<STATS>(B[i], xprev, yprev, gap_in, a.gap_limit, gx, gy, steps_u);
+                    xprev = B[i].x; yprev = B[i].y;
+                }
+            }
+            if (done) break;
+            cp += 4 * (32 / LSD_CKPT);
+            c1 = __ldg(cp <= cend ? cp : cend);
+        }
+    } else {
+        // two blocks in flight: block c+1 is fetched (table value loaded one iteration earlier) before block c is decided
         cp += 32 / LSD_CKPT;
-        const float2 c3 = __ldg(cp);
-        const RayBlock bn = ray_block_fetch(im, c2, sub, d.x, d.y, px, py);
-        if (ray_block_decide<STATS>(b, xprev, yprev, gap_in, a.gap_limit, gx, gy, steps_u)) break;
-        xprev = b.x; yprev = b.y; b = bn; c2 = c3;
+        float2 c2 = __ldg(cp);
+        RayBlock b = ray_block_fetch(im, c1, sub, d.x, d.y, px, py);
+        while (true) {
+            cp += 32 / LSD_CKPT;
+            const float2 c3 = __ldg(cp);
+            const RayBlock bn = ray_block_fetch(im, c2, sub, d.x, d.y, px, py);
+            if (ray_block_decide<STATS>(b, xprev, yprev, gap_in, a.gap_limit, gx, gy, steps_u)) break;
+            xprev = b.x; yprev = b.y; b = bn; c2 = c3;
+        }
     }
     float ex, ey;
     const float len = ray_finish(im, gx, gy, px, py, d.x, d.y, ex, ey);
@@ -508,7 +537,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                             for (uint32_t todo = am; todo; todo &= todo - 1u) {  // list full: march them here and now
                                 const int sl = __ffs(todo) - 1;
                                 const uint32_t e = __shfl_sync(FULL, l2_pack(k, gap, c), sl);
-                                l2_march_long<STATS>(im, a, e, px, py, best, steps_u);
+                                l2_march_long<STATS, (NW >= 8)>(im, a, e, px, py, best, steps_u);
                             }
                         }
                     }
@@ -544,7 +573,7 @@ __global__ void __launch_bounds__(NW * 32) k_lsd2(const LsdArgs a) {
                 // ---- survivors: one ray per warp, shared over the warps -----------------------------------
                 {
                     const uint32_t ns = min(sh.n_surv, sh.surv_end);
-                    for (uint32_t j = warp; j < ns; j += NW) l2_march_long<STATS>(im, a, sh.surv[j], px, py, best, steps_u);
+                    for (uint32_t j = warp; j < ns; j += NW) l2_march_long<STATS, (NW >= 8)>(im, a, sh.surv[j], px, py, best, steps_u);
                 }
                 // warp argmax of (len, k): the LAST index among the longest rays (D6)
                 {
