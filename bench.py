@@ -248,8 +248,15 @@ def run_e2e(args, vision, frames, roi, n, world, barrier, torch, dist, oracle_li
         del outs
     bw = gather(world, dist, torch, list(bus_ceiling(torch, barrier)))
     h2d_pf, d2h_pf = h2d / n, res["rgba"]["d2h_bytes_per_step"] / n
-    # a frame needs its upload, its download, and their sum through whatever the two directions share (host memory, root complex)
-    ceiling = sum(1.0 / max(h2d_pf / (b[0] * 1e9), d2h_pf / (b[1] * 1e9), (h2d_pf + d2h_pf) / ((b[2] + b[3]) * 1e9)) for b in bw)
+    # A frame needs its upload and its download.  While the shorter of the two is on the bus the other one runs at its
+    # two-way rate, for the rest of its bytes at its one-way rate: the least time the longer direction can take.
+    def frame_time(b):
+        up1, dn1, up2, dn2 = (x * 1e9 for x in b)
+        t_dn, t_up = d2h_pf / dn2, h2d_pf / up2            # each direction alone at its two-way rate
+        if t_up >= t_dn:                                    # uploads are the longer direction
+            return t_dn + max(h2d_pf - t_dn * up2, 0.0) / up1
+        return t_up + max(d2h_pf - t_up * dn2, 0.0) / dn1
+    ceiling = sum(1.0 / frame_time(b) for b in bw)
     return {"value": res["rgba"]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": res["rgba"]["d2h_bytes_per_step"],
             "frames_per_step": n, "steps": e_steps, "ring_frames": ring,
             "per_rank_frames_per_s": res["rgba"]["per_rank_frames_per_s"], "lines_match_oracle": res["rgba"]["lines_match_oracle"],
@@ -258,8 +265,9 @@ def run_e2e(args, vision, frames, roi, n, world, barrier, torch, dist, oracle_li
             "bus": {"per_rank_pinned_copy_GBs": {"h2d_alone": [b[0] for b in bw], "d2h_alone": [b[1] for b in bw],
                                                  "h2d_with_d2h": [b[2] for b in bw], "d2h_with_h2d": [b[3] for b in bw]},
                     "ceiling_frames_per_s": ceiling, "frac_of_ceiling": res["rgba"]["value"] / ceiling if ceiling else None,
-                    "note": "every rank copying 128 MiB pinned blocks at once; per rank a frame takes at least max(upload bytes / h2d alone, "
-                            "download bytes / d2h alone, (upload + download bytes) / (h2d + d2h with both directions busy)); ceiling = sum over ranks"},
+                    "note": "every rank copying 128 MiB pinned blocks at once; per rank and frame: the shorter direction's time at its two-way rate, "
+                            "during which the longer direction moves at its two-way rate, + the rest of the longer direction's bytes at its "
+                            "one-way rate; ceiling = sum over ranks"},
             "note": "smh_b200_process_host_stream: a ring of pinned host frames -> map + button rectangles up -> kernels -> ui_map/ocr/scales/lines "
                     "back into a ring of pinned result buffers, 3 chunks of 32 frames in flight; the grayscale ui_map crosses the bus as its L plane "
                     "and is widened to RGBA in the caller's buffer by the library's host threads inside the timed region"}
