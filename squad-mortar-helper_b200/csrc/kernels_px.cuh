@@ -5,8 +5,8 @@
 // reference kernels K1-K9 (vision-gpu/cuda/cuda.cu:312-546,616-635 + NPP dilate) and restates the vision-cpu
 // arithmetic (vision-cpu/src/lib.rs:110-280,357-375) bit for bit (vec_plain / vec_quadrant in kernels.cuh).
 //
-// Warp-autonomous, no block barrier.  A work item is (frame, band of 64 map rows = two tile-rows of the bitmap,
-// strip of 128 columns = 4 bitmap tiles) or a frame's button test.  Columns are PADDED coordinates X = x + pad,
+// Warp-autonomous, no block barrier.  A work item is (frame, band of 64 map rows — 16 when the batch is too small to
+// fill the SMs —, strip of 128 columns = 4 bitmap tiles) or a frame's button test.  Columns are PADDED coordinates X = x + pad,
 // pad = map_x & 3: the map ROI starts at an arbitrary pixel column of the capture (1219 at 1440p) and a TMA box
 // must start on a 16-byte boundary (measured: tools/tma_probe.cu — an odd pixel start raises an illegal
 // instruction), so every plane carries the capture's 16-byte phase as a left pad of 0..3 pixels and strip,
@@ -49,7 +49,7 @@ struct Pixel2Args {
     uint32_t start_y_uniform;
     uint32_t* red; uint8_t* open;
     uint32_t nstrips, n_frames;
-    // The QUAD launch's items own the strips [qs0, qs1) of the rows [qr0, qr1) (multiples of 32 around the OCR quadrant,
+    // The QUAD items own the strips [qs0, qs1) of the rows [qr0, qr1) (multiples of 32 around the OCR quadrant,
     // qr1 clipped to h) in bands of `band` rows (a multiple of 8; 64 for a batch that fills the SMs); the plain items own the rest:
     // every strip above (na bands per strip) and below (nc), the other strips beside (nb).  nq = bands of a QUAD strip.
     uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq, band;
