@@ -350,7 +350,7 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end, latency and config-4 legs")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="batches in flight: steps alternate between this many handles/streams (1 = one stream)")
     ap.add_argument("--serial", action="store_true",
                     help="one launch per kernel on one stream (no chunk overlap): the form the ncu launch list is taken on")
