@@ -11,7 +11,7 @@ fn main() {
     let csrc = src.join("squad-mortar-helper_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     for f in ["smh_b200.cu", "kernels.cuh", "kernels_px.cuh", "kernels_lsd.cuh", "kernels_next.cuh", "kernels_icons.cuh", "smh_host_widen.cpp",
-              "smh_pixel.h", "smh_synth.h", "smh_lsd_filter.h"] {
+              "smh_pixel.h", "smh_synth.h", "smh_lsd_filter.h", "smh_px_plan.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", src.join("include/smh_b200.h").display());

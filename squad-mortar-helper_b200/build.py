@@ -41,7 +41,7 @@ def _stale(target: Path, sources) -> bool:
 
 
 def cuda_sources():
-    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_lsd.cuh", CSRC / "kernels_px.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_host_widen.cpp", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h",
+    return [CSRC / "smh_b200.cu", CSRC / "kernels.cuh", CSRC / "kernels_lsd.cuh", CSRC / "kernels_px.cuh", CSRC / "kernels_next.cuh", CSRC / "kernels_icons.cuh", CSRC / "smh_host_widen.cpp", CSRC / "smh_pixel.h", CSRC / "smh_synth.h", CSRC / "smh_lsd_filter.h", CSRC / "smh_px_plan.h",
             ROOT / "include" / "smh_b200.h", ROOT / "include" / "smh_consts.h"]
 
 
@@ -57,7 +57,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
 def build_hostcheck(force: bool = False) -> Path:
     out = PKG / "libsmh_hostcheck.so"
-    src = [CSRC / "hostcheck.cpp", CSRC / "smh_pixel.h", CSRC / "smh_lsd_filter.h", ROOT / "include" / "smh_consts.h"]
+    src = [CSRC / "hostcheck.cpp", CSRC / "smh_pixel.h", CSRC / "smh_lsd_filter.h", CSRC / "smh_px_plan.h", ROOT / "include" / "smh_consts.h"]
     if force or _stale(out, src):
         subprocess.run([_gxx(), "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                         str(CSRC / "hostcheck.cpp"), "-o", str(out)], check=True)

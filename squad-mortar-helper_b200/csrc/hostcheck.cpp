@@ -4,6 +4,7 @@
 // Build: g++ -O2 -ffp-contract=off -fPIC -shared hostcheck.cpp -o ../libsmh_hostcheck.so
 #include "smh_pixel.h"
 #include "smh_lsd_filter.h"
+#include "smh_px_plan.h"
 
 #include <string.h>
 
@@ -97,5 +98,26 @@ int smh_hostcheck_lsd_filter_quarters(const uint8_t* img, uint32_t w, uint32_t h
         marked[k] = (uint8_t)on;
     }
     return F.nw;
+}
+
+// The pixel pass's cut of a map into work items (smh_px_plan.h), item by item: cover[(row / 8) * nstrips + strip] += 1 for
+// every 8-row group of every item, quad[...] = 1 where a QUAD item owns the group.  Returns the number of strips.
+uint32_t smh_hostcheck_px_plan(uint32_t pad, uint32_t w, uint32_t h, uint32_t bqw, uint32_t bqh, uint32_t band, uint32_t* cover, uint8_t* quad,
+                               uint32_t* counts) {
+    smh_px_plan p;
+    smh_px_plan_make(&p, pad, w, h, bqw, bqh, band);
+    const uint32_t nq = smh_px_plan_quad_items(&p), np = smh_px_plan_plain_items(&p);
+    for (uint32_t k = 0; k < nq + np; k++) {
+        uint32_t strip; int r0, r1;
+        if (k < nq) smh_px_plan_quad_item(&p, k, &strip, &r0, &r1);
+        else smh_px_plan_plain_item(&p, k - nq, &strip, &r0, &r1);
+        if (r0 < 0 || r1 <= r0 || r1 > (int)h || (r0 & 7) || strip >= p.nstrips) return 0xFFFFFFFFu;  // an item must own rows, 8-row aligned
+        for (int g = r0 >> 3; g <= (r1 - 1) >> 3; g++) {
+            cover[(uint32_t)g * p.nstrips + strip]++;
+            if (k < nq) quad[(uint32_t)g * p.nstrips + strip] = 1;
+        }
+    }
+    if (counts) { counts[0] = nq; counts[1] = np; counts[2] = p.qr0; counts[3] = p.qr1; counts[4] = p.qs0; counts[5] = p.qs1; }
+    return p.nstrips;
 }
 }

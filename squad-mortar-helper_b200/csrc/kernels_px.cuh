@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include "kernels.cuh"
+#include "smh_px_plan.h"
 
 namespace smh {
 
@@ -48,11 +49,8 @@ struct Pixel2Args {
     const uint32_t* start_y;  // device [n] or nullptr
     uint32_t start_y_uniform;
     uint32_t* red; uint8_t* open;
-    uint32_t nstrips, n_frames;
-    // The QUAD items own the strips [qs0, qs1) of the rows [qr0, qr1) (multiples of 32 around the OCR quadrant,
-    // qr1 clipped to h) in bands of `band` rows (a multiple of 8; 64 for a batch that fills the SMs); the plain items own the rest:
-    // every strip above (na bands per strip) and below (nc), the other strips beside (nb).  nq = bands of a QUAD strip.
-    uint32_t qr0, qr1, qs0, qs1, na, nb, nc, nq, band;
+    uint32_t n_frames;
+    smh_px_plan plan;       // how the map is cut into items (smh_px_plan.h)
     uint32_t blocks_q;      // CTAs of QUAD items in a merged launch
     const uint32_t* lut;    // marker predicate, 1 bit per colour (r<<16|g<<8|b)
     uint32_t* bits; uint64_t bits_stride; uint32_t bits_tx;  // tile-major 1-bit copy of the dilated mask
@@ -384,7 +382,6 @@ __global__ void __launch_bounds__(PX2_THREADS, PX2_MIN_CTAS) k_pixels2(const __g
         blk = quad ? q0 : blockIdx.x - q0;
     }
     const uint32_t item = blk * PX2_WARPS + warp;
-    const uint32_t nqs = a.qs1 - a.qs0;
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(px2_smem) + (uint32_t)warp * PX2_WARP_BYTES;
     const uint32_t bars = ring + PX2_STAGES * PX2_STAGE_BYTES;
     if (lane == 0) {
@@ -396,19 +393,16 @@ __global__ void __launch_bounds__(PX2_THREADS, PX2_MIN_CTAS) k_pixels2(const __g
     uint32_t f, strip;
     int r0, r1;
     if (quad) {
-        const uint32_t per_frame = a.nq * nqs;
+        const uint32_t per_frame = smh_px_plan_quad_items(&a.plan);
         f = item / per_frame;
         if (f >= a.n_frames) return;
-        const uint32_t sub = item - f * per_frame, bq = sub / nqs;
-        strip = a.qs0 + (sub - bq * nqs);
-        r0 = (int)(a.qr0 + bq * a.band); r1 = min(r0 + (int)a.band, (int)a.qr1);
+        smh_px_plan_quad_item(&a.plan, item - f * per_frame, &strip, &r0, &r1);
         if (MODE != 0) px2_item<GRAY, true>(&tmap, a, f, r0, r1, strip, ring, bars);
     } else {
-        const uint32_t above = a.na * a.nstrips, beside = a.nb * (a.nstrips - nqs), n_plain = above + beside + a.nc * a.nstrips;
-        const uint32_t per_frame = n_plain + 1u;
+        const uint32_t n_plain = smh_px_plan_plain_items(&a.plan), per_frame = n_plain + 1u;
         f = item / per_frame;
         if (f >= a.n_frames) return;
-        uint32_t sub = item - f * per_frame;
+        const uint32_t sub = item - f * per_frame;
         if (sub == n_plain) {
             // ---- close-deployment button test (vision-cpu/src/lib.rs:115-135) -----------------
             const uint8_t* frame = a.frames + (uint64_t)f * a.frame_stride;
@@ -428,18 +422,7 @@ __global__ void __launch_bounds__(PX2_THREADS, PX2_MIN_CTAS) k_pixels2(const __g
             }
             return;
         }
-        // the rows above the QUAD items', then the strips beside their own, then the rows below
-        uint32_t lo, hi, bq;
-        if (sub < above) { bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = 0u; hi = a.qr0; }
-        else if (sub < above + beside) {
-            sub -= above;
-            const uint32_t per = a.nstrips - nqs, k = sub % per;
-            bq = sub / per; strip = k < a.qs0 ? k : k + nqs; lo = a.qr0; hi = a.qr1;
-        } else {
-            sub -= above + beside;
-            bq = sub / a.nstrips; strip = sub - bq * a.nstrips; lo = a.qr1; hi = a.h;
-        }
-        r0 = (int)(lo + bq * a.band); r1 = min(r0 + (int)a.band, (int)hi);
+        smh_px_plan_plain_item(&a.plan, sub, &strip, &r0, &r1);
         if (MODE != 1) px2_item<GRAY, false>(&tmap, a, f, r0, r1, strip, ring, bars);
     }
 }
@@ -449,7 +432,7 @@ __global__ void __launch_bounds__(PX2_THREADS, PX2_MIN_CTAS) k_pixels2(const __g
 // three (vision-cpu/src/lib.rs:196-216).  One thread per (frame, seam, four rows); almost all of them read two zero
 // words and leave.
 __global__ void __launch_bounds__(256) k_px_seams(const Pixel2Args a) {
-    const uint32_t nrq = a.edge_hp >> 2, nseams = a.nstrips - 1u;
+    const uint32_t nrq = a.edge_hp >> 2, nseams = a.plan.nstrips - 1u;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t rq = (uint32_t)(idx % nrq);
     const uint64_t t = idx / nrq;

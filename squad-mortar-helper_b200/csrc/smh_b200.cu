@@ -375,26 +375,18 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
     a.ocr = P.ocr.ptr; a.scales = P.scales.ptr; a.q_stride = P.ocr.frame_stride; a.q_pitch = P.ocr.pitch; a.q_pad = P.qpad;
     a.start_y = per_frame_start_y ? P.start_y : nullptr; a.start_y_uniform = start_y_uniform;
     a.red = P.red; a.open = P.open;
-    a.nstrips = (a.pad + a.w + 127u) / 128u; a.n_frames = n;
+    a.n_frames = n;
     a.lut = h->d_lut;
     a.bits = P.bits; a.bits_stride = P.bits_stride; a.bits_tx = P.bg.tx;
     a.edge = P.edge; a.edge_stride = P.edge_stride; a.edge_hp = P.edge_hp;
-    // the QUAD launch's items: strips [qs0, qs1) x rows [qr0, qr1) around the OCR quadrant (see Pixel2Args)
-    a.qs0 = (a.bqw + a.pad) / 128u; a.qs1 = (2u * a.bqw + a.pad + 127u) / 128u;
-    if (a.qs1 > a.nstrips) a.qs1 = a.nstrips;
-    a.qr0 = a.bqh & ~31u; a.qr1 = (2u * a.bqh + 31u) & ~31u;
-    if (a.qr1 > a.h) a.qr1 = a.h;
-    if (a.qs0 >= a.qs1 || a.qr0 >= a.qr1) { a.qs0 = a.qs1 = 0; a.qr0 = a.qr1 = 0; }
     // rows per item: 64; a batch too small to fill the SMs with those (the trait's single frame) takes 16-row bands
     // (four times the warps, a quarter of the rows each: the pass of one frame is bound by a warp's chain of rows)
-    a.band = (uint64_t)n * a.nstrips * ((a.h + 63u) / 64u) >= 8ull * (uint64_t)h->sm_count ? 64u : 16u;
-    const uint32_t BP = a.band, BQ = a.band;
-    a.na = (a.qr0 + BP - 1u) / BP; a.nb = (a.qr1 - a.qr0 + BP - 1u) / BP; a.nc = (a.h - a.qr1 + BP - 1u) / BP;
-    a.nq = (a.qr1 - a.qr0 + BQ - 1u) / BQ;
+    const uint32_t nstrips = (a.pad + a.w + 127u) / 128u;
+    const uint32_t band = (uint64_t)n * nstrips * ((a.h + 63u) / 64u) >= 8ull * (uint64_t)h->sm_count ? 64u : 16u;
+    smh_px_plan_make(&a.plan, a.pad, a.w, a.h, a.bqw, a.bqh, band);
     // one warp per (frame, band, strip) item, plus one per frame for the button test (see k_pixels2)
-    const uint32_t nqs = a.qs1 - a.qs0;
-    const uint64_t items_p = (uint64_t)n * ((uint64_t)(a.na + a.nc) * a.nstrips + (uint64_t)a.nb * (a.nstrips - nqs) + 1u);
-    const uint64_t items_q = (uint64_t)n * a.nq * nqs;
+    const uint64_t items_p = (uint64_t)n * ((uint64_t)smh_px_plan_plain_items(&a.plan) + 1u);
+    const uint64_t items_q = (uint64_t)n * smh_px_plan_quad_items(&a.plan);
     const uint64_t blocks_p = (items_p + smh::PX2_WARPS - 1) / smh::PX2_WARPS, blocks_q = (items_q + smh::PX2_WARPS - 1) / smh::PX2_WARPS;
     if (blocks_p > 0x7FFFFFFFull || blocks_q > 0x7FFFFFFFull) return fail(h, SMH_E_ARG, "batch too large for one launch");
     CU(h, cudaMemsetAsync(P.edge, 0, P.edge_stride * n, st));  // the strips' notes to their neighbours: stored only where nonzero
@@ -418,8 +410,8 @@ int launch_pixels(smh_b200* h, const Planes& P, const uint8_t* frames, uint64_t 
             CU(h, cudaGetLastError());
         }
     }
-    if (a.nstrips > 1u) {  // the pixels either side of the seams between strips
-        const uint64_t threads = (uint64_t)n * (a.nstrips - 1u) * (a.edge_hp >> 2);
+    if (nstrips > 1u) {  // the pixels either side of the seams between strips
+        const uint64_t threads = (uint64_t)n * (nstrips - 1u) * (a.edge_hp >> 2);
         smh::k_px_seams<<<(unsigned)((threads + 255u) / 256u), 256, 0, st>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
