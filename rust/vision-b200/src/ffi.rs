@@ -1,6 +1,7 @@
 //! Raw bindings of include/smh_b200.h.  One `extern "C"` item per entry point; names, argument order and types
 //! are exactly the header's (tests/test_capi_cpu.py keeps the header, the library's exports and the Python
-//! mirror in step; this file is checked against the header by hand — no Rust toolchain in the build image).
+//! mirror in step, and that this file binds every entry point the header declares — by name: no Rust toolchain in the
+//! build image checks the types).
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_void};
 
@@ -67,6 +68,59 @@ pub struct smh_b200_host_results {
     pub icon_sad: *mut u32,
 }
 
+/// One output plane of a device batch (smh_b200_plane): rows `pitch` bytes apart, `pad` pixels of left padding
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct smh_b200_plane {
+    pub ptr: *mut u8,
+    pub frame_stride: u64,
+    pub pitch: u32,
+    pub pad: u32,
+    pub width: u32,
+    pub height: u32,
+    pub bytes_per_pixel: u32,
+    pub reserved: u32,
+}
+
+/// Device-resident results of smh_b200_process_batch (smh_b200_batch); owned by the handle
+#[repr(C)]
+pub struct smh_b200_batch {
+    pub n_frames: u32,
+    pub w: u32,
+    pub h: u32,
+    pub reserved: u32,
+    pub roi: [u32; 12],
+    pub ui_map: smh_b200_plane,
+    pub lsd_image: smh_b200_plane,
+    pub ocr_out: smh_b200_plane,
+    pub scales: smh_b200_plane,
+    pub lines: *mut f32,
+    pub n_lines: *mut u32,
+    pub red_pixels: *mut u32,
+    pub map_open: *mut u8,
+    pub lsd_stats: *mut u64,
+    pub minimap: *mut u32,
+    pub minimap_found: *mut u8,
+    pub icon_found: *mut u8,
+    pub icon_xy: *mut u32,
+    pub icon_sad: *mut u32,
+}
+
+/// Parameters of the synthetic capture generator (smh_b200_synth_params; tests and benchmarks)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct smh_b200_synth_params {
+    pub seed: u64,
+    pub w: u32,
+    pub h: u32,
+    pub n_segments: u32,
+    pub n_blips: u32,
+    pub n_labels: u32,
+    pub map_open: u32,
+    pub blip_band_pct: u32,
+    pub reserved: u32,
+}
+
 extern "C" {
     // ---- lifecycle + per-frame trait methods ----
     pub fn smh_b200_create(device: i32, out: *mut *mut smh_b200) -> i32;
@@ -94,6 +148,16 @@ extern "C" {
                                             debug_lines: *mut [u32; 4], n_debug: *mut u32) -> i32;
     pub fn smh_b200_process(h: *mut smh_b200, bgra: *const u8, w: u32, hgt: u32, pitch_bytes: u32, grayscale: i32, detect_markers: i32,
                             max_gap: u32, ocr: smh_b200_ocr_fn, user: *mut c_void, out: *mut smh_b200_vision_results) -> i32;
+    // ---- device-resident batches, their planes, the launch counter; generators and tables of the tests ----
+    pub fn smh_b200_process_batch(h: *mut smh_b200, d_frames: *const u8, n: u32, w: u32, hgt: u32, pitch_bytes: u32, frame_stride: u64,
+                                  start_y: *const u32, max_gap: u32, flags: u32, stream: *mut c_void, out: *mut smh_b200_batch) -> i32;
+    pub fn smh_b200_batch_meters_to_px_ratio(h: *mut smh_b200, scales: *const smh_b200_scale, n_scales: *const u8, n: u32, stream: *mut c_void,
+                                             ratio: *mut f64, found: *mut u8) -> i32;
+    pub fn smh_b200_download_plane(h: *mut smh_b200, p: *const smh_b200_plane, first: u32, count: u32, host_out: *mut u8, stream: *mut c_void) -> i32;
+    pub fn smh_b200_launch_count(h: *mut smh_b200) -> u64;
+    pub fn smh_b200_synth_frames_host(p: *const smh_b200_synth_params, first: u32, n: u32, out: *mut u8) -> i32;
+    pub fn smh_b200_synth_frames_device(h: *mut smh_b200, p: *const smh_b200_synth_params, first: u32, n: u32, d_out: *mut u8, stream: *mut c_void) -> i32;
+    pub fn smh_b200_colour_table(h: *mut smh_b200, which: u32, host_out: *mut u8) -> i32;
     // ---- Timeshares (vision-common/src/debug.rs:3-29) ----
     pub fn smh_b200_timeshares(h: *mut smh_b200, host_ms: *mut f32, device_ms: *mut f32) -> i32;
     pub fn smh_b200_stage_name(stage: u32) -> *const c_char;

@@ -24,6 +24,15 @@ def test_library_exports_every_declared_symbol():
     capi.lib()
 
 
+def test_rust_sketch_binds_every_declared_symbol():
+    """rust/vision-b200/src/ffi.rs (never compiled here) names every entry point of the header, and nothing else."""
+    header = (ROOT / "include" / "smh_b200.h").read_text()
+    declared = set(re.findall(r"\b(smh_b200_[a-z0-9_]+)\s*\(", header))
+    ffi = (ROOT / "rust" / "vision-b200" / "src" / "ffi.rs").read_text()
+    bound = set(re.findall(r"pub fn (smh_b200_[a-z0-9_]+)", ffi))
+    assert bound == declared, (sorted(declared - bound), sorted(bound - declared))
+
+
 def test_library_carries_sm100a_code_only():
     import subprocess
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", str(capi.LIB_PATH)], capture_output=True, text=True).stdout
