@@ -3,8 +3,10 @@ commented out in the reference).  TEST INFRASTRUCTURE ONLY: in the reference thi
 once per marker size with the `image` crate; the CUDA library receives the finished templates as data
 (smh_b200_load_map_markers), exactly what vision-gpu uploads (vision-gpu/src/gpumarkers.rs:24-52).
 
-Third-party arithmetic restated from the published algorithm, sources NOT under /root/reference —
-**parity unpinned**:
+Third-party arithmetic restated from the published algorithm, sources NOT under /root/reference — the template
+GENERATION (TGA decode + Gaussian resize of the `image` crate) is **parity unpinned**: the reference never runs it
+(the stage is commented out) and the crate cannot be built here; the MATCH against finished templates is pinned
+against the reference's kernels K11/K12 (tests/test_gpu_refcuda.py::test_template_match_kernels_k11_k12):
   image 0.23.14 (Cargo.lock:1487)  TGA decoder (type 10 RLE true-colour, bottom-left origin flipped),
                                    imageops::resize with FilterType::Gaussian: vertical pass into f32
                                    pixels, then horizontal pass, clamp, round-to-nearest;

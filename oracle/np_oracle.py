@@ -3,7 +3,8 @@
 Second, differently-structured statement of SURVEY.md Appendix A used to cross-check
 oracle/smh_oracle.c (whole-array float32 ops instead of per-pixel scalar code, shift-based
 dilation instead of a distance transform, ray marching vectorised over the 3600 angles).
-It shares no code with the C oracle.  PARITY STATUS: parity unpinned (see smh_oracle.h).
+It shares no code with the C oracle.  PARITY STATUS: this restatement itself is pinned only by its agreement with
+the C oracle (which is pinned against the reference's own compiled CUDA kernels, see smh_oracle.h).
 
 Reference lines restated (relative to /root/reference):
   ROI          vision-common/src/screen.rs:55-66, consts/mod.rs:7-19, vision-cpu/src/lib.rs:137-145

@@ -3,7 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product (squad-mortar-helper_b200/) never does.
 
-PARITY STATUS: parity unpinned — see oracle/smh_oracle.h.
+PARITY STATUS: pinned against the reference's own compiled CUDA kernels (oracle/_ref) — see oracle/smh_oracle.h.
 """
 from __future__ import annotations
 

@@ -1,6 +1,7 @@
 /* smh_oracle.c — CPU ORACLE (test infrastructure; see smh_oracle.h header comment).
  *
- * PARITY STATUS: parity unpinned (no reference golden vectors exist for this path).
+ * PARITY STATUS: pinned against the reference's own compiled CUDA kernels (oracle/_ref; see smh_oracle.h and
+ * DESIGN.md section 2); the vision-cpu-only branches listed there are reader-verified.
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared
  * All float arithmetic is IEEE binary32, no FMA contraction, evaluated in the order the

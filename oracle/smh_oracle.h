@@ -5,11 +5,19 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it.  The product library (libsmh_b200.so) never links or calls it.
  *
- * PARITY STATUS: **parity unpinned**.  The reference holds no golden vectors or
- * known-answer tests for this path and its Rust crates cannot be built
- * in this image (no cargo/rustc; crates.io deps un-vendored).  The oracle is pinned
- * only by (i) an independent numpy restatement (oracle/np_oracle.py), (ii) exhaustive
- * 2^24-colour tables, (iii) self-generated goldens under tests/golden/.
+ * PARITY STATUS: **pinned against outputs of the reference itself, run here** — its own CUDA backend.
+ * The reference holds no golden vectors or known-answer tests for this path and its
+ * Rust crates cannot be built in this image (no cargo/rustc; crates.io deps un-vendored), but its
+ * `vision-gpu` kernels compile unmodified for sm_100a from where they lie (oracle/Makefile `refgpu`
+ * -> oracle/_ref/libsmh_refgpu.so, driven by oracle/ref_gpu_harness.cu).  The `smh_oracle_gpuflavour_*`
+ * functions below restate those KERNELS and tests/test_gpu_refcuda.py demands bit equality with their
+ * object code on a B200: every ray of K10 (1826 seeds x 3600 rays x four max_gap values), K8 over all
+ * 2^24 colours (tests/golden/k8_marker_table.npz is K8's own output), the NPP dilation, K1-K6, K11/K12.
+ * The `vision-cpu` functions the CUDA product is checked against share their code with that flavour
+ * wherever the two backends agree, with the documented divergences switched;
+ * what stays reader-verified — branches only `vision-cpu` has, which no reference object code can
+ * execute — is listed in DESIGN.md section 2.  Beside that: an independent numpy restatement
+ * (oracle/np_oracle.py), exhaustive 2^24-colour tables, self-generated goldens under tests/golden/.
  *
  * Third-party arithmetic restated from the published algorithm (sources NOT in
  * /root/reference): image 0.23.14 (`Pixel::to_luma`, Cargo.lock:1487), imageproc 0.22.0
