@@ -106,3 +106,26 @@ def test_filter_random_noise(hostcheck):
     img = (rng.random((240, 320)) < 0.06).astype(np.uint8) * 255
     seeds = pick_seeds(img, rng, 80)
     check_seeds(hostcheck, img, seeds, 15)
+
+
+@pytest.mark.parametrize("NW", [4, 8])
+def test_ray_bitmap_words_to_warps_is_a_bijection(NW):
+    """k_lsd2 (csrc/kernels_lsd.cuh): lane l of warp p takes word `wmine` of the 113-word ray bitmap — the first 56 words by
+    p + NW l, the others shifted by half a CTA so that the two opposite directions of a line (56 words apart) fall to
+    different warps.  Restated here: every word is taken exactly once, and words w, w + 56 never share a warp."""
+    WORDS, HALF = 113, 56
+    owner = {}
+    for p in range(NW):
+        for lane in range(32):
+            if lane < 16:
+                w = p + NW * lane
+                w = w if w < HALF else WORDS
+            else:
+                w = HALF + (p + NW - NW // 2) % NW + NW * (lane - 16)
+            if w < WORDS:
+                assert w not in owner, (w, owner[w], p)
+                owner[w] = p
+    assert sorted(owner) == list(range(WORDS))
+    for w in range(HALF):
+        assert owner[w] != owner[w + HALF], w
+        assert owner[w] != owner[(w + 1) % HALF] or NW == 1
