@@ -237,13 +237,13 @@ __device__ __forceinline__ void l2_march_long(const Bits& im, const LsdArgs& a, 
     if (key >= best.key) { best.key = key; best.ex = ex; best.ey = ey; }
 }
 
-template <int NW, bool STATS>
 #ifndef L2_MIN_CTAS
 #define L2_MIN_CTAS 5
 #endif
 // (registers: the 4-warp form is held to what five resident CTAs allow, 94: left to itself the compiler takes 123, four
 // CTAs fill the register file, and the next batch's pixel pass finds no room beside the line search.  Measured with
 // batches in flight, ms per 1024-frame step: 123 registers 4.66, 94 -> 4.57 - 4.69, 80 -> 4.88, 72 -> 4.81)
+template <int NW, bool STATS>
 __global__ void __launch_bounds__(NW * 32, NW <= 4 ? L2_MIN_CTAS : 1) k_lsd2(const LsdArgs a) {
     extern __shared__ __align__(16) uint32_t l2_smem[];
     using Shared = Lsd2Shared<NW>;
